@@ -1,0 +1,116 @@
+"""Joint CTC/attention beam search around a pluggable LogitsProcessor.
+
+The reference never implements beam search itself: `JointCTCAttentionEncoderDecoder.generate`
+(src/models/ctc_encoder_plus_autoregressive_decoder.py:450-482) hands the processor built in
+`_get_logits_processor` (:360-404) to transformers 4.39.3 `GenerationMixin.beam_search`, which
+cannot run here (SURVEY.md probe table).  This module restates that loop's contract with the
+processor -- and nothing else of HF -- as device-agnostic tensor code, so that ONE loop drives the
+reference scorer (CPU), the oracle (CPU) and the sm_100a scorer (GPU) on identical inputs:
+
+  * rows are utterance-major (B*W), beam 0 starts at score 0 and the others at -1e9;
+  * the processor receives (input_ids (BW,L), log-probs (BW,V)) and returns (BW,V);
+  * candidates = top 2W of (B, W*V) after adding the running beam scores;
+  * an eos candidate ranked inside the top W is finalised with score / len**length_penalty,
+    the first W non-eos candidates continue;
+  * rows of finished utterances are fed pad tokens (pad is also the CTC blank);
+  * an utterance is done when W hypotheses are finalised and the worst of them beats the best
+    score still attainable (early_stopping=False semantics), or at max_length.
+
+Unlike HF there is no per-candidate Python loop and no .item() per utterance: the finished-
+hypothesis pool is a (B, W) tensor merged by top-k, and the only host sync is the `all done`
+test once per step.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable
+
+import torch
+
+
+@dataclass
+class BeamSearchOutput:
+    sequences: torch.Tensor  # (B, max_len) int64, pad-filled, without bos
+    lengths: torch.Tensor    # (B,) int64
+    scores: torch.Tensor     # (B,) fp32, length-normalised
+    steps: int               # processor calls made
+
+
+@torch.no_grad()
+def joint_beam_search(processor: Callable, decoder_log_probs: Callable[[torch.Tensor, int], torch.Tensor], batch: int,
+                      num_beams: int, vocab: int, bos: int, eos: int, pad: int, max_length: int = 512,
+                      length_penalty: float = 1.0, device: torch.device | str = "cpu",
+                      sync_every: int = 1) -> BeamSearchOutput:
+    """Run the decode loop; `decoder_log_probs(input_ids, step)` -> (B*W, V) log-probs (a fresh tensor)."""
+    B, W, V = batch, num_beams, vocab
+    dev = torch.device(device)
+    input_ids = torch.full((B * W, 1), bos, dtype=torch.long, device=dev)
+    beam_scores = torch.zeros(B, W, dtype=torch.float32, device=dev)
+    beam_scores[:, 1:] = -1e9
+    NEG = float("-inf")
+    pool_scores = torch.full((B, W), NEG, dtype=torch.float32, device=dev)
+    pool_seqs = torch.full((B, W, max_length), pad, dtype=torch.long, device=dev)
+    pool_lens = torch.zeros(B, W, dtype=torch.long, device=dev)
+    done = torch.zeros(B, dtype=torch.bool, device=dev)
+    rank = torch.arange(2 * W, device=dev)
+    row_base = (torch.arange(B, device=dev) * W).view(B, 1)
+    steps = 0
+
+    while True:
+        L = input_ids.shape[1]  # prefix length incl. bos == number of tokens a finalised hyp scores on
+        log_probs = decoder_log_probs(input_ids, steps)
+        proc = processor(input_ids, log_probs)
+        steps += 1
+        cand = (proc + beam_scores.view(-1, 1)).view(B, W * V)
+        top_scores, top_idx = cand.topk(2 * W, dim=1, largest=True, sorted=True)
+        src = torch.div(top_idx, V, rounding_mode="floor")
+        tok = top_idx - src * V
+        is_eos = tok == eos
+
+        # finalise eos candidates ranked inside the top W (not for utterances already done)
+        fin = is_eos & (rank < W) & ~done.view(B, 1)
+        fin_scores = torch.where(fin, top_scores / float(L) ** length_penalty, torch.full_like(top_scores, NEG))
+        prefix = input_ids.view(B, W, L)[:, :, 1:]  # drop bos
+        cand_seqs = torch.gather(prefix, 1, src.unsqueeze(-1).expand(B, 2 * W, L - 1)) if L > 1 else prefix.new_zeros(B, 2 * W, 0)
+        all_scores = torch.cat([pool_scores, fin_scores], dim=1)  # (B, 3W)
+        keep_scores, keep = all_scores.topk(W, dim=1)
+        all_seqs = torch.cat([pool_seqs, torch.nn.functional.pad(cand_seqs, (0, max_length - (L - 1)), value=pad)], dim=1)
+        all_lens = torch.cat([pool_lens, torch.full((B, 2 * W), L - 1, dtype=torch.long, device=dev)], dim=1)
+        pool_seqs = torch.gather(all_seqs, 1, keep.unsqueeze(-1).expand(B, W, max_length))
+        pool_lens = torch.gather(all_lens, 1, keep)
+        pool_scores = keep_scores
+
+        # the first W non-eos candidates continue
+        order = torch.where(is_eos, rank + 2 * W, rank).argsort(dim=1)[:, :W]
+        next_scores = torch.gather(top_scores, 1, order)
+        next_tok = torch.gather(tok, 1, order)
+        next_src = torch.gather(src, 1, order)
+
+        # done test of the utterance (BeamHypotheses.is_done, early_stopping=False)
+        full = (pool_scores > NEG).all(dim=1)
+        attainable = top_scores[:, 0] / float(L) ** length_penalty
+        done = done | (full & (pool_scores.min(dim=1).values >= attainable))
+
+        dmask = done.view(B, 1)
+        next_scores = torch.where(dmask, torch.zeros_like(next_scores), next_scores)
+        next_tok = torch.where(dmask, torch.full_like(next_tok, pad), next_tok)
+        next_src = torch.where(dmask, torch.zeros_like(next_src), next_src)
+        beam_idx = (next_src + row_base).view(-1)
+        input_ids = torch.cat([input_ids.index_select(0, beam_idx), next_tok.view(-1, 1)], dim=1)
+        beam_scores = next_scores
+
+        if input_ids.shape[1] >= max_length:
+            break
+        if steps % sync_every == 0 and bool(done.all()):
+            break
+
+    # finalize: utterances still running contribute their W open beams
+    L = input_ids.shape[1]
+    open_scores = torch.where(done.view(B, 1), torch.full_like(beam_scores, NEG), beam_scores / float(L - 1) ** length_penalty)
+    open_seqs = torch.nn.functional.pad(input_ids.view(B, W, L)[:, :, 1:], (0, max_length - (L - 1)), value=pad)
+    all_scores = torch.cat([pool_scores, open_scores], dim=1)
+    best = all_scores.argmax(dim=1)
+    all_seqs = torch.cat([pool_seqs, open_seqs], dim=1)
+    all_lens = torch.cat([pool_lens, torch.full((B, W), L - 1, dtype=torch.long, device=dev)], dim=1)
+    ar = torch.arange(B, device=dev)
+    return BeamSearchOutput(all_seqs[ar, best], all_lens[ar, best], all_scores[ar, best], steps)

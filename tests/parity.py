@@ -1,0 +1,202 @@
+"""Shared parity machinery: replay the committed golden vectors through ANY implementation that
+exposes the reference's scorer / processor surface (oracle on CPU, sm_100a scorer on GPU).
+
+Parity criterion (BASELINE.json north_star):
+  * entries where the reference is > -1e9: |new - ref| <= ATOL (1e-4 absolute, fp32 log space)
+    plus RTOL * |ref| -- the relative term only matters for |ref| >~ 100, where one fp32 ulp is
+    already 8e-6 .. 6e-5 and two correct fp32 implementations differ by a few ulps;
+  * entries where the reference is <= -1e9 ("logzero class"): new must be <= -1e9 as well.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ATOL = 1e-4
+RTOL = 2e-6
+LZ_CLASS = -1e9
+
+
+def load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+def to_np(t):
+    if isinstance(t, torch.Tensor):
+        return t.detach().cpu().numpy()
+    return np.asarray(t)
+
+
+def assert_parity(new, ref, what="", atol=ATOL, rtol=RTOL, ref64=None):
+    new, ref = to_np(new).astype(np.float64), to_np(ref).astype(np.float64)
+    assert new.shape == ref.shape, f"{what}: shape {new.shape} vs {ref.shape}"
+    assert not np.isnan(new).any(), f"{what}: NaN in output"
+    lz = ref <= LZ_CLASS
+    # also treat as logzero-class anything beyond +1e9 (garbage of finished beams: log_psi - (-1e10))
+    big = np.abs(ref) >= -LZ_CLASS
+    if lz.any():
+        assert (new[lz] <= LZ_CLASS).all(), f"{what}: {int((new[lz] > LZ_CLASS).sum())} logzero-class entries are finite"
+    hi = big & ~lz
+    if hi.any():
+        assert (new[hi] >= -LZ_CLASS).all(), f"{what}: +1e9-class entries differ"
+    fin = ~big
+    err = np.abs(new[fin] - ref[fin])
+    tol = atol + rtol * np.abs(ref[fin])
+    bad = err > tol
+    if bad.any() and ref64 is not None:
+        # adjudicate with the reference's own fp64 run: accept where new is at least as close to fp64 as 2x the
+        # reference's fp32 rounding noise
+        r64 = to_np(ref64).astype(np.float64)[fin]
+        noise = np.abs(ref[fin] - r64)
+        bad = bad & (np.abs(new[fin] - r64) > np.maximum(tol, 2 * noise))
+    assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.size} finite entries out of tolerance, max err "
+                           f"{err.max():.3e} at ref={ref[fin][err.argmax()]:.6g}")
+    return float(err.max()) if err.size else 0.0
+
+
+class Backend:
+    """What a replay needs from an implementation."""
+    device = "cpu"
+
+    def make_scorer(self, x_logp, lens, blank, eos, margin=0):
+        raise NotImplementedError
+
+    def make_processor(self, logits, lens, pad, eos, margin, w, W, space=-1, trick=False, trick_w=1.0):
+        raise NotImplementedError
+
+    def t(self, a, dtype=None):
+        x = torch.from_numpy(np.ascontiguousarray(a))
+        if dtype is not None:
+            x = x.to(dtype)
+        return x.to(self.device)
+
+
+def replay_steps(be: Backend, name: str, blank=3, eos=1):
+    """Replay a steps_* golden file: scorer-level and processor-level, every step."""
+    g = load(name)
+    W = int(g["W"])
+    w = float(g["ctc_weight"])
+    logits, lens = be.t(g["logits"]), be.t(g["lens"])
+    trick = dict(space=int(g["space_token_id"]), trick=bool(g["apply_eos_space_trick"]),
+                 trick_w=float(g["eos_space_trick_weight"])) if "space_token_id" in g else {}
+    proc = be.make_processor(logits.clone(), lens.clone(), blank, eos, 0, w, W, **trick)
+    scorer = be.make_scorer(torch.log_softmax(logits, -1), lens.clone(), blank, eos, 0)
+    state = None
+    worst = {}
+    for n in range(int(g["n_steps"])):
+        ids = be.t(g[f"input_ids_{n}"])
+        sel = None
+        if state is not None:
+            sel = scorer.index_select_state(state, ids[:, -1].reshape(-1, W))
+            worst["sel_r"] = max(worst.get("sel_r", 0), assert_parity(sel[0], g[f"sel_r_{n}"], f"{name} step {n} sel_r",
+                                                                     ref64=g.get(f"sel_r_{n}_f64")))
+            assert tuple(sel[1].shape) == (ids.shape[0], logits.shape[-1])
+            assert_parity(sel[1][:, 0], g[f"sel_s_{n}"], f"{name} step {n} sel_s", ref64=g.get(f"sel_s_{n}_f64"))
+        ts, state = scorer(ids, sel)
+        assert tuple(state[0].shape) == (logits.shape[1], 2, ids.shape[0], logits.shape[-1])
+        worst["ts"] = max(worst.get("ts", 0), assert_parity(ts, g[f"token_scores_{n}"], f"{name} step {n} token_scores",
+                                                           ref64=g.get(f"token_scores_{n}_f64")))
+        assert_parity(state[1], g[f"log_psi_{n}"], f"{name} step {n} log_psi", ref64=g.get(f"log_psi_{n}_f64"))
+        if f"r_{n}" in g:
+            worst["r"] = max(worst.get("r", 0), assert_parity(state[0], g[f"r_{n}"], f"{name} step {n} r",
+                                                             ref64=g.get(f"r_{n}_f64")))
+        att = be.t(g[f"att_{n}"])
+        out = proc(ids, att)
+        worst["out"] = max(worst.get("out", 0), assert_parity(out, g[f"out_{n}"], f"{name} step {n} processor out",
+                                                             ref64=g.get(f"out_{n}_f64")))
+        # the in-place scores[:, pad] = logzero must reach the caller's tensor (ctc_scorer.py:325)
+        assert_parity(att, g[f"att_after_{n}"], f"{name} step {n} att in-place", atol=0, rtol=0)
+    return worst
+
+
+def replay_partial(be: Backend, blank=3, eos=1):
+    g = load("partial_scoring")
+    W = int(g["W"])
+    logits, lens = be.t(g["logits"]), be.t(g["lens"])
+    scorer = be.make_scorer(torch.log_softmax(logits, -1), lens, blank, eos, 0)
+    BW = logits.shape[0] * W
+    ts0, st0 = scorer([[0]] * BW, None, scoring_ids=be.t(g["ids0"]))
+    assert_parity(ts0, g["ts0"], "partial ts0", ref64=g["ts0_f64"])
+    assert_parity(st0[0], g["r0"], "partial r0", ref64=g["r0_f64"])
+    assert_parity(st0[1], g["log_psi0"], "partial log_psi0", ref64=g["log_psi0_f64"])
+    assert (to_np(st0[4]) == g["idmap0"]).all()
+    sel = scorer.index_select_state(st0, be.t(g["best"]))
+    assert_parity(sel[0], g["sel_r"], "partial sel_r", ref64=g["sel_r_f64"])
+    assert_parity(sel[1][:, 0], g["sel_s"], "partial sel_s", ref64=g["sel_s_f64"])
+    ts1, st1 = scorer(be.t(g["y1"]), sel, scoring_ids=be.t(g["ids1"]))
+    assert_parity(ts1, g["ts1"], "partial ts1", ref64=g["ts1_f64"])
+    assert_parity(st1[0], g["r1"], "partial r1", ref64=g["r1_f64"])
+    assert_parity(st1[1], g["log_psi1"], "partial log_psi1", ref64=g["log_psi1_f64"])
+    assert (to_np(st1[4]) == g["idmap1"]).all()
+
+
+def replay_select_general(be: Backend, blank=3, eos=1):
+    g = load("select_general")
+    W = int(g["W"])
+    logits, lens = be.t(g["logits"]), be.t(g["lens"])
+    scorer = be.make_scorer(torch.log_softmax(logits, -1), lens, blank, eos, 0)
+    state = (be.t(g["r"]), be.t(g["log_psi"]), 0, 0, None)
+    sel = scorer.index_select_state(state, be.t(g["best"]))
+    # a gather: bit-exact
+    assert_parity(sel[0], g["sel_r"], "select_general r", atol=0, rtol=0)
+    assert_parity(sel[1][:, 0], g["sel_s"], "select_general s", atol=0, rtol=0)
+    assert tuple(sel[1].shape) == (logits.shape[0] * W, logits.shape[2])
+
+
+def replay_edges(be: Backend, blank=3, eos=1):
+    g = load("edges")
+    # (1) start == T-1, == T, > T
+    logits, lens = be.t(g["e1_logits"]), be.t(g["e1_lens"])
+    W = int(g["e1_W"])
+    T = logits.shape[1]
+    scorer = be.make_scorer(torch.log_softmax(logits, -1), lens, blank, eos, 0)
+    sel_s = be.t(g["e1_sel_s"])
+    sel = (be.t(g["e1_sel_r"]), sel_s.view(-1, 1).expand(-1, logits.shape[-1]), 0, 0)
+    for L in (T - 1, T, T + 1, T + 3):
+        y = [[0] + [5] * L, [0] + [6] * L]
+        ts, st = scorer(y, sel)
+        assert_parity(ts, g[f"e1_ts_L{L}"], f"edge start L={L} ts")
+        assert_parity(st[1], g[f"e1_log_psi_L{L}"], f"edge start L={L} log_psi")
+        assert_parity(st[0], g[f"e1_r_L{L}"], f"edge start L={L} r")
+    # (2) zero-length and length-1 utterances through the processor
+    logits, lens = be.t(g["e2_logits"]), be.t(g["e2_lens"])
+    W = int(g["e2_W"])
+    proc = be.make_processor(logits.clone(), lens, blank, eos, 0, 0.3, W)
+    ids = torch.zeros((logits.shape[0] * W, 1), dtype=torch.long, device=be.device)
+    out0 = proc(ids, be.t(g["e2_att0"]))
+    assert_parity(out0, g["e2_out0"], "edge len0 out0")
+    out1 = proc(be.t(g["e2_ids2"]), be.t(g["e2_att1"]))
+    assert_parity(out1, g["e2_out1"], "edge len0 out1")
+    assert_parity(proc.ctc_states[1], g["e2_log_psi1"], "edge len0 log_psi1")
+    assert_parity(proc.ctc_states[0], g["e2_r1"], "edge len0 r1")
+    # (3) token_scores == 0 -> logzero
+    logits, lens = be.t(g["e3_logits"]), be.t(g["e3_lens"])
+    scorer = be.make_scorer(torch.log_softmax(logits, -1), lens, blank, eos, 0)
+    ts, _ = scorer([[0]], (be.t(g["e3_r_prev"]), be.t(g["e3_s_prev"]), 0, 0))
+    ref = g["e3_ts"]
+    new = to_np(ts)
+    # exact zeros depend on bit-identical log_psi; require the class only where the reference hit the hack
+    hack = ref <= LZ_CLASS
+    assert ((new[hack] <= LZ_CLASS) | (np.abs(new[hack]) <= ATOL)).all()
+    assert (np.abs(new[~hack] - ref[~hack]) <= ATOL).all()
+
+
+def replay_decode(be: Backend, blank=3, eos=1, bos=0):
+    from huggingface_asr_b200.beam_search import joint_beam_search
+    from huggingface_asr_b200.synthetic import make_attention_scores
+
+    g = load("decode_1best")
+    for i in range(3):
+        logits, lens = be.t(g[f"d{i}_logits"]), be.t(g[f"d{i}_lens"])
+        W, seed = int(g[f"d{i}_W"]), int(g[f"d{i}_seed"])
+        B, T, V = logits.shape
+        proc = be.make_processor(logits.clone(), lens, blank, eos, 0, 0.3, W)
+        out = joint_beam_search(proc, lambda ids, n: make_attention_scores(B * W, V, n, seed=seed, scale=0.5).to(be.device),
+                                B, W, V, bos, eos, blank, max_length=int(g[f"d{i}_max_length"]), device=be.device)
+        assert out.steps == int(g[f"d{i}_steps"]), f"decode {i}: steps {out.steps} vs {int(g[f'd{i}_steps'])}"
+        assert (to_np(out.lengths) == g[f"d{i}_len"]).all(), f"decode {i}: lengths differ"
+        assert (to_np(out.sequences) == g[f"d{i}_seq"]).all(), f"decode {i}: 1-best token sequences differ"
+        assert np.abs(to_np(out.scores) - g[f"d{i}_score"]).max() <= 1e-4
