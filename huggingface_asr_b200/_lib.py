@@ -1,0 +1,96 @@
+"""Builds and loads libctcps_b200.so (the C ABI of include/ctcps.h) through ctypes.
+
+There is deliberately no fallback: if the library is missing and cannot be built, or a tensor is
+not on a CUDA device, the callers raise.  Python and torch are plumbing (device memory, streams);
+every kernel on the path lives in csrc/ctcps_kernels.cu.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+SRC = os.path.join(_PKG, "csrc", "ctcps_kernels.cu")
+INCLUDE = os.path.join(_ROOT, "include")
+LIB_PATH = os.path.join(_PKG, "libctcps_b200.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-shared"]
+
+_lib = None
+
+
+class CtcpsError(RuntimeError):
+    pass
+
+
+def _nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise CtcpsError("nvcc not found: cannot build libctcps_b200.so (there is no CPU fallback)")
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile csrc/ctcps_kernels.cu for sm_100a into the package directory (in-tree)."""
+    deps = [SRC, os.path.join(INCLUDE, "ctcps.h")]
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+        return LIB_PATH
+    cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, SRC, "-o", LIB_PATH]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    env = dict(os.environ)
+    env.pop("CC", None)  # the image exports a gcc wrapper nvcc must not be pointed at
+    env.pop("CXX", None)
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        raise CtcpsError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_i, _i64, _f, _p, _sz = ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+
+# symbol -> argtypes; must list every function include/ctcps.h declares (tests check this)
+SIGNATURES = {
+    "ctcps_version": [],
+    "ctcps_error_string": [_i],
+    "ctcps_padded_ld": [_i],
+    "ctcps_workspace_bytes": [_i, _i, _i, _i, _i, ctypes.POINTER(_sz)],
+    "ctcps_init": [_p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p],
+    "ctcps_log_softmax": [_p, _i, _p, _i, _i, _i, _p],
+    "ctcps_initial_state": [_p, _i, _i, _i, _i, _p, _p],
+    "ctcps_score": [_p, _i, _p, _p, _p, _i64, _i64, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _f, _f, _p, _i, _p, _p, _p,
+                    _p, _sz, _p],
+    "ctcps_select": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
+    "ctcps_eos_space_trick": [_p, _p, _p, _i, _i, _i, _i, _f, _p],
+}
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded library; builds it on first use if the .so is absent or stale."""
+    global _lib
+    if _lib is None:
+        path = build()
+        L = ctypes.CDLL(path)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.argtypes = argtypes
+            fn.restype = ctypes.c_char_p if name == "ctcps_error_string" else ctypes.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().ctcps_error_string(rc).decode()
+        kind = ValueError if rc < 0 else CtcpsError
+        raise kind(f"{what}: {msg} (code {rc})")
+
+
+def launches_per_score(S: int = 0) -> int:
+    """Kernel launches one ctcps_score call makes (for bench.py's gpu_launches count)."""
+    return 2 if S == 0 else 5

@@ -1,0 +1,859 @@
+// ctcps_kernels.cu -- sm_100a kernels + C ABI of the CTC prefix scorer (see include/ctcps.h).
+//
+// Replaces, for BUTSpeechFIT/huggingface_asr, src/decoding/ctc_scorer.py:
+//   K-a  k_init            log-softmax + length padding + blank column          (:279, :39-46)
+//        k_initial_state   blank-only forward variable of the empty prefix      (:74-85)
+//   K-b  k_prep            per-hypothesis phi stream for the recursion          (:115-124)
+//        k_score_full      forward recursion over T x (hyp, token) + log_psi +
+//                          token scores + joint combine, full vocabulary        (:98-178, :325, :332)
+//        k_score_partial   same on scoring_ids candidates                       (:90-97, :155-162)
+//   K-c  k_select          index_select_state gather                            (:180-207)
+//        k_trick           eos/space trick                                      (:333-349)
+//
+// Design of K-b (the hot kernel; DESIGN.md has the roofline arithmetic):
+//   * one CTA = (utterance b, tile of VTILE tokens, group of HW hypotheses); a thread owns
+//     4 consecutive tokens x HW hypotheses = 4*HW independent recursion chains in registers,
+//     so latency is hidden by ILP and every log-posterior x[t,b,v] fetched from shared memory
+//     is reused HW times;
+//   * x[t0:t0+TT, b, v-tile] is staged by TMA (cp.async.bulk.tensor.2d, mbarrier complete_tx)
+//     through a ring of NS stages; the token-independent per-hypothesis stream
+//     {r_sum, r_prev_blank, exp(r_sum-G), exp(r_prev_blank-G)}[t-1] + blank log-prob[t] comes in
+//     with the same barrier as one 1-D bulk copy;
+//   * the state r (T,2,BW,V) -- 8 bytes per lane-step, the HBM roofline of the path -- is written
+//     with 128-bit streaming stores, V innermost, 512 B contiguous per warp per (t, plane, hyp);
+//   * log_psi is accumulated in the linear domain against a per-hypothesis offset G (one FFMA
+//     per lane-step instead of a logaddexp), the two logaddexp of the recursion use MUFU ex2/lg2.
+//   No tensor cores: nothing here is a dense contraction.  No CPU fallback.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "ctcps.h"
+
+namespace {
+
+constexpr float LZ = CTCPS_LOGZERO;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+constexpr int TT = 8;        // frames per pipeline stage
+constexpr int NS = 3;        // pipeline stages
+constexpr int BOXC = 256;    // TMA box width (elements), the hardware maximum per dimension
+constexpr int MAX_HW = 5;    // hypotheses per thread
+
+thread_local char g_errbuf[256];
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// torch.logsumexp over two values, max + log(1 + exp(min - max)), on the MUFU pipe.
+__device__ __forceinline__ float lse2_fast(float a, float b) {
+    const float m = fmaxf(a, b);
+    const float d = -fabsf(a - b);
+    const float e = ex2_approx(d * LOG2E);
+    return fmaf(lg2_approx(1.0f + e), LN2, m);
+}
+// Same with full-precision libm-grade functions (used off the hot loop).
+__device__ __forceinline__ float lse2_precise(float a, float b) {
+    const float m = fmaxf(a, b);
+    return logf(expf(a - m) + expf(b - m)) + m;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// block-wide reductions for <= 1024 threads; `red` is 32 floats of shared memory
+__device__ __forceinline__ float block_max(float v, float *red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_max(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    v = lane < nw ? red[lane] : -INFINITY;
+    return warp_max(v);
+}
+__device__ __forceinline__ float block_sum(float v, float *red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    v = lane < nw ? red[lane] : 0.f;
+    return warp_sum(v);
+}
+
+// ------------------------------------------------------------------------------------------
+// K-a: log-softmax + length padding + blank column.  One CTA per (b, t) row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_init(const float *__restrict__ in, int ld_in, const int64_t *__restrict__ lens,
+                                              int T, int V, int blank, int apply, float *out, int ldx,
+                                              float *__restrict__ blank_lp) {
+    __shared__ float red[32];
+    const int row = blockIdx.x;
+    const int b = row / T, t = row - b * T;
+    const float *src = in + (size_t)row * ld_in;
+    float *dst = out + (size_t)row * ldx;
+    if (lens != nullptr) {
+        const long long lraw = lens[b];
+        long long l = lraw < 0 ? lraw + T : lraw;  // python slice x[i, l:, :]
+        if (l < 0) l = 0;
+        if (lraw < T && t >= l) {  // ctc_scorer.py:39-42
+            for (int v = threadIdx.x; v < V; v += blockDim.x) dst[v] = (v == blank) ? 0.f : LZ;
+            if (blank_lp != nullptr && threadIdx.x == 0) blank_lp[row] = 0.f;
+            return;
+        }
+    }
+    if (apply) {
+        float m = -INFINITY;
+        for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, src[v]);
+        m = block_max(m, red);
+        float s = 0.f;
+        for (int v = threadIdx.x; v < V; v += blockDim.x) s += expf(src[v] - m);
+        s = block_sum(s, red);
+        const float ls = logf(s);
+        for (int v = threadIdx.x; v < V; v += blockDim.x) {
+            const float o = (src[v] - m) - ls;
+            dst[v] = o;
+            if (v == blank && blank_lp != nullptr) blank_lp[row] = o;
+        }
+    } else {
+        for (int v = threadIdx.x; v < V; v += blockDim.x) {
+            const float o = src[v];
+            if (dst != src) dst[v] = o;
+            if (v == blank && blank_lp != nullptr) blank_lp[row] = o;
+        }
+    }
+}
+
+// Initial state / extend_state: thread per hypothesis, sequential fp32 running sum over t.
+__global__ void k_initial_state(const float *__restrict__ blank_lp, int B, int T, int W, int t_begin, float *r0) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    const int BW = B * W;
+    if (h >= BW) return;
+    const int b = h / W;
+    float acc = t_begin > 0 ? r0[((size_t)(t_begin - 1) * 2 + 1) * BW + h] : 0.f;
+    for (int t = t_begin; t < T; ++t) {
+        const float xb = blank_lp[(size_t)b * T + t];
+        acc = (t == 0) ? xb : acc + xb;
+        r0[((size_t)t * 2 + 0) * BW + h] = LZ;
+        r0[((size_t)t * 2 + 1) * BW + h] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K-b prep: one warp per (padded) hypothesis builds the stream the recursion consumes.
+//   aux[((b*G+g)*Tpad + t)*(HW+1) + hh] = {r_sum[t-1], r_prev[t-1,1], exp(r_sum[t-1]-Gm), exp(r_prev[t-1,1]-Gm)}
+//   aux[...                      + HW] = {blank_lp[b,t], 0, 0, 0}
+//   Gm[h] = max over the frames log_psi sums over, t-1 in [start-1, T-2]
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_prep(const float *__restrict__ r_prev, const float *__restrict__ blank_lp, int B,
+                                              int W, int T, int HW, int G, int start, int Tpad,
+                                              float4 *__restrict__ aux, float *__restrict__ Gmax) {
+    const int lane = threadIdx.x & 31;
+    const int hp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (hp >= B * G * HW) return;
+    const int BW = B * W;
+    const int b = hp / (G * HW);
+    const int rem = hp - b * (G * HW);
+    const int g = rem / HW, hh = rem - g * HW;
+    const int w = g * HW + hh;
+    const bool valid = w < W;
+    const int h = b * W + w;
+    float gm = -INFINITY;
+    if (valid) {
+        for (int t = lane; t < T; t += 32) {
+            if (t >= start - 1 && t <= T - 2) {
+                const float a = r_prev[((size_t)t * 2 + 0) * BW + h], c = r_prev[((size_t)t * 2 + 1) * BW + h];
+                gm = fmaxf(gm, lse2_precise(a, c));
+            }
+        }
+    }
+    gm = warp_max(gm);
+    if (!(gm > -INFINITY)) gm = 0.f;
+    if (valid && lane == 0) Gmax[h] = gm;
+    float4 *base = aux + ((size_t)(b * G + g) * Tpad) * (HW + 1);
+    for (int te = lane; te < Tpad; te += 32) {
+        float4 e = make_float4(LZ, LZ, 0.f, 0.f);
+        const int f = te - 1;
+        if (valid && f >= 0 && f < T) {
+            const float a = r_prev[((size_t)f * 2 + 0) * BW + h], c = r_prev[((size_t)f * 2 + 1) * BW + h];
+            const float rs = lse2_precise(a, c);
+            e.x = rs;
+            e.y = c;
+            if (f >= start - 1 && f <= T - 2) {
+                e.z = expf(rs - gm);
+                e.w = expf(c - gm);
+            }
+        }
+        base[(size_t)te * (HW + 1) + hh] = e;
+        if (hh == 0) base[(size_t)te * (HW + 1) + HW] = make_float4(te < T ? blank_lp[(size_t)b * T + te] : 0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K-b main: full-vocabulary forward recursion.
+// ------------------------------------------------------------------------------------------
+struct ScoreArgs {
+    const float4 *aux;
+    const float *Gmax;
+    const float *s_prev;
+    long long s_rs, s_cs;
+    const int64_t *last_ids;
+    float *att;
+    float omw, w;
+    float *r;
+    int ldr;
+    float *log_psi, *token_scores, *joint;
+    int B, W, T, V, blank, ol, G, Tpad, nvt;
+};
+
+template <int HW, int NT>
+struct ScoreSmem {
+    static constexpr int VTILE = NT * 4;
+    static constexpr int NBOX = VTILE / BOXC;
+    alignas(128) float xs[NS][NBOX][TT][BOXC];
+    alignas(16) float4 auxs[NS][TT][HW + 1];
+    alignas(8) uint64_t full[NS];
+};
+
+template <int HW, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_score_full(const __grid_constant__ CUtensorMap tmx, const ScoreArgs a) {
+    using Smem = ScoreSmem<HW, NT>;
+    constexpr int VTILE = Smem::VTILE;
+    constexpr int NBOX = Smem::NBOX;
+    static_assert(VTILE % BOXC == 0, "tile must be whole TMA boxes");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+
+    const int tid = threadIdx.x;
+    int idx = blockIdx.x;
+    const int g = idx % a.G;
+    idx /= a.G;
+    const int vt = idx % a.nvt;
+    const int b = idx / a.nvt;
+    const int T = a.T, V = a.V, W = a.W, BW = a.B * a.W;
+    const int start = a.ol > 1 ? a.ol : 1;
+    const int v0 = vt * VTILE + tid * 4;
+    const int h0 = b * W + g * HW;
+    const int nhyp = min(HW, W - g * HW);  // valid hypotheses of this group
+    const bool lane_ok = v0 < a.ldr;
+
+    const int c0 = (a.ol == 0 ? 0 : start) / TT;
+    const int cN = (T - 1) / TT;
+    constexpr uint32_t STAGE_BYTES = TT * VTILE * 4 + TT * (HW + 1) * 16;
+
+    auto issue = [&](int c) {
+        const int s = (c - c0) % NS;
+        mbar_expect_tx(&sm.full[s], STAGE_BYTES);
+#pragma unroll
+        for (int bx = 0; bx < NBOX; ++bx) tma_load_2d(&sm.xs[s][bx][0][0], &tmx, vt * VTILE + bx * BOXC, b * T + c * TT, &sm.full[s]);
+        bulk_load_1d(&sm.auxs[s][0][0], a.aux + ((size_t)(b * a.G + g) * a.Tpad + (size_t)c * TT) * (HW + 1), TT * (HW + 1) * 16,
+                     &sm.full[s]);
+    };
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int c = c0; c <= cN && c < c0 + NS; ++c) issue(c);
+    }
+
+    // which of my 4 tokens (if any) is the last label of hypothesis hh            (:122-124)
+    int cj[HW];
+#pragma unroll
+    for (int hh = 0; hh < HW; ++hh) cj[hh] = hh < nhyp ? (int)(a.last_ids[h0 + hh] - (long long)v0) : -1;
+
+    float rn[HW][4], rb[HW][4], psi[HW][4], x0[4];
+#pragma unroll
+    for (int hh = 0; hh < HW; ++hh)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) rn[hh][j] = LZ, rb[hh][j] = LZ, psi[hh][j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x0[j] = LZ;
+
+    const size_t plane = (size_t)BW * a.ldr;   // floats between the non-blank and blank planes
+    const size_t frame = 2 * plane;            // floats per frame of r
+    float *rbase = a.r + (size_t)h0 * a.ldr + v0;
+
+    // frames before `start` stay logzero (r = full(logzero), :106-111); frame 0 of the first step is set below
+    if (lane_ok) {
+        const float4 lz4 = make_float4(LZ, LZ, LZ, LZ);
+        for (int t = (a.ol == 0 ? 1 : 0); t < start; ++t) {
+            float *rp = rbase + (size_t)t * frame;
+            for (int hh = 0; hh < nhyp; ++hh) {
+                __stcs(reinterpret_cast<float4 *>(rp + (size_t)hh * a.ldr), lz4);
+                __stcs(reinterpret_cast<float4 *>(rp + (size_t)hh * a.ldr + plane), lz4);
+            }
+        }
+    }
+    __syncthreads();  // barrier init visible before anyone waits
+
+    for (int c = c0; c <= cN; ++c) {
+        const int s = (c - c0) % NS;
+        mbar_wait(&sm.full[s], (uint32_t)(((c - c0) / NS) & 1));
+        const int bx = (tid * 4) / BOXC, col = (tid * 4) % BOXC;
+        const int tmax = min(TT, T - c * TT);
+        for (int tt = 0; tt < tmax; ++tt) {
+            const int t = c * TT + tt;
+            const float4 xv4 = *reinterpret_cast<const float4 *>(&sm.xs[s][bx][tt][col]);
+            const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+            float *rp = rbase + (size_t)t * frame;
+            if (t < start) {
+                if (t == 0 && a.ol == 0) {  // r[0,0] = x_[0,0]                      (:112-113)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x0[j] = xv[j];
+#pragma unroll
+                    for (int hh = 0; hh < HW; ++hh)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) rn[hh][j] = xv[j];
+                    if (lane_ok)
+                        for (int hh = 0; hh < nhyp; ++hh) {
+                            __stcs(reinterpret_cast<float4 *>(rp + (size_t)hh * a.ldr), xv4);
+                            __stcs(reinterpret_cast<float4 *>(rp + (size_t)hh * a.ldr + plane), make_float4(LZ, LZ, LZ, LZ));
+                        }
+                }
+                continue;
+            }
+            const float xb = sm.auxs[s][tt][HW].x;
+            float p[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p[j] = ex2_approx(xv[j] * LOG2E);
+#pragma unroll
+            for (int hh = 0; hh < HW; ++hh) {
+                const float4 ph = sm.auxs[s][tt][hh];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool last = (cj[hh] == j);
+                    const float phi = last ? ph.y : ph.x;
+                    const float lin = last ? ph.w : ph.z;
+                    const float nn = lse2_fast(rn[hh][j], phi) + xv[j];       // :150-151, non-blank row
+                    const float nb = lse2_fast(rn[hh][j], rb[hh][j]) + xb;    // :150-151, blank row
+                    rn[hh][j] = nn;
+                    rb[hh][j] = nb;
+                    psi[hh][j] = fmaf(lin, p[j], psi[hh][j]);                 // :154,164-167 in the linear domain
+                }
+                if (lane_ok && hh < nhyp) {
+                    __stcs(reinterpret_cast<float4 *>(rp + (size_t)hh * a.ldr), make_float4(rn[hh][0], rn[hh][1], rn[hh][2], rn[hh][3]));
+                    __stcs(reinterpret_cast<float4 *>(rp + (size_t)hh * a.ldr + plane),
+                           make_float4(rb[hh][0], rb[hh][1], rb[hh][2], rb[hh][3]));
+                }
+            }
+        }
+        __syncthreads();  // every thread is done with stage s
+        if (tid == 0 && c + NS <= cN) issue(c + NS);
+    }
+
+    // epilogue: log_psi, token scores, joint scores                                 (:164-176, :325, :332)
+#pragma unroll
+    for (int hh = 0; hh < HW; ++hh) {
+        if (hh >= nhyp) break;
+        const int h = h0 + hh;
+        const float gm = a.Gmax[h];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int v = v0 + j;
+            if (v >= V) continue;
+            float lp = gm + logf(psi[hh][j]);
+            if (!(lp > LZ)) lp = LZ;
+            if (a.ol == 0) lp = lse2_precise(lp, x0[j]);
+            if (v == a.blank) lp = LZ;
+            const size_t o = (size_t)h * V + v;
+            a.log_psi[o] = lp;
+            const float sp = a.s_prev != nullptr ? a.s_prev[(long long)h * a.s_rs + (long long)v * a.s_cs] : 0.f;
+            float ts = lp - sp;
+            if (ts == 0.f) ts = LZ;
+            a.token_scores[o] = ts;
+            if (a.att != nullptr) {
+                float av = a.att[o];
+                if (v == a.blank) {
+                    av = LZ;
+                    a.att[o] = LZ;
+                }
+                a.joint[o] = __fadd_rn(__fmul_rn(a.omw, av), __fmul_rn(a.w, ts));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K-b partial scoring: one thread per (hyp, candidate) lane.  ~V/S times less work than the full
+// path; written for fidelity (libm-grade exp/log, running-max logsumexp), not for the roofline.
+// ------------------------------------------------------------------------------------------
+__global__ void k_fill_i64(int64_t *p, size_t n, int64_t v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void k_fill_f32(float *p, size_t n, float v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+// scoring_idmap[h, scoring_ids[h,s]] = s, later s wins                              (:91-95)
+__global__ void k_build_idmap(const int64_t *__restrict__ ids, int BW, int S, int V, int64_t *idmap) {
+    const int h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= BW) return;
+    for (int s = 0; s < S; ++s) {
+        const int64_t v = ids[(size_t)h * S + s];
+        if (v >= 0 && v < V) idmap[(size_t)h * V + v] = s;
+    }
+}
+
+__global__ void __launch_bounds__(128) k_score_partial(const float *__restrict__ x, int ldx, const float *__restrict__ blank_lp,
+                                                       const float *__restrict__ r_prev, const int64_t *__restrict__ last_ids,
+                                                       const int64_t *__restrict__ ids, const int64_t *__restrict__ idmap, int ol,
+                                                       int B, int W, int T, int V, int S, float *r, int ldr, float *log_psi) {
+    const int lane = blockIdx.x * blockDim.x + threadIdx.x;
+    const int BW = B * W;
+    if (lane >= BW * S) return;
+    const int h = lane / S, s = lane - h * S;
+    const int b = h / W;
+    const int64_t v = ids[lane];
+    const int64_t c = last_ids[h];
+    const bool last = (c >= 0 && c < V) ? (idmap[(size_t)h * V + c] == s) : false;  // :117-121
+    const int start = ol > 1 ? ol : 1;
+    const float *xr = x + (size_t)b * T * ldx + v;
+    const size_t plane = (size_t)BW * ldr, frame = 2 * plane;
+    float *rp = r + (size_t)h * ldr + s;
+    for (int t = 0; t < start && t < T; ++t) {
+        rp[(size_t)t * frame] = LZ;
+        rp[(size_t)t * frame + plane] = LZ;
+    }
+    float rn = LZ, rb = LZ;
+    if (ol == 0) {
+        rn = xr[0];
+        rp[0] = rn;
+    }
+    float m = rn, acc = 1.f;  // running-max logsumexp seeded with r[start-1,0]       (:158,165)
+    for (int t = start; t < T; ++t) {
+        const float p0 = r_prev[((size_t)(t - 1) * 2 + 0) * BW + h], p1 = r_prev[((size_t)(t - 1) * 2 + 1) * BW + h];
+        const float phi = last ? p1 : lse2_precise(p0, p1);
+        const float xv = xr[(size_t)t * ldx];
+        const float nn = lse2_precise(rn, phi) + xv;
+        const float nb = lse2_precise(rn, rb) + blank_lp[(size_t)b * T + t];
+        rn = nn;
+        rb = nb;
+        rp[(size_t)t * frame] = rn;
+        rp[(size_t)t * frame + plane] = rb;
+        const float term = phi + xv;
+        if (term > m) {
+            acc = acc * expf(m - term) + 1.f;
+            m = term;
+        } else {
+            acc += expf(term - m);
+        }
+    }
+    if (v >= 0 && v < V && idmap[(size_t)h * V + v] == s) log_psi[(size_t)h * V + v] = logf(acc) + m;  // :161-162, later s wins
+}
+
+// blank exclusion, relative score, zero hack, joint combine for the paths that do not fuse it
+__global__ void k_finalize(float *log_psi, const float *__restrict__ s_prev, long long s_rs, long long s_cs, float *att,
+                           float omw, float w, int BW, int V, int blank, float *token_scores, float *joint, int all_logzero) {
+    const size_t n = (size_t)BW * V;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int h = (int)(i / V), v = (int)(i - (size_t)h * V);
+        float ts;
+        if (all_logzero) {  // start > end early return                               (:138-145)
+            log_psi[i] = LZ;
+            ts = LZ;
+        } else {
+            float lp = log_psi[i];
+            if (v == blank) lp = LZ, log_psi[i] = LZ;
+            const float sp = s_prev != nullptr ? s_prev[(long long)h * s_rs + (long long)v * s_cs] : 0.f;
+            ts = lp - sp;
+            if (ts == 0.f) ts = LZ;
+        }
+        token_scores[i] = ts;
+        if (att != nullptr) {
+            float av = att[i];
+            if (v == blank) av = LZ, att[i] = LZ;
+            joint[i] = __fadd_rn(__fmul_rn(omw, av), __fmul_rn(w, ts));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K-c: index_select_state gather.
+// ------------------------------------------------------------------------------------------
+__global__ void k_select(const float *__restrict__ r, int ldr, const float *__restrict__ log_psi,
+                         const int64_t *__restrict__ best_ids, const int64_t *__restrict__ idmap, int B, int W, int T, int V,
+                         int S, float *__restrict__ r_new, float *__restrict__ s_new) {
+    const int BW = B * W;
+    const size_t n = (size_t)T * 2 * BW;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int j = (int)(i % BW);
+        const size_t tk = i / BW;
+        const int b = j / W;
+        const long long best = best_ids[j];
+        const long long flat = best + (long long)b * W * V;  // :191
+        long long hyp, lanei;
+        if (idmap != nullptr) {  // :196-202
+            hyp = best / V + (long long)b * W;
+            long long label = best % V;
+            long long si = idmap[hyp * V + label];
+            lanei = si < 0 ? 0 : si;
+        } else {
+            hyp = flat / V;
+            lanei = flat - hyp * V;
+        }
+        r_new[i] = r[(tk * BW + (size_t)hyp) * ldr + (size_t)lanei];  // :206
+        if (tk == 0) s_new[j] = log_psi[flat];                            // :193
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// eos/space trick: one CTA per row, first-max argmax like torch.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_trick(const float *__restrict__ att, const float *__restrict__ ctc, float *next, int V,
+                                               int eos, int space, float k) {
+    __shared__ float sv[2][8];
+    __shared__ int si[2][8];
+    const int row = blockIdx.x;
+    const float *pa = att + (size_t)row * V, *pc = ctc + (size_t)row * V;
+    float ba = -INFINITY, bc = -INFINITY;
+    int ia = 0x7fffffff, ic = 0x7fffffff;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        const float x = pa[v], y = pc[v];
+        if (x > ba) ba = x, ia = v;
+        if (y > bc) bc = y, ic = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float oa = __shfl_xor_sync(0xffffffffu, ba, o), oc = __shfl_xor_sync(0xffffffffu, bc, o);
+        int ja = __shfl_xor_sync(0xffffffffu, ia, o), jc = __shfl_xor_sync(0xffffffffu, ic, o);
+        if (oa > ba || (oa == ba && ja < ia)) ba = oa, ia = ja;
+        if (oc > bc || (oc == bc && jc < ic)) bc = oc, ic = jc;
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0) sv[0][wid] = ba, si[0][wid] = ia, sv[1][wid] = bc, si[1][wid] = ic;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < (int)(blockDim.x >> 5); ++q) {
+            if (sv[0][q] > ba || (sv[0][q] == ba && si[0][q] < ia)) ba = sv[0][q], ia = si[0][q];
+            if (sv[1][q] > bc || (sv[1][q] == bc && si[1][q] < ic)) bc = sv[1][q], ic = si[1][q];
+        }
+        if (ia == eos && ic == space) {
+            float *n = next + (size_t)row * V;
+            const float ne = n[eos], nsp = n[space];
+            if (ne < nsp && k * ne > nsp) n[eos] = ne * k;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+void pick_hw(int W, int *HW, int *G) {
+    int best = 1, best_pad = 1 << 30;
+    for (int hw = MAX_HW; hw >= 1; --hw) {
+        const int g = (W + hw - 1) / hw;
+        const int pad = g * hw - W;
+        // prefer no padded lanes, then the widest group (more reuse of x per shared-memory read)
+        if (pad < best_pad && hw >= 2) best = hw, best_pad = pad;
+        if (pad == 0 && hw >= 2) break;
+    }
+    if (W == 1) best = 1;
+    *HW = best;
+    *G = (W + best - 1) / best;
+}
+
+inline int tpad_of(int T) { return ((T + TT - 1) / TT) * TT + TT; }
+
+struct Workspace {
+    size_t aux_off, aux_bytes, g_off, g_bytes, total;
+};
+Workspace plan_workspace(int B, int T, int W) {
+    int HW, G;
+    pick_hw(W, &HW, &G);
+    Workspace ws;
+    ws.aux_off = 0;
+    ws.aux_bytes = (size_t)B * G * tpad_of(T) * (HW + 1) * sizeof(float4);
+    ws.g_off = (ws.aux_bytes + 255) & ~(size_t)255;
+    ws.g_bytes = (size_t)B * W * sizeof(float);
+    ws.total = ws.g_off + ((ws.g_bytes + 255) & ~(size_t)255);
+    return ws;
+}
+
+int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
+
+#define ARG_CHECK(cond, code, msg)                           \
+    do {                                                     \
+        if (!(cond)) {                                       \
+            snprintf(g_errbuf, sizeof(g_errbuf), "%s", msg); \
+            return code;                                     \
+        }                                                    \
+    } while (0)
+
+int grid_for(size_t n, int block) {
+    size_t g = (n + block - 1) / block;
+    const size_t cap = 148 * 32;
+    return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+template <int HW, int NT, int MINB>
+int launch_score_full(const CUtensorMap &tm, const ScoreArgs &a, cudaStream_t st) {
+    using Smem = ScoreSmem<HW, NT>;
+    auto kern = k_score_full<HW, NT, MINB>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+        if (e != cudaSuccess) return (int)e;
+        attr_set = true;
+    }
+    const long long nblocks = (long long)a.B * a.nvt * a.G;
+    kern<<<(unsigned)nblocks, NT, sizeof(Smem), st>>>(tm, a);
+    return cuda_rc(cudaGetLastError());
+}
+
+}  // namespace
+
+extern "C" {
+
+int ctcps_version(void) { return 100; }
+
+const char *ctcps_error_string(int code) {
+    if (code == 0) return "ok";
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    switch (code) {
+        case CTCPS_E_BADARG: return g_errbuf[0] ? g_errbuf : "bad argument";
+        case CTCPS_E_ALIGN: return g_errbuf[0] ? g_errbuf : "alignment violated";
+        case CTCPS_E_WORKSPACE: return "workspace too small (see ctcps_workspace_bytes)";
+        case CTCPS_E_NODRIVER: return "cuTensorMapEncodeTiled unavailable or failed";
+        case CTCPS_E_TOOBIG: return "problem too large for 32-bit lane indexing";
+        default: return "unknown ctcps error";
+    }
+}
+
+int ctcps_padded_ld(int n) { return (n + 3) & ~3; }
+
+int ctcps_workspace_bytes(int B, int T, int V, int W, int S, size_t *out_bytes) {
+    (void)V;
+    (void)S;
+    ARG_CHECK(out_bytes != nullptr && B > 0 && T > 0 && W > 0, CTCPS_E_BADARG, "workspace_bytes: bad sizes");
+    *out_bytes = plan_workspace(B, T, W).total;
+    return 0;
+}
+
+int ctcps_init(const float *logits, int ld_in, const int64_t *lens, int B, int T, int V, int blank, int apply_log_softmax,
+               float *x_logp, int ldx, float *blank_lp, void *stream) {
+    ARG_CHECK(logits && x_logp && B > 0 && T > 0 && V > 0, CTCPS_E_BADARG, "init: null pointer or non-positive size");
+    ARG_CHECK(blank >= 0 && blank < V, CTCPS_E_BADARG, "init: blank id outside the vocabulary");
+    ARG_CHECK(ld_in >= V && ldx >= V, CTCPS_E_BADARG, "init: row stride smaller than V");
+    ARG_CHECK((long long)B * T < (1ll << 31), CTCPS_E_TOOBIG, "init: B*T too large");
+    k_init<<<B * T, 256, 0, (cudaStream_t)stream>>>(logits, ld_in, lens, T, V, blank, apply_log_softmax, x_logp, ldx, blank_lp);
+    return cuda_rc(cudaGetLastError());
+}
+
+int ctcps_log_softmax(const float *in, int ld_in, float *out, int ld_out, int rows, int V, void *stream) {
+    ARG_CHECK(in && out && rows > 0 && V > 0 && ld_in >= V && ld_out >= V, CTCPS_E_BADARG, "log_softmax: bad argument");
+    k_init<<<rows, 256, 0, (cudaStream_t)stream>>>(in, ld_in, nullptr, rows, V, 0, 1, out, ld_out, nullptr);
+    return cuda_rc(cudaGetLastError());
+}
+
+int ctcps_initial_state(const float *blank_lp, int B, int T, int W, int t_begin, float *r0, void *stream) {
+    ARG_CHECK(blank_lp && r0 && B > 0 && T > 0 && W > 0 && t_begin >= 0 && t_begin <= T, CTCPS_E_BADARG,
+              "initial_state: bad argument");
+    const int BW = B * W;
+    k_initial_state<<<(BW + 127) / 128, 128, 0, (cudaStream_t)stream>>>(blank_lp, B, T, W, t_begin, r0);
+    return cuda_rc(cudaGetLastError());
+}
+
+int ctcps_score(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const float *s_prev,
+                int64_t s_row_stride, int64_t s_col_stride, const int64_t *last_ids, int ol, int B, int W, int T, int V,
+                int blank, const int64_t *scoring_ids, int S, int64_t *scoring_idmap, float *att_scores, float one_minus_w,
+                float w, float *r, int ldr, float *log_psi, float *token_scores, float *joint, void *workspace,
+                size_t workspace_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ARG_CHECK(x_logp && blank_lp && r_prev && last_ids && r && log_psi && token_scores, CTCPS_E_BADARG, "score: null pointer");
+    ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0 && S >= 0, CTCPS_E_BADARG, "score: non-positive size");
+    ARG_CHECK(blank >= 0 && blank < V, CTCPS_E_BADARG, "score: blank id outside the vocabulary");
+    ARG_CHECK(att_scores == nullptr || joint != nullptr, CTCPS_E_BADARG, "score: att_scores given without joint output");
+    ARG_CHECK((S == 0) == (scoring_ids == nullptr), CTCPS_E_BADARG, "score: scoring_ids and S disagree");
+    ARG_CHECK(S == 0 || scoring_idmap != nullptr, CTCPS_E_BADARG, "score: scoring_idmap output missing");
+    const int snum = S > 0 ? S : V;
+    ARG_CHECK(ldx >= V && (ldx & 3) == 0 && ldr >= snum && (ldr & 3) == 0, CTCPS_E_ALIGN, "score: ldx/ldr must be multiples of 4 and >= V/snum");
+    ARG_CHECK((((uintptr_t)x_logp) & 15) == 0 && (((uintptr_t)r) & 15) == 0, CTCPS_E_ALIGN, "score: x_logp and r must be 16-byte aligned");
+    const long long BW = (long long)B * W;
+    ARG_CHECK(BW * (long long)(V > snum ? V : snum) < (1ll << 31) && (long long)B * T < (1ll << 31), CTCPS_E_TOOBIG,
+              "score: BW*V or B*T exceeds 2^31");
+    const int start = ol > 1 ? ol : 1;
+
+    if (start > T) {  // ctc_scorer.py:138-145
+        k_fill_f32<<<grid_for((size_t)T * 2 * BW * ldr, 256), 256, 0, st>>>(r, (size_t)T * 2 * BW * ldr, LZ);
+        if (S > 0) {
+            k_fill_i64<<<grid_for((size_t)BW * V, 256), 256, 0, st>>>(scoring_idmap, (size_t)BW * V, -1);
+            k_build_idmap<<<(int)((BW + 127) / 128), 128, 0, st>>>(scoring_ids, (int)BW, S, V, scoring_idmap);
+        }
+        k_finalize<<<grid_for((size_t)BW * V, 256), 256, 0, st>>>(log_psi, s_prev, s_row_stride, s_col_stride, att_scores,
+                                                                 one_minus_w, w, (int)BW, V, blank, token_scores, joint, 1);
+        return cuda_rc(cudaGetLastError());
+    }
+
+    if (S > 0) {
+        k_fill_i64<<<grid_for((size_t)BW * V, 256), 256, 0, st>>>(scoring_idmap, (size_t)BW * V, -1);
+        k_build_idmap<<<(int)((BW + 127) / 128), 128, 0, st>>>(scoring_ids, (int)BW, S, V, scoring_idmap);
+        k_fill_f32<<<grid_for((size_t)BW * V, 256), 256, 0, st>>>(log_psi, (size_t)BW * V, LZ);  // :156
+        const long long lanes = BW * S;
+        k_score_partial<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(x_logp, ldx, blank_lp, r_prev, last_ids, scoring_ids,
+                                                                        scoring_idmap, ol, B, W, T, V, S, r, ldr, log_psi);
+        k_finalize<<<grid_for((size_t)BW * V, 256), 256, 0, st>>>(log_psi, s_prev, s_row_stride, s_col_stride, att_scores,
+                                                                 one_minus_w, w, (int)BW, V, blank, token_scores, joint, 0);
+        return cuda_rc(cudaGetLastError());
+    }
+
+    // full vocabulary
+    int HW, G;
+    pick_hw(W, &HW, &G);
+    const Workspace ws = plan_workspace(B, T, W);
+    ARG_CHECK(workspace != nullptr && workspace_bytes >= ws.total, CTCPS_E_WORKSPACE, "score: workspace too small");
+    ARG_CHECK((((uintptr_t)workspace) & 255) == 0, CTCPS_E_ALIGN, "score: workspace must be 256-byte aligned");
+    float4 *aux = reinterpret_cast<float4 *>((char *)workspace + ws.aux_off);
+    float *Gmax = reinterpret_cast<float *>((char *)workspace + ws.g_off);
+    const int Tpad = tpad_of(T);
+    {
+        const int warps = B * G * HW;
+        k_prep<<<(warps + 3) / 4, 128, 0, st>>>(r_prev, blank_lp, B, W, T, HW, G, start, Tpad, aux, Gmax);
+    }
+
+    EncodeTiledFn enc = get_encode();
+    ARG_CHECK(enc != nullptr, CTCPS_E_NODRIVER, "score: cuTensorMapEncodeTiled not found");
+    CUtensorMap tm;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)V, (cuuint64_t)B * T};
+        cuuint64_t strides[1] = {(cuuint64_t)ldx * sizeof(float)};
+        cuuint32_t box[2] = {(cuuint32_t)BOXC, (cuuint32_t)TT};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(x_logp), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (cr != CUDA_SUCCESS) {
+            snprintf(g_errbuf, sizeof(g_errbuf), "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+            return CTCPS_E_NODRIVER;
+        }
+    }
+    ScoreArgs a;
+    a.aux = aux;
+    a.Gmax = Gmax;
+    a.s_prev = s_prev;
+    a.s_rs = s_row_stride;
+    a.s_cs = s_col_stride;
+    a.last_ids = last_ids;
+    a.att = att_scores;
+    a.omw = one_minus_w;
+    a.w = w;
+    a.r = r;
+    a.ldr = ldr;
+    a.log_psi = log_psi;
+    a.token_scores = token_scores;
+    a.joint = joint;
+    a.B = B;
+    a.W = W;
+    a.T = T;
+    a.V = V;
+    a.blank = blank;
+    a.ol = ol;
+    a.G = G;
+    a.Tpad = Tpad;
+    constexpr int NT = 128;
+    a.nvt = (ldr + NT * 4 - 1) / (NT * 4);
+    int rc;
+    switch (HW) {
+        case 1: rc = launch_score_full<1, NT, 4>(tm, a, st); break;
+        case 2: rc = launch_score_full<2, NT, 4>(tm, a, st); break;
+        case 3: rc = launch_score_full<3, NT, 4>(tm, a, st); break;
+        case 4: rc = launch_score_full<4, NT, 4>(tm, a, st); break;
+        default: rc = launch_score_full<5, NT, 4>(tm, a, st); break;
+    }
+    return rc;
+}
+
+int ctcps_select(const float *r, int ldr, const float *log_psi, const int64_t *best_ids, const int64_t *scoring_idmap, int B,
+                 int W, int T, int V, int S, float *r_new, float *s_new, void *stream) {
+    ARG_CHECK(r && log_psi && best_ids && r_new && s_new, CTCPS_E_BADARG, "select: null pointer");
+    ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && S >= 0, CTCPS_E_BADARG, "select: non-positive size");
+    ARG_CHECK((S == 0) == (scoring_idmap == nullptr), CTCPS_E_BADARG, "select: scoring_idmap and S disagree");
+    ARG_CHECK(ldr >= (S > 0 ? S : V), CTCPS_E_ALIGN, "select: ldr smaller than the lane count");
+    const size_t n = (size_t)T * 2 * B * W;
+    k_select<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(r, ldr, log_psi, best_ids, scoring_idmap, B, W, T, V, S, r_new,
+                                                              s_new);
+    return cuda_rc(cudaGetLastError());
+}
+
+int ctcps_eos_space_trick(const float *att_scores, const float *ctc_scores, float *next, int BW, int V, int eos, int space,
+                          float k, void *stream) {
+    ARG_CHECK(att_scores && ctc_scores && next && BW > 0 && V > 0, CTCPS_E_BADARG, "eos_space_trick: bad argument");
+    if (eos < 0 || eos >= V || space < 0 || space >= V) return 0;  // argmax can never equal an id outside the vocabulary
+    k_trick<<<BW, 256, 0, (cudaStream_t)stream>>>(att_scores, ctc_scores, next, V, eos, space, k);
+    return cuda_rc(cudaGetLastError());
+}
+
+}  // extern "C"

@@ -1,0 +1,374 @@
+"""B200-native drop-in for BUTSpeechFIT/huggingface_asr `src/decoding/ctc_scorer.py`.
+
+Same module layout, class names, constructor signatures, call signatures, return shapes and
+in-place side effects as the reference, so `JointCTCAttentionEncoderDecoder._get_logits_processor`
+(src/models/ctc_encoder_plus_autoregressive_decoder.py:382-397, src/reguler/modeling_decred.py:456-475)
+can import this module instead of its own:
+
+    CTCPrefixScoreTH            (reference ctc_scorer.py:7)    __call__ :58, index_select_state :180,
+                                                               extend_prob :209, extend_state :231
+    CTCRescorerLogitsProcessor  (reference ctc_scorer.py:259)  __call__ :324
+    LogSoftmaxProcessor         (reference ctc_scorer.py:357)
+
+Everything numerical happens in hand-written sm_100a kernels behind the C ABI of include/ctcps.h
+(libctcps_b200.so, loaded with ctypes).  torch supplies device memory and the current stream only.
+There is no CPU path: CPU tensors raise.  No call synchronises the host.
+"""
+from __future__ import annotations
+
+import torch
+from transformers import LogitsProcessor
+
+from .. import _lib
+
+LOGZERO = -10000000000.0
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _require_cuda_f32(t: torch.Tensor, name: str, dim: int | None = None) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor, got {type(t).__name__}")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} is on {t.device}: the sm_100a CTC prefix scorer has no CPU path")
+    if t.dtype != torch.float32:
+        raise ValueError(f"{name} must be float32 (the kernels compute in fp32 log space), got {t.dtype}")
+    if dim is not None and t.dim() != dim:
+        raise ValueError(f"{name} must have {dim} dimensions, got shape {tuple(t.shape)}")
+
+
+class CTCPrefixScoreTH(object):
+    """Batched CTC prefix scorer (Watanabe et al. Algorithm 2, vectorised over hypotheses), on sm_100a.
+
+    Interface of the reference class (ctc_scorer.py:7-256).  Logical shapes of everything returned match
+    the reference; the internal layout differs where the reference's is pure redundancy:
+      * the reference materialises self.x = stack([x, blank column broadcast]) (2,T,B,V) (:44-46); here the
+        padded log-posteriors stay (B,T,V) plus a (B,T) blank column, and `.x` builds the reference tensor on demand;
+      * s_new of index_select_state is a (BW,) vector expanded to (BW,V) (the reference repeats it, :194).
+    """
+
+    def __init__(self, x, xlens, blank, eos, margin=0):
+        """x: (B,T,V) log-posteriors, padded IN PLACE like the reference (:39-42); xlens: (B,) lengths."""
+        _require_cuda_f32(x, "x", 3)
+        if not x.is_contiguous():
+            raise ValueError("x must be contiguous (B,T,V)")
+        self._setup(x, xlens, blank, eos, margin, apply_log_softmax=False)
+
+    @classmethod
+    def from_logits(cls, logits, xlens, blank, eos, margin=0):
+        """Fused log-softmax + padding (K-a): what CTCRescorerLogitsProcessor.__init__ does with
+        F.log_softmax(encoder_logits) (reference :278-284) in one pass, leaving `logits` untouched."""
+        _require_cuda_f32(logits, "encoder_logits", 3)
+        self = cls.__new__(cls)
+        self._setup(logits.contiguous(), xlens, blank, eos, margin, apply_log_softmax=True)
+        return self
+
+    def _setup(self, x, xlens, blank, eos, margin, apply_log_softmax):
+        L = _lib.lib()
+        self.logzero = LOGZERO
+        self.blank = int(blank)
+        self.eos = eos
+        self.batch, self.input_length, self.odim = (int(s) for s in x.shape)
+        self.dtype = x.dtype
+        self.device = x.device
+        self.margin = margin
+        if not 0 <= self.blank < self.odim:
+            raise ValueError(f"blank id {blank} is outside the CTC vocabulary of size {self.odim}")
+        B, T, V = self.batch, self.input_length, self.odim
+        lens = torch.as_tensor(xlens)
+        if lens.numel() != B:
+            raise ValueError(f"xlens has {lens.numel()} entries for a batch of {B}")
+        self.end_frames = lens - 1  # :47
+        self._lens = lens.to(device=self.device, dtype=torch.long).contiguous()
+        ldx = L.ctcps_padded_ld(V)
+        with torch.cuda.device(self.device):
+            self._blank_lp = torch.empty((B, T), dtype=torch.float32, device=self.device)
+            if apply_log_softmax or ldx != V:
+                self._x = torch.empty((B, T, ldx), dtype=torch.float32, device=self.device)
+            else:
+                self._x = x  # V % 4 == 0: the caller's tensor is the storage (padded in place, like the reference)
+            if not apply_log_softmax and ldx != V:
+                # pad the caller's tensor in place first (reference semantics), then stage the strided copy
+                _lib.check(L.ctcps_init(_ptr(x), V, _ptr(self._lens), B, T, V, self.blank, 0, _ptr(x), V, None,
+                                        _stream(self.device)), "ctcps_init")
+            _lib.check(L.ctcps_init(_ptr(x), V, _ptr(self._lens), B, T, V, self.blank, int(apply_log_softmax),
+                                    _ptr(self._x), ldx, _ptr(self._blank_lp), _stream(self.device)), "ctcps_init")
+        self._ldx = ldx
+        self._ws = None
+        self._ws_key = None
+        self.idx_bh = None
+        self.idx_b = torch.arange(B, device=self.device)      # :55
+        self.idx_bo = (self.idx_b * V).unsqueeze(1)           # :56
+        self.scoring_num = 0
+        if margin > 0:
+            self.frame_ids = torch.arange(T, dtype=self.dtype, device=self.device)  # :52
+
+    # -- reference attribute, built on demand --------------------------------------------------------
+    @property
+    def x(self):
+        """(2,T,B,V) tensor of the reference (:44-46).  Costs 2x the posteriors; only for inspection."""
+        xn = self._x[:, :, : self.odim].transpose(0, 1)
+        xb = self._blank_lp.transpose(0, 1).unsqueeze(2).expand(-1, -1, self.odim)
+        return torch.stack([xn, xb])
+
+    def _workspace(self, W, S):
+        key = (self.batch, self.input_length, W, S)
+        if self._ws_key != key:
+            import ctypes
+
+            n = ctypes.c_size_t(0)
+            _lib.check(_lib.lib().ctcps_workspace_bytes(self.batch, self.input_length, self.odim, W, S, ctypes.byref(n)),
+                       "ctcps_workspace_bytes")
+            self._ws = torch.empty((max(int(n.value), 256),), dtype=torch.uint8, device=self.device)
+            self._ws_key = key
+        return self._ws
+
+    def initial_state(self, n_hyps):
+        """r_prev of the empty prefix, (T,2,B*n_hyps) (reference :74-85)."""
+        r0 = torch.empty((self.input_length, 2, self.batch * n_hyps), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().ctcps_initial_state(_ptr(self._blank_lp), self.batch, self.input_length, n_hyps, 0, _ptr(r0),
+                                                      _stream(self.device)), "ctcps_initial_state")
+        return r0
+
+    def __call__(self, y, state, scoring_ids=None, att_w=None):
+        """Compute CTC prefix scores for next labels (reference :58-178).
+
+        y: prefix label sequences, a (BW,L) LongTensor or a list of sequences (only y[i][-1] and len(y[0]) are used);
+        state: None or (r_prev (T,2,BW), s_prev (BW,V) | 0.0, f_min, f_max);  scoring_ids: optional (BW,S).
+        Returns (token_scores (BW,V), (r (T,2,BW,S or V), log_psi (BW,V), 0, 0, scoring_idmap | None)).
+        """
+        ts, new_state, _ = self._score(y, state, scoring_ids, att_w, None, 0.0)
+        return ts, new_state
+
+    def _score(self, y, state, scoring_ids, att_w, att_scores, ctc_weight):
+        if att_w is not None and self.margin > 0:
+            raise NotImplementedError("CTC windowing (att_w with margin > 0, reference :127-132) is dead code in the "
+                                      "reference's processor and is not implemented")
+        L = _lib.lib()
+        dev = self.device
+        B, T, V = self.batch, self.input_length, self.odim
+        if isinstance(y, torch.Tensor):
+            if y.dim() != 2:
+                raise ValueError(f"y must be (BW, L), got {tuple(y.shape)}")
+            n_bh, ol = int(y.shape[0]), int(y.shape[1]) - 1
+            last_ids = y[:, -1].to(device=dev, dtype=torch.long).contiguous()
+        else:
+            n_bh, ol = len(y), len(y[0]) - 1                       # :68-70
+            last_ids = torch.tensor([int(yi[-1]) for yi in y], dtype=torch.long).to(dev)
+        if n_bh % B != 0:
+            raise ValueError(f"{n_bh} hypotheses are not a multiple of the batch of {B} utterances")
+        W = n_bh // B                                            # :71
+        S = 0
+        if scoring_ids is not None:
+            if not scoring_ids.is_cuda:
+                raise RuntimeError("scoring_ids must be a CUDA tensor")
+            scoring_ids = scoring_ids.to(torch.long).contiguous()
+            if scoring_ids.dim() != 2 or scoring_ids.shape[0] != n_bh:
+                raise ValueError(f"scoring_ids must be (BW,S) with BW={n_bh}, got {tuple(scoring_ids.shape)}")
+            S = int(scoring_ids.shape[1])
+        self.scoring_num = S                                     # :72
+        snum = S if S > 0 else V
+
+        if state is None:
+            r_prev, s_prev = self.initial_state(W), None
+        else:
+            r_prev, s_prev = state[0], state[1]
+            _require_cuda_f32(r_prev, "state r_prev")
+            if tuple(r_prev.shape) != (T, 2, n_bh):
+                raise ValueError(f"state r_prev must be {(T, 2, n_bh)}, got {tuple(r_prev.shape)}")
+            r_prev = r_prev.contiguous()
+        s_ptr, s_rs, s_cs = None, 0, 0
+        if isinstance(s_prev, torch.Tensor):
+            _require_cuda_f32(s_prev, "state s_prev")
+            if s_prev.dim() == 1:
+                s_prev = s_prev.view(-1, 1).expand(n_bh, V)
+            if tuple(s_prev.shape) != (n_bh, V):
+                raise ValueError(f"state s_prev must be {(n_bh, V)}, got {tuple(s_prev.shape)}")
+            s_ptr, (s_rs, s_cs) = s_prev.data_ptr(), s_prev.stride()
+        elif s_prev is not None and float(s_prev) != 0.0:
+            s_prev = torch.full((n_bh,), float(s_prev), dtype=torch.float32, device=dev)
+            s_ptr, s_rs, s_cs = s_prev.data_ptr(), 1, 0
+
+        joint = None
+        if att_scores is not None:
+            _require_cuda_f32(att_scores, "scores", 2)
+            if tuple(att_scores.shape) != (n_bh, V) or not att_scores.is_contiguous():
+                raise ValueError(f"scores must be contiguous {(n_bh, V)}, got {tuple(att_scores.shape)}")
+        ldr = L.ctcps_padded_ld(snum)
+        with torch.cuda.device(dev):
+            r = torch.empty((T, 2, n_bh, ldr), dtype=torch.float32, device=dev)
+            log_psi = torch.empty((n_bh, V), dtype=torch.float32, device=dev)
+            token_scores = torch.empty((n_bh, V), dtype=torch.float32, device=dev)
+            if att_scores is not None:
+                joint = torch.empty((n_bh, V), dtype=torch.float32, device=dev)
+            idmap = torch.empty((n_bh, V), dtype=torch.long, device=dev) if S > 0 else None
+            ws = self._workspace(W, S)
+            w = float(ctc_weight)
+            _lib.check(L.ctcps_score(_ptr(self._x), self._ldx, _ptr(self._blank_lp), _ptr(r_prev), s_ptr, s_rs, s_cs,
+                                     _ptr(last_ids), ol, B, W, T, V, self.blank, _ptr(scoring_ids), S, _ptr(idmap),
+                                     _ptr(att_scores), 1.0 - w, w, _ptr(r), ldr, _ptr(log_psi), _ptr(token_scores),
+                                     _ptr(joint), _ptr(ws), ws.numel(), _stream(dev)), "ctcps_score")
+        if ldr != snum:
+            r = r[..., :snum]
+        return token_scores, (r, log_psi, 0, 0, idmap), joint
+
+    def index_select_state(self, state, best_ids):
+        """Select CTC states according to best ids (reference :180-207).
+
+        best_ids: (B,W) ids in hyp*V + tok space.  Returns (r_new (T,2,BW), s_new (BW,V) [expanded], f_min, f_max).
+        """
+        r, s, f_min, f_max, scoring_idmap = state
+        _require_cuda_f32(r, "state r", 4)
+        _require_cuda_f32(s, "state log_psi", 2)
+        T, _, n_bh, snum = (int(v) for v in r.shape)
+        V = self.odim
+        n_hyps = n_bh // self.batch
+        S = 0 if scoring_idmap is None else snum
+        if r.stride(3) == 1 and r.stride(1) == n_bh * r.stride(2) and r.stride(0) == 2 * n_bh * r.stride(2):
+            ldr = int(r.stride(2))
+        else:
+            r = r.contiguous()
+            ldr = snum
+        best_ids = best_ids.to(device=self.device, dtype=torch.long).contiguous()
+        if best_ids.numel() != n_bh:
+            raise ValueError(f"best_ids has {best_ids.numel()} entries for {n_bh} hypotheses")
+        s = s.contiguous()
+        with torch.cuda.device(self.device):
+            r_new = torch.empty((T, 2, n_bh), dtype=torch.float32, device=self.device)
+            s_vec = torch.empty((n_bh,), dtype=torch.float32, device=self.device)
+            _lib.check(_lib.lib().ctcps_select(_ptr(r), ldr, _ptr(s), _ptr(best_ids), _ptr(scoring_idmap), self.batch, n_hyps,
+                                               T, V, S, _ptr(r_new), _ptr(s_vec), _stream(self.device)), "ctcps_select")
+        return r_new, s_vec.view(-1, 1).expand(n_bh, V), f_min, f_max
+
+    def extend_prob(self, x):
+        """Extend the posteriors with new frames (streaming helper, reference :209-229).  x: (B,T',V) log-posteriors."""
+        _require_cuda_f32(x, "x", 3)
+        T_old = self.input_length
+        if T_old < x.shape[1]:
+            B, T_new, V = (int(v) for v in x.shape)
+            if B != self.batch or V != self.odim:
+                raise ValueError("extend_prob: batch / vocabulary mismatch")
+            L = _lib.lib()
+            old_x, old_blank = self._x, self._blank_lp
+            with torch.cuda.device(self.device):
+                self._x = torch.empty((B, T_new, self._ldx), dtype=torch.float32, device=self.device)
+                self._blank_lp = torch.empty((B, T_new), dtype=torch.float32, device=self.device)
+                # xlens = [T'] in the reference (:218): nothing is padded
+                _lib.check(L.ctcps_init(_ptr(x.contiguous()), V, None, B, T_new, V, self.blank, 0, _ptr(self._x), self._ldx,
+                                        _ptr(self._blank_lp), _stream(self.device)), "ctcps_init")
+            self._x[:, :T_old] = old_x            # frames already seen keep their values (:227)
+            self._blank_lp[:, :T_old] = old_blank
+            self.input_length = T_new
+            self.end_frames = torch.as_tensor([T_new]) - 1
+            self._ws_key = None
+
+    def extend_state(self, state):
+        """Extend the blank-only chain of a state to the new input length (reference :231-256)."""
+        if state is None:
+            return state
+        r_prev, s_prev, f_min_prev, f_max_prev = state
+        _require_cuda_f32(r_prev, "state r_prev")
+        squeeze = r_prev.dim() == 2  # the reference's single-hypothesis (T,2) layout
+        rp = r_prev.unsqueeze(2) if squeeze else r_prev
+        T_old, _, n_bh = (int(v) for v in rp.shape)
+        T = self.input_length
+        r_new = torch.full((T, 2, n_bh), LOGZERO, dtype=torch.float32, device=self.device)
+        start = max(T_old, 1)
+        r_new[:T_old] = rp
+        if start < T:
+            with torch.cuda.device(self.device):
+                _lib.check(_lib.lib().ctcps_initial_state(_ptr(self._blank_lp), self.batch, T, n_bh // self.batch, start,
+                                                          _ptr(r_new), _stream(self.device)), "ctcps_initial_state")
+        return (r_new.squeeze(2) if squeeze else r_new, s_prev, f_min_prev, f_max_prev)
+
+
+class CTCRescorerLogitsProcessor(LogitsProcessor):
+    """Joint CTC/attention rescoring processor (reference ctc_scorer.py:259-354), one instance per generate()."""
+
+    def __init__(
+        self,
+        encoder_logits: torch.FloatTensor,
+        encoder_output_lens: torch.LongTensor,
+        pad_token_id: int,
+        eos_token_id: int,
+        ctc_margin: int,
+        ctc_weight: float,
+        num_beams: int,
+        space_token_id: int,
+        apply_eos_space_trick: bool,
+        eos_space_trick_weight: float,
+        debug: bool = False,
+    ):
+        super().__init__()
+        self.pad_token_id = pad_token_id
+        self.ctc_prefix_scorer = CTCPrefixScoreTH.from_logits(encoder_logits, encoder_output_lens, pad_token_id, eos_token_id,
+                                                              ctc_margin)
+        self.ctc_weight = ctc_weight
+        self.ctc_states = None
+        self.num_beams = num_beams
+        self.eos_token_id = eos_token_id
+        self.apply_eos_space_trick = apply_eos_space_trick
+        self.space_token_id = space_token_id
+        self.eos_space_trick_weight = eos_space_trick_weight
+        self.debug = debug
+
+    def __call__(self, input_ids: torch.LongTensor, scores: torch.FloatTensor) -> torch.FloatTensor:
+        sc = self.ctc_prefix_scorer
+        _require_cuda_f32(scores, "scores", 2)
+        if scores.shape[-1] != sc.odim:
+            raise ValueError(f"decoder vocabulary ({scores.shape[-1]}) != CTC vocabulary ({sc.odim}): the encoder's extra "
+                             "blank_projection column (src/models/encoders/e_branchformer.py:415,456-457) is not supported "
+                             "by the reference processor either")
+        work = scores if scores.is_contiguous() else scores.contiguous()
+        if self.ctc_states is not None:
+            self.ctc_states = sc.index_select_state(self.ctc_states, input_ids[:, -1].reshape(-1, self.num_beams))  # :326-329
+        # scores[:, pad] = logzero (:325), the scorer (:330) and the combine (:332) are one fused launch
+        ctc_scores, self.ctc_states, next_token_scores = sc._score(input_ids, self.ctc_states, None, None, work, self.ctc_weight)
+        if work is not scores:
+            scores[:, self.pad_token_id] = sc.logzero
+        if self.apply_eos_space_trick:
+            with torch.cuda.device(sc.device):
+                _lib.check(_lib.lib().ctcps_eos_space_trick(_ptr(work), _ptr(ctc_scores), _ptr(next_token_scores),
+                                                            int(scores.shape[0]), sc.odim, int(self.eos_token_id),
+                                                            int(self.space_token_id), float(self.eos_space_trick_weight),
+                                                            _stream(sc.device)), "ctcps_eos_space_trick")
+        if self.debug:
+            self.analyze_predictions(scores, ctc_scores, next_token_scores, input_ids)
+        return next_token_scores
+
+    @staticmethod
+    def analyze_predictions(scores, ctc_scores, next_token_scores, input_ids, k=10, tokenizer=None):
+        """Debug dump (reference :294-322 decodes with a hub tokenizer; offline we print ids unless one is given)."""
+        dec = (lambda ids: tokenizer.batch_decode(ids)) if tokenizer is not None else (lambda ids: [str(i.tolist()) for i in ids])
+        print("PREFIX:")
+        for index, prefix in enumerate(dec(input_ids)):
+            print(f"HYP {index}:\n{prefix}")
+        for name, t in (("ATT_SCORES", scores), ("CTC_SCORES", ctc_scores), ("NEXT_TOKEN_SCORES", next_token_scores)):
+            best = t.topk(k=k, dim=1)
+            print(f"{name}:")
+            for index, (ids, vals) in enumerate(zip(dec(best.indices), best.values)):
+                print(f"HYP {index}:\n{ids} {vals}")
+
+
+class LogSoftmaxProcessor(LogitsProcessor):
+    """log_softmax over the vocabulary (reference ctc_scorer.py:357-365); inserted for greedy decoding."""
+
+    def __init__(self):
+        super().__init__()
+
+    def __call__(self, input_ids: torch.LongTensor, scores: torch.FloatTensor) -> torch.FloatTensor:
+        _require_cuda_f32(scores, "scores", 2)
+        src = scores if scores.stride(-1) == 1 else scores.contiguous()
+        out = torch.empty(tuple(scores.shape), dtype=torch.float32, device=scores.device)
+        with torch.cuda.device(scores.device):
+            _lib.check(_lib.lib().ctcps_log_softmax(_ptr(src), int(src.stride(0)), _ptr(out), int(out.stride(0)),
+                                                    int(scores.shape[0]), int(scores.shape[1]), _stream(scores.device)),
+                       "ctcps_log_softmax")
+        return out

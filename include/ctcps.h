@@ -1,0 +1,121 @@
+/*
+ * ctcps.h -- C ABI of the sm_100a CTC prefix scorer (libctcps_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of BUTSpeechFIT/huggingface_asr that this
+ * repository accelerates: src/decoding/ctc_scorer.py (log-softmax -> prefix-score forward
+ * recursion -> state select -> joint-score combine).  The reference is pure Python/torch and has
+ * no FFI of its own; each entry point below names the reference lines it replaces, and
+ * INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless named host_*;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - fp32 log domain, int64 ids, row-major; logzero = -1e10 (ctc_scorer.py:29);
+ *   - return value: 0 = ok, < 0 = argument error (CTCPS_E_*), > 0 = cudaError_t;
+ *     ctcps_error_string() decodes both;
+ *   - the caller owns every buffer; the library keeps no global state besides the last error text.
+ *
+ * Shapes: B utterances, W hypotheses per utterance, BW = B*W, T frames, V vocabulary,
+ * S = scoring_num (0 = full vocabulary), snum = S ? S : V.
+ *   ldx : row stride (floats) of x_logp,  multiple of 4, >= V   (16-byte rows for TMA / float4)
+ *   ldr : innermost stride (floats) of r, multiple of 4, >= snum
+ */
+#ifndef CTCPS_H_
+#define CTCPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTCPS_LOGZERO (-10000000000.0f)
+
+enum {
+    CTCPS_OK = 0,
+    CTCPS_E_BADARG = -1,    /* null pointer, non-positive size, id out of range */
+    CTCPS_E_ALIGN = -2,     /* ldx / ldr / pointer alignment violated */
+    CTCPS_E_WORKSPACE = -3, /* workspace too small */
+    CTCPS_E_NODRIVER = -4,  /* cuTensorMapEncodeTiled not obtainable from the driver */
+    CTCPS_E_TOOBIG = -5     /* sizes exceed what the kernels index with 32-bit lanes */
+};
+
+int ctcps_version(void);
+const char *ctcps_error_string(int code);
+
+/* Round a vocabulary / candidate count up to the stride the kernels want (multiple of 4). */
+int ctcps_padded_ld(int n);
+
+/* Bytes of scratch ctcps_score needs for these sizes. */
+int ctcps_workspace_bytes(int B, int T, int V, int W, int S, size_t *out_bytes);
+
+/*
+ * K-a.  Replaces F.log_softmax (ctc_scorer.py:279) + the length-padding loop (:39-42) + the
+ * blank-column broadcast of self.x[1] (:44-46).
+ *   in  logits (B,T,V) rows of stride ld_in;  lens (B) int64
+ *   out x_logp (B,T,*) rows of stride ldx  (may alias logits when ld_in == ldx: in-place, as the
+ *       reference pads its argument in place);  blank_lp (B,T) = x_logp[b,t,blank]
+ *   apply_log_softmax = 0 when the input already holds log-posteriors (CTCPrefixScoreTH ctor).
+ */
+int ctcps_init(const float *logits, int ld_in, const int64_t *lens, int B, int T, int V, int blank,
+               int apply_log_softmax, float *x_logp, int ldx, float *blank_lp, void *stream);
+
+/* Row-wise log-softmax; replaces LogSoftmaxProcessor.__call__ (ctc_scorer.py:357-365). */
+int ctcps_log_softmax(const float *in, int ld_in, float *out, int ld_out, int rows, int V, void *stream);
+
+/*
+ * Initial state, replaces the `state is None` branch (ctc_scorer.py:74-85):
+ *   r0[t,0,h] = logzero, r0[t,1,h] = sum_{tau<=t} blank_lp[b,tau]   (sequential fp32 running sum,
+ *   the order torch.cumsum uses), r0 is (T,2,BW).
+ * t_begin > 0 continues a running sum for extend_state (ctc_scorer.py:231-256): rows < t_begin
+ * of r0 are left untouched and the sum restarts from r0[t_begin-1,1,h].
+ */
+int ctcps_initial_state(const float *blank_lp, int B, int T, int W, int t_begin, float *r0, void *stream);
+
+/*
+ * K-b.  Replaces CTCPrefixScoreTH.__call__ (ctc_scorer.py:58-178) for margin == 0, fused with the
+ * processor arithmetic around it (ctc_scorer.py:325,332).
+ *   in  x_logp (B,T,ldx), blank_lp (B,T)
+ *       r_prev (T,2,BW)            selected state (or ctcps_initial_state output)
+ *       s_prev                     NULL = scalar 0.0 (:83); else element (h,v) at
+ *                                  s_prev[h*s_row_stride + v*s_col_stride]  ((BW,) vector: 1, 0)
+ *       last_ids (BW) int64        y[h][-1] (:69);  ol = len(y[0]) - 1 (:68)
+ *       scoring_ids (BW,S) int64   NULL / S == 0 = full vocabulary (:98-102)
+ *       att_scores (BW,V)          NULL, or the attention log-probs: column `blank` is set to
+ *                                  logzero IN PLACE (:325) and joint = (1-w)*att + w*ctc (:332)
+ *   out r (T,2,BW,ldr)             forward variables, ALL T frames written (:106-113,148-151)
+ *       log_psi (BW,V)  token_scores (BW,V)  (:154-176)
+ *       joint (BW,V)               only with att_scores
+ *       scoring_idmap (BW,V) int64 only with scoring_ids (:91-95)
+ *   one_minus_w, w                 (float)(1 - ctc_weight) and (float)ctc_weight, rounded by the
+ *                                  caller in double like the reference's Python scalars
+ * `start > end` (ol > T, :138-145) yields r = logzero everywhere and log_psi = token_scores = logzero.
+ */
+int ctcps_score(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const float *s_prev,
+                int64_t s_row_stride, int64_t s_col_stride, const int64_t *last_ids, int ol, int B, int W, int T,
+                int V, int blank, const int64_t *scoring_ids, int S, int64_t *scoring_idmap, float *att_scores,
+                float one_minus_w, float w, float *r, int ldr, float *log_psi, float *token_scores, float *joint,
+                void *workspace, size_t workspace_bytes, void *stream);
+
+/*
+ * K-c.  Replaces CTCPrefixScoreTH.index_select_state (ctc_scorer.py:180-207).
+ *   best_ids (B,W) int64 = hyp*V + tok inside the utterance; with scoring_idmap the lane is
+ *   idmap[hyp,tok] (-1 -> 0, :196-202).
+ *   out r_new (T,2,BW), s_new (BW)  (the reference's (BW,V) s_new is this vector broadcast, :194)
+ */
+int ctcps_select(const float *r, int ldr, const float *log_psi, const int64_t *best_ids, const int64_t *scoring_idmap,
+                 int B, int W, int T, int V, int S, float *r_new, float *s_new, void *stream);
+
+/*
+ * Optional eos/space trick of the processor (ctc_scorer.py:333-349), in place on `next`:
+ * rows with argmax(att) == eos and argmax(ctc) == space and next[eos] < next[space] < k*next[eos]
+ * get next[eos] *= k.
+ */
+int ctcps_eos_space_trick(const float *att_scores, const float *ctc_scores, float *next, int BW, int V, int eos,
+                          int space, float k, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTCPS_H_ */

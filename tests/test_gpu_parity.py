@@ -1,0 +1,117 @@
+"""GPU parity: the sm_100a scorer, called through the C ABI, against the golden vectors of the
+reference and against the CPU oracle on seeded inputs.  Run on the B200 box with -m gpu."""
+import numpy as np
+import pytest
+import torch
+
+import parity
+
+pytestmark = pytest.mark.gpu
+
+
+class CudaBackend(parity.Backend):
+    device = "cuda"
+
+    def make_scorer(self, x_logp, lens, blank, eos, margin=0):
+        from huggingface_asr_b200.decoding.ctc_scorer import CTCPrefixScoreTH
+
+        return CTCPrefixScoreTH(x_logp.contiguous(), lens, blank, eos, margin)
+
+    def make_processor(self, logits, lens, pad, eos, margin, w, W, space=-1, trick=False, trick_w=1.0):
+        from huggingface_asr_b200.decoding.ctc_scorer import CTCRescorerLogitsProcessor
+
+        return CTCRescorerLogitsProcessor(logits, lens, pad, eos, margin, w, W, space, trick, trick_w)
+
+
+BE = CudaBackend()
+STEP_CASES = ["steps_peaky_w3", "steps_peaky_ragged_w10", "steps_flat_w1", "steps_flat_w20", "steps_peaky_w5_v129",
+              "steps_forced_pad", "steps_trick"]
+
+
+def test_native_library_is_loaded():
+    from huggingface_asr_b200 import _lib
+
+    assert _lib.lib().ctcps_version() >= 100
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_steps_vs_reference_golden(name):
+    worst = parity.replay_steps(BE, name)
+    print(name, worst)
+
+
+def test_partial_scoring_vs_reference_golden():
+    parity.replay_partial(BE)
+
+
+def test_select_general_vs_reference_golden():
+    parity.replay_select_general(BE)
+
+
+def test_edges_vs_reference_golden():
+    parity.replay_edges(BE)
+
+
+def test_decode_1best_vs_reference_golden():
+    parity.replay_decode(BE)
+
+
+def test_padded_posteriors_vs_reference_golden():
+    from huggingface_asr_b200.decoding.ctc_scorer import CTCPrefixScoreTH
+
+    g = parity.load("steps_peaky_ragged_w10")
+    sc = CTCPrefixScoreTH.from_logits(BE.t(g["logits"]), BE.t(g["lens"]), 3, 1)
+    parity.assert_parity(sc._x[:, :, : sc.odim], g["x_padded"], "padded log-posteriors", atol=2e-6, rtol=0)
+    ref_x = torch.from_numpy(g["x_padded"]).transpose(0, 1)
+    parity.assert_parity(sc.x[0], ref_x, "x property plane 0", atol=2e-6, rtol=0)
+    parity.assert_parity(sc.x[1], ref_x[:, :, 3:4].expand(-1, -1, sc.odim), "x property plane 1", atol=2e-6, rtol=0)
+
+
+@pytest.mark.parametrize("B,W,T,V,kind,ragged", [
+    (4, 10, 120, 1000, "peaky", True),     # several v-tiles, ragged, two hyp groups
+    (2, 7, 61, 517, "flat", True),         # W with a padded hyp group, V % 4 != 0, V tail inside a TMA box
+    (3, 1, 90, 300, "peaky", False),       # greedy-width
+    (2, 20, 200, 260, "flat", False),      # W = 20 (four groups)
+])
+def test_multi_step_vs_oracle(B, W, T, V, kind, ragged):
+    """Seeded inputs at sizes the oracle finishes in seconds; every step of a short decode, r included."""
+    from huggingface_asr_b200.decoding.ctc_scorer import CTCRescorerLogitsProcessor
+    from huggingface_asr_b200.synthetic import make_attention_scores, make_encoder_logits
+    from oracle import oracle as orc
+
+    logits, lens, _ = make_encoder_logits(B, T, V, kind, ragged, seed=1234 + W)
+    gpu = CTCRescorerLogitsProcessor(logits.cuda(), lens.cuda(), 3, 1, 0, 0.3, W, -1, False, 1.0)
+    cpu = orc.OracleCTCRescorerLogitsProcessor(logits.clone(), lens.clone(), 3, 1, 0, 0.3, W)
+    cpu64 = orc.OracleCTCRescorerLogitsProcessor(logits.double(), lens.clone(), 3, 1, 0, 0.3, W)
+    ids = torch.zeros((B * W, 1), dtype=torch.long)
+    beam_scores = torch.zeros(B, W)
+    beam_scores[:, 1:] = -1e9
+    for n in range(5):
+        att = make_attention_scores(B * W, V, n, seed=99, scale=0.5)
+        out_c = cpu(ids, att.clone())
+        out_64 = cpu64(ids, att.double())
+        out_g = gpu(ids.cuda(), att.cuda())
+        parity.assert_parity(out_g, out_c, f"step {n} joint scores", ref64=out_64)
+        parity.assert_parity(gpu.ctc_states[1], cpu.ctc_states[1], f"step {n} log_psi", ref64=cpu64.ctc_states[1])
+        parity.assert_parity(gpu.ctc_states[0], cpu.ctc_states[0], f"step {n} r", ref64=cpu64.ctc_states[0])
+        cand = (out_c + beam_scores.view(-1, 1)).view(B, W * V)
+        top, idx = cand.topk(W, dim=1)
+        src, tok = idx // V, idx % V
+        ids = torch.cat([ids[(src + (torch.arange(B) * W).view(B, 1)).view(-1)], tok.view(-1, 1)], dim=1)
+        beam_scores = top
+
+
+def test_log_softmax_processor():
+    from huggingface_asr_b200.decoding.ctc_scorer import LogSoftmaxProcessor
+
+    g = torch.Generator().manual_seed(3)
+    s = torch.randn(7, 5000, generator=g) * 3
+    out = LogSoftmaxProcessor()(None, s.cuda())
+    assert (out.cpu() - torch.log_softmax(s, -1)).abs().max() <= 2e-6
+
+
+def test_cpu_tensors_are_refused():
+    from huggingface_asr_b200.decoding.ctc_scorer import CTCPrefixScoreTH
+
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        CTCPrefixScoreTH(torch.zeros(1, 4, 8), torch.tensor([4]), 3, 1)
