@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py -- utt/s of beam-10 joint CTC/attention decoding with the sm_100a CTC prefix scorer.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C2]
+
+Metric (BASELINE.json): utterances/s of the joint decode + the prefix-score kernel's HBM GB/s against the
+measured peak.  One "step" = one full joint CTC/attention beam-search decode of one batch of synthetic
+utterances (K-a init, then per output token: state select, prefix scoring fused with the joint combine, and
+the beam update of the shared harness).  Workload = BASELINE.json configs[1] (C2: 256 x 15 s utterances,
+beam 10, 5000-token vocabulary) per GPU; weak scaling (each rank decodes its own batch, no collective on
+the data path; the final hypotheses are gathered with NCCL inside the e2e region).
+
+The attention decoder is model code outside the path: its log-probs come from
+huggingface_asr_b200.synthetic.SyntheticDecoder, the CTC head outputs are synthetic "peaky" logits.
+
+--impl reference times the CPU oracle port of the reference scorer (oracle/, all host threads) inside the
+same harness on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from huggingface_asr_b200.beam_search import joint_beam_search  # noqa: E402
+from huggingface_asr_b200.synthetic import BLANK, BOS, CONFIGS, EOS, SyntheticDecoder, make_encoder_logits  # noqa: E402
+
+METRIC = "utt/s beam-10 joint CTC/attn decode"
+UNIT = "utt/s"
+MAX_LENGTH = 128  # synthetic transcripts have T//8 + 1 <= 94 tokens; the reference recipes use 512
+ATT_POOL = 8
+
+
+def algorithmic_bytes_per_score(B, W, T, V):
+    """interface-faithful bytes of one ctcps_score launch (fp32)."""
+    BW = B * W
+    return (8 * T * BW * V      # write state r, both planes
+            + 4 * T * B * V     # read log-posteriors once (shared by the W hyps)
+            + 4 * T * B         # blank column
+            + 8 * T * BW        # read r_prev
+            + 4 * BW + 8 * BW   # s_prev, last ids
+            + 4 * BW * V * 3)   # read attention scores, write log_psi, write joint scores
+
+
+def peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_ours(args):
+    from huggingface_asr_b200 import _lib
+    from huggingface_asr_b200.decoding.ctc_scorer import CTCRescorerLogitsProcessor
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the scorer has no CPU path (use --impl reference for the CPU oracle)")
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    dev = torch.device(f"cuda:{local}")
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = CONFIGS[args.config]
+    B, W, T, V = args.batch or cfg.B, cfg.W, cfg.T, cfg.V
+    BW = B * W
+    _lib.lib()  # build / load outside the timed region
+
+    # synthetic inputs: pinned host copy for the e2e leg, device copy for the resident leg
+    logits_h, lens_h, transcripts = make_encoder_logits(B, T, V, cfg.kind, cfg.ragged, seed=20240 + 1000 * 2 + rank)
+    logits_h, lens_h = logits_h.pin_memory(), lens_h.pin_memory()
+    logits_d, lens_d = logits_h.to(dev), lens_h.to(dev)
+    decoder = SyntheticDecoder(transcripts, W, V, MAX_LENGTH, seed=7 + rank, device=dev, pool=ATT_POOL)
+    out_seq_h = torch.empty((B, MAX_LENGTH), dtype=torch.long).pin_memory()
+    out_len_h = torch.empty((B,), dtype=torch.long).pin_memory()
+    out_score_h = torch.empty((B,), dtype=torch.float32).pin_memory()
+    launches = [0]
+    score_events = []
+
+    def decode(lg, ln, timing=None):
+        proc = CTCRescorerLogitsProcessor(lg, ln, BLANK, EOS, 0, cfg.ctc_weight, W, -1, False, 1.0)
+        proc.ctc_prefix_scorer._timing = timing
+        out = joint_beam_search(proc, decoder, B, W, V, BOS, EOS, BLANK, max_length=MAX_LENGTH, device=dev)
+        # K-a (1) + initial state (1) + per step: prep + recursion (2) + select (1, all steps but the first)
+        launches[0] += 2 + 2 * out.steps + (out.steps - 1)
+        return out
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    warm = args.warmup if args.profile else max(args.warmup, 3)
+    for _ in range(warm):
+        out = decode(logits_d, lens_d)
+    sync_all()
+
+    # ---- leg 1: inputs resident in HBM, device-timed --------------------------------------------------
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches[0] = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    steps_total = 0
+    for _ in range(args.steps):
+        out = decode(logits_d, lens_d, score_events)
+        steps_total += out.steps
+    e1.record()
+    sync_all()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    n_launch = launches[0]
+    score_ms = [a.elapsed_time(b) for a, b in score_events]
+
+    # ---- leg 2: end to end through the processor API with HOST buffers --------------------------------
+    def e2e_once():
+        lg = logits_h.to(dev, non_blocking=True)
+        ln = lens_h.to(dev, non_blocking=True)
+        o = decode(lg, ln)
+        if dist is not None:  # final gather of the hypotheses: the only collective of the path
+            seqs = [torch.empty_like(o.sequences) for _ in range(world)]
+            dist.all_gather(seqs, o.sequences)
+        out_seq_h.copy_(o.sequences, non_blocking=True)
+        out_len_h.copy_(o.lengths, non_blocking=True)
+        out_score_h.copy_(o.scores, non_blocking=True)
+
+    if args.profile:
+        print(json.dumps({'profile_run': True, 'ms_per_step': ms / args.steps, 'avg_score_ms': sum(score_ms) / max(len(score_ms), 1)}))
+        return
+    e2e_once()
+    sync_all()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        e2e_once()
+    f1.record()
+    sync_all()
+    ms_e2e = f0.elapsed_time(f1)
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        abytes = algorithmic_bytes_per_score(B, W, T, V)
+        avg_score_ms = sum(score_ms) / max(len(score_ms), 1)
+        achieved = abytes / (avg_score_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {cfg.name}", "utterances_per_gpu": B, "beam": W, "frames": T, "vocab": V,
+                       "ctc_weight": cfg.ctc_weight, "logits": cfg.kind, "decode_steps_per_utterance_batch": steps_total / args.steps,
+                       "attention_scores": "SyntheticDecoder: log_softmax(noise + 10*onehot(transcript[n])) (the decoder is model code outside the path)", "max_length": MAX_LENGTH,
+                       "l2": "inputs exceed L2: every scorer launch writes 8*T*BW*V bytes of state"},
+            "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": logits_h.numel() * 4 + lens_h.numel() * 8,
+                    "d2h_bytes_per_step": out_seq_h.numel() * 8 + out_len_h.numel() * 8 + out_score_h.numel() * 4},
+            "gpu_launches": n_launch,
+            "roofline": {"bound": "hbm", "kernel": "k_score_full (+ k_prep)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src, "traffic": load_traffic(),
+                         "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": avg_score_ms, "launches_timed": len(score_ms)},
+            "clocks": clk,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(cfg, args)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def load_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))["k_score_full_dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def oracle_decode(cfg, B, seed, threads=None):
+    """The CPU oracle port inside the same harness on B utterances of cfg's shape.  Returns (seconds, steps)."""
+    from oracle import oracle as orc
+
+    if threads:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    W, T, V = cfg.W, cfg.T, cfg.V
+    logits, lens, transcripts = make_encoder_logits(B, T, V, cfg.kind, cfg.ragged, seed=seed)
+    decoder = SyntheticDecoder(transcripts, W, V, MAX_LENGTH, seed=7, pool=ATT_POOL)
+    t0 = time.perf_counter()
+    proc = orc.OracleCTCRescorerLogitsProcessor(logits, lens, BLANK, EOS, 0, cfg.ctc_weight, W)
+    out = joint_beam_search(proc, decoder, B, W, V, BOS, EOS, BLANK, max_length=MAX_LENGTH)
+    return time.perf_counter() - t0, out.steps
+
+
+def cpu_baseline(cfg, args):
+    cores = os.cpu_count() or 1
+    Bs = 2 if cores >= 16 else 1
+    sec, steps = oracle_decode(cfg, Bs, seed=20240 + 2000)
+    return {"value": Bs / sec, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{Bs} utterance(s) of the {args.config} shape (T={cfg.T}, V={cfg.V}, beam {cfg.W}), full decode of {steps} steps, "
+                      f"oracle/ctc_prefix_oracle.c with OpenMP on {cores} threads, {sec:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cfg = CONFIGS[args.config]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    Bs = args.batch or (2 if cores >= 16 else 1)
+    for _ in range(min(args.warmup, 1)):
+        oracle_decode(cfg, 1 if Bs > 1 else Bs, seed=1)
+    t = 0.0
+    steps = 0
+    for i in range(args.steps):
+        sec, st = oracle_decode(cfg, Bs, seed=20240 + 2000 + i)
+        t += sec
+        steps += st
+    val = Bs * args.steps / t
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)),
+        "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: {cfg.name}", "sample_utterances_per_step": Bs, "beam": cfg.W, "frames": cfg.T,
+                   "vocab": cfg.V, "ctc_weight": cfg.ctc_weight, "decode_steps_per_utterance_batch": steps / args.steps},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{Bs} utterance(s) per step of the {args.config} shape, full joint decode, CPU oracle port of "
+                                   f"src/decoding/ctc_scorer.py (the reference is Python/torch and cannot travel to this box)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="override utterances per GPU (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="for runs under ncu: honour a warm-up below 3 and skip the e2e/cpu legs (never a bench value)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

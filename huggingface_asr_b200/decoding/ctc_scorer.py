@@ -102,6 +102,7 @@ class CTCPrefixScoreTH(object):
         self._ldx = ldx
         self._ws = None
         self._ws_key = None
+        self._timing = None
         self.idx_bh = None
         self.idx_b = torch.arange(B, device=self.device)      # :55
         self.idx_bo = (self.idx_b * V).unsqueeze(1)           # :56
@@ -211,10 +212,17 @@ class CTCPrefixScoreTH(object):
             idmap = torch.empty((n_bh, V), dtype=torch.long, device=dev) if S > 0 else None
             ws = self._workspace(W, S)
             w = float(ctc_weight)
+            timing = self._timing
+            if timing is not None:  # bench.py: CUDA events around the K-b launches on the launching stream
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
             _lib.check(L.ctcps_score(_ptr(self._x), self._ldx, _ptr(self._blank_lp), _ptr(r_prev), s_ptr, s_rs, s_cs,
                                      _ptr(last_ids), ol, B, W, T, V, self.blank, _ptr(scoring_ids), S, _ptr(idmap),
                                      _ptr(att_scores), 1.0 - w, w, _ptr(r), ldr, _ptr(log_psi), _ptr(token_scores),
                                      _ptr(joint), _ptr(ws), ws.numel(), _stream(dev)), "ctcps_score")
+            if timing is not None:
+                ev1.record()
+                timing.append((ev0, ev1))
         if ldr != snum:
             r = r[..., :snum]
         return token_scores, (r, log_psi, 0, 0, idmap), joint

@@ -98,3 +98,33 @@ def make_attention_scores(BW: int, V: int, step: int, seed: int = 7, device: str
     gen = torch.Generator().manual_seed(seed * 100003 + step)
     s = torch.randn(BW, V, generator=gen, dtype=torch.float32) * scale
     return torch.log_softmax(s, dim=-1).to(device)
+
+
+class SyntheticDecoder:
+    """Stand-in for the attention decoder (model code outside the path).
+
+    log_softmax(noise + boost * onehot(target)), where noise cycles through a small pool of 0.5*N(0,1)
+    tensors and target is the utterance's transcript token at this output position (eos past its end) --
+    i.e. a decoder that mostly agrees with the CTC head, so that beams end with eos after about U + 1
+    steps like a trained model's do.  Deterministic given (seed, transcripts); the same object semantics
+    on CPU (oracle / reference arm) and on the GPU.
+    """
+
+    def __init__(self, transcripts, num_beams: int, vocab: int, max_length: int, seed: int = 7, device="cpu", pool: int = 8,
+                 boost: float = 10.0, noise: float = 0.5):
+        B = len(transcripts)
+        self.W, self.V = num_beams, vocab
+        dev = torch.device(device)
+        gen = torch.Generator(device=dev).manual_seed(seed)
+        self.pool = [noise * torch.randn(B * num_beams, vocab, generator=gen, device=dev, dtype=torch.float32) for _ in range(pool)]
+        tgt = torch.full((B, max_length + 1), EOS, dtype=torch.long)
+        for b, tr in enumerate(transcripts):
+            n = min(len(tr), max_length + 1)
+            tgt[b, :n] = torch.tensor(tr[:n], dtype=torch.long)
+        self.targets = tgt.to(dev).repeat_interleave(num_beams, dim=0)  # (BW, max_length + 1)
+        self.boost = boost
+
+    def __call__(self, input_ids: torch.Tensor, step: int) -> torch.Tensor:
+        logits = self.pool[step % len(self.pool)].clone()
+        logits.scatter_add_(1, self.targets[:, step: step + 1], torch.full_like(logits[:, :1], self.boost))
+        return torch.log_softmax(logits, dim=-1)
