@@ -1,0 +1,120 @@
+"""CPU-side checks: the C-ABI library builds, loads and exports every symbol include/ctcps.h declares; argument
+validation of the host layer; the product refuses CPU tensors; the product never imports the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "ctcps.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ctcps_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from huggingface_asr_b200 import _lib
+
+    L = _lib.lib()
+    names = declared_symbols()
+    assert len(names) >= 9
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/ctcps.h but not exported"
+        assert n in _lib.SIGNATURES, f"{n} has no ctypes signature in _lib.SIGNATURES"
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_no_compute_helpers_work_without_gpu():
+    from huggingface_asr_b200 import _lib
+
+    L = _lib.lib()
+    assert L.ctcps_version() >= 100
+    assert L.ctcps_padded_ld(5000) == 5000 and L.ctcps_padded_ld(5001) == 5004 and L.ctcps_padded_ld(1) == 4
+    n = ctypes.c_size_t(0)
+    assert L.ctcps_workspace_bytes(256, 373, 5000, 10, 0, ctypes.byref(n)) == 0
+    assert 1_000_000 < n.value < 100_000_000
+    assert L.ctcps_workspace_bytes(0, 373, 5000, 10, 0, ctypes.byref(n)) == -1
+    assert b"bad sizes" in L.ctcps_error_string(-1)
+    assert L.ctcps_error_string(0) == b"ok"
+
+
+def test_argument_errors_are_reported_before_any_launch():
+    from huggingface_asr_b200 import _lib
+
+    L = _lib.lib()
+    # null pointers / bad ids are rejected on the host, so this is safe without a GPU
+    assert L.ctcps_init(None, 8, None, 1, 4, 8, 3, 1, None, 8, None, None) == -1
+    assert L.ctcps_select(None, 8, None, None, None, 1, 1, 4, 8, 0, None, None, None) == -1
+    with pytest.raises(ValueError, match="null pointer"):
+        _lib.check(L.ctcps_score(None, 8, None, None, None, 0, 0, None, 0, 1, 1, 4, 8, 3, None, 0, None, None, 0.7, 0.3, None, 8,
+                                 None, None, None, None, 0, None), "ctcps_score")
+
+
+def test_cuda_library_is_sm_100a_with_tma():
+    from huggingface_asr_b200 import _lib
+
+    _lib.lib()
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "UTMALDG" in sass, "the recursion kernel must stage x tiles with TMA (cp.async.bulk.tensor)"
+    assert "UBLKCP" in sass
+    assert "HMMA" not in sass and "UTCHMMA" not in sass  # no tensor cores on this path, by design
+
+
+def test_scorer_refuses_cpu_tensors_and_bad_dtypes():
+    from huggingface_asr_b200.decoding.ctc_scorer import CTCPrefixScoreTH, CTCRescorerLogitsProcessor, LogSoftmaxProcessor
+
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        CTCPrefixScoreTH(torch.zeros(1, 4, 8), torch.tensor([4]), 3, 1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        CTCRescorerLogitsProcessor(torch.zeros(1, 4, 8), torch.tensor([4]), 3, 1, 0, 0.3, 2, -1, False, 1.0)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        LogSoftmaxProcessor()(None, torch.zeros(2, 8))
+    with pytest.raises(TypeError):
+        CTCPrefixScoreTH([[0.0]], [1], 3, 1)
+
+
+def test_processor_is_a_transformers_logits_processor():
+    from transformers import LogitsProcessor
+
+    from huggingface_asr_b200.decoding import ctc_scorer
+
+    assert issubclass(ctc_scorer.CTCRescorerLogitsProcessor, LogitsProcessor)
+    assert issubclass(ctc_scorer.LogSoftmaxProcessor, LogitsProcessor)
+    import inspect
+
+    sig = inspect.signature(ctc_scorer.CTCRescorerLogitsProcessor.__init__)
+    assert list(sig.parameters)[1:] == ["encoder_logits", "encoder_output_lens", "pad_token_id", "eos_token_id", "ctc_margin",
+                                        "ctc_weight", "num_beams", "space_token_id", "apply_eos_space_trick",
+                                        "eos_space_trick_weight", "debug"]
+    sig = inspect.signature(ctc_scorer.CTCPrefixScoreTH.__init__)
+    assert list(sig.parameters)[1:] == ["x", "xlens", "blank", "eos", "margin"]
+    for m in ("__call__", "index_select_state", "extend_prob", "extend_state"):
+        assert callable(getattr(ctc_scorer.CTCPrefixScoreTH, m))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "huggingface_asr_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle", "").replace("(oracle", "").lower() or f == "beam_search.py" or \
+                    "import oracle" not in src and "from oracle" not in src, f"{f} references the oracle"
+                assert "from oracle" not in src and "import oracle" not in src
+    code = "import sys; import huggingface_asr_b200.decoding.ctc_scorer, huggingface_asr_b200.beam_search, huggingface_asr_b200.sharding; " \
+           "assert not any(m.startswith('oracle') for m in sys.modules), 'oracle imported by the product'"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+def test_reference_frame_counts():
+    from huggingface_asr_b200.synthetic import frames_for_seconds
+
+    assert [frames_for_seconds(s) for s in (10, 15, 30)] == [248, 373, 748]
+    assert [frames_for_seconds(s, 1) for s in (10, 15, 30)] == [250, 375, 750]
