@@ -92,7 +92,7 @@ class CTCPrefixScoreTH(object):
             if apply_log_softmax or ldx != V:
                 self._x = torch.empty((B, T, ldx), dtype=torch.float32, device=self.device)
             else:
-                self._x = x  # V % 4 == 0: the caller's tensor is the storage (padded in place, like the reference)
+                self._x = x  # V % 64 == 0: the caller's tensor is the storage (padded in place, like the reference)
             if not apply_log_softmax and ldx != V:
                 # pad the caller's tensor in place first (reference semantics), then stage the strided copy
                 _lib.check(L.ctcps_init(_ptr(x), V, _ptr(self._lens), B, T, V, self.blank, 0, _ptr(x), V, None,

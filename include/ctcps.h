@@ -44,7 +44,8 @@ enum {
 int ctcps_version(void);
 const char *ctcps_error_string(int code);
 
-/* Round a vocabulary / candidate count up to the stride the kernels want (multiple of 4). */
+/* Round a vocabulary / candidate count up to the stride the kernels run fastest with (multiple of 64 floats =
+ * 256-byte rows; any multiple of 4 is accepted by ctcps_score). */
 int ctcps_padded_ld(int n);
 
 /* Bytes of scratch ctcps_score needs for these sizes. */
