@@ -431,6 +431,227 @@ __global__ void __launch_bounds__(NT, MINB) k_score_full(const __grid_constant__
 }
 
 // ------------------------------------------------------------------------------------------
+// Lazy-state variant of K-b ("survivor recompute"): log_psi -- and with it the token
+// and joint scores -- depends only on phi = f(r_prev) and x, NOT on the new forward variables r.  The only
+// consumer of r is index_select_state, which keeps W columns per utterance out of W*V.  So in lazy mode the
+// (T,2,BW,V) state is never written: k_psi_full computes the scores (reads x once: 4*T*B*V bytes instead of
+// writing 8*T*BW*V), and k_select_lazy re-runs the recursion for the BW surviving (hyp, token) columns only.
+// Results are identical to the materialising kernels (same operations in the same order per lane).
+// ------------------------------------------------------------------------------------------
+struct PsiArgs {
+    const float *lin;    // (B*G, Tpad, HWP) exp(r_sum[t-1] - Gm), zero outside the summed range
+    const float *Gmax;   // (BW)
+    const float *psic;   // (BW) linear-domain sum for the column of the last label (phi = r_prev blank there)
+    const float *s_prev;
+    long long s_rs, s_cs;
+    const int64_t *last_ids;
+    float *att;
+    float omw, w;
+    float *log_psi, *token_scores, *joint;
+    int B, W, T, V, blank, ol, G, Tpad, nvt;
+};
+
+template <int HWP, int NT>
+struct PsiSmem {
+    static constexpr int VTILE = NT * 4;
+    static constexpr int NBOX = VTILE / BOXC;
+    alignas(128) float xs[NS][NBOX][TT][BOXC];
+    alignas(16) float lin[NS][TT][HWP];
+    alignas(8) uint64_t full[NS];
+};
+
+// one warp per (padded) hypothesis: lin stream, Gmax and the last-label column sum
+__global__ void __launch_bounds__(128) k_prep_psi(const float *__restrict__ r_prev, const float *__restrict__ x, int ldx,
+                                                  const int64_t *__restrict__ last_ids, int B, int W, int T, int V, int HW,
+                                                  int HWP, int G, int start, int Tpad, float *__restrict__ lin,
+                                                  float *__restrict__ Gmax, float *__restrict__ psic) {
+    const int lane = threadIdx.x & 31;
+    const int hp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (hp >= B * G * HWP) return;
+    const int BW = B * W;
+    const int b = hp / (G * HWP);
+    const int rem = hp - b * (G * HWP);
+    const int g = rem / HWP, hh = rem - g * HWP;
+    const int w = g * HW + hh;
+    const bool valid = hh < HW && w < W;
+    const int h = b * W + w;
+    float gm = -INFINITY;
+    if (valid)
+        for (int t = lane; t < T; t += 32)
+            if (t >= start - 1 && t <= T - 2)
+                gm = fmaxf(gm, lse2_precise(r_prev[((size_t)t * 2 + 0) * BW + h], r_prev[((size_t)t * 2 + 1) * BW + h]));
+    gm = warp_max(gm);
+    if (!(gm > -INFINITY)) gm = 0.f;
+    float *base = lin + ((size_t)(b * G + g) * Tpad) * HWP + hh;
+    long long c = valid ? last_ids[h] : -1;
+    if (c < 0 || c >= V) c = -1;
+    float sc = 0.f;
+    for (int te = lane; te < Tpad; te += 32) {
+        float e = 0.f;
+        const int f = te - 1;
+        if (valid && f >= start - 1 && f <= T - 2) {
+            const float a = r_prev[((size_t)f * 2 + 0) * BW + h], cb = r_prev[((size_t)f * 2 + 1) * BW + h];
+            e = expf(lse2_precise(a, cb) - gm);
+            if (c >= 0) sc += expf(cb - gm) * expf(x[((size_t)b * T + te) * ldx + c]);
+        }
+        base[(size_t)te * HWP] = e;
+    }
+    sc = warp_sum(sc);
+    if (valid && lane == 0) {
+        Gmax[h] = gm;
+        psic[h] = sc;
+    }
+}
+
+template <int HW, int HWP, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ CUtensorMap tmx, const PsiArgs a) {
+    using Smem = PsiSmem<HWP, NT>;
+    constexpr int VTILE = Smem::VTILE;
+    constexpr int NBOX = Smem::NBOX;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    const int tid = threadIdx.x;
+    int idx = blockIdx.x;
+    const int g = idx % a.G;
+    idx /= a.G;
+    const int vt = idx % a.nvt;
+    const int b = idx / a.nvt;
+    const int T = a.T, V = a.V, W = a.W;
+    const int start = a.ol > 1 ? a.ol : 1;
+    const int v0 = vt * VTILE + tid * 4;
+    const int h0 = b * W + g * HW;
+    const int nhyp = min(HW, W - g * HW);
+    const int c0 = (a.ol == 0 ? 0 : start) / TT;
+    const int cN = (T - 1) / TT;
+    constexpr uint32_t STAGE_BYTES = TT * VTILE * 4 + TT * HWP * 4;
+
+    auto issue = [&](int c) {
+        const int s = (c - c0) % NS;
+        mbar_expect_tx(&sm.full[s], STAGE_BYTES);
+#pragma unroll
+        for (int bx = 0; bx < NBOX; ++bx) tma_load_2d(&sm.xs[s][bx][0][0], &tmx, vt * VTILE + bx * BOXC, b * T + c * TT, &sm.full[s]);
+        bulk_load_1d(&sm.lin[s][0][0], a.lin + ((size_t)(b * a.G + g) * a.Tpad + (size_t)c * TT) * HWP, TT * HWP * 4, &sm.full[s]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(&sm.full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int c = c0; c <= cN && c < c0 + NS; ++c) issue(c);
+    }
+    float acc[HW][4], x0[4];
+#pragma unroll
+    for (int hh = 0; hh < HW; ++hh)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[hh][j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x0[j] = LZ;
+    __syncthreads();
+
+    for (int c = c0; c <= cN; ++c) {
+        const int s = (c - c0) % NS;
+        mbar_wait(&sm.full[s], (uint32_t)(((c - c0) / NS) & 1));
+        const int bx = (tid * 4) / BOXC, col = (tid * 4) % BOXC;
+        const int tmax = min(TT, T - c * TT);
+        for (int tt = 0; tt < tmax; ++tt) {
+            const int t = c * TT + tt;
+            const float4 xv4 = *reinterpret_cast<const float4 *>(&sm.xs[s][bx][tt][col]);
+            if (t < start) {
+                if (t == 0 && a.ol == 0) x0[0] = xv4.x, x0[1] = xv4.y, x0[2] = xv4.z, x0[3] = xv4.w;
+                continue;
+            }
+            const float p[4] = {ex2_approx(xv4.x * LOG2E), ex2_approx(xv4.y * LOG2E), ex2_approx(xv4.z * LOG2E),
+                                ex2_approx(xv4.w * LOG2E)};
+            float l[HWP];
+#pragma unroll
+            for (int q = 0; q < HWP / 4; ++q) {
+                const float4 l4 = *reinterpret_cast<const float4 *>(&sm.lin[s][tt][q * 4]);
+                l[q * 4 + 0] = l4.x, l[q * 4 + 1] = l4.y, l[q * 4 + 2] = l4.z, l[q * 4 + 3] = l4.w;
+            }
+#pragma unroll
+            for (int hh = 0; hh < HW; ++hh)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[hh][j] = fmaf(l[hh], p[j], acc[hh][j]);
+        }
+        __syncthreads();
+        if (tid == 0 && c + NS <= cN) issue(c + NS);
+    }
+
+#pragma unroll
+    for (int hh = 0; hh < HW; ++hh) {
+        if (hh >= nhyp) break;
+        const int h = h0 + hh;
+        const float gm = a.Gmax[h];
+        const long long ch = a.last_ids[h];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int v = v0 + j;
+            if (v >= V) continue;
+            const float S = (v == ch) ? a.psic[h] : acc[hh][j];
+            float lp = gm + logf(S);
+            if (!(lp > LZ)) lp = LZ;
+            if (a.ol == 0) lp = lse2_precise(lp, x0[j]);
+            if (v == a.blank) lp = LZ;
+            const size_t o = (size_t)h * V + v;
+            a.log_psi[o] = lp;
+            const float sp = a.s_prev != nullptr ? a.s_prev[(long long)h * a.s_rs + (long long)v * a.s_cs] : 0.f;
+            float ts = lp - sp;
+            if (ts == 0.f) ts = LZ;
+            a.token_scores[o] = ts;
+            if (a.att != nullptr) {
+                float av = a.att[o];
+                if (v == a.blank) {
+                    av = LZ;
+                    a.att[o] = LZ;
+                }
+                a.joint[o] = __fadd_rn(__fmul_rn(a.omw, av), __fmul_rn(a.w, ts));
+            }
+        }
+    }
+}
+
+// Lazy index_select_state: re-run the forward recursion of the PREVIOUS step for the surviving (hyp, token)
+// column of every output hypothesis j -- exactly the lane k_score_full would have written to r[:, :, hyp, tok].
+__global__ void __launch_bounds__(128) k_select_lazy(const float *__restrict__ x, int ldx, const float *__restrict__ blank_lp,
+                                                     const float *__restrict__ r_prev, const int64_t *__restrict__ last_ids,
+                                                     int ol, const float *__restrict__ log_psi,
+                                                     const int64_t *__restrict__ best_ids, int B, int W, int T, int V,
+                                                     float *__restrict__ r_new, float *__restrict__ s_new) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int BW = B * W;
+    if (j >= BW) return;
+    const int b = j / W;
+    const long long flat = best_ids[j] + (long long)b * W * V;  // :191
+    const long long hs = flat / V;
+    const long long tok = flat - hs * V;
+    s_new[j] = log_psi[flat];                                   // :193
+    const bool last = (last_ids[hs] == tok);
+    const int start = ol > 1 ? ol : 1;
+    const float *xr = x + (size_t)b * T * ldx + tok;
+    const float *xb = blank_lp + (size_t)b * T;
+    for (int t = 0; t < start && t < T; ++t) {
+        r_new[((size_t)t * 2 + 0) * BW + j] = LZ;
+        r_new[((size_t)t * 2 + 1) * BW + j] = LZ;
+    }
+    float rn = LZ, rb = LZ;
+    if (ol == 0) {
+        rn = xr[0];
+        r_new[j] = rn;
+    }
+#pragma unroll 4
+    for (int t = start; t < T; ++t) {
+        const float p0 = r_prev[((size_t)(t - 1) * 2 + 0) * BW + hs], p1 = r_prev[((size_t)(t - 1) * 2 + 1) * BW + hs];
+        const float phi = last ? p1 : lse2_precise(p0, p1);
+        const float nn = lse2_fast(rn, phi) + xr[(size_t)t * ldx];
+        const float nb = lse2_fast(rn, rb) + xb[t];
+        rn = nn;
+        rb = nb;
+        r_new[((size_t)t * 2 + 0) * BW + j] = rn;
+        r_new[((size_t)t * 2 + 1) * BW + j] = rb;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K-b partial scoring: one thread per (hyp, candidate) lane.  ~V/S times less work than the full
 // path; written for fidelity (libm-grade exp/log, running-max logsumexp), not for the roofline.
 // ------------------------------------------------------------------------------------------
@@ -643,6 +864,35 @@ Workspace plan_workspace(int B, int T, int W) {
     return ws;
 }
 
+// lazy mode: hyps per thread of k_psi_full and the padded width of its lin stream
+void pick_hw_psi(int W, int *HW, int *HWP, int *G) {
+    static const int cand[] = {10, 8, 6, 5, 4, 3, 2, 1};
+    int best = 1, best_pad = 1 << 30;
+    for (int hw : cand) {
+        const int g = (W + hw - 1) / hw;
+        const int pad = g * hw - W;
+        if (pad < best_pad) best = hw, best_pad = pad;
+    }
+    *HW = best;
+    *HWP = (best + 3) & ~3;
+    *G = (W + best - 1) / best;
+}
+struct WorkspaceLazy {
+    size_t lin_off, lin_bytes, g_off, c_off, total;
+};
+WorkspaceLazy plan_workspace_lazy(int B, int T, int W) {
+    int HW, HWP, G;
+    pick_hw_psi(W, &HW, &HWP, &G);
+    WorkspaceLazy ws;
+    ws.lin_off = 0;
+    ws.lin_bytes = (size_t)B * G * tpad_of(T) * HWP * sizeof(float);
+    ws.g_off = (ws.lin_bytes + 255) & ~(size_t)255;
+    const size_t gb = ((size_t)B * W * sizeof(float) + 255) & ~(size_t)255;
+    ws.c_off = ws.g_off + gb;
+    ws.total = ws.c_off + gb;
+    return ws;
+}
+
 int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
 
 #define ARG_CHECK(cond, code, msg)                           \
@@ -674,6 +924,34 @@ int launch_score_full(const CUtensorMap &tm, const ScoreArgs &a, cudaStream_t st
     return cuda_rc(cudaGetLastError());
 }
 
+template <int HW, int HWP, int NT, int MINB>
+int launch_psi_full(const CUtensorMap &tm, const PsiArgs &a, cudaStream_t st) {
+    using Smem = PsiSmem<HWP, NT>;
+    auto kern = k_psi_full<HW, HWP, NT, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return (int)e;
+    const long long nblocks = (long long)a.B * a.nvt * a.G;
+    kern<<<(unsigned)nblocks, NT, sizeof(Smem), st>>>(tm, a);
+    return cuda_rc(cudaGetLastError());
+}
+
+int encode_x_map(CUtensorMap *tm, const float *x_logp, int ldx, int B, int T, int V) {
+    EncodeTiledFn enc = get_encode();
+    ARG_CHECK(enc != nullptr, CTCPS_E_NODRIVER, "cuTensorMapEncodeTiled not found");
+    cuuint64_t dims[2] = {(cuuint64_t)V, (cuuint64_t)B * T};
+    cuuint64_t strides[1] = {(cuuint64_t)ldx * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BOXC, (cuuint32_t)TT};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(x_logp), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) {
+        snprintf(g_errbuf, sizeof(g_errbuf), "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
+        return CTCPS_E_NODRIVER;
+    }
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -701,7 +979,8 @@ int ctcps_workspace_bytes(int B, int T, int V, int W, int S, size_t *out_bytes) 
     (void)V;
     (void)S;
     ARG_CHECK(out_bytes != nullptr && B > 0 && T > 0 && W > 0, CTCPS_E_BADARG, "workspace_bytes: bad sizes");
-    *out_bytes = plan_workspace(B, T, W).total;
+    const size_t a = plan_workspace(B, T, W).total, l = plan_workspace_lazy(B, T, W).total;
+    *out_bytes = a > l ? a : l;
     return 0;
 }
 
@@ -836,6 +1115,89 @@ int ctcps_score(const float *x_logp, int ldx, const float *blank_lp, const float
         default: rc = launch_score_full<5, NT, 4>(tm, a, st); break;
     }
     return rc;
+}
+
+int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const float *s_prev,
+                     int64_t s_row_stride, int64_t s_col_stride, const int64_t *last_ids, int ol, int B, int W, int T, int V,
+                     int blank, float *att_scores, float one_minus_w, float w, float *log_psi, float *token_scores,
+                     float *joint, void *workspace, size_t workspace_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    (void)blank_lp;
+    ARG_CHECK(x_logp && r_prev && last_ids && log_psi && token_scores, CTCPS_E_BADARG, "score_lazy: null pointer");
+    ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0, CTCPS_E_BADARG, "score_lazy: non-positive size");
+    ARG_CHECK(blank >= 0 && blank < V, CTCPS_E_BADARG, "score_lazy: blank id outside the vocabulary");
+    ARG_CHECK(att_scores == nullptr || joint != nullptr, CTCPS_E_BADARG, "score_lazy: att_scores given without joint output");
+    ARG_CHECK(ldx >= V && (ldx & 3) == 0 && (((uintptr_t)x_logp) & 15) == 0, CTCPS_E_ALIGN, "score_lazy: ldx must be a multiple of 4 and x_logp 16-byte aligned");
+    const long long BW = (long long)B * W;
+    ARG_CHECK(BW * (long long)V < (1ll << 31) && (long long)B * T < (1ll << 31), CTCPS_E_TOOBIG, "score_lazy: BW*V or B*T exceeds 2^31");
+    const int start = ol > 1 ? ol : 1;
+    if (start > T) {  // ctc_scorer.py:138-145
+        k_finalize<<<grid_for((size_t)BW * V, 256), 256, 0, st>>>(log_psi, s_prev, s_row_stride, s_col_stride, att_scores,
+                                                                 one_minus_w, w, (int)BW, V, blank, token_scores, joint, 1);
+        return cuda_rc(cudaGetLastError());
+    }
+    int HW, HWP, G;
+    pick_hw_psi(W, &HW, &HWP, &G);
+    const WorkspaceLazy ws = plan_workspace_lazy(B, T, W);
+    ARG_CHECK(workspace != nullptr && workspace_bytes >= ws.total, CTCPS_E_WORKSPACE, "score_lazy: workspace too small");
+    ARG_CHECK((((uintptr_t)workspace) & 255) == 0, CTCPS_E_ALIGN, "score_lazy: workspace must be 256-byte aligned");
+    float *lin = reinterpret_cast<float *>((char *)workspace + ws.lin_off);
+    float *Gmax = reinterpret_cast<float *>((char *)workspace + ws.g_off);
+    float *psic = reinterpret_cast<float *>((char *)workspace + ws.c_off);
+    const int Tpad = tpad_of(T);
+    {
+        const int warps = B * G * HWP;
+        k_prep_psi<<<(warps + 3) / 4, 128, 0, st>>>(r_prev, x_logp, ldx, last_ids, B, W, T, V, HW, HWP, G, start, Tpad, lin, Gmax, psic);
+    }
+    CUtensorMap tm;
+    int rc = encode_x_map(&tm, x_logp, ldx, B, T, V);
+    if (rc) return rc;
+    PsiArgs a;
+    a.lin = lin;
+    a.Gmax = Gmax;
+    a.psic = psic;
+    a.s_prev = s_prev;
+    a.s_rs = s_row_stride;
+    a.s_cs = s_col_stride;
+    a.last_ids = last_ids;
+    a.att = att_scores;
+    a.omw = one_minus_w;
+    a.w = w;
+    a.log_psi = log_psi;
+    a.token_scores = token_scores;
+    a.joint = joint;
+    a.B = B;
+    a.W = W;
+    a.T = T;
+    a.V = V;
+    a.blank = blank;
+    a.ol = ol;
+    a.G = G;
+    a.Tpad = Tpad;
+    constexpr int NT = 128;
+    a.nvt = (V + NT * 4 - 1) / (NT * 4);
+    switch (HW) {
+        case 1: return launch_psi_full<1, 4, NT, 4>(tm, a, st);
+        case 2: return launch_psi_full<2, 4, NT, 4>(tm, a, st);
+        case 3: return launch_psi_full<3, 4, NT, 4>(tm, a, st);
+        case 4: return launch_psi_full<4, 4, NT, 4>(tm, a, st);
+        case 5: return launch_psi_full<5, 8, NT, 4>(tm, a, st);
+        case 6: return launch_psi_full<6, 8, NT, 4>(tm, a, st);
+        case 8: return launch_psi_full<8, 8, NT, 4>(tm, a, st);
+        default: return launch_psi_full<10, 12, NT, 4>(tm, a, st);
+    }
+}
+
+int ctcps_select_lazy(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const int64_t *last_ids, int ol,
+                      const float *log_psi, const int64_t *best_ids, int B, int W, int T, int V, float *r_new, float *s_new,
+                      void *stream) {
+    ARG_CHECK(x_logp && blank_lp && r_prev && last_ids && log_psi && best_ids && r_new && s_new, CTCPS_E_BADARG,
+              "select_lazy: null pointer");
+    ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0 && ldx >= V, CTCPS_E_BADARG, "select_lazy: bad size");
+    const int BW = B * W;
+    k_select_lazy<<<(BW + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x_logp, ldx, blank_lp, r_prev, last_ids, ol, log_psi, best_ids,
+                                                                      B, W, T, V, r_new, s_new);
+    return cuda_rc(cudaGetLastError());
 }
 
 int ctcps_select(const float *r, int ldr, const float *log_psi, const int64_t *best_ids, const int64_t *scoring_idmap, int B,

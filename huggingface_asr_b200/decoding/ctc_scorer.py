@@ -16,6 +16,8 @@ There is no CPU path: CPU tensors raise.  No call synchronises the host.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from transformers import LogitsProcessor
 
@@ -41,6 +43,34 @@ def _require_cuda_f32(t: torch.Tensor, name: str, dim: int | None = None) -> Non
         raise ValueError(f"{name} must be float32 (the kernels compute in fp32 log space), got {t.dtype}")
     if dim is not None and t.dim() != dim:
         raise ValueError(f"{name} must have {dim} dimensions, got shape {tuple(t.shape)}")
+
+
+class LazyForwardVariables:
+    """Stands in for the forward variables r (T,2,BW,V) of a step scored in lazy-state mode.
+
+    The scores of a step do not depend on r, and index_select_state keeps BW of its BW*V columns, so in lazy mode r is
+    never written; index_select_state recomputes the surviving columns from what this object remembers (the inputs of the
+    step).  `materialize()` produces the full tensor on demand (runs the materialising kernel), so code that inspects
+    `ctc_states[0]` still finds the reference's tensor.
+    """
+
+    def __init__(self, scorer, r_prev, last_ids, ol, n_hyps):
+        self.scorer, self.r_prev, self.last_ids, self.ol, self.n_hyps = scorer, r_prev, last_ids, ol, n_hyps
+        self.shape = (scorer.input_length, 2, scorer.batch * n_hyps, scorer.odim)
+        self.dtype, self.device = torch.float32, scorer.device
+
+    def size(self, dim=None):
+        return self.shape if dim is None else self.shape[dim]
+
+    def dim(self):
+        return 4
+
+    def materialize(self):
+        _, state, _ = self.scorer._launch_score(self.r_prev, None, self.last_ids, self.ol, self.n_hyps, None, None, 0.0, False)
+        return state[0]
+
+    def __getitem__(self, idx):
+        return self.materialize()[idx]
 
 
 class CTCPrefixScoreTH(object):
@@ -103,6 +133,7 @@ class CTCPrefixScoreTH(object):
         self._ws = None
         self._ws_key = None
         self._timing = None
+        self.lazy_state = False  # True: never materialise r (see LazyForwardVariables)
         self.idx_bh = None
         self.idx_b = torch.arange(B, device=self.device)      # :55
         self.idx_bo = (self.idx_b * V).unsqueeze(1)           # :56
@@ -175,7 +206,6 @@ class CTCPrefixScoreTH(object):
                 raise ValueError(f"scoring_ids must be (BW,S) with BW={n_bh}, got {tuple(scoring_ids.shape)}")
             S = int(scoring_ids.shape[1])
         self.scoring_num = S                                     # :72
-        snum = S if S > 0 else V
 
         if state is None:
             r_prev, s_prev = self.initial_state(W), None
@@ -185,6 +215,16 @@ class CTCPrefixScoreTH(object):
             if tuple(r_prev.shape) != (T, 2, n_bh):
                 raise ValueError(f"state r_prev must be {(T, 2, n_bh)}, got {tuple(r_prev.shape)}")
             r_prev = r_prev.contiguous()
+        return self._launch_score(r_prev, s_prev, last_ids, ol, W, scoring_ids, att_scores, ctc_weight,
+                                  self.lazy_state and scoring_ids is None)
+
+    def _launch_score(self, r_prev, s_prev, last_ids, ol, W, scoring_ids, att_scores, ctc_weight, lazy):
+        L = _lib.lib()
+        dev = self.device
+        B, T, V = self.batch, self.input_length, self.odim
+        n_bh = B * W
+        S = 0 if scoring_ids is None else int(scoring_ids.shape[1])
+        snum = S if S > 0 else V
         s_ptr, s_rs, s_cs = None, 0, 0
         if isinstance(s_prev, torch.Tensor):
             _require_cuda_f32(s_prev, "state s_prev")
@@ -204,7 +244,6 @@ class CTCPrefixScoreTH(object):
                 raise ValueError(f"scores must be contiguous {(n_bh, V)}, got {tuple(att_scores.shape)}")
         ldr = L.ctcps_padded_ld(snum)
         with torch.cuda.device(dev):
-            r = torch.empty((T, 2, n_bh, ldr), dtype=torch.float32, device=dev)
             log_psi = torch.empty((n_bh, V), dtype=torch.float32, device=dev)
             token_scores = torch.empty((n_bh, V), dtype=torch.float32, device=dev)
             if att_scores is not None:
@@ -216,15 +255,23 @@ class CTCPrefixScoreTH(object):
             if timing is not None:  # bench.py: CUDA events around the K-b launches on the launching stream
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
-            _lib.check(L.ctcps_score(_ptr(self._x), self._ldx, _ptr(self._blank_lp), _ptr(r_prev), s_ptr, s_rs, s_cs,
-                                     _ptr(last_ids), ol, B, W, T, V, self.blank, _ptr(scoring_ids), S, _ptr(idmap),
-                                     _ptr(att_scores), 1.0 - w, w, _ptr(r), ldr, _ptr(log_psi), _ptr(token_scores),
-                                     _ptr(joint), _ptr(ws), ws.numel(), _stream(dev)), "ctcps_score")
+            if lazy:
+                r = LazyForwardVariables(self, r_prev, last_ids, ol, W)
+                _lib.check(L.ctcps_score_lazy(_ptr(self._x), self._ldx, _ptr(self._blank_lp), _ptr(r_prev), s_ptr, s_rs, s_cs,
+                                              _ptr(last_ids), ol, B, W, T, V, self.blank, _ptr(att_scores), 1.0 - w, w,
+                                              _ptr(log_psi), _ptr(token_scores), _ptr(joint), _ptr(ws), ws.numel(),
+                                              _stream(dev)), "ctcps_score_lazy")
+            else:
+                r = torch.empty((T, 2, n_bh, ldr), dtype=torch.float32, device=dev)
+                _lib.check(L.ctcps_score(_ptr(self._x), self._ldx, _ptr(self._blank_lp), _ptr(r_prev), s_ptr, s_rs, s_cs,
+                                         _ptr(last_ids), ol, B, W, T, V, self.blank, _ptr(scoring_ids), S, _ptr(idmap),
+                                         _ptr(att_scores), 1.0 - w, w, _ptr(r), ldr, _ptr(log_psi), _ptr(token_scores),
+                                         _ptr(joint), _ptr(ws), ws.numel(), _stream(dev)), "ctcps_score")
+                if ldr != snum:
+                    r = r[..., :snum]
             if timing is not None:
                 ev1.record()
                 timing.append((ev0, ev1))
-        if ldr != snum:
-            r = r[..., :snum]
         return token_scores, (r, log_psi, 0, 0, idmap), joint
 
     def index_select_state(self, state, best_ids):
@@ -233,8 +280,22 @@ class CTCPrefixScoreTH(object):
         best_ids: (B,W) ids in hyp*V + tok space.  Returns (r_new (T,2,BW), s_new (BW,V) [expanded], f_min, f_max).
         """
         r, s, f_min, f_max, scoring_idmap = state
-        _require_cuda_f32(r, "state r", 4)
         _require_cuda_f32(s, "state log_psi", 2)
+        if isinstance(r, LazyForwardVariables):
+            n_bh = int(s.shape[0])
+            best_ids = best_ids.to(device=self.device, dtype=torch.long).contiguous()
+            if best_ids.numel() != n_bh:
+                raise ValueError(f"best_ids has {best_ids.numel()} entries for {n_bh} hypotheses")
+            T, V = self.input_length, self.odim
+            s = s.contiguous()
+            with torch.cuda.device(self.device):
+                r_new = torch.empty((T, 2, n_bh), dtype=torch.float32, device=self.device)
+                s_vec = torch.empty((n_bh,), dtype=torch.float32, device=self.device)
+                _lib.check(_lib.lib().ctcps_select_lazy(_ptr(self._x), self._ldx, _ptr(self._blank_lp), _ptr(r.r_prev),
+                                                        _ptr(r.last_ids), r.ol, _ptr(s), _ptr(best_ids), self.batch, r.n_hyps, T, V,
+                                                        _ptr(r_new), _ptr(s_vec), _stream(self.device)), "ctcps_select_lazy")
+            return r_new, s_vec.view(-1, 1).expand(n_bh, V), f_min, f_max
+        _require_cuda_f32(r, "state r", 4)
         T, _, n_bh, snum = (int(v) for v in r.shape)
         V = self.odim
         n_hyps = n_bh // self.batch
@@ -313,11 +374,22 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
         apply_eos_space_trick: bool,
         eos_space_trick_weight: float,
         debug: bool = False,
+        *,
+        materialize_state: bool | None = None,
     ):
+        """Same positional signature as the reference.  materialize_state (keyword-only, not in the reference):
+        True  = write the full state r (T,2,BW,V) every step, exactly the reference's data flow (default);
+        False = lazy state: never write r, recompute the W surviving columns per utterance at the next step --
+                identical scores and selected states, ~20x fewer HBM bytes per step.
+        None  = take it from the environment variable CTCPS_MATERIALIZE_STATE (default "1")."""
         super().__init__()
         self.pad_token_id = pad_token_id
         self.ctc_prefix_scorer = CTCPrefixScoreTH.from_logits(encoder_logits, encoder_output_lens, pad_token_id, eos_token_id,
                                                               ctc_margin)
+        if materialize_state is None:
+            materialize_state = os.environ.get("CTCPS_MATERIALIZE_STATE", "1") not in ("0", "false", "False", "no")
+        self.materialize_state = bool(materialize_state)
+        self.ctc_prefix_scorer.lazy_state = not self.materialize_state
         self.ctc_weight = ctc_weight
         self.ctc_states = None
         self.num_beams = num_beams

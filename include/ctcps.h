@@ -109,6 +109,23 @@ int ctcps_select(const float *r, int ldr, const float *log_psi, const int64_t *b
                  int B, int W, int T, int V, int S, float *r_new, float *s_new, void *stream);
 
 /*
+ * Lazy-state ("survivor recompute") variants of K-b / K-c.  log_psi, token_scores and joint do not depend on the
+ * new forward variables r, and index_select_state keeps only BW of the BW*V columns of r; so the (T,2,BW,V) state
+ * need not exist.  ctcps_score_lazy computes the same outputs as ctcps_score (full vocabulary) without writing r;
+ * ctcps_select_lazy re-runs the recursion of THAT step (same r_prev, last_ids, ol) for the selected
+ * (hyp, token) columns and returns what ctcps_select would have gathered from r.  Same arithmetic per lane as the
+ * materialising kernels.  HBM bytes per step drop from 8*T*BW*V (write) to 4*T*B*V (read).
+ */
+int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const float *s_prev,
+                     int64_t s_row_stride, int64_t s_col_stride, const int64_t *last_ids, int ol, int B, int W, int T,
+                     int V, int blank, float *att_scores, float one_minus_w, float w, float *log_psi,
+                     float *token_scores, float *joint, void *workspace, size_t workspace_bytes, void *stream);
+
+int ctcps_select_lazy(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const int64_t *last_ids,
+                      int ol, const float *log_psi, const int64_t *best_ids, int B, int W, int T, int V, float *r_new,
+                      float *s_new, void *stream);
+
+/*
  * Optional eos/space trick of the processor (ctc_scorer.py:333-349), in place on `next`:
  * rows with argmax(att) == eos and argmax(ctc) == space and next[eos] < next[space] < k*next[eos]
  * get next[eos] *= k.

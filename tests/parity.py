@@ -25,6 +25,8 @@ def load(name):
 
 
 def to_np(t):
+    if hasattr(t, "materialize"):  # LazyForwardVariables of the lazy-state mode
+        t = t.materialize()
     if isinstance(t, torch.Tensor):
         return t.detach().cpu().numpy()
     return np.asarray(t)

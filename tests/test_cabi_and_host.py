@@ -90,9 +90,12 @@ def test_processor_is_a_transformers_logits_processor():
     import inspect
 
     sig = inspect.signature(ctc_scorer.CTCRescorerLogitsProcessor.__init__)
-    assert list(sig.parameters)[1:] == ["encoder_logits", "encoder_output_lens", "pad_token_id", "eos_token_id", "ctc_margin",
-                                        "ctc_weight", "num_beams", "space_token_id", "apply_eos_space_trick",
-                                        "eos_space_trick_weight", "debug"]
+    # the reference's positional signature, then our keyword-only extension
+    assert list(sig.parameters)[1:12] == ["encoder_logits", "encoder_output_lens", "pad_token_id", "eos_token_id", "ctc_margin",
+                                          "ctc_weight", "num_beams", "space_token_id", "apply_eos_space_trick",
+                                          "eos_space_trick_weight", "debug"]
+    extra = list(sig.parameters.values())[12:]
+    assert all(p.kind is inspect.Parameter.KEYWORD_ONLY for p in extra)
     sig = inspect.signature(ctc_scorer.CTCPrefixScoreTH.__init__)
     assert list(sig.parameters)[1:] == ["x", "xlens", "blank", "eos", "margin"]
     for m in ("__call__", "index_select_state", "extend_prob", "extend_state"):

@@ -23,7 +23,22 @@ class CudaBackend(parity.Backend):
         return CTCRescorerLogitsProcessor(logits, lens, pad, eos, margin, w, W, space, trick, trick_w)
 
 
+class CudaLazyBackend(CudaBackend):
+    """Same scorer in lazy-state mode: r is never materialised, survivors are recomputed at select time."""
+
+    def make_scorer(self, x_logp, lens, blank, eos, margin=0):
+        sc = super().make_scorer(x_logp, lens, blank, eos, margin)
+        sc.lazy_state = True
+        return sc
+
+    def make_processor(self, logits, lens, pad, eos, margin, w, W, space=-1, trick=False, trick_w=1.0):
+        from huggingface_asr_b200.decoding.ctc_scorer import CTCRescorerLogitsProcessor
+
+        return CTCRescorerLogitsProcessor(logits, lens, pad, eos, margin, w, W, space, trick, trick_w, materialize_state=False)
+
+
 BE = CudaBackend()
+BE_LAZY = CudaLazyBackend()
 STEP_CASES = ["steps_peaky_w3", "steps_peaky_ragged_w10", "steps_flat_w1", "steps_flat_w20", "steps_peaky_w5_v129",
               "steps_forced_pad", "steps_trick"]
 
@@ -38,6 +53,51 @@ def test_native_library_is_loaded():
 def test_steps_vs_reference_golden(name):
     worst = parity.replay_steps(BE, name)
     print(name, worst)
+
+
+@pytest.mark.parametrize("name", STEP_CASES)
+def test_lazy_steps_vs_reference_golden(name):
+    worst = parity.replay_steps(BE_LAZY, name)
+    print(name, worst)
+
+
+def test_lazy_edges_and_decode_vs_reference_golden():
+    parity.replay_edges(BE_LAZY)
+    parity.replay_decode(BE_LAZY)
+
+
+@pytest.mark.parametrize("B,W,T,V", [(3, 10, 100, 1200), (2, 7, 61, 517), (2, 20, 90, 260), (3, 1, 50, 300)])
+def test_lazy_state_is_bit_identical_to_materialised(B, W, T, V):
+    """Lazy mode must reproduce the materialising kernels exactly: same joint scores, same selected states."""
+    from huggingface_asr_b200.decoding.ctc_scorer import CTCRescorerLogitsProcessor, LazyForwardVariables
+    from huggingface_asr_b200.synthetic import make_attention_scores, make_encoder_logits
+
+    logits, lens, _ = make_encoder_logits(B, T, V, "peaky", True, seed=4321 + W)
+    mat = CTCRescorerLogitsProcessor(logits.cuda(), lens.cuda(), 3, 1, 0, 0.3, W, -1, False, 1.0, materialize_state=True)
+    lazy = CTCRescorerLogitsProcessor(logits.cuda(), lens.cuda(), 3, 1, 0, 0.3, W, -1, False, 1.0, materialize_state=False)
+    ids = torch.zeros((B * W, 1), dtype=torch.long, device="cuda")
+    beam_scores = torch.zeros(B, W, device="cuda")
+    beam_scores[:, 1:] = -1e9
+    for n in range(6):
+        att = make_attention_scores(B * W, V, n, seed=5, scale=0.5).cuda()
+        out_m = mat(ids, att.clone())
+        out_l = lazy(ids, att.clone())
+        assert isinstance(lazy.ctc_states[0], LazyForwardVariables)
+        # log_psi: the linear-domain sum is accumulated in a different association (all hyps of a thread) -> ulp-level
+        assert (out_m - out_l).abs().max().item() <= 2e-5, f"step {n}: joint scores differ"
+        if n > 0:
+            pass
+        r_l = lazy.ctc_states[0].materialize()
+        assert torch.equal(r_l, mat.ctc_states[0]), f"step {n}: materialised lazy state differs"
+        sel_m = mat.ctc_prefix_scorer.index_select_state(mat.ctc_states, ids[:, -1].reshape(-1, W) * 0 + 5)
+        sel_l = lazy.ctc_prefix_scorer.index_select_state(lazy.ctc_states, ids[:, -1].reshape(-1, W) * 0 + 5)
+        assert torch.equal(sel_m[0], sel_l[0]), f"step {n}: recomputed survivors differ from the gathered ones"
+        cand = (out_m + beam_scores.view(-1, 1)).view(B, W * V)
+        top, idx = cand.topk(W, dim=1)
+        src, tok = idx // V, idx % V
+        base = (torch.arange(B, device="cuda") * W).view(B, 1)
+        ids = torch.cat([ids[(src + base).view(-1)], tok.view(-1, 1)], dim=1)
+        beam_scores = top
 
 
 def test_partial_scoring_vs_reference_golden():
