@@ -131,17 +131,6 @@ def run_ours(args):
     out_seq_h = torch.empty((B, MAX_LENGTH), dtype=torch.long).pin_memory()
     out_len_h = torch.empty((B,), dtype=torch.long).pin_memory()
     out_score_h = torch.empty((B,), dtype=torch.float32).pin_memory()
-    launches = [0]
-    score_events = []
-
-    def decode(lg, ln, timing=None):
-        proc = CTCRescorerLogitsProcessor(lg, ln, BLANK, EOS, 0, cfg.ctc_weight, W, -1, False, 1.0)
-        proc.ctc_prefix_scorer._timing = timing
-        out = joint_beam_search(proc, decoder, B, W, V, BOS, EOS, BLANK, max_length=MAX_LENGTH, device=dev)
-        # K-a (1) + initial state (1) + per step: prep + recursion (2) + select (1, all steps but the first)
-        launches[0] += 2 + 2 * out.steps + (out.steps - 1)
-        return out
-
     def sync_all():
         torch.cuda.synchronize(dev)
         if dist is not None:
@@ -149,80 +138,124 @@ def run_ours(args):
             torch.cuda.synchronize(dev)
 
     warm = args.warmup if args.profile else max(args.warmup, 3)
-    for _ in range(warm):
-        out = decode(logits_d, lens_d)
-    sync_all()
 
-    # ---- leg 1: inputs resident in HBM, device-timed --------------------------------------------------
-    clocks = ClockSampler(local)
-    clocks.start()
-    launches[0] = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync_all()
-    e0.record()
-    steps_total = 0
-    for _ in range(args.steps):
-        out = decode(logits_d, lens_d, score_events)
-        steps_total += out.steps
-    e1.record()
-    sync_all()
-    clk = clocks.stop()
-    ms = e0.elapsed_time(e1)
-    n_launch = launches[0]
-    score_ms = [a.elapsed_time(b) for a, b in score_events]
+    def measure(materialize):
+        """Both legs for one state mode.  Returns a dict of raw measurements (max over ranks for the times)."""
+        launches = [0]
+        score_events = []
 
-    # ---- leg 2: end to end through the processor API with HOST buffers --------------------------------
-    def e2e_once():
-        lg = logits_h.to(dev, non_blocking=True)
-        ln = lens_h.to(dev, non_blocking=True)
-        o = decode(lg, ln)
-        if dist is not None:  # final gather of the hypotheses: the only collective of the path
-            seqs = [torch.empty_like(o.sequences) for _ in range(world)]
-            dist.all_gather(seqs, o.sequences)
-        out_seq_h.copy_(o.sequences, non_blocking=True)
-        out_len_h.copy_(o.lengths, non_blocking=True)
-        out_score_h.copy_(o.scores, non_blocking=True)
+        def decode(lg, ln, timing=None):
+            proc = CTCRescorerLogitsProcessor(lg, ln, BLANK, EOS, 0, cfg.ctc_weight, W, -1, False, 1.0, materialize_state=materialize)
+            proc.ctc_prefix_scorer._timing = timing
+            out = joint_beam_search(proc, decoder, B, W, V, BOS, EOS, BLANK, max_length=MAX_LENGTH, device=dev)
+            # K-a (1) + initial state (1) + per step: prep + scoring kernel (2) + select (1, all steps but the first)
+            launches[0] += 2 + 2 * out.steps + (out.steps - 1)
+            return out
 
-    if args.profile:
-        print(json.dumps({'profile_run': True, 'ms_per_step': ms / args.steps, 'avg_score_ms': sum(score_ms) / max(len(score_ms), 1)}))
-        return
-    e2e_once()
-    sync_all()
-    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    f0.record()
-    for _ in range(args.steps):
+        for _ in range(warm):
+            decode(logits_d, lens_d)
+        sync_all()
+        # ---- leg 1: inputs resident in HBM, device-timed ------------------------------------------------
+        clocks = ClockSampler(local)
+        clocks.start()
+        launches[0] = 0
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        steps_total = 0
+        for _ in range(args.steps):
+            out = decode(logits_d, lens_d, score_events)
+            steps_total += out.steps
+        e1.record()
+        sync_all()
+        clk = clocks.stop()
+        ms = e0.elapsed_time(e1)
+        n_launch = launches[0]
+        score_ms = [a.elapsed_time(b) for a, b in score_events]
+        res = {"ms": ms, "launches": n_launch, "score_ms": sum(score_ms) / max(len(score_ms), 1), "n_score": len(score_ms),
+               "decode_steps": steps_total / args.steps, "clocks": clk, "ms_e2e": float("nan")}
+        if args.profile:
+            return res
+
+        # ---- leg 2: end to end through the processor API with HOST buffers ------------------------------
+        def e2e_once():
+            lg = logits_h.to(dev, non_blocking=True)
+            ln = lens_h.to(dev, non_blocking=True)
+            o = decode(lg, ln)
+            if dist is not None:  # final gather of the hypotheses: the only collective of the path
+                seqs = [torch.empty_like(o.sequences) for _ in range(world)]
+                dist.all_gather(seqs, o.sequences)
+            out_seq_h.copy_(o.sequences, non_blocking=True)
+            out_len_h.copy_(o.lengths, non_blocking=True)
+            out_score_h.copy_(o.scores, non_blocking=True)
+
         e2e_once()
-    f1.record()
-    sync_all()
-    ms_e2e = f0.elapsed_time(f1)
+        sync_all()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(args.steps):
+            e2e_once()
+        f1.record()
+        sync_all()
+        res["ms_e2e"] = f0.elapsed_time(f1)
+        t = torch.tensor([res["ms"], res["ms_e2e"]], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res["ms"], res["ms_e2e"] = float(t[0]), float(t[1])
+        return res
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    main_mode = args.state == "materialized"
+    res = measure(main_mode)
+    if args.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "state": args.state, "ms_per_step": res["ms"] / args.steps,
+                              "avg_score_ms": res["score_ms"]}))
+        return
+    other = None if args.single_mode else measure(not main_mode)
 
     if rank == 0:
         peak, peak_src = peak_hbm()
         abytes = algorithmic_bytes_per_score(B, W, T, V)
-        avg_score_ms = sum(score_ms) / max(len(score_ms), 1)
-        achieved = abytes / (avg_score_ms * 1e-3) / 1e9
+        lazy_bytes = 4 * T * B * V + 4 * T * B * W + 8 * T * B * W + 12 * B * W + 12 * B * W * V  # x once + lin stream + r_prev + scores
+
+        def roofline(r, materialized):
+            true_bytes = abytes if materialized else lazy_bytes
+            d = {"bound": "hbm", "kernel": "k_score_full (+ k_prep)" if materialized else "k_psi_full (+ k_prep_psi)",
+                 "achieved": true_bytes / (r["score_ms"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                 "traffic": load_traffic("k_score_full" if materialized else "k_psi_full"),
+                 "algorithmic_bytes_per_launch": true_bytes, "avg_launch_ms": r["score_ms"], "launches_timed": r["n_score"]}
+            d["frac"] = d["achieved"] / peak
+            if not materialized:
+                d["note"] = ("lazy state: r (T,2,BW,V) is not written; true bytes = posteriors read once + scores; "
+                             "effective_* is the interface-faithful figure of SURVEY 8(d) divided by the same time")
+                d["effective_achieved"] = abytes / (r["score_ms"] * 1e-3) / 1e9
+                d["effective_frac"] = d["effective_achieved"] / peak
+            return d
+
+        def summary(r, materialized):
+            return {"value": world * B * args.steps / (r["ms"] * 1e-3), "unit": UNIT, "ms_per_step": r["ms"] / args.steps,
+                    "e2e": {"value": world * B * args.steps / (r["ms_e2e"] * 1e-3), "unit": UNIT,
+                            "h2d_bytes_per_step": logits_h.numel() * 4 + lens_h.numel() * 8,
+                            "d2h_bytes_per_step": out_seq_h.numel() * 8 + out_len_h.numel() * 8 + out_score_h.numel() * 4},
+                    "gpu_launches": r["launches"], "roofline": roofline(r, materialized), "clocks": r["clocks"],
+                    "decode_steps_per_utterance_batch": r["decode_steps"]}
+
+        m = summary(res, main_mode)
         line = {
-            "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": warm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
             "config": {"workload": f"{args.config}: {cfg.name}", "utterances_per_gpu": B, "beam": W, "frames": T, "vocab": V,
-                       "ctc_weight": cfg.ctc_weight, "logits": cfg.kind, "decode_steps_per_utterance_batch": steps_total / args.steps,
-                       "attention_scores": "SyntheticDecoder: log_softmax(noise + 10*onehot(transcript[n])) (the decoder is model code outside the path)", "max_length": MAX_LENGTH,
-                       "l2": "inputs exceed L2: every scorer launch writes 8*T*BW*V bytes of state"},
-            "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": logits_h.numel() * 4 + lens_h.numel() * 8,
-                    "d2h_bytes_per_step": out_seq_h.numel() * 8 + out_len_h.numel() * 8 + out_score_h.numel() * 4},
-            "gpu_launches": n_launch,
-            "roofline": {"bound": "hbm", "kernel": "k_score_full (+ k_prep)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "peak_source": peak_src, "traffic": load_traffic(),
-                         "algorithmic_bytes_per_launch": abytes, "avg_launch_ms": avg_score_ms, "launches_timed": len(score_ms)},
-            "clocks": clk,
+                       "ctc_weight": cfg.ctc_weight, "logits": cfg.kind, "state": args.state,
+                       "decode_steps_per_utterance_batch": m["decode_steps_per_utterance_batch"],
+                       "attention_scores": "SyntheticDecoder: log_softmax(noise + 10*onehot(transcript[n])) (the decoder is model code outside the path)",
+                       "max_length": MAX_LENGTH,
+                       "l2": "inputs exceed L2: posteriors are 1.9 GB and (materialized) every scorer launch writes 8*T*BW*V bytes of state"},
+            "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "roofline": m["roofline"], "clocks": m["clocks"],
         }
+        if other is not None:
+            o = summary(other, not main_mode)
+            line["lazy_state" if main_mode else "materialized_state"] = o
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(cfg, args)
         print(json.dumps(line), flush=True)
@@ -230,11 +263,11 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def load_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), if any."""
+def load_traffic(kernel):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json), if any."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(p))["k_score_full_dram_bytes_per_launch"]
+        return json.load(open(p))[f"{kernel}_dram_bytes_per_launch"]
     except Exception:
         return None
 
@@ -302,6 +335,9 @@ def main():
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=None, help="override utterances per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--state", default="materialized", choices=["materialized", "lazy"],
+                    help="state mode of the headline keys; the other mode is measured too and reported under its own key")
+    ap.add_argument("--single-mode", action="store_true", help="measure only --state")
     ap.add_argument("--profile", action="store_true", help="for runs under ncu: honour a warm-up below 3 and skip the e2e/cpu legs (never a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -612,37 +612,75 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
 
 // Lazy index_select_state: re-run the forward recursion of the PREVIOUS step for the surviving (hyp, token)
 // column of every output hypothesis j -- exactly the lane k_score_full would have written to r[:, :, hyp, tok].
-__global__ void __launch_bounds__(128) k_select_lazy(const float *__restrict__ x, int ldx, const float *__restrict__ blank_lp,
-                                                     const float *__restrict__ r_prev, const int64_t *__restrict__ last_ids,
-                                                     int ol, const float *__restrict__ log_psi,
-                                                     const int64_t *__restrict__ best_ids, int B, int W, int T, int V,
-                                                     float *__restrict__ r_new, float *__restrict__ s_new) {
+// Two launches: (a) fully parallel over (t, j): stage phi[t-1] and x[t, tok] into r_new[t, 0:2, j] (gathers,
+// libm-grade logsumexp off the dependent chain); (b) one thread per j walks T in place with coalesced,
+// prefetched reads -- only the two MUFU logaddexp remain on the serial chain.
+__device__ __forceinline__ void lazy_source(const int64_t *__restrict__ best_ids, int j, int W, int V, long long *flat,
+                                            long long *hs, long long *tok) {
+    const int b = j / W;
+    *flat = best_ids[j] + (long long)b * W * V;  // :191
+    *hs = *flat / V;
+    *tok = *flat - *hs * V;
+}
+
+__global__ void __launch_bounds__(256) k_select_lazy_stage(const float *__restrict__ x, int ldx, const float *__restrict__ r_prev,
+                                                           const int64_t *__restrict__ last_ids, int ol,
+                                                           const int64_t *__restrict__ best_ids, int B, int W, int T, int V,
+                                                           float *__restrict__ r_new) {
+    const int BW = B * W;
+    const size_t n = (size_t)T * BW;
+    const int start = ol > 1 ? ol : 1;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int t = (int)(i / BW), j = (int)(i - (size_t)t * BW);
+        long long flat, hs, tok;
+        lazy_source(best_ids, j, W, V, &flat, &hs, &tok);
+        float a = LZ, c = LZ;
+        if (t >= start) {
+            const float p0 = r_prev[((size_t)(t - 1) * 2 + 0) * BW + hs], p1 = r_prev[((size_t)(t - 1) * 2 + 1) * BW + hs];
+            a = (last_ids[hs] == tok) ? p1 : lse2_precise(p0, p1);
+            c = x[((size_t)(j / W) * T + t) * ldx + tok];
+        } else if (t == 0 && ol == 0) {
+            a = x[((size_t)(j / W) * T) * ldx + tok];  // r[0,0] = x_[0,0] (:112-113); the blank plane stays logzero
+        }
+        r_new[((size_t)t * 2 + 0) * BW + j] = a;
+        r_new[((size_t)t * 2 + 1) * BW + j] = c;
+    }
+}
+
+__global__ void __launch_bounds__(64) k_select_lazy_scan(const float *__restrict__ blank_lp, int ol, const float *__restrict__ log_psi,
+                                                         const int64_t *__restrict__ best_ids, int B, int W, int T, int V,
+                                                         float *r_new, float *__restrict__ s_new) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int BW = B * W;
     if (j >= BW) return;
-    const int b = j / W;
-    const long long flat = best_ids[j] + (long long)b * W * V;  // :191
-    const long long hs = flat / V;
-    const long long tok = flat - hs * V;
-    s_new[j] = log_psi[flat];                                   // :193
-    const bool last = (last_ids[hs] == tok);
+    long long flat, hs, tok;
+    lazy_source(best_ids, j, W, V, &flat, &hs, &tok);
+    s_new[j] = log_psi[flat];  // :193
     const int start = ol > 1 ? ol : 1;
-    const float *xr = x + (size_t)b * T * ldx + tok;
-    const float *xb = blank_lp + (size_t)b * T;
-    for (int t = 0; t < start && t < T; ++t) {
-        r_new[((size_t)t * 2 + 0) * BW + j] = LZ;
-        r_new[((size_t)t * 2 + 1) * BW + j] = LZ;
+    const float *xb = blank_lp + (size_t)(j / W) * T;
+    float rn = (ol == 0) ? r_new[j] : LZ, rb = LZ;
+    constexpr int U = 8;
+    int t = start;
+    for (; t + U <= T; t += U) {
+        float ph[U], xv[U], bl[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            ph[u] = r_new[((size_t)(t + u) * 2 + 0) * BW + j];
+            xv[u] = r_new[((size_t)(t + u) * 2 + 1) * BW + j];
+            bl[u] = xb[t + u];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float nn = lse2_fast(rn, ph[u]) + xv[u];
+            const float nb = lse2_fast(rn, rb) + bl[u];
+            rn = nn;
+            rb = nb;
+            r_new[((size_t)(t + u) * 2 + 0) * BW + j] = rn;
+            r_new[((size_t)(t + u) * 2 + 1) * BW + j] = rb;
+        }
     }
-    float rn = LZ, rb = LZ;
-    if (ol == 0) {
-        rn = xr[0];
-        r_new[j] = rn;
-    }
-#pragma unroll 4
-    for (int t = start; t < T; ++t) {
-        const float p0 = r_prev[((size_t)(t - 1) * 2 + 0) * BW + hs], p1 = r_prev[((size_t)(t - 1) * 2 + 1) * BW + hs];
-        const float phi = last ? p1 : lse2_precise(p0, p1);
-        const float nn = lse2_fast(rn, phi) + xr[(size_t)t * ldx];
+    for (; t < T; ++t) {
+        const float nn = lse2_fast(rn, r_new[((size_t)t * 2 + 0) * BW + j]) + r_new[((size_t)t * 2 + 1) * BW + j];
         const float nb = lse2_fast(rn, rb) + xb[t];
         rn = nn;
         rb = nb;
@@ -1195,8 +1233,9 @@ int ctcps_select_lazy(const float *x_logp, int ldx, const float *blank_lp, const
               "select_lazy: null pointer");
     ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0 && ldx >= V, CTCPS_E_BADARG, "select_lazy: bad size");
     const int BW = B * W;
-    k_select_lazy<<<(BW + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x_logp, ldx, blank_lp, r_prev, last_ids, ol, log_psi, best_ids,
-                                                                      B, W, T, V, r_new, s_new);
+    k_select_lazy_stage<<<grid_for((size_t)T * BW, 256), 256, 0, (cudaStream_t)stream>>>(x_logp, ldx, r_prev, last_ids, ol, best_ids, B, W,
+                                                                                        T, V, r_new);
+    k_select_lazy_scan<<<(BW + 63) / 64, 64, 0, (cudaStream_t)stream>>>(blank_lp, ol, log_psi, best_ids, B, W, T, V, r_new, s_new);
     return cuda_rc(cudaGetLastError());
 }
 
