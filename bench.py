@@ -208,8 +208,7 @@ def run_ours(args):
     res = measure(main_mode)
     if args.profile:
         if rank == 0:
-            print(json.dumps({"profile_run": True, "state": args.state, "ms_per_step": res["ms"] / args.steps,
-                              "avg_score_ms": res["score_ms"]}))
+            emit({"profile_run": True, "state": args.state, "ms_per_step": res["ms"] / args.steps, "avg_score_ms": res["score_ms"]})
         return
     other = None if args.single_mode else measure(not main_mode)
 
@@ -258,7 +257,7 @@ def run_ours(args):
             line["lazy_state" if main_mode else "materialized_state"] = o
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(cfg, args)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -276,8 +275,7 @@ def oracle_decode(cfg, B, seed, threads=None):
     """The CPU oracle port inside the same harness on B utterances of cfg's shape.  Returns (seconds, steps)."""
     from oracle import oracle as orc
 
-    if threads:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
+    orc.set_threads(threads or os.cpu_count() or 1)
     W, T, V = cfg.W, cfg.T, cfg.V
     logits, lens, transcripts = make_encoder_logits(B, T, V, cfg.kind, cfg.ragged, seed=seed)
     decoder = SyntheticDecoder(transcripts, W, V, MAX_LENGTH, seed=7, pool=ATT_POOL)
@@ -313,7 +311,7 @@ def run_reference(args):
         t += sec
         steps += st
     val = Bs * args.steps / t
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)),
         "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -323,10 +321,24 @@ def run_reference(args):
                          "sample": f"{Bs} utterance(s) per step of the {args.config} shape, full joint decode, CPU oracle port of "
                                    f"src/decoding/ctc_scorer.py (the reference is Python/torch and cannot travel to this box)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    })
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The one JSON line of the contract, on the real stdout (libraries such as NCCL print banners to fd 1, so fd 1 is
+    pointed at stderr for the rest of the run)."""
+    data = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

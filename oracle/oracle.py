@@ -41,6 +41,17 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
+def set_threads(n: int) -> int:
+    """Set the OpenMP team size of the oracle (torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants every core)."""
+    lib()
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(int(n))
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return 0
+
+
 def _dt(prec: int):
     return np.float32 if prec == 32 else np.float64
 
