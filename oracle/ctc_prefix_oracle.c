@@ -53,6 +53,17 @@ static inline REAL lse2(REAL a, REAL b) {
 
 int FN(real_bytes)(void) { return (int)sizeof(REAL); }
 
+/* OpenMP team size of THIS library's runtime (torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants every core). */
+#ifdef _OPENMP
+#include <omp.h>
+int FN(set_threads)(int n) {
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+}
+#else
+int FN(set_threads)(int n) { (void)n; return 1; }
+#endif
+
 /* F.log_softmax(encoder_logits, dim=-1)                                  ctc_scorer.py:279 */
 void FN(log_softmax)(const REAL *logits, int64_t rows, int64_t V, REAL *out) {
 #pragma omp parallel for schedule(static)

@@ -43,13 +43,9 @@ def lib() -> ctypes.CDLL:
 
 def set_threads(n: int) -> int:
     """Set the OpenMP team size of the oracle (torchrun exports OMP_NUM_THREADS=1; the CPU baseline wants every core)."""
-    lib()
-    try:
-        gomp = ctypes.CDLL("libgomp.so.1")
-        gomp.omp_set_num_threads(int(n))
-        return int(gomp.omp_get_max_threads())
-    except OSError:
-        return 0
+    L = lib()
+    L.ctcps_oracle32_set_threads.restype = ctypes.c_int
+    return int(L.ctcps_oracle32_set_threads(ctypes.c_int(int(n))))
 
 
 def _dt(prec: int):
