@@ -31,7 +31,7 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-from huggingface_asr_b200.beam_search import joint_beam_search  # noqa: E402
+from huggingface_asr_b200.beam_search import joint_beam_search, joint_beam_search_fused  # noqa: E402
 from huggingface_asr_b200.synthetic import BLANK, BOS, CONFIGS, EOS, SyntheticDecoder, make_encoder_logits  # noqa: E402
 
 METRIC = "utt/s beam-10 joint CTC/attn decode"
@@ -147,9 +147,15 @@ def run_ours(args):
         def decode(lg, ln, timing=None):
             proc = CTCRescorerLogitsProcessor(lg, ln, BLANK, EOS, 0, cfg.ctc_weight, W, -1, False, 1.0, materialize_state=materialize)
             proc.ctc_prefix_scorer._timing = timing
-            out = joint_beam_search(proc, decoder, B, W, V, BOS, EOS, BLANK, max_length=MAX_LENGTH, device=dev)
-            # K-a (1) + initial state (1) + per step: prep + scoring kernel (2) + select (1, all steps but the first)
-            launches[0] += 2 + 2 * out.steps + (out.steps - 1)
+            if args.harness == "fused":
+                out = joint_beam_search_fused(proc, decoder, B, W, V, BOS, EOS, BLANK, max_length=MAX_LENGTH, device=dev,
+                                              done_check_lag=args.done_check_lag)
+            else:
+                out = joint_beam_search(proc, decoder, B, W, V, BOS, EOS, BLANK, max_length=MAX_LENGTH, device=dev)
+            # our kernels: K-a (1) + initial state (1); per step: prep + scoring kernel (2) [+ fused beam step (1)];
+            # all steps but the first: select (1 gather, or 2 for the lazy stage + scan)
+            launches[0] += (2 + out.steps * (2 + (1 if args.harness == "fused" else 0))
+                            + (out.steps - 1) * (1 if materialize else 2))
             return out
 
         for _ in range(warm):
@@ -245,7 +251,7 @@ def run_ours(args):
             "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.config}: {cfg.name}", "utterances_per_gpu": B, "beam": W, "frames": T, "vocab": V,
-                       "ctc_weight": cfg.ctc_weight, "logits": cfg.kind, "state": args.state,
+                       "ctc_weight": cfg.ctc_weight, "logits": cfg.kind, "state": args.state, "harness": args.harness,
                        "decode_steps_per_utterance_batch": m["decode_steps_per_utterance_batch"],
                        "attention_scores": "SyntheticDecoder: log_softmax(noise + 10*onehot(transcript[n])) (the decoder is model code outside the path)",
                        "max_length": MAX_LENGTH,
@@ -350,6 +356,9 @@ def main():
     ap.add_argument("--state", default="materialized", choices=["materialized", "lazy"],
                     help="state mode of the headline keys; the other mode is measured too and reported under its own key")
     ap.add_argument("--single-mode", action="store_true", help="measure only --state")
+    ap.add_argument("--harness", default="fused", choices=["fused", "torch"],
+                    help="beam update between processor calls: one ctcps_beam_step launch (default) or the torch restatement")
+    ap.add_argument("--done-check-lag", type=int, default=2, help="fused harness: steps the CPU may run ahead of the GPU")
     ap.add_argument("--profile", action="store_true", help="for runs under ncu: honour a warm-up below 3 and skip the e2e/cpu legs (never a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -28,6 +28,21 @@ from typing import Callable
 import torch
 
 
+def _finalize(input_ids, beam_scores, pool_scores, pool_seqs, pool_lens, done, B, W, max_length, pad, length_penalty, steps):
+    """BeamSearchScorer.finalize: utterances still running contribute their W open beams; best hypothesis wins."""
+    dev = input_ids.device
+    NEG = float("-inf")
+    L = input_ids.shape[1]
+    open_scores = torch.where(done.view(B, 1), torch.full_like(beam_scores, NEG), beam_scores / float(L - 1) ** length_penalty)
+    open_seqs = torch.nn.functional.pad(input_ids.reshape(B, W, L)[:, :, 1:], (0, max_length - (L - 1)), value=pad)
+    all_scores = torch.cat([pool_scores, open_scores], dim=1)
+    best = all_scores.argmax(dim=1)
+    all_seqs = torch.cat([pool_seqs, open_seqs], dim=1)
+    all_lens = torch.cat([pool_lens, torch.full((B, W), L - 1, dtype=torch.long, device=dev)], dim=1)
+    ar = torch.arange(B, device=dev)
+    return BeamSearchOutput(all_seqs[ar, best], all_lens[ar, best], all_scores[ar, best], steps)
+
+
 @dataclass
 class BeamSearchOutput:
     sequences: torch.Tensor  # (B, max_len) int64, pad-filled, without bos
@@ -104,13 +119,67 @@ def joint_beam_search(processor: Callable, decoder_log_probs: Callable[[torch.Te
         if steps % sync_every == 0 and bool(done.all()):
             break
 
-    # finalize: utterances still running contribute their W open beams
-    L = input_ids.shape[1]
-    open_scores = torch.where(done.view(B, 1), torch.full_like(beam_scores, NEG), beam_scores / float(L - 1) ** length_penalty)
-    open_seqs = torch.nn.functional.pad(input_ids.view(B, W, L)[:, :, 1:], (0, max_length - (L - 1)), value=pad)
-    all_scores = torch.cat([pool_scores, open_scores], dim=1)
-    best = all_scores.argmax(dim=1)
-    all_seqs = torch.cat([pool_seqs, open_seqs], dim=1)
-    all_lens = torch.cat([pool_lens, torch.full((B, W), L - 1, dtype=torch.long, device=dev)], dim=1)
-    ar = torch.arange(B, device=dev)
-    return BeamSearchOutput(all_seqs[ar, best], all_lens[ar, best], all_scores[ar, best], steps)
+    return _finalize(input_ids, beam_scores, pool_scores, pool_seqs, pool_lens, done, B, W, max_length, pad, length_penalty, steps)
+
+
+@torch.no_grad()
+def joint_beam_search_fused(processor: Callable, decoder_log_probs: Callable[[torch.Tensor, int], torch.Tensor], batch: int,
+                            num_beams: int, vocab: int, bos: int, eos: int, pad: int, max_length: int = 512,
+                            length_penalty: float = 1.0, device: torch.device | str = "cuda", done_check_lag: int = 0) -> BeamSearchOutput:
+    """Same loop as joint_beam_search with the whole beam update of a step in ONE kernel (ctcps_beam_step).
+
+    The processor boundary is unchanged: `processor(input_ids (BW,L), log_probs (BW,V))` is still called once per step.
+    The host never synchronises: the kernel publishes (step, #done utterances) into pinned memory and the loop reads the
+    entry of `done_check_lag` steps ago (0 = wait for the current step, the exact semantics of the torch harness;
+    k > 0 = let the CPU run k steps ahead of the GPU, at the price of up to k extra steps after everything is done --
+    extra steps never change the result, finished utterances are frozen).
+    """
+    from . import _lib
+
+    L_ = _lib.lib()
+    B, W, V = batch, num_beams, vocab
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("joint_beam_search_fused needs a CUDA device (there is no CPU path)")
+    NEG = float("-inf")
+    ids = [torch.full((B * W, max_length), pad, dtype=torch.long, device=dev) for _ in range(2)]
+    ids[0][:, 0] = bos
+    beam_scores = torch.zeros(B, W, dtype=torch.float32, device=dev)
+    beam_scores[:, 1:] = -1e9
+    pool_scores = torch.full((B, W), NEG, dtype=torch.float32, device=dev)
+    pool_seqs = torch.full((B, W, max_length), pad, dtype=torch.long, device=dev)
+    pool_lens = torch.zeros(B, W, dtype=torch.long, device=dev)
+    done = torch.zeros(B, dtype=torch.uint8, device=dev)
+    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+    RING = 8
+    ring = torch.full((RING,), -1, dtype=torch.int64).pin_memory()
+    ring_np = ring.numpy()
+    stream = torch.cuda.current_stream(dev)
+    cur, L, steps = 0, 1, 0
+    while True:
+        input_ids = ids[cur][:, :L]
+        log_probs = decoder_log_probs(input_ids, steps)
+        proc = processor(input_ids, log_probs)
+        if not proc.is_contiguous():
+            proc = proc.contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(L_.ctcps_beam_step(proc.data_ptr(), beam_scores.data_ptr(), ids[cur].data_ptr(), ids[1 - cur].data_ptr(),
+                                          max_length, L, B, W, V, eos, pad, float(L) ** length_penalty, pool_scores.data_ptr(),
+                                          pool_lens.data_ptr(), pool_seqs.data_ptr(), max_length, done.data_ptr(), ticket.data_ptr(),
+                                          ring.data_ptr(), RING, steps, stream.cuda_stream), "ctcps_beam_step")
+        cur ^= 1
+        L += 1
+        steps += 1
+        if L >= max_length:
+            break
+        look = steps - 1 - done_check_lag
+        if look >= 0:
+            if done_check_lag == 0:
+                stream.synchronize()
+            else:  # the entry of an older step: wait (briefly) until the GPU has published it
+                while int(ring_np[look % RING]) >> 32 != look:
+                    pass
+            if (int(ring_np[look % RING]) & 0xFFFFFFFF) == B:
+                break
+    return _finalize(ids[cur][:, :L], beam_scores, pool_scores, pool_seqs, pool_lens, done.bool(), B, W, max_length, pad,
+                     length_penalty, steps)

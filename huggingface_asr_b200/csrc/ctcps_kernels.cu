@@ -851,6 +851,177 @@ __global__ void __launch_bounds__(256) k_trick(const float *__restrict__ att, co
 }
 
 // ------------------------------------------------------------------------------------------
+// N1: the beam-search step that follows the processor, fused into one launch.
+// One CTA per utterance: top-2W of (joint + running beam score) over the W*V candidates, eos finalisation into
+// the finished-hypothesis pool, choice of the W continuing beams, done test, and the reordered + extended
+// input_ids rows.  Restates huggingface_asr_b200/beam_search.py::joint_beam_search (itself the contract of HF
+// 4.39.3 beam_search / BeamSearchScorer.process with the processor) without ~60 small torch launches per step.
+// Ordering: higher score first; equal scores: lower hyp*V+tok first.
+// ------------------------------------------------------------------------------------------
+constexpr int BEAM_NT = 256;
+constexpr int BEAM_MAXK = 64;  // 2W <= 64
+
+struct Cand {
+    float s;
+    int i;
+};
+__device__ __forceinline__ bool cand_beats(float s1, int i1, float s2, int i2) { return s1 > s2 || (s1 == s2 && i1 < i2); }
+
+__global__ void __launch_bounds__(BEAM_NT) k_beam_step(const float *__restrict__ joint, float *beam_scores,
+                                                       const int64_t *__restrict__ ids_cur, int64_t *__restrict__ ids_next,
+                                                       long long ld_ids, int L, int W, int V, int eos, int pad, float len_norm,
+                                                       float *pool_scores, int64_t *pool_lens, int64_t *pool_seqs,
+                                                       long long ld_pool, unsigned char *done, unsigned int *ticket,
+                                                       long long *done_ring, int ring, long long step_tag) {
+    constexpr int NW = BEAM_NT / 32;
+    __shared__ Cand wl[NW][BEAM_MAXK];          // per-warp candidate lists (unsorted)
+    __shared__ Cand top[BEAM_MAXK];             // final list, sorted
+    __shared__ int job_src[2 * 32], job_dst[2 * 32], n_pool_jobs, next_tok_s[32], next_src_s[32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int K = 2 * W;
+    const float NEG = -INFINITY;
+
+    // ---- 1. per-warp top-K by threshold insertion ------------------------------------------------------
+    for (int k = lane; k < BEAM_MAXK; k += 32) wl[wid][k].s = NEG, wl[wid][k].i = 0x7fffffff;
+    __syncwarp();
+    float thr = NEG;   // current K-th best of this warp (the entry that would be evicted)
+    int thr_pos = 0;
+    const int per = ((V + NW * 32 - 1) / (NW * 32)) * 32;  // columns per warp, multiple of 32
+    for (int w = 0; w < W; ++w) {
+        const float bs = beam_scores[b * W + w];
+        const float *row = joint + ((size_t)b * W + w) * V;
+        const int v_end = min(V, (wid + 1) * per);
+        for (int vb = wid * per; vb < v_end; vb += 32) {
+            const int v = vb + lane;
+            const float c = v < v_end ? row[v] + bs : NEG;
+            unsigned m = __ballot_sync(0xffffffffu, c > thr);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const float cs = __shfl_sync(0xffffffffu, c, src);
+                if (cs > thr) {  // strict: on ties the earlier (lower index) candidate stays
+                    if (lane == 0) wl[wid][thr_pos].s = cs, wl[wid][thr_pos].i = w * V + vb + src;
+                    __syncwarp();
+                    // new eviction candidate: the worst of the K entries (lowest score, then highest index)
+                    float ws = INFINITY;
+                    int wi = -1, wp = 0;
+                    for (int k = lane; k < K; k += 32) {
+                        const Cand e = wl[wid][k];
+                        if (e.s < ws || (e.s == ws && e.i > wi)) ws = e.s, wi = e.i, wp = k;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float os = __shfl_xor_sync(0xffffffffu, ws, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, wi, o), op = __shfl_xor_sync(0xffffffffu, wp, o);
+                        if (os < ws || (os == ws && oi > wi)) ws = os, wi = oi, wp = op;
+                    }
+                    thr = ws;
+                    thr_pos = wp;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- 2. merge: rank every candidate among all NW*K by counting who beats it ------------------------
+    for (int q = tid; q < NW * K; q += BEAM_NT) {
+        const Cand me = wl[q / K][q % K];
+        int rank = 0;
+        for (int o = 0; o < NW * K; ++o) {
+            const Cand e = wl[o / K][o % K];
+            rank += cand_beats(e.s, e.i, me.s, me.i) ? 1 : 0;
+        }
+        if (rank < K) top[rank] = me;
+    }
+    __syncthreads();
+
+    // ---- 3. bookkeeping (serial, tiny) ------------------------------------------------------------------
+    if (tid == 0) {
+        const float inv_norm = 1.0f / len_norm;  // torch divides a tensor by a scalar as a * (1 / scalar)
+        const bool dn = done[b] != 0;
+        float *ps = pool_scores + (size_t)b * W;
+        int njobs = 0;
+        for (int r = 0; r < W; ++r) {  // eos candidates ranked inside the top W are finalised
+            const int tok = top[r].i % V;
+            if (tok == eos && !dn && top[r].s > NEG) {
+                const float fs = top[r].s * inv_norm;
+                int slot = 0;
+                float worst = ps[0];
+                for (int k = 1; k < W; ++k)
+                    if (ps[k] < worst) worst = ps[k], slot = k;
+                if (fs > worst) {
+                    ps[slot] = fs;
+                    pool_lens[(size_t)b * W + slot] = L - 1;
+                    int jq = -1;  // a later candidate may overwrite a slot filled in this same step
+                    for (int q = 0; q < njobs; ++q)
+                        if (job_dst[q] == slot) jq = q;
+                    if (jq < 0) jq = njobs++;
+                    job_src[jq] = top[r].i / V;
+                    job_dst[jq] = slot;
+                }
+            }
+        }
+        n_pool_jobs = njobs;
+        int o = 0;
+        float ns[32];
+        for (int r = 0; r < K && o < W; ++r) {  // the first W non-eos candidates continue
+            const int tok = top[r].i % V;
+            if (tok != eos) ns[o] = top[r].s, next_tok_s[o] = tok, next_src_s[o] = top[r].i / V, ++o;
+        }
+        for (; o < W; ++o) ns[o] = NEG, next_tok_s[o] = pad, next_src_s[o] = 0;
+        bool full = true;
+        float worst = INFINITY;
+        for (int k = 0; k < W; ++k) {
+            full = full && ps[k] > NEG;
+            worst = fminf(worst, ps[k]);
+        }
+        const bool dn_new = dn || (full && worst >= top[0].s * inv_norm);
+        for (int k = 0; k < W; ++k) {
+            if (dn_new) ns[k] = 0.f, next_tok_s[k] = pad, next_src_s[k] = 0;
+            beam_scores[b * W + k] = ns[k];
+        }
+        done[b] = dn_new ? 1 : 0;
+    }
+    __syncthreads();
+
+    // ---- 4. copies: finished prefixes into the pool, reordered + extended rows into ids_next ----------
+    for (int q = 0; q < n_pool_jobs; ++q) {
+        const int64_t *src = ids_cur + ((size_t)b * W + job_src[q]) * ld_ids + 1;  // drop bos
+        int64_t *dst = pool_seqs + ((size_t)b * W + job_dst[q]) * ld_pool;
+        for (int k = tid; k < L - 1; k += BEAM_NT) dst[k] = src[k];
+    }
+    for (int o = 0; o < W; ++o) {
+        const int64_t *src = ids_cur + ((size_t)b * W + next_src_s[o]) * ld_ids;
+        int64_t *dst = ids_next + ((size_t)b * W + o) * ld_ids;
+        for (int k = tid; k < L; k += BEAM_NT) dst[k] = src[k];
+        if (tid == 0) dst[L] = next_tok_s[o];
+    }
+
+    // ---- 5. last CTA publishes (step, number of finished utterances) to host-visible memory -----------
+    if (done_ring != nullptr) {
+        __shared__ unsigned int last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+        __syncthreads();
+        if (last) {
+            int cnt = 0;
+            for (int k = tid; k < (int)gridDim.x; k += BEAM_NT) cnt += ((volatile unsigned char *)done)[k] ? 1 : 0;
+            __shared__ int tot;
+            if (tid == 0) tot = 0;
+            __syncthreads();
+            atomicAdd(&tot, cnt);
+            __syncthreads();
+            if (tid == 0) {
+                *ticket = 0;
+                done_ring[step_tag % ring] = (step_tag << 32) | (long long)tot;
+                __threadfence_system();
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -1236,6 +1407,22 @@ int ctcps_select_lazy(const float *x_logp, int ldx, const float *blank_lp, const
     k_select_lazy_stage<<<grid_for((size_t)T * BW, 256), 256, 0, (cudaStream_t)stream>>>(x_logp, ldx, r_prev, last_ids, ol, best_ids, B, W,
                                                                                         T, V, r_new);
     k_select_lazy_scan<<<(BW + 63) / 64, 64, 0, (cudaStream_t)stream>>>(blank_lp, ol, log_psi, best_ids, B, W, T, V, r_new, s_new);
+    return cuda_rc(cudaGetLastError());
+}
+
+int ctcps_beam_step(const float *joint, float *beam_scores, const int64_t *ids_cur, int64_t *ids_next, int64_t ld_ids, int L, int B,
+                    int W, int V, int eos, int pad, float len_norm, float *pool_scores, int64_t *pool_lens, int64_t *pool_seqs,
+                    int64_t ld_pool, unsigned char *done, unsigned int *ticket, int64_t *done_ring, int ring, int64_t step_tag,
+                    void *stream) {
+    ARG_CHECK(joint && beam_scores && ids_cur && ids_next && pool_scores && pool_lens && pool_seqs && done, CTCPS_E_BADARG,
+              "beam_step: null pointer");
+    ARG_CHECK(B > 0 && W > 0 && V > 0 && L >= 1 && L < ld_ids && L - 1 <= ld_pool, CTCPS_E_BADARG, "beam_step: bad size");
+    ARG_CHECK(2 * W <= BEAM_MAXK && W <= 32, CTCPS_E_TOOBIG, "beam_step: num_beams > 32 is not supported");
+    ARG_CHECK((long long)W * V < (1ll << 31) && (long long)W * V >= 2 * W, CTCPS_E_TOOBIG, "beam_step: need 2W <= W*V < 2^31");
+    ARG_CHECK(done_ring == nullptr || (ticket != nullptr && ring > 0), CTCPS_E_BADARG, "beam_step: done_ring without ticket");
+    k_beam_step<<<B, BEAM_NT, 0, (cudaStream_t)stream>>>(joint, beam_scores, ids_cur, ids_next, ld_ids, L, W, V, eos, pad, len_norm,
+                                                        pool_scores, pool_lens, pool_seqs, ld_pool, done, ticket,
+                                                        (long long *)done_ring, ring, step_tag);
     return cuda_rc(cudaGetLastError());
 }
 

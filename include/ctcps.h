@@ -126,6 +126,22 @@ int ctcps_select_lazy(const float *x_logp, int ldx, const float *blank_lp, const
                       float *s_new, void *stream);
 
 /*
+ * N1 (the step right after the path): one fused beam-search step around the processor output.  Replaces, for one
+ * decode step, what transformers 4.39.3 beam_search + BeamSearchScorer.process do between two processor calls (and
+ * what huggingface_asr_b200/beam_search.py restates with torch ops): candidates = joint + running beam score, top 2W of
+ * (B, W*V), eos candidates ranked inside the top W go to the finished pool with score / len_norm, the first W non-eos
+ * candidates continue, done test (early_stopping=False), rows of done utterances continue with pad.
+ *   joint (BW,V) processor output;  beam_scores (B,W) in/out;  ids_cur/ids_next (BW, ld_ids) int64, first L columns
+ *   valid (bos first), ids_next gets L+1 columns;  pool_* (B,W[,ld_pool]) finished hypotheses (scores -inf = empty);
+ *   done (B) bytes.  If done_ring (host-visible, e.g. pinned memory) is given, the last CTA stores
+ *   (step_tag << 32 | number of done utterances) into done_ring[step_tag % ring]; ticket is a zeroed device counter.
+ */
+int ctcps_beam_step(const float *joint, float *beam_scores, const int64_t *ids_cur, int64_t *ids_next, int64_t ld_ids, int L,
+                    int B, int W, int V, int eos, int pad, float len_norm, float *pool_scores, int64_t *pool_lens,
+                    int64_t *pool_seqs, int64_t ld_pool, unsigned char *done, unsigned int *ticket, int64_t *done_ring,
+                    int ring, int64_t step_tag, void *stream);
+
+/*
  * Optional eos/space trick of the processor (ctc_scorer.py:333-349), in place on `next`:
  * rows with argmax(att) == eos and argmax(ctc) == space and next[eos] < next[space] < k*next[eos]
  * get next[eos] *= k.
