@@ -149,7 +149,7 @@ def run_ours(args):
             proc.ctc_prefix_scorer._timing = timing
             if args.harness == "fused":
                 out = joint_beam_search_fused(proc, decoder, B, W, V, BOS, EOS, BLANK, max_length=MAX_LENGTH, device=dev,
-                                              done_check_lag=args.done_check_lag)
+                                              done_check_lag=(0 if materialize else 1) if args.done_check_lag is None else args.done_check_lag)
             else:
                 out = joint_beam_search(proc, decoder, B, W, V, BOS, EOS, BLANK, max_length=MAX_LENGTH, device=dev)
             # our kernels: K-a (1) + initial state (1); per step: prep + scoring kernel (2) [+ fused beam step (1)];
@@ -358,7 +358,8 @@ def main():
     ap.add_argument("--single-mode", action="store_true", help="measure only --state")
     ap.add_argument("--harness", default="fused", choices=["fused", "torch"],
                     help="beam update between processor calls: one ctcps_beam_step launch (default) or the torch restatement")
-    ap.add_argument("--done-check-lag", type=int, default=2, help="fused harness: steps the CPU may run ahead of the GPU")
+    ap.add_argument("--done-check-lag", type=int, default=None,
+                    help="fused harness: steps the CPU may run ahead of the GPU (default: 0 materialized, 1 lazy)")
     ap.add_argument("--profile", action="store_true", help="for runs under ncu: honour a warm-up below 3 and skip the e2e/cpu legs (never a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":

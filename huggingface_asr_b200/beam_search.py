@@ -150,7 +150,11 @@ def joint_beam_search_fused(processor: Callable, decoder_log_probs: Callable[[to
     pool_seqs = torch.full((B, W, max_length), pad, dtype=torch.long, device=dev)
     pool_lens = torch.zeros(B, W, dtype=torch.long, device=dev)
     done = torch.zeros(B, dtype=torch.uint8, device=dev)
-    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+    import ctypes
+
+    nws = ctypes.c_size_t(0)
+    _lib.check(L_.ctcps_beam_step_workspace_bytes(B, W, ctypes.byref(nws)), "ctcps_beam_step_workspace_bytes")
+    ws = torch.zeros((nws.value + 15) // 16 * 2, dtype=torch.int64, device=dev)  # zeroed: holds the arrival tickets
     RING = 8
     ring = torch.full((RING,), -1, dtype=torch.int64).pin_memory()
     ring_np = ring.numpy()
@@ -165,8 +169,8 @@ def joint_beam_search_fused(processor: Callable, decoder_log_probs: Callable[[to
         with torch.cuda.device(dev):
             _lib.check(L_.ctcps_beam_step(proc.data_ptr(), beam_scores.data_ptr(), ids[cur].data_ptr(), ids[1 - cur].data_ptr(),
                                           max_length, L, B, W, V, eos, pad, float(L) ** length_penalty, pool_scores.data_ptr(),
-                                          pool_lens.data_ptr(), pool_seqs.data_ptr(), max_length, done.data_ptr(), ticket.data_ptr(),
-                                          ring.data_ptr(), RING, steps, stream.cuda_stream), "ctcps_beam_step")
+                                          pool_lens.data_ptr(), pool_seqs.data_ptr(), max_length, done.data_ptr(), ws.data_ptr(),
+                                          ws.numel() * 8, ring.data_ptr(), RING, steps, stream.cuda_stream), "ctcps_beam_step")
         cur ^= 1
         L += 1
         steps += 1

@@ -858,8 +858,10 @@ __global__ void __launch_bounds__(256) k_trick(const float *__restrict__ att, co
 // 4.39.3 beam_search / BeamSearchScorer.process with the processor) without ~60 small torch launches per step.
 // Ordering: higher score first; equal scores: lower hyp*V+tok first.
 // ------------------------------------------------------------------------------------------
-constexpr int BEAM_NT = 256;
-constexpr int BEAM_MAXK = 64;  // 2W <= 64
+constexpr int BEAM_NT = 128;
+constexpr int BEAM_NW = BEAM_NT / 32;
+constexpr int BEAM_MAXK = 64;   // 2W <= 64
+constexpr int BEAM_MAXP = 8;    // CTAs per utterance
 
 struct Cand {
     float s;
@@ -867,76 +869,153 @@ struct Cand {
 };
 __device__ __forceinline__ bool cand_beats(float s1, int i1, float s2, int i2) { return s1 > s2 || (s1 == s2 && i1 < i2); }
 
-__global__ void __launch_bounds__(BEAM_NT) k_beam_step(const float *__restrict__ joint, float *beam_scores,
-                                                       const int64_t *__restrict__ ids_cur, int64_t *__restrict__ ids_next,
-                                                       long long ld_ids, int L, int W, int V, int eos, int pad, float len_norm,
-                                                       float *pool_scores, int64_t *pool_lens, int64_t *pool_seqs,
-                                                       long long ld_pool, unsigned char *done, unsigned int *ticket,
-                                                       long long *done_ring, int ring, long long step_tag) {
-    constexpr int NW = BEAM_NT / 32;
-    __shared__ Cand wl[NW][BEAM_MAXK];          // per-warp candidate lists (unsorted)
-    __shared__ Cand top[BEAM_MAXK];             // final list, sorted
-    __shared__ int job_src[2 * 32], job_dst[2 * 32], n_pool_jobs, next_tok_s[32], next_src_s[32];
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int K = 2 * W;
-    const float NEG = -INFINITY;
-
-    // ---- 1. per-warp top-K by threshold insertion ------------------------------------------------------
-    for (int k = lane; k < BEAM_MAXK; k += 32) wl[wid][k].s = NEG, wl[wid][k].i = 0x7fffffff;
-    __syncwarp();
-    float thr = NEG;   // current K-th best of this warp (the entry that would be evicted)
-    int thr_pos = 0;
-    const int per = ((V + NW * 32 - 1) / (NW * 32)) * 32;  // columns per warp, multiple of 32
-    for (int w = 0; w < W; ++w) {
-        const float bs = beam_scores[b * W + w];
-        const float *row = joint + ((size_t)b * W + w) * V;
-        const int v_end = min(V, (wid + 1) * per);
-        for (int vb = wid * per; vb < v_end; vb += 32) {
-            const int v = vb + lane;
-            const float c = v < v_end ? row[v] + bs : NEG;
-            unsigned m = __ballot_sync(0xffffffffu, c > thr);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const float cs = __shfl_sync(0xffffffffu, c, src);
-                if (cs > thr) {  // strict: on ties the earlier (lower index) candidate stays
-                    if (lane == 0) wl[wid][thr_pos].s = cs, wl[wid][thr_pos].i = w * V + vb + src;
-                    __syncwarp();
-                    // new eviction candidate: the worst of the K entries (lowest score, then highest index)
-                    float ws = INFINITY;
-                    int wi = -1, wp = 0;
-                    for (int k = lane; k < K; k += 32) {
-                        const Cand e = wl[wid][k];
-                        if (e.s < ws || (e.s == ws && e.i > wi)) ws = e.s, wi = e.i, wp = k;
-                    }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const float os = __shfl_xor_sync(0xffffffffu, ws, o);
-                        const int oi = __shfl_xor_sync(0xffffffffu, wi, o), op = __shfl_xor_sync(0xffffffffu, wp, o);
-                        if (os < ws || (os == ws && oi > wi)) ws = os, wi = oi, wp = op;
-                    }
-                    thr = ws;
-                    thr_pos = wp;
-                }
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- 2. merge: rank every candidate among all NW*K by counting who beats it ------------------------
-    for (int q = tid; q < NW * K; q += BEAM_NT) {
-        const Cand me = wl[q / K][q % K];
+// rank-select: out[rank] = cand for the K best of n candidates in shared memory (all-pairs counting, with a
+// lower bound that skips candidates which cannot be among the K best)
+__device__ __forceinline__ void rank_select(const Cand *cands, int n, int K, float bound, Cand *out) {
+    for (int q = threadIdx.x; q < n; q += BEAM_NT) {
+        const Cand me = cands[q];
+        if (me.s < bound) continue;
         int rank = 0;
-        for (int o = 0; o < NW * K; ++o) {
-            const Cand e = wl[o / K][o % K];
+        for (int o = 0; o < n; ++o) {
+            const Cand e = cands[o];
             rank += cand_beats(e.s, e.i, me.s, me.i) ? 1 : 0;
         }
-        if (rank < K) top[rank] = me;
+        if (rank < K) out[rank] = me;
     }
+}
+
+// grid = B * P: CTA (b, p) reduces slice p of the W*V candidates of utterance b to its K best, the last CTA of the
+// utterance to arrive (ticket) merges the P partial lists and does the bookkeeping and the copies.
+template <int KL>
+__global__ void __launch_bounds__(BEAM_NT) k_beam_step(const float *__restrict__ joint, float *beam_scores,
+                                                       const int64_t *__restrict__ ids_cur, int64_t *__restrict__ ids_next,
+                                                       long long ld_ids, int L, int W, int V, int P, int eos, int pad,
+                                                       float len_norm, float *pool_scores, int64_t *pool_lens,
+                                                       int64_t *pool_seqs, long long ld_pool, unsigned char *done,
+                                                       Cand *part, unsigned int *utt_ticket, unsigned int *ticket,
+                                                       long long *done_ring, int ring, long long step_tag) {
+    __shared__ Cand wl[BEAM_MAXP * BEAM_MAXK];  // per-warp lists (phase 1), then the P partial lists (phase 2)
+    __shared__ Cand top[BEAM_MAXK];             // sorted result of a rank_select
+    __shared__ float kth[BEAM_MAXP];
+    __shared__ int job_src[32], job_dst[32], n_pool_jobs, next_tok_s[32], next_src_s[32];
+    __shared__ unsigned int is_last;
+    const int b = blockIdx.x / P, p = blockIdx.x - b * P;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int K = 2 * W;
+    const float NEG = -INFINITY;
+    const int n = W * V;
+
+    // ---- 1. per-warp top-K of a contiguous slice: sorted list of 32*KL entries held in registers (entry q of list j
+    //         lives in lane q), candidates above the current K-th best are inserted with warp shuffles ----------
+    Cand *mine = wl + wid * BEAM_MAXK;
+    float ls[KL];
+    int li[KL];
+#pragma unroll
+    for (int j = 0; j < KL; ++j) ls[j] = NEG, li[j] = 0x7fffffff;
+    float thr = NEG;  // score of entry K-1
+    const int thr_lane = (K - 1) & 31, thr_list = (K - 1) >> 5;
+    {
+        const int per_cta = (((n + P - 1) / P + 127) / 128) * 128;
+        const int per_warp = per_cta / BEAM_NW;  // multiple of 32
+        const int s0 = min(n, p * per_cta + wid * per_warp), e0 = min(n, s0 + per_warp);
+        const float *flat = joint + (size_t)b * n;
+        int w = s0 / V;
+        for (int s = s0; s < e0;) {
+            const int e = min(e0, (w + 1) * V);  // segment [s, e) lies in hypothesis w
+            const float bs = beam_scores[b * W + w];
+            constexpr int U = 8;  // independent 128-byte loads in flight per warp
+            for (int vb0 = s; vb0 < e; vb0 += 32 * U) {
+                float cu[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = vb0 + u * 32 + lane;
+                    cu[u] = i < e ? __ldg(flat + i) + bs : NEG;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const float c = cu[u];
+                    unsigned m = __ballot_sync(0xffffffffu, c > thr);
+                    while (m) {
+                        const int src = __ffs(m) - 1;
+                        m &= m - 1;
+                        const float cs = __shfl_sync(0xffffffffu, c, src);
+                        if (cs > thr) {  // strict: on ties the earlier (lower index) candidate stays
+                            const int ci = vb0 + u * 32 + src;
+                            // list 0: entries that stay ahead of the candidate form a prefix
+                            const int pos0 = __popc(__ballot_sync(0xffffffffu, cand_beats(ls[0], li[0], cs, ci)));
+                            const float fall_s = __shfl_sync(0xffffffffu, ls[0], 31);
+                            const int fall_i = __shfl_sync(0xffffffffu, li[0], 31);
+                            float up_s = __shfl_up_sync(0xffffffffu, ls[0], 1);
+                            int up_i = __shfl_up_sync(0xffffffffu, li[0], 1);
+                            if (lane == pos0) ls[0] = cs, li[0] = ci;
+                            else if (lane > pos0) ls[0] = up_s, li[0] = up_i;
+                            if (KL == 2) {
+                                if (pos0 < 32) {  // the entry that fell off list 0 enters list 1 at the front
+                                    up_s = __shfl_up_sync(0xffffffffu, ls[KL - 1], 1);
+                                    up_i = __shfl_up_sync(0xffffffffu, li[KL - 1], 1);
+                                    if (lane == 0) ls[KL - 1] = fall_s, li[KL - 1] = fall_i;
+                                    else ls[KL - 1] = up_s, li[KL - 1] = up_i;
+                                } else {
+                                    const int pos1 = __popc(__ballot_sync(0xffffffffu, cand_beats(ls[KL - 1], li[KL - 1], cs, ci)));
+                                    up_s = __shfl_up_sync(0xffffffffu, ls[KL - 1], 1);
+                                    up_i = __shfl_up_sync(0xffffffffu, li[KL - 1], 1);
+                                    if (lane == pos1) ls[KL - 1] = cs, li[KL - 1] = ci;
+                                    else if (lane > pos1) ls[KL - 1] = up_s, li[KL - 1] = up_i;
+                                }
+                            }
+                            thr = __shfl_sync(0xffffffffu, (KL == 2 && thr_list) ? ls[KL - 1] : ls[0], thr_lane);
+                        }
+                    }
+                }
+            }
+            s = e;
+            ++w;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < KL; ++j) mine[j * 32 + lane].s = ls[j], mine[j * 32 + lane].i = li[j];
+    if (KL == 1) mine[32 + lane].s = NEG, mine[32 + lane].i = 0x7fffffff;
+    if (lane == 0) kth[wid] = thr;
     __syncthreads();
 
-    // ---- 3. bookkeeping (serial, tiny) ------------------------------------------------------------------
+    // ---- 2. CTA merge of the warp lists -> this slice's K best, published for the utterance's last CTA --
+    {
+        float bound = kth[0];
+        for (int q = 1; q < BEAM_NW; ++q) bound = fmaxf(bound, kth[q]);
+        for (int k = tid; k < BEAM_MAXK; k += BEAM_NT) top[k].s = NEG, top[k].i = 0x7fffffff;
+        __syncthreads();
+        rank_select(wl, BEAM_NW * BEAM_MAXK, K, bound, top);
+        __syncthreads();
+        Cand *dst = part + ((size_t)b * P + p) * BEAM_MAXK;
+        for (int k = tid; k < K; k += BEAM_NT) dst[k] = top[k];
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) is_last = (atomicAdd(utt_ticket + b, 1u) == (unsigned)(P - 1)) ? 1u : 0u;
+        __syncthreads();
+        if (!is_last) return;
+    }
+
+    // ---- 3. last CTA of the utterance: merge the P partial lists ---------------------------------------
+    {
+        const volatile Cand *src = part + (size_t)b * P * BEAM_MAXK;
+        for (int q = tid; q < P * BEAM_MAXK; q += BEAM_NT) {
+            Cand c;
+            if ((q % BEAM_MAXK) < K) c.s = src[q].s, c.i = src[q].i;
+            else c.s = NEG, c.i = 0x7fffffff;
+            wl[q] = c;
+        }
+        __syncthreads();
+        if (tid < P) kth[tid] = wl[tid * BEAM_MAXK + K - 1].s;  // partial lists are sorted: entry K-1 is the slice's K-th
+        __syncthreads();
+        float bound = kth[0];
+        for (int q = 1; q < P; ++q) bound = fmaxf(bound, kth[q]);
+        rank_select(wl, P * BEAM_MAXK, K, bound, top);
+        __syncthreads();
+    }
+
+    // ---- 4. bookkeeping (serial, tiny) ------------------------------------------------------------------
     if (tid == 0) {
+        utt_ticket[b] = 0;
         const float inv_norm = 1.0f / len_norm;  // torch divides a tensor by a scalar as a * (1 / scalar)
         const bool dn = done[b] != 0;
         float *ps = pool_scores + (size_t)b * W;
@@ -984,7 +1063,7 @@ __global__ void __launch_bounds__(BEAM_NT) k_beam_step(const float *__restrict__
     }
     __syncthreads();
 
-    // ---- 4. copies: finished prefixes into the pool, reordered + extended rows into ids_next ----------
+    // ---- 5. copies: finished prefixes into the pool, reordered + extended rows into ids_next ----------
     for (int q = 0; q < n_pool_jobs; ++q) {
         const int64_t *src = ids_cur + ((size_t)b * W + job_src[q]) * ld_ids + 1;  // drop bos
         int64_t *dst = pool_seqs + ((size_t)b * W + job_dst[q]) * ld_pool;
@@ -997,19 +1076,18 @@ __global__ void __launch_bounds__(BEAM_NT) k_beam_step(const float *__restrict__
         if (tid == 0) dst[L] = next_tok_s[o];
     }
 
-    // ---- 5. last CTA publishes (step, number of finished utterances) to host-visible memory -----------
+    // ---- 6. the last utterance to finish its step publishes (step, #done utterances) to host-visible memory
     if (done_ring != nullptr) {
+        const int B = gridDim.x / P;
         __shared__ unsigned int last;
+        __shared__ int tot;
         __threadfence();
         __syncthreads();
-        if (tid == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+        if (tid == 0) last = (atomicAdd(ticket, 1u) == (unsigned)(B - 1)) ? 1u : 0u, tot = 0;
         __syncthreads();
         if (last) {
             int cnt = 0;
-            for (int k = tid; k < (int)gridDim.x; k += BEAM_NT) cnt += ((volatile unsigned char *)done)[k] ? 1 : 0;
-            __shared__ int tot;
-            if (tid == 0) tot = 0;
-            __syncthreads();
+            for (int k = tid; k < B; k += BEAM_NT) cnt += ((volatile unsigned char *)done)[k] ? 1 : 0;
             atomicAdd(&tot, cnt);
             __syncthreads();
             if (tid == 0) {
@@ -1410,19 +1488,41 @@ int ctcps_select_lazy(const float *x_logp, int ldx, const float *blank_lp, const
     return cuda_rc(cudaGetLastError());
 }
 
+int ctcps_beam_step_workspace_bytes(int B, int W, size_t *out_bytes) {
+    ARG_CHECK(out_bytes != nullptr && B > 0 && W > 0, CTCPS_E_BADARG, "beam_step_workspace_bytes: bad argument");
+    // partial candidate lists + one ticket per utterance + the global ticket (tickets must be zeroed once by the caller)
+    *out_bytes = (size_t)B * BEAM_MAXP * BEAM_MAXK * sizeof(Cand) + ((size_t)B + 1) * sizeof(unsigned int);
+    return 0;
+}
+
 int ctcps_beam_step(const float *joint, float *beam_scores, const int64_t *ids_cur, int64_t *ids_next, int64_t ld_ids, int L, int B,
                     int W, int V, int eos, int pad, float len_norm, float *pool_scores, int64_t *pool_lens, int64_t *pool_seqs,
-                    int64_t ld_pool, unsigned char *done, unsigned int *ticket, int64_t *done_ring, int ring, int64_t step_tag,
-                    void *stream) {
-    ARG_CHECK(joint && beam_scores && ids_cur && ids_next && pool_scores && pool_lens && pool_seqs && done, CTCPS_E_BADARG,
-              "beam_step: null pointer");
+                    int64_t ld_pool, unsigned char *done, void *workspace, size_t workspace_bytes, int64_t *done_ring, int ring,
+                    int64_t step_tag, void *stream) {
+    ARG_CHECK(joint && beam_scores && ids_cur && ids_next && pool_scores && pool_lens && pool_seqs && done && workspace,
+              CTCPS_E_BADARG, "beam_step: null pointer");
     ARG_CHECK(B > 0 && W > 0 && V > 0 && L >= 1 && L < ld_ids && L - 1 <= ld_pool, CTCPS_E_BADARG, "beam_step: bad size");
     ARG_CHECK(2 * W <= BEAM_MAXK && W <= 32, CTCPS_E_TOOBIG, "beam_step: num_beams > 32 is not supported");
     ARG_CHECK((long long)W * V < (1ll << 31) && (long long)W * V >= 2 * W, CTCPS_E_TOOBIG, "beam_step: need 2W <= W*V < 2^31");
-    ARG_CHECK(done_ring == nullptr || (ticket != nullptr && ring > 0), CTCPS_E_BADARG, "beam_step: done_ring without ticket");
-    k_beam_step<<<B, BEAM_NT, 0, (cudaStream_t)stream>>>(joint, beam_scores, ids_cur, ids_next, ld_ids, L, W, V, eos, pad, len_norm,
-                                                        pool_scores, pool_lens, pool_seqs, ld_pool, done, ticket,
-                                                        (long long *)done_ring, ring, step_tag);
+    ARG_CHECK(done_ring == nullptr || ring > 0, CTCPS_E_BADARG, "beam_step: done_ring without ring size");
+    size_t need = 0;
+    ctcps_beam_step_workspace_bytes(B, W, &need);
+    ARG_CHECK(workspace_bytes >= need, CTCPS_E_WORKSPACE, "beam_step: workspace too small");
+    ARG_CHECK((((uintptr_t)workspace) & 15) == 0, CTCPS_E_ALIGN, "beam_step: workspace must be 16-byte aligned");
+    Cand *part = reinterpret_cast<Cand *>(workspace);
+    unsigned int *utt_ticket = reinterpret_cast<unsigned int *>(part + (size_t)B * BEAM_MAXP * BEAM_MAXK);
+    unsigned int *ticket = utt_ticket + B;
+    int P = (148 * 8 + B - 1) / B;  // about 8 CTAs of 128 threads per SM in one wave
+    P = P < 1 ? 1 : (P > BEAM_MAXP ? BEAM_MAXP : P);
+    while (P > 1 && (long long)W * V / P < 4 * 2 * W) --P;  // keep slices much longer than K
+    if (2 * W <= 32)
+        k_beam_step<1><<<B * P, BEAM_NT, 0, (cudaStream_t)stream>>>(joint, beam_scores, ids_cur, ids_next, ld_ids, L, W, V, P, eos, pad,
+                                                                   len_norm, pool_scores, pool_lens, pool_seqs, ld_pool, done, part,
+                                                                   utt_ticket, ticket, (long long *)done_ring, ring, step_tag);
+    else
+        k_beam_step<2><<<B * P, BEAM_NT, 0, (cudaStream_t)stream>>>(joint, beam_scores, ids_cur, ids_next, ld_ids, L, W, V, P, eos, pad,
+                                                                   len_norm, pool_scores, pool_lens, pool_seqs, ld_pool, done, part,
+                                                                   utt_ticket, ticket, (long long *)done_ring, ring, step_tag);
     return cuda_rc(cudaGetLastError());
 }
 

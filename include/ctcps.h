@@ -134,12 +134,14 @@ int ctcps_select_lazy(const float *x_logp, int ldx, const float *blank_lp, const
  *   joint (BW,V) processor output;  beam_scores (B,W) in/out;  ids_cur/ids_next (BW, ld_ids) int64, first L columns
  *   valid (bos first), ids_next gets L+1 columns;  pool_* (B,W[,ld_pool]) finished hypotheses (scores -inf = empty);
  *   done (B) bytes.  If done_ring (host-visible, e.g. pinned memory) is given, the last CTA stores
- *   (step_tag << 32 | number of done utterances) into done_ring[step_tag % ring]; ticket is a zeroed device counter.
+ *   (step_tag << 32 | number of done utterances) into done_ring[step_tag % ring].  workspace: ctcps_beam_step_workspace_bytes
+ *   bytes, 16-byte aligned, ZEROED once before the first step (it holds arrival tickets that the kernel resets itself).
  */
+int ctcps_beam_step_workspace_bytes(int B, int W, size_t *out_bytes);
 int ctcps_beam_step(const float *joint, float *beam_scores, const int64_t *ids_cur, int64_t *ids_next, int64_t ld_ids, int L,
                     int B, int W, int V, int eos, int pad, float len_norm, float *pool_scores, int64_t *pool_lens,
-                    int64_t *pool_seqs, int64_t ld_pool, unsigned char *done, unsigned int *ticket, int64_t *done_ring,
-                    int ring, int64_t step_tag, void *stream);
+                    int64_t *pool_seqs, int64_t ld_pool, unsigned char *done, void *workspace, size_t workspace_bytes,
+                    int64_t *done_ring, int ring, int64_t step_tag, void *stream);
 
 /*
  * Optional eos/space trick of the processor (ctc_scorer.py:333-349), in place on `next`:
