@@ -79,6 +79,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -247,6 +250,84 @@ __global__ void __launch_bounds__(128) k_prep(const float *__restrict__ r_prev, 
 // ------------------------------------------------------------------------------------------
 // K-b main: full-vocabulary forward recursion.
 // ------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------
+// Shared epilogue of the two full-vocabulary scoring kernels: linear-domain sums -> log_psi, token scores, joint
+// scores (:164-176, :325, :332).  One call handles the 4 tokens x HW hyps of a thread; rows are accessed as float4
+// when V % 4 == 0 (always 16-byte aligned then), the attention rows of all hyps are requested before any is used.
+// ------------------------------------------------------------------------------------------
+struct EpiArgs {
+    const float *Gmax;
+    const float *s_prev;
+    long long s_rs, s_cs;
+    float *att;
+    float omw, w;
+    float *log_psi, *token_scores, *joint;  // token_scores may be null (the processor does not need it)
+    int V, blank, ol;
+};
+
+__device__ __forceinline__ void epi_lane(const EpiArgs &e, int h, int v, float S, float gm, float x0, float sp_row, float av,
+                                         float &lp_out, float &ts_out, float &jt_out, float &av_out) {
+    float lp = gm + logf(S);
+    if (!(lp > LZ)) lp = LZ;
+    if (e.ol == 0) lp = lse2_precise(lp, x0);
+    if (v == e.blank) lp = LZ;
+    const float sp = e.s_prev == nullptr ? 0.f : (e.s_cs == 0 ? sp_row : e.s_prev[(long long)h * e.s_rs + (long long)v * e.s_cs]);
+    float ts = lp - sp;
+    if (ts == 0.f) ts = LZ;
+    if (v == e.blank) av = LZ;
+    lp_out = lp;
+    ts_out = ts;
+    av_out = av;
+    jt_out = __fadd_rn(__fmul_rn(e.omw, av), __fmul_rn(e.w, ts));
+}
+
+template <int HW>
+__device__ __forceinline__ void epilogue_tile(const EpiArgs &e, const float (&S)[HW][4], const float (&x0)[4], int h0, int nhyp,
+                                              int v0) {
+    const int V = e.V;
+    if (v0 >= V) return;
+    const bool vec = ((V & 3) == 0);  // then v0 + 3 < V and every row start is 16-byte aligned
+    const bool has_att = e.att != nullptr;
+    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec && has_att) nxt = *reinterpret_cast<const float4 *>(e.att + (size_t)h0 * V + v0);
+#pragma unroll
+    for (int hh = 0; hh < HW; ++hh) {
+        if (hh >= nhyp) break;
+        const int h = h0 + hh;
+        const float gm = e.Gmax[h];
+        const float sp_row = (e.s_prev != nullptr && e.s_cs == 0) ? e.s_prev[(long long)h * e.s_rs] : 0.f;
+        const size_t o = (size_t)h * V + v0;
+        if (vec) {
+            const float4 cur = nxt;
+            if (has_att && hh + 1 < nhyp) nxt = *reinterpret_cast<const float4 *>(e.att + o + V);  // next hyp's row, one ahead
+            const float av_in[4] = {cur.x, cur.y, cur.z, cur.w};
+            float lp[4], ts[4], jt[4], av[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) epi_lane(e, h, v0 + j, S[hh][j], gm, x0[j], sp_row, av_in[j], lp[j], ts[j], jt[j], av[j]);
+            *reinterpret_cast<float4 *>(e.log_psi + o) = make_float4(lp[0], lp[1], lp[2], lp[3]);
+            if (e.token_scores != nullptr) *reinterpret_cast<float4 *>(e.token_scores + o) = make_float4(ts[0], ts[1], ts[2], ts[3]);
+            if (has_att) {
+                *reinterpret_cast<float4 *>(e.joint + o) = make_float4(jt[0], jt[1], jt[2], jt[3]);
+                if (e.blank >= v0 && e.blank < v0 + 4) e.att[(size_t)h * V + e.blank] = LZ;  // scores[:, pad] = logzero in place
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int v = v0 + j;
+                if (v >= V) continue;
+                float lp, ts, jt, av;
+                epi_lane(e, h, v, S[hh][j], gm, x0[j], sp_row, has_att ? e.att[o + j] : 0.f, lp, ts, jt, av);
+                e.log_psi[o + j] = lp;
+                if (e.token_scores != nullptr) e.token_scores[o + j] = ts;
+                if (has_att) {
+                    e.joint[o + j] = jt;
+                    if (v == e.blank) e.att[o + j] = LZ;
+                }
+            }
+        }
+    }
+}
+
 struct ScoreArgs {
     const float4 *aux;
     const float *Gmax;
@@ -399,35 +480,10 @@ __global__ void __launch_bounds__(NT, MINB) k_score_full(const __grid_constant__
     }
 
     // epilogue: log_psi, token scores, joint scores                                 (:164-176, :325, :332)
-#pragma unroll
-    for (int hh = 0; hh < HW; ++hh) {
-        if (hh >= nhyp) break;
-        const int h = h0 + hh;
-        const float gm = a.Gmax[h];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int v = v0 + j;
-            if (v >= V) continue;
-            float lp = gm + logf(psi[hh][j]);
-            if (!(lp > LZ)) lp = LZ;
-            if (a.ol == 0) lp = lse2_precise(lp, x0[j]);
-            if (v == a.blank) lp = LZ;
-            const size_t o = (size_t)h * V + v;
-            a.log_psi[o] = lp;
-            const float sp = a.s_prev != nullptr ? a.s_prev[(long long)h * a.s_rs + (long long)v * a.s_cs] : 0.f;
-            float ts = lp - sp;
-            if (ts == 0.f) ts = LZ;
-            a.token_scores[o] = ts;
-            if (a.att != nullptr) {
-                float av = a.att[o];
-                if (v == a.blank) {
-                    av = LZ;
-                    a.att[o] = LZ;
-                }
-                a.joint[o] = __fadd_rn(__fmul_rn(a.omw, av), __fmul_rn(a.w, ts));
-            }
-        }
-    }
+    EpiArgs e;
+    e.Gmax = a.Gmax, e.s_prev = a.s_prev, e.s_rs = a.s_rs, e.s_cs = a.s_cs, e.att = a.att, e.omw = a.omw, e.w = a.w;
+    e.log_psi = a.log_psi, e.token_scores = a.token_scores, e.joint = a.joint, e.V = V, e.blank = a.blank, e.ol = a.ol;
+    epilogue_tile<HW>(e, psi, x0, h0, nhyp, v0);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -458,6 +514,7 @@ struct PsiSmem {
     alignas(128) float xs[NS][NBOX][TT][BOXC];
     alignas(16) float lin[NS][TT][HWP];
     alignas(8) uint64_t full[NS];
+    alignas(8) uint64_t empty[NS];
 };
 
 // one warp per (padded) hypothesis: lin stream, Gmax and the last-label column sum
@@ -503,30 +560,41 @@ __global__ void __launch_bounds__(128) k_prep_psi(const float *__restrict__ r_pr
     }
 }
 
+// Persistent kernel: grid = #SMs x resident CTAs, CTA i walks tiles i, i+grid, ... (tile = (utterance, 512-token
+// tile, hyp group)).  The chunks of all its tiles form one flat sequence that thread 0 keeps NS-1 stages ahead of the
+// consumers with TMA; stages are handed back through `empty` mbarriers (one arrival per warp), so warps never meet at
+// a CTA-wide barrier inside the stream.  The lin stream is zero outside the summed frame range, which makes the inner
+// loop branch-free: 8 frames x (1 LDS.128 of x, 4 ex2, HWP/4 LDS.128 of lin, 4*HW FFMA).
 template <int HW, int HWP, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ CUtensorMap tmx, const PsiArgs a) {
     using Smem = PsiSmem<HWP, NT>;
     constexpr int VTILE = Smem::VTILE;
     constexpr int NBOX = Smem::NBOX;
+    constexpr int NWARP = NT / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
     const int tid = threadIdx.x;
-    int idx = blockIdx.x;
-    const int g = idx % a.G;
-    idx /= a.G;
-    const int vt = idx % a.nvt;
-    const int b = idx / a.nvt;
     const int T = a.T, V = a.V, W = a.W;
     const int start = a.ol > 1 ? a.ol : 1;
-    const int v0 = vt * VTILE + tid * 4;
-    const int h0 = b * W + g * HW;
-    const int nhyp = min(HW, W - g * HW);
     const int c0 = (a.ol == 0 ? 0 : start) / TT;
     const int cN = (T - 1) / TT;
+    const int nchunk = cN - c0 + 1;
+    const int ntiles = a.B * a.nvt * a.G;
+    const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int nitems = my_tiles * nchunk;
     constexpr uint32_t STAGE_BYTES = TT * VTILE * 4 + TT * HWP * 4;
 
-    auto issue = [&](int c) {
-        const int s = (c - c0) % NS;
+    auto decode_tile = [&](int tile, int &b, int &vt, int &g) {
+        g = tile % a.G;
+        tile /= a.G;
+        vt = tile % a.nvt;
+        b = tile / a.nvt;
+    };
+    auto issue = [&](int k) {  // item k = (k / nchunk)-th tile of this CTA, chunk c0 + k % nchunk
+        int b, vt, g;
+        decode_tile((int)blockIdx.x + (k / nchunk) * (int)gridDim.x, b, vt, g);
+        const int c = c0 + k % nchunk;
+        const int s = k % NS;
         mbar_expect_tx(&sm.full[s], STAGE_BYTES);
 #pragma unroll
         for (int bx = 0; bx < NBOX; ++bx) tma_load_2d(&sm.xs[s][bx][0][0], &tmx, vt * VTILE + bx * BOXC, b * T + c * TT, &sm.full[s]);
@@ -534,79 +602,74 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
     };
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NS; ++s) mbar_init(&sm.full[s], 1);
+        for (int s = 0; s < NS; ++s) mbar_init(&sm.full[s], 1), mbar_init(&sm.empty[s], NWARP);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int c = c0; c <= cN && c < c0 + NS; ++c) issue(c);
+        for (int k = 0; k < nitems && k < NS; ++k) issue(k);
     }
-    float acc[HW][4], x0[4];
-#pragma unroll
-    for (int hh = 0; hh < HW; ++hh)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[hh][j] = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) x0[j] = LZ;
     __syncthreads();
 
-    for (int c = c0; c <= cN; ++c) {
-        const int s = (c - c0) % NS;
-        mbar_wait(&sm.full[s], (uint32_t)(((c - c0) / NS) & 1));
-        const int bx = (tid * 4) / BOXC, col = (tid * 4) % BOXC;
-        const int tmax = min(TT, T - c * TT);
-        for (int tt = 0; tt < tmax; ++tt) {
-            const int t = c * TT + tt;
-            const float4 xv4 = *reinterpret_cast<const float4 *>(&sm.xs[s][bx][tt][col]);
-            if (t < start) {
-                if (t == 0 && a.ol == 0) x0[0] = xv4.x, x0[1] = xv4.y, x0[2] = xv4.z, x0[3] = xv4.w;
-                continue;
-            }
-            const float p[4] = {ex2_approx(xv4.x * LOG2E), ex2_approx(xv4.y * LOG2E), ex2_approx(xv4.z * LOG2E),
-                                ex2_approx(xv4.w * LOG2E)};
-            float l[HWP];
+    const int bx = (tid * 4) / BOXC, col = (tid * 4) % BOXC;
+    int k = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+        int b, vt, g;
+        decode_tile((int)blockIdx.x + ti * (int)gridDim.x, b, vt, g);
+        float acc[HW][4], x0[4];
 #pragma unroll
-            for (int q = 0; q < HWP / 4; ++q) {
-                const float4 l4 = *reinterpret_cast<const float4 *>(&sm.lin[s][tt][q * 4]);
-                l[q * 4 + 0] = l4.x, l[q * 4 + 1] = l4.y, l[q * 4 + 2] = l4.z, l[q * 4 + 3] = l4.w;
-            }
+        for (int hh = 0; hh < HW; ++hh)
 #pragma unroll
-            for (int hh = 0; hh < HW; ++hh)
+            for (int j = 0; j < 4; ++j) acc[hh][j] = 0.f;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[hh][j] = fmaf(l[hh], p[j], acc[hh][j]);
-        }
-        __syncthreads();
-        if (tid == 0 && c + NS <= cN) issue(c + NS);
-    }
+        for (int j = 0; j < 4; ++j) x0[j] = LZ;
 
+        for (int ci = 0; ci < nchunk; ++ci, ++k) {
+            const int s = k % NS;
+            mbar_wait(&sm.full[s], (uint32_t)((k / NS) & 1));
+            if (a.ol == 0 && ci == 0) {  // r[0,0] = x_[0,0] enters log_psi as its own term (:158,165)
+                const float4 xv4 = *reinterpret_cast<const float4 *>(&sm.xs[s][bx][0][col]);
+                x0[0] = xv4.x, x0[1] = xv4.y, x0[2] = xv4.z, x0[3] = xv4.w;
+            }
 #pragma unroll
-    for (int hh = 0; hh < HW; ++hh) {
-        if (hh >= nhyp) break;
-        const int h = h0 + hh;
-        const float gm = a.Gmax[h];
-        const long long ch = a.last_ids[h];
+            for (int tt = 0; tt < TT; ++tt) {
+                const float4 xv4 = *reinterpret_cast<const float4 *>(&sm.xs[s][bx][tt][col]);
+                const float p[4] = {ex2_approx(xv4.x * LOG2E), ex2_approx(xv4.y * LOG2E), ex2_approx(xv4.z * LOG2E),
+                                    ex2_approx(xv4.w * LOG2E)};
+                float l[HWP];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int v = v0 + j;
-            if (v >= V) continue;
-            const float S = (v == ch) ? a.psic[h] : acc[hh][j];
-            float lp = gm + logf(S);
-            if (!(lp > LZ)) lp = LZ;
-            if (a.ol == 0) lp = lse2_precise(lp, x0[j]);
-            if (v == a.blank) lp = LZ;
-            const size_t o = (size_t)h * V + v;
-            a.log_psi[o] = lp;
-            const float sp = a.s_prev != nullptr ? a.s_prev[(long long)h * a.s_rs + (long long)v * a.s_cs] : 0.f;
-            float ts = lp - sp;
-            if (ts == 0.f) ts = LZ;
-            a.token_scores[o] = ts;
-            if (a.att != nullptr) {
-                float av = a.att[o];
-                if (v == a.blank) {
-                    av = LZ;
-                    a.att[o] = LZ;
+                for (int q = 0; q < HWP / 4; ++q) {
+                    const float4 l4 = *reinterpret_cast<const float4 *>(&sm.lin[s][tt][q * 4]);
+                    l[q * 4 + 0] = l4.x, l[q * 4 + 1] = l4.y, l[q * 4 + 2] = l4.z, l[q * 4 + 3] = l4.w;
                 }
-                a.joint[o] = __fadd_rn(__fmul_rn(a.omw, av), __fmul_rn(a.w, ts));
+#pragma unroll
+                for (int hh = 0; hh < HW; ++hh)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[hh][j] = fmaf(l[hh], p[j], acc[hh][j]);
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&sm.empty[s]);
+            if (tid == 0 && k + NS < nitems) {  // refill the stage just released, once every warp is done with it
+                mbar_wait(&sm.empty[s], (uint32_t)((k / NS) & 1));
+                issue(k + NS);
             }
         }
+
+        const int v0 = vt * VTILE + tid * 4;
+        const int h0 = b * W + g * HW;
+        const int nhyp = min(HW, W - g * HW);
+        // the column of each hypothesis' last label sums r_prev_blank instead of r_sum: take it from k_prep_psi
+#pragma unroll
+        for (int hh = 0; hh < HW; ++hh) {
+            if (hh < nhyp) {
+                const int cj = (int)(a.last_ids[h0 + hh] - (long long)v0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (cj == j) acc[hh][j] = a.psic[h0 + hh];
+            }
+        }
+        EpiArgs e;
+        e.Gmax = a.Gmax, e.s_prev = a.s_prev, e.s_rs = a.s_rs, e.s_cs = a.s_cs, e.att = a.att, e.omw = a.omw, e.w = a.w;
+        e.log_psi = a.log_psi, e.token_scores = a.token_scores, e.joint = a.joint, e.V = V, e.blank = a.blank, e.ol = a.ol;
+        epilogue_tile<HW>(e, acc, x0, h0, nhyp, v0);
     }
 }
 
@@ -773,7 +836,7 @@ __global__ void k_finalize(float *log_psi, const float *__restrict__ s_prev, lon
             ts = lp - sp;
             if (ts == 0.f) ts = LZ;
         }
-        token_scores[i] = ts;
+        if (token_scores != nullptr) token_scores[i] = ts;
         if (att != nullptr) {
             float av = att[i];
             if (v == blank) av = LZ, att[i] = LZ;
@@ -1217,8 +1280,19 @@ int launch_psi_full(const CUtensorMap &tm, const PsiArgs &a, cudaStream_t st) {
     auto kern = k_psi_full<HW, HWP, NT, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return (int)e;
-    const long long nblocks = (long long)a.B * a.nvt * a.G;
-    kern<<<(unsigned)nblocks, NT, sizeof(Smem), st>>>(tm, a);
+    const long long ntiles = (long long)a.B * a.nvt * a.G;
+    static int slots = 0;  // resident CTAs on the whole device for this instantiation (same on every B200 of a box)
+    if (slots == 0) {
+        int per_sm = 0, dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, sizeof(Smem));
+        if (e != cudaSuccess) return (int)e;
+        slots = sms * (per_sm < 1 ? 1 : per_sm);
+    }
+    long long grid = slots;
+    if (grid > ntiles) grid = ntiles;
+    kern<<<(unsigned)grid, NT, sizeof(Smem), st>>>(tm, a);
     return cuda_rc(cudaGetLastError());
 }
 
@@ -1301,7 +1375,8 @@ int ctcps_score(const float *x_logp, int ldx, const float *blank_lp, const float
                 float w, float *r, int ldr, float *log_psi, float *token_scores, float *joint, void *workspace,
                 size_t workspace_bytes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    ARG_CHECK(x_logp && blank_lp && r_prev && last_ids && r && log_psi && token_scores, CTCPS_E_BADARG, "score: null pointer");
+    ARG_CHECK(x_logp && blank_lp && r_prev && last_ids && r && log_psi, CTCPS_E_BADARG, "score: null pointer");
+    ARG_CHECK(token_scores != nullptr || (S == 0 && ol <= T), CTCPS_E_BADARG, "score: token_scores may only be omitted on the full-vocabulary path");
     ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0 && S >= 0, CTCPS_E_BADARG, "score: non-positive size");
     ARG_CHECK(blank >= 0 && blank < V, CTCPS_E_BADARG, "score: blank id outside the vocabulary");
     ARG_CHECK(att_scores == nullptr || joint != nullptr, CTCPS_E_BADARG, "score: att_scores given without joint output");
@@ -1410,7 +1485,7 @@ int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const 
                      float *joint, void *workspace, size_t workspace_bytes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     (void)blank_lp;
-    ARG_CHECK(x_logp && r_prev && last_ids && log_psi && token_scores, CTCPS_E_BADARG, "score_lazy: null pointer");
+    ARG_CHECK(x_logp && r_prev && last_ids && log_psi, CTCPS_E_BADARG, "score_lazy: null pointer");
     ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0, CTCPS_E_BADARG, "score_lazy: non-positive size");
     ARG_CHECK(blank >= 0 && blank < V, CTCPS_E_BADARG, "score_lazy: blank id outside the vocabulary");
     ARG_CHECK(att_scores == nullptr || joint != nullptr, CTCPS_E_BADARG, "score_lazy: att_scores given without joint output");

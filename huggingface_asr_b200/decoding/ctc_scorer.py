@@ -179,7 +179,7 @@ class CTCPrefixScoreTH(object):
         ts, new_state, _ = self._score(y, state, scoring_ids, att_w, None, 0.0)
         return ts, new_state
 
-    def _score(self, y, state, scoring_ids, att_w, att_scores, ctc_weight):
+    def _score(self, y, state, scoring_ids, att_w, att_scores, ctc_weight, need_token_scores=True):
         if att_w is not None and self.margin > 0:
             raise NotImplementedError("CTC windowing (att_w with margin > 0, reference :127-132) is dead code in the "
                                       "reference's processor and is not implemented")
@@ -216,9 +216,9 @@ class CTCPrefixScoreTH(object):
                 raise ValueError(f"state r_prev must be {(T, 2, n_bh)}, got {tuple(r_prev.shape)}")
             r_prev = r_prev.contiguous()
         return self._launch_score(r_prev, s_prev, last_ids, ol, W, scoring_ids, att_scores, ctc_weight,
-                                  self.lazy_state and scoring_ids is None)
+                                  self.lazy_state and scoring_ids is None, need_token_scores)
 
-    def _launch_score(self, r_prev, s_prev, last_ids, ol, W, scoring_ids, att_scores, ctc_weight, lazy):
+    def _launch_score(self, r_prev, s_prev, last_ids, ol, W, scoring_ids, att_scores, ctc_weight, lazy, need_token_scores=True):
         L = _lib.lib()
         dev = self.device
         B, T, V = self.batch, self.input_length, self.odim
@@ -245,7 +245,9 @@ class CTCPrefixScoreTH(object):
         ldr = L.ctcps_padded_ld(snum)
         with torch.cuda.device(dev):
             log_psi = torch.empty((n_bh, V), dtype=torch.float32, device=dev)
-            token_scores = torch.empty((n_bh, V), dtype=torch.float32, device=dev)
+            # the processor only needs the joint scores; skipping token_scores saves a (BW,V) write per step
+            skip_ts = not need_token_scores and att_scores is not None and S == 0 and ol <= T
+            token_scores = None if skip_ts else torch.empty((n_bh, V), dtype=torch.float32, device=dev)
             if att_scores is not None:
                 joint = torch.empty((n_bh, V), dtype=torch.float32, device=dev)
             idmap = torch.empty((n_bh, V), dtype=torch.long, device=dev) if S > 0 else None
@@ -410,7 +412,8 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
         if self.ctc_states is not None:
             self.ctc_states = sc.index_select_state(self.ctc_states, input_ids[:, -1].reshape(-1, self.num_beams))  # :326-329
         # scores[:, pad] = logzero (:325), the scorer (:330) and the combine (:332) are one fused launch
-        ctc_scores, self.ctc_states, next_token_scores = sc._score(input_ids, self.ctc_states, None, None, work, self.ctc_weight)
+        ctc_scores, self.ctc_states, next_token_scores = sc._score(input_ids, self.ctc_states, None, None, work, self.ctc_weight,
+                                                                   need_token_scores=self.apply_eos_space_trick or self.debug)
         if work is not scores:
             scores[:, self.pad_token_id] = sc.logzero
         if self.apply_eos_space_trick:
