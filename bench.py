@@ -184,23 +184,44 @@ def run_ours(args):
             return res
 
         # ---- leg 2: end to end through the processor API with HOST buffers ------------------------------
-        def e2e_once():
-            lg = logits_h.to(dev, non_blocking=True)
-            ln = lens_h.to(dev, non_blocking=True)
-            o = decode(lg, ln)
-            if dist is not None:  # final gather of the hypotheses: the only collective of the path
-                seqs = [torch.empty_like(o.sequences) for _ in range(world)]
-                dist.all_gather(seqs, o.sequences)
-            out_seq_h.copy_(o.sequences, non_blocking=True)
-            out_len_h.copy_(o.lengths, non_blocking=True)
-            out_score_h.copy_(o.scores, non_blocking=True)
+        # Every step copies its encoder logits from pinned host memory (H2D) and reads its hypotheses back (D2H) inside
+        # the timed region.  The H2D copy of step i+1 is enqueued on a copy stream while step i decodes (two device
+        # buffers), the way a serving loop prefetches its next batch; nothing is copied outside the region.
+        copy_stream = torch.cuda.Stream(dev)
+        main = torch.cuda.current_stream(dev)
+        bufs = [(torch.empty_like(logits_d), torch.empty_like(lens_d)) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        free = [torch.cuda.Event() for _ in range(2)]
 
-        e2e_once()
+        def prefetch(i):
+            copy_stream.wait_event(free[i % 2])  # the decode that last read this buffer is finished
+            with torch.cuda.stream(copy_stream):
+                bufs[i % 2][0].copy_(logits_h, non_blocking=True)
+                bufs[i % 2][1].copy_(lens_h, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        def e2e_run(n):
+            for ev in free:
+                ev.record(main)
+            prefetch(0)
+            for i in range(n):
+                main.wait_event(ready[i % 2])
+                if i + 1 < n:
+                    prefetch(i + 1)
+                o = decode(*bufs[i % 2])
+                free[i % 2].record(main)
+                if dist is not None:  # final gather of the hypotheses: the only collective of the path
+                    seqs = [torch.empty_like(o.sequences) for _ in range(world)]
+                    dist.all_gather(seqs, o.sequences)
+                out_seq_h.copy_(o.sequences, non_blocking=True)
+                out_len_h.copy_(o.lengths, non_blocking=True)
+                out_score_h.copy_(o.scores, non_blocking=True)
+
+        e2e_run(1)
         sync_all()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        for _ in range(args.steps):
-            e2e_once()
+        e2e_run(args.steps)
         f1.record()
         sync_all()
         res["ms_e2e"] = f0.elapsed_time(f1)
@@ -353,7 +374,7 @@ def main():
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=None, help="override utterances per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--state", default="materialized", choices=["materialized", "lazy"],
+    ap.add_argument("--state", default="lazy", choices=["materialized", "lazy"],
                     help="state mode of the headline keys; the other mode is measured too and reported under its own key")
     ap.add_argument("--single-mode", action="store_true", help="measure only --state")
     ap.add_argument("--harness", default="fused", choices=["fused", "torch"],

@@ -72,6 +72,11 @@ class LazyForwardVariables:
     def __getitem__(self, idx):
         return self.materialize()[idx]
 
+    def __getattr__(self, name):  # anything else a tensor can do (.cpu(), .sum(), ...): do it on the materialised tensor
+        if name.startswith("__"):
+            raise AttributeError(name)
+        return getattr(self.materialize(), name)
+
 
 class CTCPrefixScoreTH(object):
     """Batched CTC prefix scorer (Watanabe et al. Algorithm 2, vectorised over hypotheses), on sm_100a.
@@ -380,16 +385,17 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
         materialize_state: bool | None = None,
     ):
         """Same positional signature as the reference.  materialize_state (keyword-only, not in the reference):
-        True  = write the full state r (T,2,BW,V) every step, exactly the reference's data flow (default);
-        False = lazy state: never write r, recompute the W surviving columns per utterance at the next step --
-                identical scores and selected states, ~20x fewer HBM bytes per step.
-        None  = take it from the environment variable CTCPS_MATERIALIZE_STATE (default "1")."""
+        False = lazy state (default): never write r (T,2,BW,V); the W surviving columns per utterance are recomputed at
+                the next step -- same joint scores (ulp-level), bit-identical selected states, ~20x fewer HBM bytes per
+                step.  `ctc_states[0]` is then a LazyForwardVariables that materialises the tensor on demand.
+        True  = write the full state every step, exactly the reference's data flow.
+        None  = take it from the environment variable CTCPS_MATERIALIZE_STATE (default "0")."""
         super().__init__()
         self.pad_token_id = pad_token_id
         self.ctc_prefix_scorer = CTCPrefixScoreTH.from_logits(encoder_logits, encoder_output_lens, pad_token_id, eos_token_id,
                                                               ctc_margin)
         if materialize_state is None:
-            materialize_state = os.environ.get("CTCPS_MATERIALIZE_STATE", "1") not in ("0", "false", "False", "no")
+            materialize_state = os.environ.get("CTCPS_MATERIALIZE_STATE", "0") not in ("0", "false", "False", "no")
         self.materialize_state = bool(materialize_state)
         self.ctc_prefix_scorer.lazy_state = not self.materialize_state
         self.ctc_weight = ctc_weight

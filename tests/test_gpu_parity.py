@@ -20,7 +20,7 @@ class CudaBackend(parity.Backend):
     def make_processor(self, logits, lens, pad, eos, margin, w, W, space=-1, trick=False, trick_w=1.0):
         from huggingface_asr_b200.decoding.ctc_scorer import CTCRescorerLogitsProcessor
 
-        return CTCRescorerLogitsProcessor(logits, lens, pad, eos, margin, w, W, space, trick, trick_w)
+        return CTCRescorerLogitsProcessor(logits, lens, pad, eos, margin, w, W, space, trick, trick_w, materialize_state=True)
 
 
 class CudaLazyBackend(CudaBackend):
@@ -140,7 +140,7 @@ def test_multi_step_vs_oracle(B, W, T, V, kind, ragged):
     from oracle import oracle as orc
 
     logits, lens, _ = make_encoder_logits(B, T, V, kind, ragged, seed=1234 + W)
-    gpu = CTCRescorerLogitsProcessor(logits.cuda(), lens.cuda(), 3, 1, 0, 0.3, W, -1, False, 1.0)
+    gpu = CTCRescorerLogitsProcessor(logits.cuda(), lens.cuda(), 3, 1, 0, 0.3, W, -1, False, 1.0, materialize_state=True)
     cpu = orc.OracleCTCRescorerLogitsProcessor(logits.clone(), lens.clone(), 3, 1, 0, 0.3, W)
     cpu64 = orc.OracleCTCRescorerLogitsProcessor(logits.double(), lens.clone(), 3, 1, 0, 0.3, W)
     ids = torch.zeros((B * W, 1), dtype=torch.long)
