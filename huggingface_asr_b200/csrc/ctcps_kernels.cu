@@ -71,6 +71,21 @@ __device__ __forceinline__ float lse2_precise(float a, float b) {
     return logf(expf(a - m) + expf(b - m)) + m;
 }
 
+// packed 2 x fp32 (sm_100: FFMA2 issues two FMAs per instruction slot)
+__device__ __forceinline__ unsigned long long pack2(float a, float b) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void unpack2(unsigned long long v, float &a, float &b) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -640,11 +655,10 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
     for (int ti = 0; ti < my_tiles; ++ti) {
         int b, vt, g;
         decode_tile((int)blockIdx.x + ti * (int)gridDim.x, b, vt, g);
-        float acc[HW][4], x0[4];
+        unsigned long long acc2[HW][2];  // (token 0, token 1), (token 2, token 3) packed for FFMA2
+        float x0[4];
 #pragma unroll
-        for (int hh = 0; hh < HW; ++hh)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[hh][j] = 0.f;
+        for (int hh = 0; hh < HW; ++hh) acc2[hh][0] = acc2[hh][1] = 0ull;
 #pragma unroll
         for (int j = 0; j < 4; ++j) x0[j] = LZ;
 
@@ -658,8 +672,8 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
 #pragma unroll
             for (int tt = 0; tt < TT; ++tt) {
                 const float4 xv4 = *reinterpret_cast<const float4 *>(&sm.xs[s][bx][tt][col]);
-                const float p[4] = {ex2_approx(xv4.x * LOG2E), ex2_approx(xv4.y * LOG2E), ex2_approx(xv4.z * LOG2E),
-                                    ex2_approx(xv4.w * LOG2E)};
+                const unsigned long long p01 = pack2(ex2_approx(xv4.x * LOG2E), ex2_approx(xv4.y * LOG2E));
+                const unsigned long long p23 = pack2(ex2_approx(xv4.z * LOG2E), ex2_approx(xv4.w * LOG2E));
                 float l[HWP];
 #pragma unroll
                 for (int q = 0; q < HWP / 4; ++q) {
@@ -667,9 +681,11 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
                     l[q * 4 + 0] = l4.x, l[q * 4 + 1] = l4.y, l[q * 4 + 2] = l4.z, l[q * 4 + 3] = l4.w;
                 }
 #pragma unroll
-                for (int hh = 0; hh < HW; ++hh)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[hh][j] = fmaf(l[hh], p[j], acc[hh][j]);
+                for (int hh = 0; hh < HW; ++hh) {
+                    const unsigned long long ll = pack2(l[hh], l[hh]);
+                    acc2[hh][0] = ffma2(ll, p01, acc2[hh][0]);
+                    acc2[hh][1] = ffma2(ll, p23, acc2[hh][1]);
+                }
             }
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&sm.empty[s]);
@@ -682,6 +698,12 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
         const int v0 = vt * VTILE + tid * 4;
         const int h0 = b * W + g * HW;
         const int nhyp = min(HW, W - g * HW);
+        float acc[HW][4];
+#pragma unroll
+        for (int hh = 0; hh < HW; ++hh) {
+            unpack2(acc2[hh][0], acc[hh][0], acc[hh][1]);
+            unpack2(acc2[hh][1], acc[hh][2], acc[hh][3]);
+        }
         // the column of each hypothesis' last label sums r_prev_blank instead of r_sum: take it from k_prep_psi
 #pragma unroll
         for (int hh = 0; hh < HW; ++hh) {
