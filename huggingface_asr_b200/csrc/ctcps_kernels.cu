@@ -770,33 +770,35 @@ __global__ void __launch_bounds__(64) k_select_lazy_scan(const float *__restrict
     const int start = ol > 1 ? ol : 1;
     const float *xb = blank_lp + (size_t)(j / W) * T;
     float rn = (ol == 0) ? r_new[j] : LZ, rb = LZ;
+    // software pipeline: the loads of batch k+1 are in flight while the serial chain of batch k runs
     constexpr int U = 8;
-    int t = start;
-    for (; t + U <= T; t += U) {
-        float ph[U], xv[U], bl[U];
+    float ph[U], xv[U], bl[U];
+    auto load = [&](int t0, float (&a)[U], float (&c)[U], float (&d)[U]) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            ph[u] = r_new[((size_t)(t + u) * 2 + 0) * BW + j];
-            xv[u] = r_new[((size_t)(t + u) * 2 + 1) * BW + j];
-            bl[u] = xb[t + u];
+            const int t = min(t0 + u, T - 1);
+            a[u] = r_new[((size_t)t * 2 + 0) * BW + j];
+            c[u] = r_new[((size_t)t * 2 + 1) * BW + j];
+            d[u] = xb[t];
         }
+    };
+    load(start, ph, xv, bl);
+    for (int t0 = start; t0 < T; t0 += U) {
+        float ph2[U], xv2[U], bl2[U];
+        if (t0 + U < T) load(t0 + U, ph2, xv2, bl2);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const float nn = lse2_fast(rn, ph[u]) + xv[u];
-            const float nb = lse2_fast(rn, rb) + bl[u];
-            rn = nn;
-            rb = nb;
-            r_new[((size_t)(t + u) * 2 + 0) * BW + j] = rn;
-            r_new[((size_t)(t + u) * 2 + 1) * BW + j] = rb;
+            if (t0 + u < T) {
+                const float nn = lse2_fast(rn, ph[u]) + xv[u];
+                const float nb = lse2_fast(rn, rb) + bl[u];
+                rn = nn;
+                rb = nb;
+                r_new[((size_t)(t0 + u) * 2 + 0) * BW + j] = rn;
+                r_new[((size_t)(t0 + u) * 2 + 1) * BW + j] = rb;
+            }
         }
-    }
-    for (; t < T; ++t) {
-        const float nn = lse2_fast(rn, r_new[((size_t)t * 2 + 0) * BW + j]) + r_new[((size_t)t * 2 + 1) * BW + j];
-        const float nb = lse2_fast(rn, rb) + xb[t];
-        rn = nn;
-        rb = nb;
-        r_new[((size_t)t * 2 + 0) * BW + j] = rn;
-        r_new[((size_t)t * 2 + 1) * BW + j] = rb;
+#pragma unroll
+        for (int u = 0; u < U; ++u) ph[u] = ph2[u], xv[u] = xv2[u], bl[u] = bl2[u];
     }
 }
 
