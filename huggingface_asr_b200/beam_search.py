@@ -159,6 +159,7 @@ def joint_beam_search_fused(processor: Callable, decoder_log_probs: Callable[[to
     ring = torch.full((RING,), -1, dtype=torch.int64).pin_memory()
     ring_np = ring.numpy()
     stream = torch.cuda.current_stream(dev)
+    prefetch = getattr(processor, "prefetch_state", None)
     cur, L, steps = 0, 1, 0
     while True:
         input_ids = ids[cur][:, :L]
@@ -176,6 +177,8 @@ def joint_beam_search_fused(processor: Callable, decoder_log_probs: Callable[[to
         steps += 1
         if L >= max_length:
             break
+        if prefetch is not None:  # state selection of the next step overlaps the decoder's forward pass
+            prefetch(ids[cur][:, :L])
         look = steps - 1 - done_check_lag
         if look >= 0:
             if done_check_lag == 0:

@@ -155,11 +155,16 @@ __device__ __forceinline__ float block_sum(float v, float *red) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K-a: log-softmax + length padding + blank column.  One CTA per (b, t) row.
+// K-a: log-softmax + length padding + blank column.  One CTA per (b, t) row.  The row is read ONCE into registers
+// (float4 when the row is 16-byte aligned; up to K_INIT_MAXV columns), reduced, and written once: 8*V bytes per row.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_init(const float *__restrict__ in, int ld_in, const int64_t *__restrict__ lens,
-                                              int T, int V, int blank, int apply, float *out, int ldx,
-                                              float *__restrict__ blank_lp) {
+constexpr int K_INIT_NT = 256;
+constexpr int K_INIT_R4 = 8;                                // float4 per thread held in registers
+constexpr int K_INIT_MAXV = K_INIT_NT * K_INIT_R4 * 4;      // 8192 columns; wider rows take the 3-pass path
+
+__global__ void __launch_bounds__(K_INIT_NT) k_init(const float *__restrict__ in, int ld_in, const int64_t *__restrict__ lens,
+                                                    int T, int V, int blank, int apply, float *out, int ldx,
+                                                    float *__restrict__ blank_lp) {
     __shared__ float red[32];
     const int row = blockIdx.x;
     const int b = row / T, t = row - b * T;
@@ -175,25 +180,59 @@ __global__ void __launch_bounds__(256) k_init(const float *__restrict__ in, int 
             return;
         }
     }
-    if (apply) {
-        float m = -INFINITY;
-        for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, src[v]);
-        m = block_max(m, red);
-        float s = 0.f;
-        for (int v = threadIdx.x; v < V; v += blockDim.x) s += expf(src[v] - m);
-        s = block_sum(s, red);
-        const float ls = logf(s);
-        for (int v = threadIdx.x; v < V; v += blockDim.x) {
-            const float o = (src[v] - m) - ls;
-            dst[v] = o;
-            if (v == blank && blank_lp != nullptr) blank_lp[row] = o;
-        }
-    } else {
+    if (!apply) {
         for (int v = threadIdx.x; v < V; v += blockDim.x) {
             const float o = src[v];
             if (dst != src) dst[v] = o;
             if (v == blank && blank_lp != nullptr) blank_lp[row] = o;
         }
+        return;
+    }
+    const bool vec = V <= K_INIT_MAXV && (V & 3) == 0 && (ld_in & 3) == 0 && (ldx & 3) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (vec) {
+        const int n4 = V >> 2;
+        float4 v4[K_INIT_R4];
+        float m = -INFINITY;
+#pragma unroll
+        for (int q = 0; q < K_INIT_R4; ++q) {
+            const int i = threadIdx.x + q * K_INIT_NT;
+            if (i < n4) {
+                v4[q] = __ldcs(reinterpret_cast<const float4 *>(src) + i);
+                m = fmaxf(m, fmaxf(fmaxf(v4[q].x, v4[q].y), fmaxf(v4[q].z, v4[q].w)));
+            }
+        }
+        m = block_max(m, red);
+        float s = 0.f;
+#pragma unroll
+        for (int q = 0; q < K_INIT_R4; ++q) {
+            const int i = threadIdx.x + q * K_INIT_NT;
+            if (i < n4) s += expf(v4[q].x - m) + expf(v4[q].y - m) + expf(v4[q].z - m) + expf(v4[q].w - m);
+        }
+        s = block_sum(s, red);
+        const float ls = logf(s);
+#pragma unroll
+        for (int q = 0; q < K_INIT_R4; ++q) {
+            const int i = threadIdx.x + q * K_INIT_NT;
+            if (i < n4) {
+                const float4 o = make_float4((v4[q].x - m) - ls, (v4[q].y - m) - ls, (v4[q].z - m) - ls, (v4[q].w - m) - ls);
+                reinterpret_cast<float4 *>(dst)[i] = o;
+                if (blank_lp != nullptr && (blank >> 2) == i) blank_lp[row] = (&o.x)[blank & 3];
+            }
+        }
+        return;
+    }
+    float m = -INFINITY;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) m = fmaxf(m, src[v]);
+    m = block_max(m, red);
+    float s = 0.f;
+    for (int v = threadIdx.x; v < V; v += blockDim.x) s += expf(src[v] - m);
+    s = block_sum(s, red);
+    const float ls = logf(s);
+    for (int v = threadIdx.x; v < V; v += blockDim.x) {
+        const float o = (src[v] - m) - ls;
+        dst[v] = o;
+        if (v == blank && blank_lp != nullptr) blank_lp[row] = o;
     }
 }
 

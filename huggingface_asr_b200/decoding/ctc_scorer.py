@@ -281,7 +281,7 @@ class CTCPrefixScoreTH(object):
                 timing.append((ev0, ev1))
         return token_scores, (r, log_psi, 0, 0, idmap), joint
 
-    def index_select_state(self, state, best_ids):
+    def index_select_state(self, state, best_ids, _out=None):
         """Select CTC states according to best ids (reference :180-207).
 
         best_ids: (B,W) ids in hyp*V + tok space.  Returns (r_new (T,2,BW), s_new (BW,V) [expanded], f_min, f_max).
@@ -296,8 +296,11 @@ class CTCPrefixScoreTH(object):
             T, V = self.input_length, self.odim
             s = s.contiguous()
             with torch.cuda.device(self.device):
-                r_new = torch.empty((T, 2, n_bh), dtype=torch.float32, device=self.device)
-                s_vec = torch.empty((n_bh,), dtype=torch.float32, device=self.device)
+                if _out is not None:  # caller-owned buffers (prefetch_state: no allocation on the side stream)
+                    r_new, s_vec = _out
+                else:
+                    r_new = torch.empty((T, 2, n_bh), dtype=torch.float32, device=self.device)
+                    s_vec = torch.empty((n_bh,), dtype=torch.float32, device=self.device)
                 _lib.check(_lib.lib().ctcps_select_lazy(_ptr(self._x), self._ldx, _ptr(self._blank_lp), _ptr(r.r_prev),
                                                         _ptr(r.last_ids), r.ol, _ptr(s), _ptr(best_ids), self.batch, r.n_hyps, T, V,
                                                         _ptr(r_new), _ptr(s_vec), _stream(self.device)), "ctcps_select_lazy")
@@ -317,8 +320,11 @@ class CTCPrefixScoreTH(object):
             raise ValueError(f"best_ids has {best_ids.numel()} entries for {n_bh} hypotheses")
         s = s.contiguous()
         with torch.cuda.device(self.device):
-            r_new = torch.empty((T, 2, n_bh), dtype=torch.float32, device=self.device)
-            s_vec = torch.empty((n_bh,), dtype=torch.float32, device=self.device)
+            if _out is not None:
+                r_new, s_vec = _out
+            else:
+                r_new = torch.empty((T, 2, n_bh), dtype=torch.float32, device=self.device)
+                s_vec = torch.empty((n_bh,), dtype=torch.float32, device=self.device)
             _lib.check(_lib.lib().ctcps_select(_ptr(r), ldr, _ptr(s), _ptr(best_ids), _ptr(scoring_idmap), self.batch, n_hyps,
                                                T, V, S, _ptr(r_new), _ptr(s_vec), _stream(self.device)), "ctcps_select")
         return r_new, s_vec.view(-1, 1).expand(n_bh, V), f_min, f_max
@@ -400,6 +406,10 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
         self.ctc_prefix_scorer.lazy_state = not self.materialize_state
         self.ctc_weight = ctc_weight
         self.ctc_states = None
+        self._prefetched = None  # (last-token tensor, selected state, event) produced by prefetch_state()
+        self._side_stream = None
+        self._prefetch_bufs = None
+        self._prefetch_turn = 0
         self.num_beams = num_beams
         self.eos_token_id = eos_token_id
         self.apply_eos_space_trick = apply_eos_space_trick
@@ -415,7 +425,14 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
                              "blank_projection column (src/models/encoders/e_branchformer.py:415,456-457) is not supported "
                              "by the reference processor either")
         work = scores if scores.is_contiguous() else scores.contiguous()
-        if self.ctc_states is not None:
+        if self._prefetched is not None:
+            last, selected, done = self._prefetched
+            self._prefetched = None
+            if last.numel() != input_ids.shape[0]:
+                raise RuntimeError("prefetch_state() was called for a different batch than this step")
+            torch.cuda.current_stream(sc.device).wait_event(done)
+            self.ctc_states = selected
+        elif self.ctc_states is not None:
             self.ctc_states = sc.index_select_state(self.ctc_states, input_ids[:, -1].reshape(-1, self.num_beams))  # :326-329
         # scores[:, pad] = logzero (:325), the scorer (:330) and the combine (:332) are one fused launch
         ctc_scores, self.ctc_states, next_token_scores = sc._score(input_ids, self.ctc_states, None, None, work, self.ctc_weight,
@@ -431,6 +448,36 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
         if self.debug:
             self.analyze_predictions(scores, ctc_scores, next_token_scores, input_ids)
         return next_token_scores
+
+    def prefetch_state(self, input_ids: torch.LongTensor) -> None:
+        """Optional hook, not in the reference: start the state selection of the NEXT step (reference :326-329) as soon as
+        its last tokens are known, on a side stream, so that it overlaps the attention decoder's forward pass.  A decode
+        loop that owns its beam search (beam_search.joint_beam_search_fused) calls it right after the beam update; HF's
+        loop never does and then __call__ selects the state itself.  The next __call__ must be for these input_ids."""
+        if self.ctc_states is None or self._prefetched is not None:
+            return
+        sc = self.ctc_prefix_scorer
+        main = torch.cuda.current_stream(sc.device)
+        if self._side_stream is None:
+            self._side_stream = torch.cuda.Stream(sc.device)
+        side = self._side_stream
+        last = input_ids[:, -1].reshape(-1, self.num_beams).contiguous()  # on the main stream, before the hand-over
+        n_bh = int(input_ids.shape[0])
+        if self._prefetch_bufs is None or self._prefetch_bufs[0][0].shape[2] != n_bh:
+            # two sets: the state selected for step n is still being read while the one for step n+1 is written
+            self._prefetch_bufs = [(torch.empty((sc.input_length, 2, n_bh), dtype=torch.float32, device=sc.device),
+                                    torch.empty((n_bh,), dtype=torch.float32, device=sc.device)) for _ in range(2)]
+            self._prefetch_turn = 0
+        out = self._prefetch_bufs[self._prefetch_turn]
+        self._prefetch_turn ^= 1
+        ready = torch.cuda.Event()
+        ready.record(main)
+        side.wait_event(ready)
+        with torch.cuda.stream(side):
+            selected = sc.index_select_state(self.ctc_states, last, _out=out)
+            done = torch.cuda.Event()
+            done.record(side)
+        self._prefetched = (last, selected, done)
 
     @staticmethod
     def analyze_predictions(scores, ctc_scores, next_token_scores, input_ids, k=10, tokenizer=None):
