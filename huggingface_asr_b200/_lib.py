@@ -35,20 +35,38 @@ def _nvcc() -> str:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/ctcps_kernels.cu for sm_100a into the package directory (in-tree)."""
+    import fcntl
+
     deps = [SRC, os.path.join(INCLUDE, "ctcps.h")]
-    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps):
+
+    def fresh():
+        return os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps)
+
+    if not force and fresh():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, SRC, "-o", LIB_PATH]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    env = dict(os.environ)
-    env.pop("CC", None)  # the image exports a gcc wrapper nvcc must not be pointed at
-    env.pop("CXX", None)
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
-    if res.returncode != 0:
-        raise CtcpsError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
-    if verbose:
-        print(res.stderr)
+    # several ranks of one torchrun job may get here together: one builds, the others wait and reuse
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and fresh():
+                return LIB_PATH
+            tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
+            cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, SRC, "-o", tmp]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            env = dict(os.environ)
+            env.pop("CC", None)  # the image exports a gcc wrapper nvcc must not be pointed at
+            env.pop("CXX", None)
+            res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise CtcpsError(f"nvcc failed:\n{res.stdout}\n{res.stderr}")
+            os.replace(tmp, LIB_PATH)  # atomic: a concurrent loader sees the old or the new file, never a partial one
+            if verbose:
+                print(res.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 
