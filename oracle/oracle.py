@@ -193,6 +193,32 @@ class OracleCTCPrefixScore:
         return torch.from_numpy(r_new), s_new, f_min, f_max
 
 
+    def extend_prob(self, x):
+        """ctc_scorer.py:209-229: append frames; frames already seen keep their values; nothing is padded (xlens = [T'])."""
+        torch = self._torch
+        if self._x.shape[1] < x.shape[1]:
+            new = np.ascontiguousarray(x.numpy()).astype(self._x.dtype, copy=True)
+            new[:, : self._x.shape[1]] = self._x
+            self._x = new
+            self.input_length = x.shape[1]
+            self.end_frames = torch.as_tensor([x.shape[1]]) - 1
+
+    def extend_state(self, state):
+        """ctc_scorer.py:231-256: extend the blank-only chain r_prev[t,1] = r_prev[t-1,1] + x[t,blank] to the new length."""
+        torch = self._torch
+        if state is None:
+            return state
+        r_prev, s_prev, f_min, f_max = state
+        rp = r_prev.numpy()
+        T = self.input_length
+        out = np.full((T,) + rp.shape[1:], LOGZERO, dtype=rp.dtype)
+        start = max(rp.shape[0], 1)
+        out[: rp.shape[0]] = rp
+        for t in range(start, T):
+            out[t, 1] = out[t - 1, 1] + self._x[0, t, self.blank]  # single utterance, like the reference (:254)
+        return torch.from_numpy(out), s_prev, f_min, f_max
+
+
 class OracleCTCRescorerLogitsProcessor:
     """Same surface as CTCRescorerLogitsProcessor (ctc_scorer.py:259-354), on the oracle."""
 

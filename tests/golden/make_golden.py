@@ -231,8 +231,25 @@ def case_decode():
     save("decode_1best", rec)
 
 
+def case_extend():
+    """Streaming helpers extend_prob / extend_state (ctc_scorer.py:209-256), single utterance as in ESPnet's streaming use."""
+    T1, T2, V, W = 12, 20, 24, 1
+    logits, _, _ = make_encoder_logits(1, T2, V, "flat", False, seed=51)
+    x_full = torch.log_softmax(logits, -1)
+    scorer = CTCPrefixScoreTH(x_full[:, :T1].clone(), torch.tensor([T1]), BLANK, EOS, 0)
+    ts, st = scorer([[BOS]], None)
+    tok = 7
+    sel = scorer.index_select_state(st, torch.tensor([[tok]]))
+    scorer.extend_prob(x_full.clone())
+    ext = scorer.extend_state((sel[0].squeeze(2), sel[1], sel[2], sel[3]))
+    ts2, st2 = scorer([[BOS, tok]], (ext[0].unsqueeze(2), ext[1], 0, 0))
+    save("extend", dict(x_full=x_full.numpy(), T1=T1, tok=tok, sel_r=sel[0].numpy(), sel_s=sel[1][:, 0].numpy(),
+                        ext_r=ext[0].numpy(), x_after=scorer.x.numpy(), ts2=ts2.numpy(), r2=st2[0].numpy(), log_psi2=st2[1].numpy()))
+
+
 if __name__ == "__main__":
     case_steps()
     case_partial_and_select()
     case_edges()
     case_decode()
+    case_extend()

@@ -186,6 +186,26 @@ def replay_edges(be: Backend, blank=3, eos=1):
     assert (np.abs(new[~hack] - ref[~hack]) <= ATOL).all()
 
 
+def replay_extend(be: Backend, blank=3, eos=1):
+    """Streaming helpers extend_prob / extend_state (ctc_scorer.py:209-256) on the reference's single-utterance use."""
+    g = load("extend")
+    T1, tok = int(g["T1"]), int(g["tok"])
+    x_full = be.t(g["x_full"])
+    scorer = be.make_scorer(x_full[:, :T1].clone().contiguous(), torch.tensor([T1]), blank, eos, 0)
+    V = x_full.shape[-1]
+    sel_s = be.t(g["sel_s"])
+    scorer.extend_prob(x_full.clone())
+    ext = scorer.extend_state((be.t(g["sel_r"]).squeeze(2), sel_s.view(-1, 1).expand(-1, V), 0, 0))
+    assert_parity(ext[0], g["ext_r"], "extend_state r_prev")
+    assert tuple(ext[0].shape) == tuple(g["ext_r"].shape)
+    if hasattr(scorer, "x") and not callable(getattr(scorer, "x")):
+        assert_parity(scorer.x, g["x_after"], "x after extend_prob", atol=2e-6, rtol=0)
+    ts2, st2 = scorer([[0, tok]], (ext[0].unsqueeze(2), ext[1], 0, 0))
+    assert_parity(ts2, g["ts2"], "token_scores after extend")
+    assert_parity(st2[0], g["r2"], "r after extend")
+    assert_parity(st2[1], g["log_psi2"], "log_psi after extend")
+
+
 def replay_decode(be: Backend, blank=3, eos=1, bos=0):
     from huggingface_asr_b200.beam_search import joint_beam_search
     from huggingface_asr_b200.synthetic import make_attention_scores

@@ -112,6 +112,36 @@ def test_edges_vs_reference_golden():
     parity.replay_edges(BE)
 
 
+def test_extend_prob_and_state_vs_reference_golden():
+    parity.replay_extend(BE)
+    parity.replay_extend(BE_LAZY)
+
+
+def test_processor_input_validation_and_strided_scores():
+    """Wrong vocabulary raises; a non-contiguous `scores` tensor still gets its pad column set in place (:325)."""
+    from huggingface_asr_b200.decoding.ctc_scorer import CTCRescorerLogitsProcessor
+    from huggingface_asr_b200.synthetic import make_attention_scores, make_encoder_logits
+
+    B, W, T, V = 2, 3, 20, 32
+    logits, lens, _ = make_encoder_logits(B, T, V, "flat", True, seed=8)
+    ids = torch.zeros((B * W, 1), dtype=torch.long, device="cuda")
+    att = make_attention_scores(B * W, V, 0, seed=8).cuda()
+    ref = CTCRescorerLogitsProcessor(logits.cuda(), lens.cuda(), 3, 1, 0, 0.3, W, -1, False, 1.0)(ids, att.clone())
+    wide = torch.zeros(B * W, 2 * V, device="cuda")
+    wide[:, ::2] = att
+    strided = wide[:, ::2]
+    assert not strided.is_contiguous()
+    out = CTCRescorerLogitsProcessor(logits.cuda(), lens.cuda(), 3, 1, 0, 0.3, W, -1, False, 1.0)(ids, strided)
+    assert torch.equal(out, ref)
+    assert (strided[:, 3] == -1e10).all() and (wide[:, 6] == -1e10).all()
+    with pytest.raises(ValueError, match="vocabulary"):
+        CTCRescorerLogitsProcessor(logits.cuda(), lens.cuda(), 3, 1, 0, 0.3, W, -1, False, 1.0)(ids, torch.zeros(B * W, V + 1, device="cuda"))
+    with pytest.raises(ValueError, match="multiple of the batch"):
+        CTCRescorerLogitsProcessor(logits.cuda(), lens.cuda(), 3, 1, 0, 0.3, W, -1, False, 1.0)(ids[:5], att[:5].clone())
+    with pytest.raises(ValueError, match="float32"):
+        CTCRescorerLogitsProcessor(logits.cuda().half(), lens.cuda(), 3, 1, 0, 0.3, W, -1, False, 1.0)
+
+
 def test_decode_1best_vs_reference_golden():
     parity.replay_decode(BE)
 

@@ -41,6 +41,10 @@ def test_oracle_edges():
     parity.replay_edges(BE)
 
 
+def test_oracle_extend_prob_and_state():
+    parity.replay_extend(BE)
+
+
 def test_oracle_decode_1best():
     parity.replay_decode(BE)
 
