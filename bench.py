@@ -72,7 +72,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
             self.thread.start()
         except Exception:
@@ -158,12 +158,14 @@ def run_ours(args):
                             + (out.steps - 1) * (1 if materialize else 2))
             return out
 
+        # clocks are sampled from the warm-up on (same load as the timed steps), so that short timed regions still
+        # get enough nvidia-smi samples; the sampler stops right after the timed region
+        clocks = ClockSampler(local)
+        clocks.start()
         for _ in range(warm):
             decode(logits_d, lens_d)
         sync_all()
         # ---- leg 1: inputs resident in HBM, device-timed ------------------------------------------------
-        clocks = ClockSampler(local)
-        clocks.start()
         launches[0] = 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         sync_all()
