@@ -152,9 +152,11 @@ def run_ours(args):
                                               done_check_lag=(0 if materialize else 1) if args.done_check_lag is None else args.done_check_lag)
             else:
                 out = joint_beam_search(proc, decoder, B, W, V, BOS, EOS, BLANK, max_length=MAX_LENGTH, device=dev)
-            # our kernels: K-a (1) + initial state (1); per step: prep + scoring kernel (2) [+ fused beam step (1)];
-            # all steps but the first: select (1 gather, or 2 for the lazy stage + scan)
-            launches[0] += (2 + out.steps * (2 + (1 if args.harness == "fused" else 0))
+            # our kernels: K-a (1) + initial state (1); per step: scoring kernel (1) [+ fused beam step (1)], plus its
+            # preparation kernel (every step when materialised; first step only in lazy mode, where the select scan of
+            # the previous step prepares it); all steps but the first: select (1 gather, or 2 for the lazy stage + scan)
+            beam = 1 if args.harness == "fused" else 0
+            launches[0] += (2 + out.steps * (1 + beam) + (out.steps if materialize else 1)
                             + (out.steps - 1) * (1 if materialize else 2))
             return out
 

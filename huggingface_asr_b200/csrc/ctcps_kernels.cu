@@ -797,18 +797,42 @@ __global__ void __launch_bounds__(256) k_select_lazy_stage(const float *__restri
     }
 }
 
-__global__ void __launch_bounds__(64) k_select_lazy_scan(const float *__restrict__ blank_lp, int ol, const float *__restrict__ log_psi,
+// NEXT: with `lin` given, the thread also produces what k_prep_psi would compute from r_new for the NEXT score call
+// (its hypothesis j, last label = the selected token, prefix length ol + 1): the lin stream, the offset and the
+// last-label column sum.  The offset is s_new[j] = log psi(prefix j) instead of max_t r_sum[t]: psi(h) >= gamma_t(h)
+// for every t (a path whose first t frames collapse to h has h as a prefix) and psi(h) <= T * max_t gamma_t(h), so
+// exp(r_sum - s_new) lies in [~1/T, 1] at its largest -- as good an offset, and known before the scan starts.
+template <bool NEXT>
+__global__ void __launch_bounds__(64) k_select_lazy_scan(const float *__restrict__ x, int ldx, const float *__restrict__ blank_lp, int ol,
+                                                         const float *__restrict__ log_psi,
                                                          const int64_t *__restrict__ best_ids, int B, int W, int T, int V,
-                                                         float *r_new, float *__restrict__ s_new) {
+                                                         float *r_new, float *__restrict__ s_new, float *__restrict__ lin,
+                                                         float *__restrict__ Gmax, float *__restrict__ psic, int HW, int HWP, int G,
+                                                         int Tpad) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int BW = B * W;
     if (j >= BW) return;
     long long flat, hs, tok;
     lazy_source(best_ids, j, W, V, &flat, &hs, &tok);
-    s_new[j] = log_psi[flat];  // :193
+    const float sj = log_psi[flat];
+    s_new[j] = sj;  // :193
     const int start = ol > 1 ? ol : 1;
     const float *xb = blank_lp + (size_t)(j / W) * T;
     float rn = (ol == 0) ? r_new[j] : LZ, rb = LZ;
+
+    // NEXT: frames f of r_new that the next log_psi sums over are [ol, T-2]; lin entry te = f + 1
+    float *lbase = nullptr;
+    float pc = 0.f, mx = -INFINITY;  // mx: max of r_sum over the summed frames
+    if (NEXT) {
+        const int w = j % W;
+        lbase = lin + ((size_t)((j / W) * G + w / HW) * Tpad) * HWP + (w % HW);
+        for (int te = 0; te <= ol && te < Tpad; ++te) lbase[(size_t)te * HWP] = 0.f;
+        for (int te = T; te < Tpad; ++te) lbase[(size_t)te * HWP] = 0.f;
+        if (ol == 0 && T >= 2) {  // f = 0
+            mx = lse2_precise(rn, LZ);
+            lbase[(size_t)1 * HWP] = expf(fminf(mx - sj, 0.f));
+        }
+    }
     // software pipeline: the loads of batch k+1 are in flight while the serial chain of batch k runs
     constexpr int U = 8;
     float ph[U], xv[U], bl[U];
@@ -827,17 +851,43 @@ __global__ void __launch_bounds__(64) k_select_lazy_scan(const float *__restrict
         if (t0 + U < T) load(t0 + U, ph2, xv2, bl2);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            if (t0 + u < T) {
+            const int t = t0 + u;
+            if (t < T) {
+                if (NEXT && t - 1 >= ol)  // last-label column: r_prev_blank[f = t-1] * p[t, tok]   (f in [ol, T-2])
+                    pc = fmaf(expf(fminf(rb - sj, 0.f)), expf(xv[u]), pc);
                 const float nn = lse2_fast(rn, ph[u]) + xv[u];
                 const float nb = lse2_fast(rn, rb) + bl[u];
                 rn = nn;
                 rb = nb;
-                r_new[((size_t)(t0 + u) * 2 + 0) * BW + j] = rn;
-                r_new[((size_t)(t0 + u) * 2 + 1) * BW + j] = rb;
+                r_new[((size_t)t * 2 + 0) * BW + j] = rn;
+                r_new[((size_t)t * 2 + 1) * BW + j] = rb;
+                if (NEXT && t >= ol && t <= T - 2) {
+                    const float rs = lse2_precise(rn, rb);
+                    mx = fmaxf(mx, rs);
+                    lbase[(size_t)(t + 1) * HWP] = expf(fminf(rs - sj, 0.f));
+                }
             }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) ph[u] = ph2[u], xv[u] = xv2[u], bl[u] = bl2[u];
+    }
+    if (NEXT) {
+        float gm = sj;
+        // s_new is not a usable offset when it is not a prefix probability (finished beam: last label = pad, s_new = logzero)
+        // or when every summed frame lies far below it (label aligned to the very last frames): redo this hypothesis'
+        // stream against max_t r_sum, exactly like k_prep_psi.  Rare, and off the serial chain (plain loads).
+        if (!(sj > -1e9f) || mx < sj - 60.f) {
+            gm = mx > -INFINITY ? mx : 0.f;
+            pc = 0.f;
+            const float *xr = x + (size_t)(j / W) * T * ldx + tok;
+            for (int f = ol; f <= T - 2; ++f) {
+                const float a = r_new[((size_t)f * 2 + 0) * BW + j], c = r_new[((size_t)f * 2 + 1) * BW + j];
+                lbase[(size_t)(f + 1) * HWP] = expf(lse2_precise(a, c) - gm);
+                pc = fmaf(expf(c - gm), expf(xr[(size_t)(f + 1) * ldx]), pc);
+            }
+        }
+        Gmax[j] = gm;
+        psic[j] = pc;
     }
 }
 
@@ -1581,7 +1631,7 @@ int ctcps_score(const float *x_logp, int ldx, const float *blank_lp, const float
 int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const float *s_prev,
                      int64_t s_row_stride, int64_t s_col_stride, const int64_t *last_ids, int ol, int B, int W, int T, int V,
                      int blank, float *att_scores, float one_minus_w, float w, float *log_psi, float *token_scores,
-                     float *joint, void *workspace, size_t workspace_bytes, void *stream) {
+                     float *joint, void *workspace, size_t workspace_bytes, int workspace_prepared, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     (void)blank_lp;
     ARG_CHECK(x_logp && r_prev && last_ids && log_psi, CTCPS_E_BADARG, "score_lazy: null pointer");
@@ -1606,7 +1656,7 @@ int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const 
     float *Gmax = reinterpret_cast<float *>((char *)workspace + ws.g_off);
     float *psic = reinterpret_cast<float *>((char *)workspace + ws.c_off);
     const int Tpad = tpad_of(T);
-    {
+    if (!workspace_prepared) {  // else ctcps_select_lazy already wrote lin / Gmax / psic for this very call
         const int warps = B * G * HWP;
         k_prep_psi<<<(warps + 3) / 4, 128, 0, st>>>(r_prev, x_logp, ldx, last_ids, B, W, T, V, HW, HWP, G, start, Tpad, lin, Gmax, psic);
     }
@@ -1651,14 +1701,28 @@ int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const 
 
 int ctcps_select_lazy(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const int64_t *last_ids, int ol,
                       const float *log_psi, const int64_t *best_ids, int B, int W, int T, int V, float *r_new, float *s_new,
-                      void *stream) {
+                      void *next_workspace, size_t next_workspace_bytes, void *stream) {
     ARG_CHECK(x_logp && blank_lp && r_prev && last_ids && log_psi && best_ids && r_new && s_new, CTCPS_E_BADARG,
               "select_lazy: null pointer");
     ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0 && ldx >= V, CTCPS_E_BADARG, "select_lazy: bad size");
     const int BW = B * W;
     k_select_lazy_stage<<<grid_for((size_t)T * BW, 256), 256, 0, (cudaStream_t)stream>>>(x_logp, ldx, r_prev, last_ids, ol, best_ids, B, W,
                                                                                         T, V, r_new);
-    k_select_lazy_scan<<<(BW + 63) / 64, 64, 0, (cudaStream_t)stream>>>(blank_lp, ol, log_psi, best_ids, B, W, T, V, r_new, s_new);
+    if (next_workspace != nullptr && ol + 1 <= T) {  // also prepare the next ctcps_score_lazy call (it may then pass workspace_prepared = 1)
+        int HW, HWP, G;
+        pick_hw_psi(W, &HW, &HWP, &G);
+        const WorkspaceLazy ws = plan_workspace_lazy(B, T, W);
+        ARG_CHECK(next_workspace_bytes >= ws.total, CTCPS_E_WORKSPACE, "select_lazy: workspace too small");
+        ARG_CHECK((((uintptr_t)next_workspace) & 255) == 0, CTCPS_E_ALIGN, "select_lazy: workspace must be 256-byte aligned");
+        float *lin = reinterpret_cast<float *>((char *)next_workspace + ws.lin_off);
+        float *Gmax = reinterpret_cast<float *>((char *)next_workspace + ws.g_off);
+        float *psic = reinterpret_cast<float *>((char *)next_workspace + ws.c_off);
+        k_select_lazy_scan<true><<<(BW + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x_logp, ldx, blank_lp, ol, log_psi, best_ids, B, W, T, V, r_new, s_new,
+                                                                                  lin, Gmax, psic, HW, HWP, G, tpad_of(T));
+    } else {
+        k_select_lazy_scan<false><<<(BW + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x_logp, ldx, blank_lp, ol, log_psi, best_ids, B, W, T, V, r_new,
+                                                                                   s_new, nullptr, nullptr, nullptr, 1, 4, 1, 0);
+    }
     return cuda_rc(cudaGetLastError());
 }
 

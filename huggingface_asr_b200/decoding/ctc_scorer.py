@@ -78,6 +78,12 @@ class LazyForwardVariables:
         return getattr(self.materialize(), name)
 
 
+class _SelectedState(tuple):
+    """(r_prev, s_prev, f_min, f_max) of index_select_state, plus the generation of the scorer workspace that the lazy
+    select already prepared for the next scoring call (None if it did not)."""
+    prepared_gen = None
+
+
 class CTCPrefixScoreTH(object):
     """Batched CTC prefix scorer (Watanabe et al. Algorithm 2, vectorised over hypotheses), on sm_100a.
 
@@ -137,6 +143,7 @@ class CTCPrefixScoreTH(object):
         self._ldx = ldx
         self._ws = None
         self._ws_key = None
+        self._ws_gen = 0  # bumped by every call that overwrites the workspace
         self._timing = None
         self.lazy_state = False  # True: never materialise r (see LazyForwardVariables)
         self.idx_bh = None
@@ -220,10 +227,12 @@ class CTCPrefixScoreTH(object):
             if tuple(r_prev.shape) != (T, 2, n_bh):
                 raise ValueError(f"state r_prev must be {(T, 2, n_bh)}, got {tuple(r_prev.shape)}")
             r_prev = r_prev.contiguous()
+        prepared = state is not None and getattr(state, "prepared_gen", None) == self._ws_gen and self._ws_key == (B, T, W, S)
         return self._launch_score(r_prev, s_prev, last_ids, ol, W, scoring_ids, att_scores, ctc_weight,
-                                  self.lazy_state and scoring_ids is None, need_token_scores)
+                                  self.lazy_state and scoring_ids is None, need_token_scores, prepared)
 
-    def _launch_score(self, r_prev, s_prev, last_ids, ol, W, scoring_ids, att_scores, ctc_weight, lazy, need_token_scores=True):
+    def _launch_score(self, r_prev, s_prev, last_ids, ol, W, scoring_ids, att_scores, ctc_weight, lazy, need_token_scores=True,
+                      prepared=False):
         L = _lib.lib()
         dev = self.device
         B, T, V = self.batch, self.input_length, self.odim
@@ -257,6 +266,7 @@ class CTCPrefixScoreTH(object):
                 joint = torch.empty((n_bh, V), dtype=torch.float32, device=dev)
             idmap = torch.empty((n_bh, V), dtype=torch.long, device=dev) if S > 0 else None
             ws = self._workspace(W, S)
+            self._ws_gen += 1
             w = float(ctc_weight)
             timing = self._timing
             if timing is not None:  # bench.py: CUDA events around the K-b launches on the launching stream
@@ -267,7 +277,7 @@ class CTCPrefixScoreTH(object):
                 _lib.check(L.ctcps_score_lazy(_ptr(self._x), self._ldx, _ptr(self._blank_lp), _ptr(r_prev), s_ptr, s_rs, s_cs,
                                               _ptr(last_ids), ol, B, W, T, V, self.blank, _ptr(att_scores), 1.0 - w, w,
                                               _ptr(log_psi), _ptr(token_scores), _ptr(joint), _ptr(ws), ws.numel(),
-                                              _stream(dev)), "ctcps_score_lazy")
+                                              int(bool(prepared)), _stream(dev)), "ctcps_score_lazy")
             else:
                 r = torch.empty((T, 2, n_bh, ldr), dtype=torch.float32, device=dev)
                 _lib.check(L.ctcps_score(_ptr(self._x), self._ldx, _ptr(self._blank_lp), _ptr(r_prev), s_ptr, s_rs, s_cs,
@@ -301,10 +311,17 @@ class CTCPrefixScoreTH(object):
                 else:
                     r_new = torch.empty((T, 2, n_bh), dtype=torch.float32, device=self.device)
                     s_vec = torch.empty((n_bh,), dtype=torch.float32, device=self.device)
+                # the scan also prepares the workspace of the scoring call that follows (same W, full vocabulary)
+                ws = self._workspace(r.n_hyps, 0) if self.lazy_state else None
                 _lib.check(_lib.lib().ctcps_select_lazy(_ptr(self._x), self._ldx, _ptr(self._blank_lp), _ptr(r.r_prev),
                                                         _ptr(r.last_ids), r.ol, _ptr(s), _ptr(best_ids), self.batch, r.n_hyps, T, V,
-                                                        _ptr(r_new), _ptr(s_vec), _stream(self.device)), "ctcps_select_lazy")
-            return r_new, s_vec.view(-1, 1).expand(n_bh, V), f_min, f_max
+                                                        _ptr(r_new), _ptr(s_vec), _ptr(ws), 0 if ws is None else ws.numel(),
+                                                        _stream(self.device)), "ctcps_select_lazy")
+            out = _SelectedState((r_new, s_vec.view(-1, 1).expand(n_bh, V), f_min, f_max))
+            if ws is not None and r.ol + 1 <= T:
+                self._ws_gen += 1
+                out.prepared_gen = self._ws_gen
+            return out
         _require_cuda_f32(r, "state r", 4)
         T, _, n_bh, snum = (int(v) for v in r.shape)
         V = self.odim

@@ -119,11 +119,15 @@ int ctcps_select(const float *r, int ldr, const float *log_psi, const int64_t *b
 int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const float *s_prev,
                      int64_t s_row_stride, int64_t s_col_stride, const int64_t *last_ids, int ol, int B, int W, int T,
                      int V, int blank, float *att_scores, float one_minus_w, float w, float *log_psi,
-                     float *token_scores, float *joint, void *workspace, size_t workspace_bytes, void *stream);
+                     float *token_scores, float *joint, void *workspace, size_t workspace_bytes, int workspace_prepared,
+                     void *stream);
 
+/* next_workspace (nullable): the workspace of the NEXT ctcps_score_lazy call.  When given, the scan also writes the
+ * per-hypothesis stream that call needs (for r_prev = r_new, s_prev = s_new, last ids = the selected tokens,
+ * ol + 1), and the call may pass workspace_prepared = 1 to skip its own preparation kernel. */
 int ctcps_select_lazy(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const int64_t *last_ids,
                       int ol, const float *log_psi, const int64_t *best_ids, int B, int W, int T, int V, float *r_new,
-                      float *s_new, void *stream);
+                      float *s_new, void *next_workspace, size_t next_workspace_bytes, void *stream);
 
 /*
  * N1 (the step right after the path): one fused beam-search step around the processor output.  Replaces, for one
