@@ -828,10 +828,6 @@ __global__ void __launch_bounds__(64) k_select_lazy_scan(const float *__restrict
         lbase = lin + ((size_t)((j / W) * G + w / HW) * Tpad) * HWP + (w % HW);
         for (int te = 0; te <= ol && te < Tpad; ++te) lbase[(size_t)te * HWP] = 0.f;
         for (int te = T; te < Tpad; ++te) lbase[(size_t)te * HWP] = 0.f;
-        if (ol == 0 && T >= 2) {  // f = 0
-            mx = lse2_precise(rn, LZ);
-            lbase[(size_t)1 * HWP] = expf(fminf(mx - sj, 0.f));
-        }
     }
     // software pipeline: the loads of batch k+1 are in flight while the serial chain of batch k runs
     constexpr int U = 8;
@@ -853,19 +849,18 @@ __global__ void __launch_bounds__(64) k_select_lazy_scan(const float *__restrict
         for (int u = 0; u < U; ++u) {
             const int t = t0 + u;
             if (t < T) {
-                if (NEXT && t - 1 >= ol)  // last-label column: r_prev_blank[f = t-1] * p[t, tok]   (f in [ol, T-2])
-                    pc = fmaf(expf(fminf(rb - sj, 0.f)), expf(xv[u]), pc);
+                const float ls = lse2_fast(rn, rb);  // = r_sum[t-1], a by-product of the blank row
+                if (NEXT && t - 1 >= ol) {           // frame f = t-1 of the next step's sums (f in [ol, T-2]), entry te = t
+                    mx = fmaxf(mx, ls);
+                    lbase[(size_t)t * HWP] = ex2_approx(fminf(ls - sj, 0.f) * LOG2E);
+                    // last-label column: r_prev_blank[f] * p[f+1, tok]
+                    pc = fmaf(ex2_approx(fminf(rb - sj, 0.f) * LOG2E), ex2_approx(xv[u] * LOG2E), pc);
+                }
                 const float nn = lse2_fast(rn, ph[u]) + xv[u];
-                const float nb = lse2_fast(rn, rb) + bl[u];
                 rn = nn;
-                rb = nb;
+                rb = ls + bl[u];
                 r_new[((size_t)t * 2 + 0) * BW + j] = rn;
                 r_new[((size_t)t * 2 + 1) * BW + j] = rb;
-                if (NEXT && t >= ol && t <= T - 2) {
-                    const float rs = lse2_precise(rn, rb);
-                    mx = fmaxf(mx, rs);
-                    lbase[(size_t)(t + 1) * HWP] = expf(fminf(rs - sj, 0.f));
-                }
             }
         }
 #pragma unroll
