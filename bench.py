@@ -250,7 +250,7 @@ def run_ours(args):
 
         def roofline(r, materialized):
             true_bytes = abytes if materialized else lazy_bytes
-            d = {"bound": "hbm", "kernel": "k_score_full (+ k_prep)" if materialized else "k_psi_full (+ k_prep_psi)",
+            d = {"bound": "hbm", "kernel": "k_score_full (+ k_prep)" if materialized else "k_psi_full",
                  "achieved": true_bytes / (r["score_ms"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
                  "traffic": load_traffic("k_score_full" if materialized else "k_psi_full"),
                  "algorithmic_bytes_per_launch": true_bytes, "avg_launch_ms": r["score_ms"], "launches_timed": r["n_score"]}
