@@ -139,13 +139,16 @@ def run_ours(args):
 
     warm = args.warmup if args.profile else max(args.warmup, 3)
 
-    def measure(materialize):
+    last_sequences = {}
+
+    def measure(materialize, pre_beam=0):
         """Both legs for one state mode.  Returns a dict of raw measurements (max over ranks for the times)."""
         launches = [0]
         score_events = []
 
         def decode(lg, ln, timing=None):
-            proc = CTCRescorerLogitsProcessor(lg, ln, BLANK, EOS, 0, cfg.ctc_weight, W, -1, False, 1.0, materialize_state=materialize)
+            proc = CTCRescorerLogitsProcessor(lg, ln, BLANK, EOS, 0, cfg.ctc_weight, W, -1, False, 1.0, materialize_state=materialize,
+                                              pre_beam_size=pre_beam)
             proc.ctc_prefix_scorer._timing = timing
             if args.harness == "fused":
                 out = joint_beam_search_fused(proc, decoder, B, W, V, BOS, EOS, BLANK, max_length=MAX_LENGTH, device=dev,
@@ -156,8 +159,15 @@ def run_ours(args):
             # preparation kernel (every step when materialised; first step only in lazy mode, where the select scan of
             # the previous step prepares it); all steps but the first: select (1 gather, or 2 for the lazy stage + scan)
             beam = 1 if args.harness == "fused" else 0
-            launches[0] += (2 + out.steps * (1 + beam) + (out.steps if materialize else 1)
-                            + (out.steps - 1) * (1 if materialize else 2))
+            if pre_beam:
+                # K-a + transpose + initial state; per step: top-S, candidate scores, [dense scatter when the harness is not
+                # sparse], [beam step]; first step: k_prep_psi; all steps but the first: select stage + scan
+                dense = 0 if (args.harness == "fused" and pre_beam >= 2) else 1
+                launches[0] += 3 + out.steps * (2 + dense + beam) + 1 + (out.steps - 1) * 2
+            else:
+                launches[0] += (2 + out.steps * (1 + beam) + (out.steps if materialize else 1)
+                                + (out.steps - 1) * (1 if materialize else 2))
+            last_sequences[(materialize, pre_beam)] = out.sequences
             return out
 
         # clocks are sampled from the warm-up on (same load as the timed steps), so that short timed regions still
@@ -242,6 +252,11 @@ def run_ours(args):
             emit({"profile_run": True, "state": args.state, "ms_per_step": res["ms"] / args.steps, "avg_score_ms": res["score_ms"]})
         return
     other = None if args.single_mode else measure(not main_mode)
+    pre = measure(False, args.pre_beam) if (args.pre_beam > 0 and not args.single_mode) else None
+    agreement = None
+    if pre is not None and (False, 0) in last_sequences:
+        same = (last_sequences[(False, 0)] == last_sequences[(False, args.pre_beam)]).all(dim=1).float().mean()
+        agreement = float(same)
 
     if rank == 0:
         peak, peak_src = peak_hbm()
@@ -286,6 +301,21 @@ def run_ours(args):
         if other is not None:
             o = summary(other, not main_mode)
             line["lazy_state" if main_mode else "materialized_state"] = o
+        if pre is not None:
+            S = args.pre_beam
+            line["pre_beam"] = {
+                "pre_beam_size": S, "value": world * B * args.steps / (pre["ms"] * 1e-3), "unit": UNIT,
+                "ms_per_step": pre["ms"] / args.steps,
+                "e2e": {"value": world * B * args.steps / (pre["ms_e2e"] * 1e-3), "unit": UNIT,
+                        "h2d_bytes_per_step": logits_h.numel() * 4 + lens_h.numel() * 8,
+                        "d2h_bytes_per_step": out_seq_h.numel() * 8 + out_len_h.numel() * 8 + out_score_h.numel() * 4},
+                "gpu_launches": pre["launches"], "decode_steps_per_utterance_batch": pre["decode_steps"],
+                "score_candidates_ms": pre["score_ms"], "clocks": pre["clocks"],
+                "one_best_agreement_with_full_vocabulary": agreement,
+                "note": ("SURVEY 8(f) N2, not the reference's behaviour: only the top-S decoder tokens of every hypothesis are "
+                         "CTC-scored (ESPnet pre-beam, S = 1.5 * beam by default), states selected with hyp*V+tok; sparse fused "
+                         "harness (no (BW,V) tensor); score_candidates_ms = CUDA-event time of ctcps_score_candidates"),
+            }
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(cfg, args)
         emit(line)
@@ -381,6 +411,8 @@ def main():
     ap.add_argument("--state", default="lazy", choices=["materialized", "lazy"],
                     help="state mode of the headline keys; the other mode is measured too and reported under its own key")
     ap.add_argument("--single-mode", action="store_true", help="measure only --state")
+    ap.add_argument("--pre-beam", type=int, default=15,
+                    help="also measure pre-beam decoding with this many candidates per hypothesis (0 = skip); reported under 'pre_beam'")
     ap.add_argument("--harness", default="fused", choices=["fused", "torch"],
                     help="beam update between processor calls: one ctcps_beam_step launch (default) or the torch restatement")
     ap.add_argument("--done-check-lag", type=int, default=None,

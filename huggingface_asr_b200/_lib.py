@@ -2,7 +2,7 @@
 
 There is deliberately no fallback: if the library is missing and cannot be built, or a tensor is
 not on a CUDA device, the callers raise.  Python and torch are plumbing (device memory, streams);
-every kernel on the path lives in csrc/ctcps_kernels.cu.
+every kernel on the path lives in csrc/ (ctcps_kernels.cu + the .cuh files it includes).
 """
 from __future__ import annotations
 
@@ -37,7 +37,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/ctcps_kernels.cu for sm_100a into the package directory (in-tree)."""
     import fcntl
 
-    deps = [SRC, os.path.join(INCLUDE, "ctcps.h")]
+    csrc = os.path.dirname(SRC)
+    deps = [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith((".cu", ".cuh"))] + [os.path.join(INCLUDE, "ctcps.h")]
 
     def fresh():
         return os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(d) for d in deps)
@@ -86,7 +87,15 @@ SIGNATURES = {
     "ctcps_score_lazy": [_p, _i, _p, _p, _p, _i64, _i64, _p, _i, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _sz, _i, _p],
     "ctcps_select_lazy": [_p, _i, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p],
     "ctcps_beam_step_workspace_bytes": [_i, _i, ctypes.POINTER(_sz)],
-    "ctcps_beam_step": [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i64, _p, _p, _sz, _p, _i, _i64, _p],
+    "ctcps_beam_step": [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i64, _p, _p, _sz, _p, _i, _i64, _p, _p],
+    "ctcps_padded_lt": [_i],
+    "ctcps_transpose_vt": [_p, _i, _i, _i, _i, _p, _i, _p],
+    "ctcps_prebeam_topk": [_p, _i, _i, _i, _i, _p, _p, _p],
+    "ctcps_score_candidates": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _f, _f, _p, _p, _p, _p, _sz, _i, _p],
+    "ctcps_candidates_to_dense": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _i, _p, _p, _p, _p],
+    "ctcps_select_lazy_candidates": [_p, _i, _p, _p, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p],
+    "ctcps_beam_step_candidates": [_p, _p, _i, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i64, _p, _p, _sz, _p, _i,
+                                   _i64, _p, _p],
     "ctcps_select": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
     "ctcps_eos_space_trick": [_p, _p, _p, _i, _i, _i, _i, _f, _p],
 }

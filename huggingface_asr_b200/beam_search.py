@@ -69,6 +69,7 @@ def joint_beam_search(processor: Callable, decoder_log_probs: Callable[[torch.Te
     done = torch.zeros(B, dtype=torch.bool, device=dev)
     rank = torch.arange(2 * W, device=dev)
     row_base = (torch.arange(B, device=dev) * W).view(B, 1)
+    set_beam_idx = getattr(processor, "set_beam_idx", None)
     steps = 0
 
     while True:
@@ -113,6 +114,8 @@ def joint_beam_search(processor: Callable, decoder_log_probs: Callable[[torch.Te
         beam_idx = (next_src + row_base).view(-1)
         input_ids = torch.cat([input_ids.index_select(0, beam_idx), next_tok.view(-1, 1)], dim=1)
         beam_scores = next_scores
+        if set_beam_idx is not None:  # what HF hands to the model's _reorder_cache; the reference's processor never sees it
+            set_beam_idx(beam_idx)
 
         if input_ids.shape[1] >= max_length:
             break
@@ -128,7 +131,9 @@ def joint_beam_search_fused(processor: Callable, decoder_log_probs: Callable[[to
                             length_penalty: float = 1.0, device: torch.device | str = "cuda", done_check_lag: int = 0) -> BeamSearchOutput:
     """Same loop as joint_beam_search with the whole beam update of a step in ONE kernel (ctcps_beam_step).
 
-    The processor boundary is unchanged: `processor(input_ids (BW,L), log_probs (BW,V))` is still called once per step.
+    The processor boundary is unchanged: `processor(input_ids (BW,L), log_probs (BW,V))` is still called once per step --
+    except for a processor in pre-beam mode (pre_beam_size > 0, lazy state), whose sparse form `score_candidates` is used:
+    the step then ranks the W*S candidates directly (ctcps_beam_step_candidates) and no (BW,V) tensor is ever written.
     The host never synchronises: the kernel publishes (step, #done utterances) into pinned memory and the loop reads the
     entry of `done_check_lag` steps ago (0 = wait for the current step, the exact semantics of the torch harness;
     k > 0 = let the CPU run k steps ahead of the GPU, at the price of up to k extra steps after everything is done --
@@ -160,25 +165,39 @@ def joint_beam_search_fused(processor: Callable, decoder_log_probs: Callable[[to
     ring_np = ring.numpy()
     stream = torch.cuda.current_stream(dev)
     prefetch = getattr(processor, "prefetch_state", None)
+    wants_best = bool(getattr(processor, "use_beam_idx", False)) and prefetch is not None
+    best_ids = torch.empty((B, W), dtype=torch.long, device=dev) if wants_best else None
+    sparse = (getattr(processor, "pre_beam_size", 0) >= 2 and not getattr(processor, "materialize_state", True)
+              and not getattr(processor, "apply_eos_space_trick", False) and hasattr(processor, "score_candidates"))
     cur, L, steps = 0, 1, 0
     while True:
         input_ids = ids[cur][:, :L]
         log_probs = decoder_log_probs(input_ids, steps)
-        proc = processor(input_ids, log_probs)
-        if not proc.is_contiguous():
-            proc = proc.contiguous()
-        with torch.cuda.device(dev):
-            _lib.check(L_.ctcps_beam_step(proc.data_ptr(), beam_scores.data_ptr(), ids[cur].data_ptr(), ids[1 - cur].data_ptr(),
-                                          max_length, L, B, W, V, eos, pad, float(L) ** length_penalty, pool_scores.data_ptr(),
-                                          pool_lens.data_ptr(), pool_seqs.data_ptr(), max_length, done.data_ptr(), ws.data_ptr(),
-                                          ws.numel() * 8, ring.data_ptr(), RING, steps, stream.cuda_stream), "ctcps_beam_step")
+        common = (beam_scores.data_ptr(), ids[cur].data_ptr(), ids[1 - cur].data_ptr(), max_length, L, B, W, V, eos, pad,
+                  float(L) ** length_penalty, pool_scores.data_ptr(), pool_lens.data_ptr(), pool_seqs.data_ptr(), max_length,
+                  done.data_ptr(), ws.data_ptr(), ws.numel() * 8, ring.data_ptr(), RING, steps,
+                  None if best_ids is None else best_ids.data_ptr(), stream.cuda_stream)
+        if sparse:
+            cand_ids, cand_joint = processor.score_candidates(input_ids, log_probs)
+            with torch.cuda.device(dev):
+                _lib.check(L_.ctcps_beam_step_candidates(cand_joint.data_ptr(), cand_ids.data_ptr(), int(cand_ids.shape[1]), *common),
+                           "ctcps_beam_step_candidates")
+        else:
+            proc = processor(input_ids, log_probs)
+            if not proc.is_contiguous():
+                proc = proc.contiguous()
+            with torch.cuda.device(dev):
+                _lib.check(L_.ctcps_beam_step(proc.data_ptr(), *common), "ctcps_beam_step")
         cur ^= 1
         L += 1
         steps += 1
         if L >= max_length:
             break
         if prefetch is not None:  # state selection of the next step overlaps the decoder's forward pass
-            prefetch(ids[cur][:, :L])
+            if wants_best:
+                prefetch(ids[cur][:, :L], best_ids)
+            else:
+                prefetch(ids[cur][:, :L])
         look = steps - 1 - done_check_lag
         if look >= 0:
             if done_check_lag == 0:

@@ -88,6 +88,14 @@ __device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsign
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// The log-posteriors in either HBM layout: frame-major (B,T,ldx) for the TMA-fed full-vocabulary kernels, or token-major
+// (B,V,ldt) ("vt": a token's time series is contiguous) for the pre-beam kernels that gather a few tokens per hypothesis.
+struct XView {
+    const float *p;
+    long long sb, st, sv;  // element (b,t,v) at p[b*sb + t*st + v*sv]
+    __device__ __forceinline__ float at(int b, int t, long long v) const { return p[(long long)b * sb + (long long)t * st + v * sv]; }
+};
+
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -598,7 +606,7 @@ struct PsiSmem {
 };
 
 // one warp per (padded) hypothesis: lin stream, Gmax and the last-label column sum
-__global__ void __launch_bounds__(128) k_prep_psi(const float *__restrict__ r_prev, const float *__restrict__ x, int ldx,
+__global__ void __launch_bounds__(128) k_prep_psi(const float *__restrict__ r_prev, const XView x,
                                                   const int64_t *__restrict__ last_ids, int B, int W, int T, int V, int HW,
                                                   int HWP, int G, int start, int Tpad, float *__restrict__ lin,
                                                   float *__restrict__ Gmax, float *__restrict__ psic) {
@@ -629,7 +637,7 @@ __global__ void __launch_bounds__(128) k_prep_psi(const float *__restrict__ r_pr
         if (valid && f >= start - 1 && f <= T - 2) {
             const float a = r_prev[((size_t)f * 2 + 0) * BW + h], cb = r_prev[((size_t)f * 2 + 1) * BW + h];
             e = expf(lse2_precise(a, cb) - gm);
-            if (c >= 0) sc += expf(cb - gm) * expf(x[((size_t)b * T + te) * ldx + c]);
+            if (c >= 0) sc += expf(cb - gm) * expf(x.at(b, te, c));
         }
         base[(size_t)te * HWP] = e;
     }
@@ -765,32 +773,56 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
 // Two launches: (a) fully parallel over (t, j): stage phi[t-1] and x[t, tok] into r_new[t, 0:2, j] (gathers,
 // libm-grade logsumexp off the dependent chain); (b) one thread per j walks T in place with coalesced,
 // prefetched reads -- only the two MUFU logaddexp remain on the serial chain.
-__device__ __forceinline__ void lazy_source(const int64_t *__restrict__ best_ids, int j, int W, int V, long long *flat,
-                                            long long *hs, long long *tok) {
+struct LazySel {
+    long long hs;   // source hypothesis (global row) whose column of r is taken
+    long long tok;  // token of that column
+    long long src;  // where s_new comes from: index into log_psi (BW,V) or, with candidates, cand_log_psi (BW,S); -1 = logzero
+};
+// cand_ids (BW,S) non-null = the step was scored on candidates only (ids unique per hypothesis): the lane is
+// scoring_idmap[hyp, tok], a token that was not scored selects lane 0 (:196-202) and its prefix score is logzero (:156).
+__device__ __forceinline__ LazySel lazy_source(const int64_t *__restrict__ best_ids, const int64_t *__restrict__ cand_ids, int S,
+                                               int j, int W, int V) {
     const int b = j / W;
-    *flat = best_ids[j] + (long long)b * W * V;  // :191
-    *hs = *flat / V;
-    *tok = *flat - *hs * V;
+    const long long flat = best_ids[j] + (long long)b * W * V;  // :191
+    LazySel q;
+    q.hs = flat / V;
+    q.tok = flat - q.hs * V;
+    q.src = flat;
+    if (cand_ids != nullptr) {
+        const int64_t *c = cand_ids + q.hs * S;
+        int pos = -1;
+        for (int s = 0; s < S; ++s)
+            if (c[s] == q.tok) pos = s;
+        q.src = pos < 0 ? -1 : q.hs * S + pos;
+        if (pos < 0) q.tok = c[0];
+    }
+    return q;
 }
 
-__global__ void __launch_bounds__(256) k_select_lazy_stage(const float *__restrict__ x, int ldx, const float *__restrict__ r_prev,
+// (a) thread = (output hypothesis j, chunk of LAZY_TC frames): resolves its source column once, then stages
+// phi[t-1] (non-blank plane of r_new) and x[t, tok] (blank plane) for its frames.
+constexpr int LAZY_TC = 8;
+__global__ void __launch_bounds__(128) k_select_lazy_stage(const XView x, const float *__restrict__ r_prev,
                                                            const int64_t *__restrict__ last_ids, int ol,
-                                                           const int64_t *__restrict__ best_ids, int B, int W, int T, int V,
+                                                           const int64_t *__restrict__ best_ids,
+                                                           const int64_t *__restrict__ cand_ids, int S, int B, int W, int T, int V,
                                                            float *__restrict__ r_new) {
     const int BW = B * W;
-    const size_t n = (size_t)T * BW;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= BW) return;
     const int start = ol > 1 ? ol : 1;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const int t = (int)(i / BW), j = (int)(i - (size_t)t * BW);
-        long long flat, hs, tok;
-        lazy_source(best_ids, j, W, V, &flat, &hs, &tok);
+    const LazySel q = lazy_source(best_ids, cand_ids, S, j, W, V);
+    const bool last = last_ids[q.hs] == q.tok;
+    const int b = j / W;
+    const int t0 = blockIdx.y * LAZY_TC, t1 = min(T, t0 + LAZY_TC);
+    for (int t = t0; t < t1; ++t) {
         float a = LZ, c = LZ;
         if (t >= start) {
-            const float p0 = r_prev[((size_t)(t - 1) * 2 + 0) * BW + hs], p1 = r_prev[((size_t)(t - 1) * 2 + 1) * BW + hs];
-            a = (last_ids[hs] == tok) ? p1 : lse2_precise(p0, p1);
-            c = x[((size_t)(j / W) * T + t) * ldx + tok];
+            const float p0 = r_prev[((size_t)(t - 1) * 2 + 0) * BW + q.hs], p1 = r_prev[((size_t)(t - 1) * 2 + 1) * BW + q.hs];
+            a = last ? p1 : lse2_precise(p0, p1);
+            c = x.at(b, t, q.tok);
         } else if (t == 0 && ol == 0) {
-            a = x[((size_t)(j / W) * T) * ldx + tok];  // r[0,0] = x_[0,0] (:112-113); the blank plane stays logzero
+            a = x.at(b, 0, q.tok);  // r[0,0] = x_[0,0] (:112-113); the blank plane stays logzero
         }
         r_new[((size_t)t * 2 + 0) * BW + j] = a;
         r_new[((size_t)t * 2 + 1) * BW + j] = c;
@@ -803,18 +835,18 @@ __global__ void __launch_bounds__(256) k_select_lazy_stage(const float *__restri
 // for every t (a path whose first t frames collapse to h has h as a prefix) and psi(h) <= T * max_t gamma_t(h), so
 // exp(r_sum - s_new) lies in [~1/T, 1] at its largest -- as good an offset, and known before the scan starts.
 template <bool NEXT>
-__global__ void __launch_bounds__(64) k_select_lazy_scan(const float *__restrict__ x, int ldx, const float *__restrict__ blank_lp, int ol,
-                                                         const float *__restrict__ log_psi,
-                                                         const int64_t *__restrict__ best_ids, int B, int W, int T, int V,
+__global__ void __launch_bounds__(64) k_select_lazy_scan(const XView x, const float *__restrict__ blank_lp, int ol,
+                                                         const float *__restrict__ log_psi,  // (BW,V), or (BW,S) with cand_ids
+                                                         const int64_t *__restrict__ best_ids,
+                                                         const int64_t *__restrict__ cand_ids, int S, int B, int W, int T, int V,
                                                          float *r_new, float *__restrict__ s_new, float *__restrict__ lin,
                                                          float *__restrict__ Gmax, float *__restrict__ psic, int HW, int HWP, int G,
                                                          int Tpad) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int BW = B * W;
     if (j >= BW) return;
-    long long flat, hs, tok;
-    lazy_source(best_ids, j, W, V, &flat, &hs, &tok);
-    const float sj = log_psi[flat];
+    const LazySel q = lazy_source(best_ids, cand_ids, S, j, W, V);
+    const float sj = q.src < 0 ? LZ : log_psi[q.src];
     s_new[j] = sj;  // :193
     const int start = ol > 1 ? ol : 1;
     const float *xb = blank_lp + (size_t)(j / W) * T;
@@ -874,11 +906,10 @@ __global__ void __launch_bounds__(64) k_select_lazy_scan(const float *__restrict
         if (!(sj > -1e9f) || mx < sj - 60.f) {
             gm = mx > -INFINITY ? mx : 0.f;
             pc = 0.f;
-            const float *xr = x + (size_t)(j / W) * T * ldx + tok;
             for (int f = ol; f <= T - 2; ++f) {
                 const float a = r_new[((size_t)f * 2 + 0) * BW + j], c = r_new[((size_t)f * 2 + 1) * BW + j];
                 lbase[(size_t)(f + 1) * HWP] = expf(lse2_precise(a, c) - gm);
-                pc = fmaf(expf(c - gm), expf(xr[(size_t)(f + 1) * ldx]), pc);
+                pc = fmaf(expf(c - gm), expf(x.at(j / W, f + 1, q.tok)), pc);
             }
         }
         Gmax[j] = gm;
@@ -1066,6 +1097,34 @@ struct Cand {
 };
 __device__ __forceinline__ bool cand_beats(float s1, int i1, float s2, int i2) { return s1 > s2 || (s1 == s2 && i1 < i2); }
 
+// Sorted top-(32*KL) list of a warp, held in registers: entry q of list j lives in lane q.  Inserts candidate (cs, ci),
+// which the caller has already tested against the current K-th best; all 32 lanes call it together.
+template <int KL>
+__device__ __forceinline__ void warp_list_insert(float (&ls)[KL], int (&li)[KL], float cs, int ci, int lane) {
+    // list 0: entries that stay ahead of the candidate form a prefix
+    const int pos0 = __popc(__ballot_sync(0xffffffffu, cand_beats(ls[0], li[0], cs, ci)));
+    const float fall_s = __shfl_sync(0xffffffffu, ls[0], 31);
+    const int fall_i = __shfl_sync(0xffffffffu, li[0], 31);
+    float up_s = __shfl_up_sync(0xffffffffu, ls[0], 1);
+    int up_i = __shfl_up_sync(0xffffffffu, li[0], 1);
+    if (lane == pos0) ls[0] = cs, li[0] = ci;
+    else if (lane > pos0) ls[0] = up_s, li[0] = up_i;
+    if (KL == 2) {
+        if (pos0 < 32) {  // the entry that fell off list 0 enters list 1 at the front
+            up_s = __shfl_up_sync(0xffffffffu, ls[KL - 1], 1);
+            up_i = __shfl_up_sync(0xffffffffu, li[KL - 1], 1);
+            if (lane == 0) ls[KL - 1] = fall_s, li[KL - 1] = fall_i;
+            else ls[KL - 1] = up_s, li[KL - 1] = up_i;
+        } else {
+            const int pos1 = __popc(__ballot_sync(0xffffffffu, cand_beats(ls[KL - 1], li[KL - 1], cs, ci)));
+            up_s = __shfl_up_sync(0xffffffffu, ls[KL - 1], 1);
+            up_i = __shfl_up_sync(0xffffffffu, li[KL - 1], 1);
+            if (lane == pos1) ls[KL - 1] = cs, li[KL - 1] = ci;
+            else if (lane > pos1) ls[KL - 1] = up_s, li[KL - 1] = up_i;
+        }
+    }
+}
+
 // rank-select: out[rank] = cand for the K best of n candidates in shared memory (all-pairs counting, with a
 // lower bound that skips candidates which cannot be among the K best)
 __device__ __forceinline__ void rank_select(const Cand *cands, int n, int K, float bound, Cand *out) {
@@ -1083,8 +1142,12 @@ __device__ __forceinline__ void rank_select(const Cand *cands, int n, int K, flo
 
 // grid = B * P: CTA (b, p) reduces slice p of the W*V candidates of utterance b to its K best, the last CTA of the
 // utterance to arrive (ticket) merges the P partial lists and does the bookkeeping and the copies.
-template <int KL>
-__global__ void __launch_bounds__(BEAM_NT) k_beam_step(const float *__restrict__ joint, float *beam_scores,
+// SPARSE: the candidates are the S pre-beam tokens of each hypothesis, `joint` is (BW,S) and cand_ids (BW,S) names them;
+// one CTA per utterance (P = 1).  Candidate i of the utterance has the dense index (i / S) * V + cand_ids[i], so ranking,
+// tie-breaking and bookkeeping are those of the dense kernel on a joint tensor that is -inf outside the candidates.
+template <int KL, bool SPARSE>
+__global__ void __launch_bounds__(BEAM_NT) k_beam_step(const float *__restrict__ joint, const int64_t *__restrict__ cand_ids, int S,
+                                                       float *beam_scores, int64_t *__restrict__ best_ids_out,
                                                        const int64_t *__restrict__ ids_cur, int64_t *__restrict__ ids_next,
                                                        long long ld_ids, int L, int W, int V, int P, int eos, int pad,
                                                        float len_norm, float *pool_scores, int64_t *pool_lens,
@@ -1111,7 +1174,35 @@ __global__ void __launch_bounds__(BEAM_NT) k_beam_step(const float *__restrict__
     for (int j = 0; j < KL; ++j) ls[j] = NEG, li[j] = 0x7fffffff;
     float thr = NEG;  // score of entry K-1
     const int thr_lane = (K - 1) & 31, thr_list = (K - 1) >> 5;
-    {
+    if (SPARSE) {
+        // candidates arrive in score order inside a hypothesis, not in index order: compare (score, index) with the K-th
+        int thr_i = 0x7fffffff;
+        const int ns = W * S;
+        const float *cj = joint + (size_t)b * ns;
+        const int64_t *ci64 = cand_ids + (size_t)b * ns;
+        for (int i0 = wid * 32; i0 < ns; i0 += BEAM_NT) {
+            const int i = i0 + lane;
+            float c = NEG;
+            int ci = 0x7fffffff;
+            if (i < ns) {
+                const int w = i / S;
+                c = cj[i] + beam_scores[b * W + w];
+                ci = w * V + (int)ci64[i];
+            }
+            unsigned m = __ballot_sync(0xffffffffu, cand_beats(c, ci, thr, thr_i));
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const float cs = __shfl_sync(0xffffffffu, c, src);
+                const int cs_i = __shfl_sync(0xffffffffu, ci, src);
+                if (cand_beats(cs, cs_i, thr, thr_i)) {
+                    warp_list_insert<KL>(ls, li, cs, cs_i, lane);
+                    thr = __shfl_sync(0xffffffffu, (KL == 2 && thr_list) ? ls[KL - 1] : ls[0], thr_lane);
+                    thr_i = __shfl_sync(0xffffffffu, (KL == 2 && thr_list) ? li[KL - 1] : li[0], thr_lane);
+                }
+            }
+        }
+    } else {
         const int per_cta = (((n + P - 1) / P + 127) / 128) * 128;
         const int per_warp = per_cta / BEAM_NW;  // multiple of 32
         const int s0 = min(n, p * per_cta + wid * per_warp), e0 = min(n, s0 + per_warp);
@@ -1137,29 +1228,7 @@ __global__ void __launch_bounds__(BEAM_NT) k_beam_step(const float *__restrict__
                         m &= m - 1;
                         const float cs = __shfl_sync(0xffffffffu, c, src);
                         if (cs > thr) {  // strict: on ties the earlier (lower index) candidate stays
-                            const int ci = vb0 + u * 32 + src;
-                            // list 0: entries that stay ahead of the candidate form a prefix
-                            const int pos0 = __popc(__ballot_sync(0xffffffffu, cand_beats(ls[0], li[0], cs, ci)));
-                            const float fall_s = __shfl_sync(0xffffffffu, ls[0], 31);
-                            const int fall_i = __shfl_sync(0xffffffffu, li[0], 31);
-                            float up_s = __shfl_up_sync(0xffffffffu, ls[0], 1);
-                            int up_i = __shfl_up_sync(0xffffffffu, li[0], 1);
-                            if (lane == pos0) ls[0] = cs, li[0] = ci;
-                            else if (lane > pos0) ls[0] = up_s, li[0] = up_i;
-                            if (KL == 2) {
-                                if (pos0 < 32) {  // the entry that fell off list 0 enters list 1 at the front
-                                    up_s = __shfl_up_sync(0xffffffffu, ls[KL - 1], 1);
-                                    up_i = __shfl_up_sync(0xffffffffu, li[KL - 1], 1);
-                                    if (lane == 0) ls[KL - 1] = fall_s, li[KL - 1] = fall_i;
-                                    else ls[KL - 1] = up_s, li[KL - 1] = up_i;
-                                } else {
-                                    const int pos1 = __popc(__ballot_sync(0xffffffffu, cand_beats(ls[KL - 1], li[KL - 1], cs, ci)));
-                                    up_s = __shfl_up_sync(0xffffffffu, ls[KL - 1], 1);
-                                    up_i = __shfl_up_sync(0xffffffffu, li[KL - 1], 1);
-                                    if (lane == pos1) ls[KL - 1] = cs, li[KL - 1] = ci;
-                                    else if (lane > pos1) ls[KL - 1] = up_s, li[KL - 1] = up_i;
-                                }
-                            }
+                            warp_list_insert<KL>(ls, li, cs, vb0 + u * 32 + src, lane);
                             thr = __shfl_sync(0xffffffffu, (KL == 2 && thr_list) ? ls[KL - 1] : ls[0], thr_lane);
                         }
                     }
@@ -1255,6 +1324,8 @@ __global__ void __launch_bounds__(BEAM_NT) k_beam_step(const float *__restrict__
         for (int k = 0; k < W; ++k) {
             if (dn_new) ns[k] = 0.f, next_tok_s[k] = pad, next_src_s[k] = 0;
             beam_scores[b * W + k] = ns[k];
+            // what index_select_state wants (ESPnet ids: source hypothesis * V + token, :180-191)
+            if (best_ids_out != nullptr) best_ids_out[b * W + k] = (long long)next_src_s[k] * V + next_tok_s[k];
         }
         done[b] = dn_new ? 1 : 0;
     }
@@ -1295,6 +1366,8 @@ __global__ void __launch_bounds__(BEAM_NT) k_beam_step(const float *__restrict__
         }
     }
 }
+
+#include "ctcps_prebeam.cuh"
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -1457,11 +1530,77 @@ int encode_x_map(CUtensorMap *tm, const float *x_logp, int ldx, int B, int T, in
     return 0;
 }
 
+// index_select_state on a state that was never written (see k_select_lazy_*): shared by the full-vocabulary entry point
+// (frame-major x, s_new from the dense log_psi) and the pre-beam one (token-major x, s_new from the candidate scores).
+int select_lazy_impl(const XView x, const float *blank_lp, const float *r_prev, const int64_t *last_ids, int ol, const float *scores,
+                     const int64_t *cand_ids, int S, const int64_t *best_ids, int B, int W, int T, int V, float *r_new, float *s_new,
+                     void *next_workspace, size_t next_workspace_bytes, cudaStream_t st) {
+    ARG_CHECK(blank_lp && r_prev && last_ids && scores && best_ids && r_new && s_new, CTCPS_E_BADARG, "select_lazy: null pointer");
+    ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0, CTCPS_E_BADARG, "select_lazy: bad size");
+    const int BW = B * W;
+    const dim3 grid((BW + 127) / 128, (T + LAZY_TC - 1) / LAZY_TC);
+    k_select_lazy_stage<<<grid, 128, 0, st>>>(x, r_prev, last_ids, ol, best_ids, cand_ids, S, B, W, T, V, r_new);
+    if (next_workspace != nullptr && ol + 1 <= T) {  // also prepare the next scoring call (it may then pass workspace_prepared = 1)
+        int HW, HWP, G;
+        pick_hw_psi(W, &HW, &HWP, &G);
+        const WorkspaceLazy ws = plan_workspace_lazy(B, T, W);
+        ARG_CHECK(next_workspace_bytes >= ws.total, CTCPS_E_WORKSPACE, "select_lazy: workspace too small");
+        ARG_CHECK((((uintptr_t)next_workspace) & 255) == 0, CTCPS_E_ALIGN, "select_lazy: workspace must be 256-byte aligned");
+        float *lin = reinterpret_cast<float *>((char *)next_workspace + ws.lin_off);
+        float *Gmax = reinterpret_cast<float *>((char *)next_workspace + ws.g_off);
+        float *psic = reinterpret_cast<float *>((char *)next_workspace + ws.c_off);
+        k_select_lazy_scan<true><<<(BW + 63) / 64, 64, 0, st>>>(x, blank_lp, ol, scores, best_ids, cand_ids, S, B, W, T, V, r_new, s_new, lin,
+                                                               Gmax, psic, HW, HWP, G, tpad_of(T));
+    } else {
+        k_select_lazy_scan<false><<<(BW + 63) / 64, 64, 0, st>>>(x, blank_lp, ol, scores, best_ids, cand_ids, S, B, W, T, V, r_new, s_new,
+                                                                nullptr, nullptr, nullptr, 1, 4, 1, 0);
+    }
+    return cuda_rc(cudaGetLastError());
+}
+
+int beam_step_impl(const float *joint, const int64_t *cand_ids, int S, float *beam_scores, const int64_t *ids_cur, int64_t *ids_next,
+                   int64_t ld_ids, int L, int B, int W, int V, int eos, int pad, float len_norm, float *pool_scores, int64_t *pool_lens,
+                   int64_t *pool_seqs, int64_t ld_pool, unsigned char *done, void *workspace, size_t workspace_bytes,
+                   int64_t *done_ring, int ring, int64_t step_tag, int64_t *best_ids_out, cudaStream_t st) {
+    ARG_CHECK(joint && beam_scores && ids_cur && ids_next && pool_scores && pool_lens && pool_seqs && done && workspace,
+              CTCPS_E_BADARG, "beam_step: null pointer");
+    ARG_CHECK(B > 0 && W > 0 && V > 0 && L >= 1 && L < ld_ids && L - 1 <= ld_pool, CTCPS_E_BADARG, "beam_step: bad size");
+    ARG_CHECK(2 * W <= BEAM_MAXK && W <= 32, CTCPS_E_TOOBIG, "beam_step: num_beams > 32 is not supported");
+    ARG_CHECK((long long)W * V < (1ll << 31) && (long long)W * V >= 2 * W, CTCPS_E_TOOBIG, "beam_step: need 2W <= W*V < 2^31");
+    ARG_CHECK(done_ring == nullptr || ring > 0, CTCPS_E_BADARG, "beam_step: done_ring without ring size");
+    size_t need = 0;
+    ctcps_beam_step_workspace_bytes(B, W, &need);
+    ARG_CHECK(workspace_bytes >= need, CTCPS_E_WORKSPACE, "beam_step: workspace too small");
+    ARG_CHECK((((uintptr_t)workspace) & 15) == 0, CTCPS_E_ALIGN, "beam_step: workspace must be 16-byte aligned");
+    Cand *part = reinterpret_cast<Cand *>(workspace);
+    unsigned int *utt_ticket = reinterpret_cast<unsigned int *>(part + (size_t)B * BEAM_MAXP * BEAM_MAXK);
+    unsigned int *ticket = utt_ticket + B;
+    int P = 1;
+    if (cand_ids == nullptr) {
+        P = (148 * 8 + B - 1) / B;  // about 8 CTAs of 128 threads per SM in one wave
+        P = P < 1 ? 1 : (P > BEAM_MAXP ? BEAM_MAXP : P);
+        while (P > 1 && (long long)W * V / P < 4 * 2 * W) --P;  // keep slices much longer than K
+    }
+#define CTCPS_BEAM_LAUNCH(KL, SP)                                                                                                  \
+    k_beam_step<KL, SP><<<B * P, BEAM_NT, 0, st>>>(joint, cand_ids, S, beam_scores, best_ids_out, ids_cur, ids_next, ld_ids, L, W, V, P, \
+                                                   eos, pad, len_norm, pool_scores, pool_lens, pool_seqs, ld_pool, done, part,      \
+                                                   utt_ticket, ticket, (long long *)done_ring, ring, step_tag)
+    if (cand_ids != nullptr) {
+        if (2 * W <= 32) CTCPS_BEAM_LAUNCH(1, true);
+        else CTCPS_BEAM_LAUNCH(2, true);
+    } else {
+        if (2 * W <= 32) CTCPS_BEAM_LAUNCH(1, false);
+        else CTCPS_BEAM_LAUNCH(2, false);
+    }
+#undef CTCPS_BEAM_LAUNCH
+    return cuda_rc(cudaGetLastError());
+}
+
 }  // namespace
 
 extern "C" {
 
-int ctcps_version(void) { return 100; }
+int ctcps_version(void) { return 110; }
 
 const char *ctcps_error_string(int code) {
     if (code == 0) return "ok";
@@ -1653,7 +1792,7 @@ int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const 
     const int Tpad = tpad_of(T);
     if (!workspace_prepared) {  // else ctcps_select_lazy already wrote lin / Gmax / psic for this very call
         const int warps = B * G * HWP;
-        k_prep_psi<<<(warps + 3) / 4, 128, 0, st>>>(r_prev, x_logp, ldx, last_ids, B, W, T, V, HW, HWP, G, start, Tpad, lin, Gmax, psic);
+        k_prep_psi<<<(warps + 3) / 4, 128, 0, st>>>(r_prev, XView{x_logp, (long long)T * ldx, (long long)ldx, 1}, last_ids, B, W, T, V, HW, HWP, G, start, Tpad, lin, Gmax, psic);
     }
     CUtensorMap tm;
     int rc = encode_x_map(&tm, x_logp, ldx, B, T, V);
@@ -1697,28 +1836,11 @@ int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const 
 int ctcps_select_lazy(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const int64_t *last_ids, int ol,
                       const float *log_psi, const int64_t *best_ids, int B, int W, int T, int V, float *r_new, float *s_new,
                       void *next_workspace, size_t next_workspace_bytes, void *stream) {
-    ARG_CHECK(x_logp && blank_lp && r_prev && last_ids && log_psi && best_ids && r_new && s_new, CTCPS_E_BADARG,
-              "select_lazy: null pointer");
-    ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0 && ldx >= V, CTCPS_E_BADARG, "select_lazy: bad size");
-    const int BW = B * W;
-    k_select_lazy_stage<<<grid_for((size_t)T * BW, 256), 256, 0, (cudaStream_t)stream>>>(x_logp, ldx, r_prev, last_ids, ol, best_ids, B, W,
-                                                                                        T, V, r_new);
-    if (next_workspace != nullptr && ol + 1 <= T) {  // also prepare the next ctcps_score_lazy call (it may then pass workspace_prepared = 1)
-        int HW, HWP, G;
-        pick_hw_psi(W, &HW, &HWP, &G);
-        const WorkspaceLazy ws = plan_workspace_lazy(B, T, W);
-        ARG_CHECK(next_workspace_bytes >= ws.total, CTCPS_E_WORKSPACE, "select_lazy: workspace too small");
-        ARG_CHECK((((uintptr_t)next_workspace) & 255) == 0, CTCPS_E_ALIGN, "select_lazy: workspace must be 256-byte aligned");
-        float *lin = reinterpret_cast<float *>((char *)next_workspace + ws.lin_off);
-        float *Gmax = reinterpret_cast<float *>((char *)next_workspace + ws.g_off);
-        float *psic = reinterpret_cast<float *>((char *)next_workspace + ws.c_off);
-        k_select_lazy_scan<true><<<(BW + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x_logp, ldx, blank_lp, ol, log_psi, best_ids, B, W, T, V, r_new, s_new,
-                                                                                  lin, Gmax, psic, HW, HWP, G, tpad_of(T));
-    } else {
-        k_select_lazy_scan<false><<<(BW + 63) / 64, 64, 0, (cudaStream_t)stream>>>(x_logp, ldx, blank_lp, ol, log_psi, best_ids, B, W, T, V, r_new,
-                                                                                   s_new, nullptr, nullptr, nullptr, 1, 4, 1, 0);
-    }
-    return cuda_rc(cudaGetLastError());
+    ARG_CHECK(x_logp && log_psi, CTCPS_E_BADARG, "select_lazy: null pointer");
+    ARG_CHECK(T > 0 && V > 0 && ldx >= V, CTCPS_E_BADARG, "select_lazy: bad size");
+    const XView x = {x_logp, (long long)T * ldx, (long long)ldx, 1};
+    return select_lazy_impl(x, blank_lp, r_prev, last_ids, ol, log_psi, nullptr, 0, best_ids, B, W, T, V, r_new, s_new, next_workspace,
+                            next_workspace_bytes, (cudaStream_t)stream);
 }
 
 int ctcps_beam_step_workspace_bytes(int B, int W, size_t *out_bytes) {
@@ -1731,32 +1853,21 @@ int ctcps_beam_step_workspace_bytes(int B, int W, size_t *out_bytes) {
 int ctcps_beam_step(const float *joint, float *beam_scores, const int64_t *ids_cur, int64_t *ids_next, int64_t ld_ids, int L, int B,
                     int W, int V, int eos, int pad, float len_norm, float *pool_scores, int64_t *pool_lens, int64_t *pool_seqs,
                     int64_t ld_pool, unsigned char *done, void *workspace, size_t workspace_bytes, int64_t *done_ring, int ring,
-                    int64_t step_tag, void *stream) {
-    ARG_CHECK(joint && beam_scores && ids_cur && ids_next && pool_scores && pool_lens && pool_seqs && done && workspace,
-              CTCPS_E_BADARG, "beam_step: null pointer");
-    ARG_CHECK(B > 0 && W > 0 && V > 0 && L >= 1 && L < ld_ids && L - 1 <= ld_pool, CTCPS_E_BADARG, "beam_step: bad size");
-    ARG_CHECK(2 * W <= BEAM_MAXK && W <= 32, CTCPS_E_TOOBIG, "beam_step: num_beams > 32 is not supported");
-    ARG_CHECK((long long)W * V < (1ll << 31) && (long long)W * V >= 2 * W, CTCPS_E_TOOBIG, "beam_step: need 2W <= W*V < 2^31");
-    ARG_CHECK(done_ring == nullptr || ring > 0, CTCPS_E_BADARG, "beam_step: done_ring without ring size");
-    size_t need = 0;
-    ctcps_beam_step_workspace_bytes(B, W, &need);
-    ARG_CHECK(workspace_bytes >= need, CTCPS_E_WORKSPACE, "beam_step: workspace too small");
-    ARG_CHECK((((uintptr_t)workspace) & 15) == 0, CTCPS_E_ALIGN, "beam_step: workspace must be 16-byte aligned");
-    Cand *part = reinterpret_cast<Cand *>(workspace);
-    unsigned int *utt_ticket = reinterpret_cast<unsigned int *>(part + (size_t)B * BEAM_MAXP * BEAM_MAXK);
-    unsigned int *ticket = utt_ticket + B;
-    int P = (148 * 8 + B - 1) / B;  // about 8 CTAs of 128 threads per SM in one wave
-    P = P < 1 ? 1 : (P > BEAM_MAXP ? BEAM_MAXP : P);
-    while (P > 1 && (long long)W * V / P < 4 * 2 * W) --P;  // keep slices much longer than K
-    if (2 * W <= 32)
-        k_beam_step<1><<<B * P, BEAM_NT, 0, (cudaStream_t)stream>>>(joint, beam_scores, ids_cur, ids_next, ld_ids, L, W, V, P, eos, pad,
-                                                                   len_norm, pool_scores, pool_lens, pool_seqs, ld_pool, done, part,
-                                                                   utt_ticket, ticket, (long long *)done_ring, ring, step_tag);
-    else
-        k_beam_step<2><<<B * P, BEAM_NT, 0, (cudaStream_t)stream>>>(joint, beam_scores, ids_cur, ids_next, ld_ids, L, W, V, P, eos, pad,
-                                                                   len_norm, pool_scores, pool_lens, pool_seqs, ld_pool, done, part,
-                                                                   utt_ticket, ticket, (long long *)done_ring, ring, step_tag);
-    return cuda_rc(cudaGetLastError());
+                    int64_t step_tag, int64_t *best_ids_out, void *stream) {
+    return beam_step_impl(joint, nullptr, 0, beam_scores, ids_cur, ids_next, ld_ids, L, B, W, V, eos, pad, len_norm, pool_scores, pool_lens,
+                          pool_seqs, ld_pool, done, workspace, workspace_bytes, done_ring, ring, step_tag, best_ids_out,
+                          (cudaStream_t)stream);
+}
+
+int ctcps_beam_step_candidates(const float *cand_joint, const int64_t *cand_ids, int S, float *beam_scores, const int64_t *ids_cur,
+                               int64_t *ids_next, int64_t ld_ids, int L, int B, int W, int V, int eos, int pad, float len_norm,
+                               float *pool_scores, int64_t *pool_lens, int64_t *pool_seqs, int64_t ld_pool, unsigned char *done,
+                               void *workspace, size_t workspace_bytes, int64_t *done_ring, int ring, int64_t step_tag,
+                               int64_t *best_ids_out, void *stream) {
+    ARG_CHECK(cand_ids != nullptr && S >= 2, CTCPS_E_BADARG, "beam_step_candidates: need candidate ids and S >= 2");
+    return beam_step_impl(cand_joint, cand_ids, S, beam_scores, ids_cur, ids_next, ld_ids, L, B, W, V, eos, pad, len_norm, pool_scores,
+                          pool_lens, pool_seqs, ld_pool, done, workspace, workspace_bytes, done_ring, ring, step_tag, best_ids_out,
+                          (cudaStream_t)stream);
 }
 
 int ctcps_select(const float *r, int ldr, const float *log_psi, const int64_t *best_ids, const int64_t *scoring_idmap, int B,
@@ -1777,6 +1888,104 @@ int ctcps_eos_space_trick(const float *att_scores, const float *ctc_scores, floa
     if (eos < 0 || eos >= V || space < 0 || space >= V) return 0;  // argmax can never equal an id outside the vocabulary
     k_trick<<<BW, 256, 0, (cudaStream_t)stream>>>(att_scores, ctc_scores, next, V, eos, space, k);
     return cuda_rc(cudaGetLastError());
+}
+
+/* ---- pre-beam (candidate) decode step, SURVEY.md 8(f) N2 ------------------------------------------------------ */
+
+int ctcps_padded_lt(int T) { return (T + 7) & ~7; }
+
+int ctcps_transpose_vt(const float *x_logp, int ldx, int B, int T, int V, float *x_vt, int ldt, void *stream) {
+    ARG_CHECK(x_logp && x_vt && B > 0 && T > 0 && V > 0, CTCPS_E_BADARG, "transpose_vt: bad argument");
+    ARG_CHECK(ldx >= V && ldt >= T && (ldt & 3) == 0 && (((uintptr_t)x_vt) & 15) == 0, CTCPS_E_ALIGN,
+              "transpose_vt: ldt must be a multiple of 4 and >= T, x_vt 16-byte aligned");
+    ARG_CHECK(B < 65536 && (ldt + 31) / 32 < 65536, CTCPS_E_TOOBIG, "transpose_vt: B or T too large for one launch");
+    const dim3 grid((V + 31) / 32, (ldt + 31) / 32, B);
+    k_transpose_vt<<<grid, 256, 0, (cudaStream_t)stream>>>(x_logp, ldx, T, V, x_vt, ldt);
+    return cuda_rc(cudaGetLastError());
+}
+
+int ctcps_prebeam_topk(float *att_scores, int BW, int V, int blank, int S, int64_t *scoring_ids, float *cand_att, void *stream) {
+    ARG_CHECK(att_scores && scoring_ids && cand_att && BW > 0 && V > 0, CTCPS_E_BADARG, "prebeam_topk: bad argument");
+    ARG_CHECK(blank >= 0 && blank < V, CTCPS_E_BADARG, "prebeam_topk: blank id outside the vocabulary");
+    ARG_CHECK(S >= 1 && S <= 64 && S <= V, CTCPS_E_TOOBIG, "prebeam_topk: need 1 <= S <= min(64, V)");
+    const int grid = (BW + 3) / 4;
+    if (S <= 32)
+        k_prebeam_topk<1><<<grid, 128, 0, (cudaStream_t)stream>>>(att_scores, BW, V, blank, S, scoring_ids, cand_att);
+    else
+        k_prebeam_topk<2><<<grid, 128, 0, (cudaStream_t)stream>>>(att_scores, BW, V, blank, S, scoring_ids, cand_att);
+    return cuda_rc(cudaGetLastError());
+}
+
+int ctcps_score_candidates(const float *x_vt, int ldt, const float *r_prev, const float *s_prev, const int64_t *last_ids, int ol,
+                           int B, int W, int T, int V, int blank, const int64_t *scoring_ids, int S, const float *cand_att,
+                           float one_minus_w, float w, float *cand_log_psi, float *cand_token_scores, float *cand_joint,
+                           void *workspace, size_t workspace_bytes, int workspace_prepared, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ARG_CHECK(x_vt && r_prev && last_ids && scoring_ids && cand_log_psi, CTCPS_E_BADARG, "score_candidates: null pointer");
+    ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0 && S > 0, CTCPS_E_BADARG, "score_candidates: non-positive size");
+    ARG_CHECK(blank >= 0 && blank < V, CTCPS_E_BADARG, "score_candidates: blank id outside the vocabulary");
+    ARG_CHECK(cand_joint == nullptr || cand_att != nullptr, CTCPS_E_BADARG, "score_candidates: cand_joint needs cand_att");
+    const int Tpad = tpad_of(T);
+    ARG_CHECK(ldt >= T && ldt <= Tpad && (ldt & 3) == 0 && (((uintptr_t)x_vt) & 15) == 0, CTCPS_E_ALIGN,
+              "score_candidates: ldt must be ctcps_padded_lt(T) and x_vt 16-byte aligned");
+    const long long BW = (long long)B * W;
+    ARG_CHECK(BW * (long long)S < (1ll << 31) && (long long)B * V < (1ll << 31), CTCPS_E_TOOBIG, "score_candidates: sizes exceed 2^31");
+    const int start = ol > 1 ? ol : 1;
+    if (start > T) {  // ctc_scorer.py:138-145
+        const size_t n = (size_t)BW * S;
+        k_cand_all_logzero<<<grid_for(n, 256), 256, 0, st>>>(cand_att, one_minus_w, w, n, cand_log_psi, cand_token_scores, cand_joint);
+        return cuda_rc(cudaGetLastError());
+    }
+    int HW, HWP, G;
+    pick_hw_psi(W, &HW, &HWP, &G);
+    const WorkspaceLazy ws = plan_workspace_lazy(B, T, W);
+    ARG_CHECK(workspace != nullptr && workspace_bytes >= ws.total, CTCPS_E_WORKSPACE, "score_candidates: workspace too small");
+    ARG_CHECK((((uintptr_t)workspace) & 255) == 0, CTCPS_E_ALIGN, "score_candidates: workspace must be 256-byte aligned");
+    float *lin = reinterpret_cast<float *>((char *)workspace + ws.lin_off);
+    float *Gmax = reinterpret_cast<float *>((char *)workspace + ws.g_off);
+    float *psic = reinterpret_cast<float *>((char *)workspace + ws.c_off);
+    if (!workspace_prepared) {
+        const int warps = B * G * HWP;
+        k_prep_psi<<<(warps + 3) / 4, 128, 0, st>>>(r_prev, XView{x_vt, (long long)V * ldt, 1, (long long)ldt}, last_ids, B, W, T, V, HW, HWP,
+                                                    G, start, Tpad, lin, Gmax, psic);
+    }
+    CandArgs a;
+    a.xt = x_vt, a.ldt = ldt, a.lin = lin, a.Gmax = Gmax, a.psic = psic, a.s_prev = s_prev, a.last_ids = last_ids, a.ids = scoring_ids;
+    a.cand_att = cand_att, a.omw = one_minus_w, a.w = w, a.cand_log_psi = cand_log_psi, a.cand_ts = cand_token_scores;
+    a.cand_joint = cand_joint, a.B = B, a.W = W, a.T = T, a.V = V, a.S = S, a.blank = blank, a.ol = ol, a.G = G, a.HW = HW, a.HWP = HWP;
+    a.Tpad = Tpad;
+    const size_t smem = (size_t)4 * ldt * sizeof(float);
+    ARG_CHECK(smem <= 200 * 1024, CTCPS_E_TOOBIG, "score_candidates: T too large for the shared-memory stream");
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(k_psi_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const long long items = BW * ((S + 31) / 32);
+    k_psi_cand<<<(unsigned)((items + 3) / 4), 128, smem, st>>>(a);
+    return cuda_rc(cudaGetLastError());
+}
+
+int ctcps_candidates_to_dense(const float *att_scores, const float *s_prev, const int64_t *scoring_ids, const float *cand_log_psi,
+                              const float *cand_token_scores, const float *cand_joint, int BW, int V, int S, float one_minus_w,
+                              float w, int ol, int T, float *log_psi, float *token_scores, float *joint, void *stream) {
+    ARG_CHECK(scoring_ids && cand_log_psi && BW > 0 && V > 0 && S > 0, CTCPS_E_BADARG, "candidates_to_dense: bad argument");
+    ARG_CHECK(joint == nullptr || (att_scores && cand_joint), CTCPS_E_BADARG, "candidates_to_dense: joint needs att_scores and cand_joint");
+    ARG_CHECK(token_scores == nullptr || cand_token_scores, CTCPS_E_BADARG, "candidates_to_dense: token_scores needs cand_token_scores");
+    const int start = ol > 1 ? ol : 1;
+    k_cand_to_dense<<<BW, 256, 0, (cudaStream_t)stream>>>(att_scores, s_prev, scoring_ids, cand_log_psi, cand_token_scores, cand_joint, V,
+                                                         S, one_minus_w, w, start > T ? 1 : 0, log_psi, token_scores, joint);
+    return cuda_rc(cudaGetLastError());
+}
+
+int ctcps_select_lazy_candidates(const float *x_vt, int ldt, const float *blank_lp, const float *r_prev, const int64_t *last_ids,
+                                 int ol, const int64_t *scoring_ids, int S, const float *cand_log_psi, const int64_t *best_ids, int B,
+                                 int W, int T, int V, float *r_new, float *s_new, void *next_workspace,
+                                 size_t next_workspace_bytes, void *stream) {
+    ARG_CHECK(x_vt && scoring_ids && cand_log_psi && S > 0, CTCPS_E_BADARG, "select_lazy_candidates: null pointer");
+    ARG_CHECK(T > 0 && V > 0 && ldt >= T, CTCPS_E_BADARG, "select_lazy_candidates: bad size");
+    const XView x = {x_vt, (long long)V * ldt, 1, (long long)ldt};
+    return select_lazy_impl(x, blank_lp, r_prev, last_ids, ol, cand_log_psi, scoring_ids, S, best_ids, B, W, T, V, r_new, s_new,
+                            next_workspace, next_workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

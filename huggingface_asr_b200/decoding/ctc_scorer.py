@@ -54,9 +54,11 @@ class LazyForwardVariables:
     `ctc_states[0]` still finds the reference's tensor.
     """
 
-    def __init__(self, scorer, r_prev, last_ids, ol, n_hyps):
+    def __init__(self, scorer, r_prev, last_ids, ol, n_hyps, scoring_ids=None):
         self.scorer, self.r_prev, self.last_ids, self.ol, self.n_hyps = scorer, r_prev, last_ids, ol, n_hyps
-        self.shape = (scorer.input_length, 2, scorer.batch * n_hyps, scorer.odim)
+        self.scoring_ids = scoring_ids  # (BW,S) when the step was scored on candidates only
+        snum = scorer.odim if scoring_ids is None else int(scoring_ids.shape[1])
+        self.shape = (scorer.input_length, 2, scorer.batch * n_hyps, snum)
         self.dtype, self.device = torch.float32, scorer.device
 
     def size(self, dim=None):
@@ -66,7 +68,8 @@ class LazyForwardVariables:
         return 4
 
     def materialize(self):
-        _, state, _ = self.scorer._launch_score(self.r_prev, None, self.last_ids, self.ol, self.n_hyps, None, None, 0.0, False)
+        _, state, _ = self.scorer._launch_score(self.r_prev, None, self.last_ids, self.ol, self.n_hyps, self.scoring_ids, None, 0.0,
+                                                False)
         return state[0]
 
     def __getitem__(self, idx):
@@ -82,6 +85,38 @@ class _SelectedState(tuple):
     """(r_prev, s_prev, f_min, f_max) of index_select_state, plus the generation of the scorer workspace that the lazy
     select already prepared for the next scoring call (None if it did not)."""
     prepared_gen = None
+
+
+class CandidateState:
+    """State of a step that was scored on `scoring_ids` candidates in lazy mode (pre-beam decoding).  Holds only what the
+    next index_select_state needs -- the inputs of the step, the candidate ids and their prefix scores -- and behaves like
+    the reference's 5-tuple (r (T,2,BW,S), log_psi (BW,V), 0, 0, scoring_idmap (BW,V)) when indexed: those tensors are built
+    on demand (inspection only; the decode path never touches them)."""
+
+    def __init__(self, scorer, r_prev, last_ids, ol, n_hyps, scoring_ids, cand_log_psi):
+        self.r = LazyForwardVariables(scorer, r_prev, last_ids, ol, n_hyps, scoring_ids)
+        self.scoring_ids, self.cand_log_psi = scoring_ids, cand_log_psi
+
+    def __len__(self):
+        return 5
+
+    def __iter__(self):
+        return (self[i] for i in range(5))
+
+    def __getitem__(self, i):
+        if i == 0:
+            return self.r
+        if i in (2, 3):
+            return 0
+        n_bh, V = self.scoring_ids.shape[0], self.r.scorer.odim
+        if i == 1:  # log_psi: logzero outside the candidates (:156, :161-162)
+            return torch.full((n_bh, V), LOGZERO, dtype=torch.float32, device=self.cand_log_psi.device).scatter_(
+                1, self.scoring_ids, self.cand_log_psi)
+        if i == 4:  # scoring_idmap (:91-95)
+            S = self.scoring_ids.shape[1]
+            return torch.full((n_bh, V), -1, dtype=torch.long, device=self.scoring_ids.device).scatter_(
+                1, self.scoring_ids, torch.arange(S, device=self.scoring_ids.device).expand(n_bh, S))
+        raise IndexError(i)
 
 
 class CTCPrefixScoreTH(object):
@@ -102,15 +137,17 @@ class CTCPrefixScoreTH(object):
         self._setup(x, xlens, blank, eos, margin, apply_log_softmax=False)
 
     @classmethod
-    def from_logits(cls, logits, xlens, blank, eos, margin=0):
+    def from_logits(cls, logits, xlens, blank, eos, margin=0, token_major=False):
         """Fused log-softmax + padding (K-a): what CTCRescorerLogitsProcessor.__init__ does with
-        F.log_softmax(encoder_logits) (reference :278-284) in one pass, leaving `logits` untouched."""
+        F.log_softmax(encoder_logits) (reference :278-284) in one pass, leaving `logits` untouched.
+        token_major=True keeps the posteriors as (B,V,ldt) -- a token's time series contiguous -- which is the layout the
+        pre-beam (candidate) kernels gather from; the frame-major copy is then rebuilt only if a full-vocabulary call needs it."""
         _require_cuda_f32(logits, "encoder_logits", 3)
         self = cls.__new__(cls)
-        self._setup(logits.contiguous(), xlens, blank, eos, margin, apply_log_softmax=True)
+        self._setup(logits.contiguous(), xlens, blank, eos, margin, apply_log_softmax=True, token_major=token_major)
         return self
 
-    def _setup(self, x, xlens, blank, eos, margin, apply_log_softmax):
+    def _setup(self, x, xlens, blank, eos, margin, apply_log_softmax, token_major=False):
         L = _lib.lib()
         self.logzero = LOGZERO
         self.blank = int(blank)
@@ -141,6 +178,14 @@ class CTCPrefixScoreTH(object):
             _lib.check(L.ctcps_init(_ptr(x), V, _ptr(self._lens), B, T, V, self.blank, int(apply_log_softmax),
                                     _ptr(self._x), ldx, _ptr(self._blank_lp), _stream(self.device)), "ctcps_init")
         self._ldx = ldx
+        self._xt, self._ldt = None, L.ctcps_padded_lt(T)
+        if token_major:
+            with torch.cuda.device(self.device):
+                self._xt = torch.empty((B, V, self._ldt), dtype=torch.float32, device=self.device)
+                _lib.check(L.ctcps_transpose_vt(_ptr(self._x), ldx, B, T, V, _ptr(self._xt), self._ldt, _stream(self.device)),
+                           "ctcps_transpose_vt")
+            if self._x is not x:
+                self._x = None  # rebuilt on demand by _frame_major()
         self._ws = None
         self._ws_key = None
         self._ws_gen = 0  # bumped by every call that overwrites the workspace
@@ -157,9 +202,26 @@ class CTCPrefixScoreTH(object):
     @property
     def x(self):
         """(2,T,B,V) tensor of the reference (:44-46).  Costs 2x the posteriors; only for inspection."""
-        xn = self._x[:, :, : self.odim].transpose(0, 1)
+        xn = self._frame_major()[:, :, : self.odim].transpose(0, 1)
         xb = self._blank_lp.transpose(0, 1).unsqueeze(2).expand(-1, -1, self.odim)
         return torch.stack([xn, xb])
+
+    def _frame_major(self):
+        """The (B,T,ldx) log-posteriors the full-vocabulary kernels stream through TMA; a token-major scorer builds them
+        from its (B,V,ldt) copy the first time a full-vocabulary call (or an inspection of .x / r) asks."""
+        if self._x is None:
+            T, V = self.input_length, self.odim
+            self._x = torch.nn.functional.pad(self._xt[:, :, :T].transpose(1, 2), (0, self._ldx - V)).contiguous()
+        return self._x
+
+    def _token_major(self):
+        if self._xt is None:
+            B, T, V = self.batch, self.input_length, self.odim
+            with torch.cuda.device(self.device):
+                self._xt = torch.empty((B, V, self._ldt), dtype=torch.float32, device=self.device)
+                _lib.check(_lib.lib().ctcps_transpose_vt(_ptr(self._x), self._ldx, B, T, V, _ptr(self._xt), self._ldt,
+                                                         _stream(self.device)), "ctcps_transpose_vt")
+        return self._xt
 
     def _workspace(self, W, S):
         key = (self.batch, self.input_length, W, S)
@@ -191,13 +253,13 @@ class CTCPrefixScoreTH(object):
         ts, new_state, _ = self._score(y, state, scoring_ids, att_w, None, 0.0)
         return ts, new_state
 
-    def _score(self, y, state, scoring_ids, att_w, att_scores, ctc_weight, need_token_scores=True):
+    def _parse_step(self, y, state, scoring_ids, att_w):
+        """Shared argument handling of a scoring call: (n_bh, ol, last_ids, W, S, scoring_ids, r_prev, s_prev)."""
         if att_w is not None and self.margin > 0:
             raise NotImplementedError("CTC windowing (att_w with margin > 0, reference :127-132) is dead code in the "
                                       "reference's processor and is not implemented")
-        L = _lib.lib()
         dev = self.device
-        B, T, V = self.batch, self.input_length, self.odim
+        B, T = self.batch, self.input_length
         if isinstance(y, torch.Tensor):
             if y.dim() != 2:
                 raise ValueError(f"y must be (BW, L), got {tuple(y.shape)}")
@@ -218,7 +280,6 @@ class CTCPrefixScoreTH(object):
                 raise ValueError(f"scoring_ids must be (BW,S) with BW={n_bh}, got {tuple(scoring_ids.shape)}")
             S = int(scoring_ids.shape[1])
         self.scoring_num = S                                     # :72
-
         if state is None:
             r_prev, s_prev = self.initial_state(W), None
         else:
@@ -227,9 +288,60 @@ class CTCPrefixScoreTH(object):
             if tuple(r_prev.shape) != (T, 2, n_bh):
                 raise ValueError(f"state r_prev must be {(T, 2, n_bh)}, got {tuple(r_prev.shape)}")
             r_prev = r_prev.contiguous()
-        prepared = state is not None and getattr(state, "prepared_gen", None) == self._ws_gen and self._ws_key == (B, T, W, S)
+        return n_bh, ol, last_ids, W, S, scoring_ids, r_prev, s_prev
+
+    def _score(self, y, state, scoring_ids, att_w, att_scores, ctc_weight, need_token_scores=True):
+        n_bh, ol, last_ids, W, S, scoring_ids, r_prev, s_prev = self._parse_step(y, state, scoring_ids, att_w)
+        prepared = (state is not None and getattr(state, "prepared_gen", None) == self._ws_gen
+                    and self._ws_key == (self.batch, self.input_length, W, S))
         return self._launch_score(r_prev, s_prev, last_ids, ol, W, scoring_ids, att_scores, ctc_weight,
                                   self.lazy_state and scoring_ids is None, need_token_scores, prepared)
+
+    def _score_candidates(self, y, state, scoring_ids, cand_att, ctc_weight, need_token_scores=False):
+        """Lazy-state scoring of `scoring_ids` (BW,S) candidates (unique per hypothesis): the (BW,S) prefix scores, token
+        scores and joint scores (with cand_att, the decoder scores of the candidates), and a CandidateState from which
+        index_select_state recomputes the survivors' forward variables.  No (T,2,BW,S) state, no (BW,V) tensor."""
+        L = _lib.lib()
+        dev = self.device
+        B, T, V = self.batch, self.input_length, self.odim
+        n_bh, ol, last_ids, W, S, scoring_ids, r_prev, s_prev = self._parse_step(y, state, scoring_ids, None)
+        if S == 0:
+            raise ValueError("_score_candidates needs scoring_ids")
+        s_vec = None
+        if isinstance(s_prev, torch.Tensor):
+            _require_cuda_f32(s_prev, "state s_prev")
+            s_vec = (s_prev if s_prev.dim() == 1 else s_prev[:, 0]).contiguous()  # the reference's s_prev is a row broadcast (:194)
+            if s_vec.numel() != n_bh:
+                raise ValueError(f"state s_prev must have {n_bh} rows, got {tuple(s_prev.shape)}")
+        elif s_prev is not None and float(s_prev) != 0.0:
+            s_vec = torch.full((n_bh,), float(s_prev), dtype=torch.float32, device=dev)
+        # the workspace layout does not depend on S: a select of the previous step prepared it for this call
+        prepared = (state is not None and getattr(state, "prepared_gen", None) == self._ws_gen
+                    and self._ws_key == (B, T, W, 0))
+        if cand_att is not None:
+            _require_cuda_f32(cand_att, "cand_att", 2)
+            if tuple(cand_att.shape) != (n_bh, S) or not cand_att.is_contiguous():
+                raise ValueError(f"cand_att must be contiguous {(n_bh, S)}, got {tuple(cand_att.shape)}")
+        xt = self._token_major()
+        w = float(ctc_weight)
+        with torch.cuda.device(dev):
+            cand_log_psi = torch.empty((n_bh, S), dtype=torch.float32, device=dev)
+            cand_ts = torch.empty((n_bh, S), dtype=torch.float32, device=dev) if need_token_scores else None
+            cand_joint = torch.empty((n_bh, S), dtype=torch.float32, device=dev) if cand_att is not None else None
+            ws = self._workspace(W, 0)
+            self._ws_gen += 1
+            timing = self._timing
+            if timing is not None:
+                ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev0.record()
+            _lib.check(L.ctcps_score_candidates(_ptr(xt), self._ldt, _ptr(r_prev), _ptr(s_vec), _ptr(last_ids), ol, B, W, T, V,
+                                                self.blank, _ptr(scoring_ids), S, _ptr(cand_att), 1.0 - w, w, _ptr(cand_log_psi),
+                                                _ptr(cand_ts), _ptr(cand_joint), _ptr(ws), ws.numel(), int(bool(prepared)),
+                                                _stream(dev)), "ctcps_score_candidates")
+            if timing is not None:
+                ev1.record()
+                timing.append((ev0, ev1))
+        return cand_log_psi, cand_ts, cand_joint, CandidateState(self, r_prev, last_ids, ol, W, scoring_ids, cand_log_psi), s_vec
 
     def _launch_score(self, r_prev, s_prev, last_ids, ol, W, scoring_ids, att_scores, ctc_weight, lazy, need_token_scores=True,
                       prepared=False):
@@ -272,15 +384,16 @@ class CTCPrefixScoreTH(object):
             if timing is not None:  # bench.py: CUDA events around the K-b launches on the launching stream
                 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 ev0.record()
+            x_fm = self._frame_major()
             if lazy:
                 r = LazyForwardVariables(self, r_prev, last_ids, ol, W)
-                _lib.check(L.ctcps_score_lazy(_ptr(self._x), self._ldx, _ptr(self._blank_lp), _ptr(r_prev), s_ptr, s_rs, s_cs,
+                _lib.check(L.ctcps_score_lazy(_ptr(x_fm), self._ldx, _ptr(self._blank_lp), _ptr(r_prev), s_ptr, s_rs, s_cs,
                                               _ptr(last_ids), ol, B, W, T, V, self.blank, _ptr(att_scores), 1.0 - w, w,
                                               _ptr(log_psi), _ptr(token_scores), _ptr(joint), _ptr(ws), ws.numel(),
                                               int(bool(prepared)), _stream(dev)), "ctcps_score_lazy")
             else:
                 r = torch.empty((T, 2, n_bh, ldr), dtype=torch.float32, device=dev)
-                _lib.check(L.ctcps_score(_ptr(self._x), self._ldx, _ptr(self._blank_lp), _ptr(r_prev), s_ptr, s_rs, s_cs,
+                _lib.check(L.ctcps_score(_ptr(x_fm), self._ldx, _ptr(self._blank_lp), _ptr(r_prev), s_ptr, s_rs, s_cs,
                                          _ptr(last_ids), ol, B, W, T, V, self.blank, _ptr(scoring_ids), S, _ptr(idmap),
                                          _ptr(att_scores), 1.0 - w, w, _ptr(r), ldr, _ptr(log_psi), _ptr(token_scores),
                                          _ptr(joint), _ptr(ws), ws.numel(), _stream(dev)), "ctcps_score")
@@ -296,6 +409,8 @@ class CTCPrefixScoreTH(object):
 
         best_ids: (B,W) ids in hyp*V + tok space.  Returns (r_new (T,2,BW), s_new (BW,V) [expanded], f_min, f_max).
         """
+        if isinstance(state, CandidateState):
+            return self._select_candidates(state, best_ids, _out)
         r, s, f_min, f_max, scoring_idmap = state
         _require_cuda_f32(s, "state log_psi", 2)
         if isinstance(r, LazyForwardVariables):
@@ -313,7 +428,7 @@ class CTCPrefixScoreTH(object):
                     s_vec = torch.empty((n_bh,), dtype=torch.float32, device=self.device)
                 # the scan also prepares the workspace of the scoring call that follows (same W, full vocabulary)
                 ws = self._workspace(r.n_hyps, 0) if self.lazy_state else None
-                _lib.check(_lib.lib().ctcps_select_lazy(_ptr(self._x), self._ldx, _ptr(self._blank_lp), _ptr(r.r_prev),
+                _lib.check(_lib.lib().ctcps_select_lazy(_ptr(self._frame_major()), self._ldx, _ptr(self._blank_lp), _ptr(r.r_prev),
                                                         _ptr(r.last_ids), r.ol, _ptr(s), _ptr(best_ids), self.batch, r.n_hyps, T, V,
                                                         _ptr(r_new), _ptr(s_vec), _ptr(ws), 0 if ws is None else ws.numel(),
                                                         _stream(self.device)), "ctcps_select_lazy")
@@ -346,6 +461,32 @@ class CTCPrefixScoreTH(object):
                                                T, V, S, _ptr(r_new), _ptr(s_vec), _stream(self.device)), "ctcps_select")
         return r_new, s_vec.view(-1, 1).expand(n_bh, V), f_min, f_max
 
+    def _select_candidates(self, state, best_ids, _out=None):
+        """index_select_state after a candidate step (reference :196-202 on a state that was never written)."""
+        r = state.r
+        n_bh, S = (int(v) for v in state.scoring_ids.shape)
+        T, V = self.input_length, self.odim
+        best_ids = best_ids.to(device=self.device, dtype=torch.long).contiguous()
+        if best_ids.numel() != n_bh:
+            raise ValueError(f"best_ids has {best_ids.numel()} entries for {n_bh} hypotheses")
+        with torch.cuda.device(self.device):
+            if _out is not None:
+                r_new, s_vec = _out
+            else:
+                r_new = torch.empty((T, 2, n_bh), dtype=torch.float32, device=self.device)
+                s_vec = torch.empty((n_bh,), dtype=torch.float32, device=self.device)
+            ws = self._workspace(r.n_hyps, 0)
+            _lib.check(_lib.lib().ctcps_select_lazy_candidates(_ptr(self._token_major()), self._ldt, _ptr(self._blank_lp),
+                                                               _ptr(r.r_prev), _ptr(r.last_ids), r.ol, _ptr(state.scoring_ids), S,
+                                                               _ptr(state.cand_log_psi), _ptr(best_ids), self.batch, r.n_hyps, T, V,
+                                                               _ptr(r_new), _ptr(s_vec), _ptr(ws), ws.numel(),
+                                                               _stream(self.device)), "ctcps_select_lazy_candidates")
+        out = _SelectedState((r_new, s_vec.view(-1, 1).expand(n_bh, V), 0, 0))
+        if r.ol + 1 <= T:
+            self._ws_gen += 1
+            out.prepared_gen = self._ws_gen
+        return out
+
     def extend_prob(self, x):
         """Extend the posteriors with new frames (streaming helper, reference :209-229).  x: (B,T',V) log-posteriors."""
         _require_cuda_f32(x, "x", 3)
@@ -355,7 +496,8 @@ class CTCPrefixScoreTH(object):
             if B != self.batch or V != self.odim:
                 raise ValueError("extend_prob: batch / vocabulary mismatch")
             L = _lib.lib()
-            old_x, old_blank = self._x, self._blank_lp
+            old_x, old_blank = self._frame_major(), self._blank_lp
+            self._xt = None
             with torch.cuda.device(self.device):
                 self._x = torch.empty((B, T_new, self._ldx), dtype=torch.float32, device=self.device)
                 self._blank_lp = torch.empty((B, T_new), dtype=torch.float32, device=self.device)
@@ -365,6 +507,7 @@ class CTCPrefixScoreTH(object):
             self._x[:, :T_old] = old_x            # frames already seen keep their values (:227)
             self._blank_lp[:, :T_old] = old_blank
             self.input_length = T_new
+            self._ldt = L.ctcps_padded_lt(T_new)
             self.end_frames = torch.as_tensor([T_new]) - 1
             self._ws_key = None
 
@@ -406,23 +549,42 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
         debug: bool = False,
         *,
         materialize_state: bool | None = None,
+        pre_beam_size: int = 0,
+        use_beam_idx: bool | None = None,
     ):
-        """Same positional signature as the reference.  materialize_state (keyword-only, not in the reference):
-        False = lazy state (default): never write r (T,2,BW,V); the W surviving columns per utterance are recomputed at
-                the next step -- same joint scores (ulp-level), bit-identical selected states, ~20x fewer HBM bytes per
-                step.  `ctc_states[0]` is then a LazyForwardVariables that materialises the tensor on demand.
-        True  = write the full state every step, exactly the reference's data flow.
-        None  = take it from the environment variable CTCPS_MATERIALIZE_STATE (default "0")."""
+        """Same positional signature as the reference.  Keyword-only extensions (not in the reference):
+
+        materialize_state
+            False = lazy state (default): never write r (T,2,BW,V); the W surviving columns per utterance are recomputed
+                    at the next step -- same joint scores (ulp-level), bit-identical selected states, ~20x fewer HBM bytes
+                    per step.  `ctc_states[0]` is then a LazyForwardVariables that materialises the tensor on demand.
+            True  = write the full state every step, exactly the reference's data flow.
+            None  = take it from the environment variable CTCPS_MATERIALIZE_STATE (default "0").
+        pre_beam_size
+            0 (default) = score the full vocabulary, like the reference's processor.  S > 0 = ESPnet's pre-beam: only the
+            top-S tokens of the decoder scores of every hypothesis are CTC-scored (the scorer's `scoring_ids` path,
+            reference :90-97); every other token gets the reference's logzero-class score.  Changes results (tokens
+            outside the candidates can no longer win), hence off by default.
+        use_beam_idx
+            False = select the state of the next step from token ids only, the reference processor's behaviour (:326-329:
+            every beam inherits from hypothesis 0 of its utterance).  True = use the ids handed over by `set_beam_idx` /
+            `prefetch_state(best_ids=...)` (source hypothesis * V + token, ESPnet's semantics, reference :180-191).
+            None = True when pre_beam_size > 0 (a token is only scored for the hypothesis that proposed it), else False."""
         super().__init__()
         self.pad_token_id = pad_token_id
+        self.pre_beam_size = int(pre_beam_size)
+        if self.pre_beam_size < 0 or self.pre_beam_size > 64:
+            raise ValueError("pre_beam_size must be in [0, 64]")
         self.ctc_prefix_scorer = CTCPrefixScoreTH.from_logits(encoder_logits, encoder_output_lens, pad_token_id, eos_token_id,
-                                                              ctc_margin)
+                                                              ctc_margin, token_major=self.pre_beam_size > 0)
         if materialize_state is None:
             materialize_state = os.environ.get("CTCPS_MATERIALIZE_STATE", "0") not in ("0", "false", "False", "no")
         self.materialize_state = bool(materialize_state)
         self.ctc_prefix_scorer.lazy_state = not self.materialize_state
+        self.use_beam_idx = (self.pre_beam_size > 0) if use_beam_idx is None else bool(use_beam_idx)
         self.ctc_weight = ctc_weight
         self.ctc_states = None
+        self._best_ids = None    # (B,W) ids for the next index_select_state, from set_beam_idx()
         self._prefetched = None  # (last-token tensor, selected state, event) produced by prefetch_state()
         self._side_stream = None
         self._prefetch_bufs = None
@@ -434,26 +596,56 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
         self.eos_space_trick_weight = eos_space_trick_weight
         self.debug = debug
 
-    def __call__(self, input_ids: torch.LongTensor, scores: torch.FloatTensor) -> torch.FloatTensor:
+    # -- state selection ----------------------------------------------------------------------------------
+    def set_beam_idx(self, beam_idx: torch.LongTensor) -> None:
+        """Tell the processor which rows of the previous step the current rows continue (HF's `beam_idx`, global row
+        indices b*W + source hypothesis; what the model's `_reorder_cache` receives).  Only used with use_beam_idx."""
+        if not self.use_beam_idx:
+            return
+        W = self.num_beams
+        self._best_ids = (beam_idx.to(self.ctc_prefix_scorer.device).view(-1, W) % W) * self.ctc_prefix_scorer.odim  # + token, in _select
+
+    def _select_ids(self, input_ids, best_ids=None):
+        """ids for index_select_state: ESPnet's hyp*V + tok when the beam indices are known, else token ids only (:326-329)."""
+        last = input_ids[:, -1].reshape(-1, self.num_beams)
+        if best_ids is not None:
+            return best_ids.reshape(-1, self.num_beams)
+        if self.use_beam_idx and self._best_ids is not None:
+            ids, self._best_ids = self._best_ids + last, None
+            return ids
+        return last
+
+    def _select(self, input_ids):
+        if self._prefetched is not None:
+            last, selected, done = self._prefetched
+            self._prefetched = None
+            if last.numel() != input_ids.shape[0]:
+                raise RuntimeError("prefetch_state() was called for a different batch than this step")
+            torch.cuda.current_stream(self.ctc_prefix_scorer.device).wait_event(done)
+            self.ctc_states = selected
+        elif self.ctc_states is not None:
+            self.ctc_states = self.ctc_prefix_scorer.index_select_state(self.ctc_states, self._select_ids(input_ids))
+
+    def _check_scores(self, scores):
         sc = self.ctc_prefix_scorer
         _require_cuda_f32(scores, "scores", 2)
         if scores.shape[-1] != sc.odim:
             raise ValueError(f"decoder vocabulary ({scores.shape[-1]}) != CTC vocabulary ({sc.odim}): the encoder's extra "
                              "blank_projection column (src/models/encoders/e_branchformer.py:415,456-457) is not supported "
                              "by the reference processor either")
-        work = scores if scores.is_contiguous() else scores.contiguous()
-        if self._prefetched is not None:
-            last, selected, done = self._prefetched
-            self._prefetched = None
-            if last.numel() != input_ids.shape[0]:
-                raise RuntimeError("prefetch_state() was called for a different batch than this step")
-            torch.cuda.current_stream(sc.device).wait_event(done)
-            self.ctc_states = selected
-        elif self.ctc_states is not None:
-            self.ctc_states = sc.index_select_state(self.ctc_states, input_ids[:, -1].reshape(-1, self.num_beams))  # :326-329
-        # scores[:, pad] = logzero (:325), the scorer (:330) and the combine (:332) are one fused launch
-        ctc_scores, self.ctc_states, next_token_scores = sc._score(input_ids, self.ctc_states, None, None, work, self.ctc_weight,
-                                                                   need_token_scores=self.apply_eos_space_trick or self.debug)
+        return scores if scores.is_contiguous() else scores.contiguous()
+
+    def __call__(self, input_ids: torch.LongTensor, scores: torch.FloatTensor) -> torch.FloatTensor:
+        sc = self.ctc_prefix_scorer
+        work = self._check_scores(scores)
+        self._select(input_ids)
+        need_ts = self.apply_eos_space_trick or self.debug
+        if self.pre_beam_size > 0:
+            ctc_scores, next_token_scores = self._call_pre_beam(input_ids, work, need_ts)
+        else:
+            # scores[:, pad] = logzero (:325), the scorer (:330) and the combine (:332) are one fused launch
+            ctc_scores, self.ctc_states, next_token_scores = sc._score(input_ids, self.ctc_states, None, None, work, self.ctc_weight,
+                                                                       need_token_scores=need_ts)
         if work is not scores:
             scores[:, self.pad_token_id] = sc.logzero
         if self.apply_eos_space_trick:
@@ -466,11 +658,64 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
             self.analyze_predictions(scores, ctc_scores, next_token_scores, input_ids)
         return next_token_scores
 
-    def prefetch_state(self, input_ids: torch.LongTensor) -> None:
+    # -- pre-beam (candidate) decoding ----------------------------------------------------------------------
+    def _top_candidates(self, work):
+        """scores[:, pad] = logzero in place (:325) and the top pre_beam_size (ids, scores) of every row."""
+        sc = self.ctc_prefix_scorer
+        n_bh, S = int(work.shape[0]), self.pre_beam_size
+        with torch.cuda.device(sc.device):
+            ids = torch.empty((n_bh, S), dtype=torch.long, device=sc.device)
+            cand_att = torch.empty((n_bh, S), dtype=torch.float32, device=sc.device)
+            _lib.check(_lib.lib().ctcps_prebeam_topk(_ptr(work), n_bh, sc.odim, sc.blank, S, _ptr(ids), _ptr(cand_att),
+                                                     _stream(sc.device)), "ctcps_prebeam_topk")
+        return ids, cand_att
+
+    def _call_pre_beam(self, input_ids, work, need_ts):
+        """The reference-shaped (BW,V) outputs of a pre-beam step."""
+        sc = self.ctc_prefix_scorer
+        ids, cand_att = self._top_candidates(work)
+        if self.materialize_state:  # the reference's data flow: scorer(..., scoring_ids) writes r (T,2,BW,S) and the idmap
+            ctc_scores, self.ctc_states, joint = sc._score(input_ids, self.ctc_states, ids, None, work, self.ctc_weight)
+            return ctc_scores, joint
+        L = input_ids.shape[1] - 1
+        cand_log_psi, cand_ts, cand_joint, self.ctc_states, s_vec = sc._score_candidates(input_ids, self.ctc_states, ids, cand_att,
+                                                                                         self.ctc_weight, need_token_scores=need_ts)
+        n_bh, V = int(work.shape[0]), sc.odim
+        w = float(self.ctc_weight)
+        with torch.cuda.device(sc.device):
+            joint = torch.empty((n_bh, V), dtype=torch.float32, device=sc.device)
+            ctc_scores = torch.empty((n_bh, V), dtype=torch.float32, device=sc.device) if need_ts else None
+            _lib.check(_lib.lib().ctcps_candidates_to_dense(_ptr(work), _ptr(s_vec), _ptr(ids), _ptr(cand_log_psi), _ptr(cand_ts),
+                                                            _ptr(cand_joint), n_bh, V, self.pre_beam_size, 1.0 - w, w, L,
+                                                            sc.input_length, None, _ptr(ctc_scores), _ptr(joint),
+                                                            _stream(sc.device)), "ctcps_candidates_to_dense")
+        return ctc_scores, joint
+
+    def score_candidates(self, input_ids: torch.LongTensor, scores: torch.FloatTensor):
+        """Sparse form of __call__ for a decode loop that owns its beam step (beam_search.joint_beam_search_fused): returns
+        (cand_ids (BW,S) int64, cand_joint (BW,S)) -- the joint scores of the pre-beam candidates -- and never builds a (BW,V)
+        tensor.  Every other token has the logzero-class joint score __call__ would return and can never be selected.
+        Same side effect on `scores` ([:, pad] = logzero) as __call__."""
+        if self.pre_beam_size <= 0 or self.materialize_state:
+            raise RuntimeError("score_candidates needs pre_beam_size > 0 and lazy state")
+        if self.apply_eos_space_trick:
+            raise RuntimeError("the eos/space trick needs the dense scores: use __call__")
+        work = self._check_scores(scores)
+        if work is not scores:
+            raise ValueError("scores must be contiguous")
+        self._select(input_ids)
+        ids, cand_att = self._top_candidates(work)
+        _, _, cand_joint, self.ctc_states, _ = self.ctc_prefix_scorer._score_candidates(input_ids, self.ctc_states, ids, cand_att,
+                                                                                      self.ctc_weight)
+        return ids, cand_joint
+
+    def prefetch_state(self, input_ids: torch.LongTensor, best_ids: torch.LongTensor | None = None) -> None:
         """Optional hook, not in the reference: start the state selection of the NEXT step (reference :326-329) as soon as
         its last tokens are known, on a side stream, so that it overlaps the attention decoder's forward pass.  A decode
         loop that owns its beam search (beam_search.joint_beam_search_fused) calls it right after the beam update; HF's
-        loop never does and then __call__ selects the state itself.  The next __call__ must be for these input_ids."""
+        loop never does and then __call__ selects the state itself.  The next __call__ must be for these input_ids.
+        best_ids (B,W): source hypothesis * V + token of every row (ctcps_beam_step's best_ids_out); used when the
+        processor was built with use_beam_idx, else ignored (the reference's token-only selection)."""
         if self.ctc_states is None or self._prefetched is not None:
             return
         sc = self.ctc_prefix_scorer
@@ -478,7 +723,8 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
         if self._side_stream is None:
             self._side_stream = torch.cuda.Stream(sc.device)
         side = self._side_stream
-        last = input_ids[:, -1].reshape(-1, self.num_beams).contiguous()  # on the main stream, before the hand-over
+        # on the main stream, before the hand-over
+        last = self._select_ids(input_ids, best_ids if self.use_beam_idx else None).contiguous()
         n_bh = int(input_ids.shape[0])
         if self._prefetch_bufs is None or self._prefetch_bufs[0][0].shape[2] != n_bh:
             # two sets: the state selected for step n is still being read while the one for step n+1 is written

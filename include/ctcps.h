@@ -145,7 +145,53 @@ int ctcps_beam_step_workspace_bytes(int B, int W, size_t *out_bytes);
 int ctcps_beam_step(const float *joint, float *beam_scores, const int64_t *ids_cur, int64_t *ids_next, int64_t ld_ids, int L,
                     int B, int W, int V, int eos, int pad, float len_norm, float *pool_scores, int64_t *pool_lens,
                     int64_t *pool_seqs, int64_t ld_pool, unsigned char *done, void *workspace, size_t workspace_bytes,
-                    int64_t *done_ring, int ring, int64_t step_tag, void *stream);
+                    int64_t *done_ring, int ring, int64_t step_tag, int64_t *best_ids_out, void *stream);
+/* best_ids_out (nullable, (B,W) int64): source hypothesis * V + token of every continuing beam -- the ESPnet ids that
+ * index_select_state expects (ctc_scorer.py:180-191).  HF hands its processors token ids only, so the reference's
+ * processor selects every state from hypothesis 0; a loop that owns its beam step can pass these. */
+
+/*
+ * N2: pre-beam (partial scoring) decode step.  The reference scorer scores only `scoring_ids` when given
+ * (ctc_scorer.py:90-97,117-121,155-162,196-202); the policy that picks them -- the top `pre_beam_size` tokens of the
+ * decoder scores of every hypothesis -- is ESPnet's (espnet/nets/batch_beam_search.py, BatchBeamSearch.batch_beam /
+ * beam_search.py pre_beam_score_key = "full"), the library the scorer was copied from (ctc_scorer.py:2).
+ * Layout: x_vt (B,V,ldt) token-major log-posteriors, ldt = ctcps_padded_lt(T), frames >= T zero-filled.
+ * scoring_ids of a hypothesis must be unique (ctcps_prebeam_topk's are).
+ */
+int ctcps_padded_lt(int T);
+int ctcps_transpose_vt(const float *x_logp, int ldx, int B, int T, int V, float *x_vt, int ldt, void *stream);
+
+/* scores[:, blank] = logzero in place (:325), then the S best (id, score) of every row, best first, ties by lower id. */
+int ctcps_prebeam_topk(float *att_scores, int BW, int V, int blank, int S, int64_t *scoring_ids, float *cand_att, void *stream);
+
+/* log_psi / token score / joint score (:154-176, :332) of the S candidates of every hypothesis, lazy state (no r):
+ * outputs are (BW,S), aligned with scoring_ids; s_prev is a (BW) vector or NULL; cand_att (BW,S) the decoder scores of
+ * the candidates (NULL: no joint).  Same workspace (and workspace_prepared meaning) as ctcps_score_lazy. */
+int ctcps_score_candidates(const float *x_vt, int ldt, const float *r_prev, const float *s_prev, const int64_t *last_ids, int ol,
+                           int B, int W, int T, int V, int blank, const int64_t *scoring_ids, int S, const float *cand_att,
+                           float one_minus_w, float w, float *cand_log_psi, float *cand_token_scores, float *cand_joint,
+                           void *workspace, size_t workspace_bytes, int workspace_prepared, void *stream);
+
+/* The (BW,V) tensors the reference returns for a candidate step: log_psi = logzero outside the candidates (:156),
+ * token_scores = log_psi - s_prev (:175-176), joint = (1-w)*att + w*token_scores (:332).  Outputs are nullable. */
+int ctcps_candidates_to_dense(const float *att_scores, const float *s_prev, const int64_t *scoring_ids, const float *cand_log_psi,
+                              const float *cand_token_scores, const float *cand_joint, int BW, int V, int S, float one_minus_w,
+                              float w, int ol, int T, float *log_psi, float *token_scores, float *joint, void *stream);
+
+/* index_select_state (:180-207 with scoring_idmap, :196-202) after a candidate step scored in lazy state: like
+ * ctcps_select_lazy, s_new from cand_log_psi; a token that was not scored selects candidate 0 and s_new = logzero. */
+int ctcps_select_lazy_candidates(const float *x_vt, int ldt, const float *blank_lp, const float *r_prev, const int64_t *last_ids,
+                                 int ol, const int64_t *scoring_ids, int S, const float *cand_log_psi, const int64_t *best_ids, int B,
+                                 int W, int T, int V, float *r_new, float *s_new, void *next_workspace,
+                                 size_t next_workspace_bytes, void *stream);
+
+/* ctcps_beam_step over the candidates only: cand_joint / cand_ids are (BW,S); ranking, ties and bookkeeping are those of
+ * the dense step on a joint tensor that is -inf outside the candidates.  S >= 2. */
+int ctcps_beam_step_candidates(const float *cand_joint, const int64_t *cand_ids, int S, float *beam_scores, const int64_t *ids_cur,
+                               int64_t *ids_next, int64_t ld_ids, int L, int B, int W, int V, int eos, int pad, float len_norm,
+                               float *pool_scores, int64_t *pool_lens, int64_t *pool_seqs, int64_t ld_pool, unsigned char *done,
+                               void *workspace, size_t workspace_bytes, int64_t *done_ring, int ring, int64_t step_tag,
+                               int64_t *best_ids_out, void *stream);
 
 /*
  * Optional eos/space trick of the processor (ctc_scorer.py:333-349), in place on `next`:

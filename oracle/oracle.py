@@ -223,7 +223,11 @@ class OracleCTCRescorerLogitsProcessor:
     """Same surface as CTCRescorerLogitsProcessor (ctc_scorer.py:259-354), on the oracle."""
 
     def __init__(self, encoder_logits, encoder_output_lens, pad_token_id, eos_token_id, ctc_margin, ctc_weight,
-                 num_beams, space_token_id=-1, apply_eos_space_trick=False, eos_space_trick_weight=1.0, debug=False):
+                 num_beams, space_token_id=-1, apply_eos_space_trick=False, eos_space_trick_weight=1.0, debug=False,
+                 pre_beam_size=0, use_beam_idx=None):
+        """pre_beam_size / use_beam_idx restate the policy ESPnet wraps around this scorer (espnet/nets/batch_beam_search.py:
+        the top pre_beam_size tokens of the decoder scores of every hypothesis are handed to the scorer as scoring_ids;
+        states are selected with source hypothesis * V + token); the reference's processor does neither (:326-330)."""
         import torch
 
         self._torch = torch
@@ -236,13 +240,27 @@ class OracleCTCRescorerLogitsProcessor:
         self.eos_token_id, self.space_token_id = eos_token_id, space_token_id
         self.apply_eos_space_trick, self.eos_space_trick_weight = apply_eos_space_trick, eos_space_trick_weight
         self.ctc_states = None
+        self.pre_beam_size = int(pre_beam_size)
+        self.use_beam_idx = (self.pre_beam_size > 0) if use_beam_idx is None else bool(use_beam_idx)
+        self._best_ids = None
+
+    def set_beam_idx(self, beam_idx):
+        if self.use_beam_idx:
+            W = self.num_beams
+            self._best_ids = (beam_idx.view(-1, W) % W) * self.ctc_prefix_scorer.odim
 
     def __call__(self, input_ids, scores):
         torch = self._torch
         if self.ctc_states is not None:
-            self.ctc_states = self.ctc_prefix_scorer.index_select_state(
-                self.ctc_states, input_ids[:, -1].reshape(-1, self.num_beams))
-        ctc_scores, self.ctc_states = self.ctc_prefix_scorer(input_ids, self.ctc_states)
+            best = input_ids[:, -1].reshape(-1, self.num_beams)
+            if self.use_beam_idx and self._best_ids is not None:
+                best, self._best_ids = best + self._best_ids, None
+            self.ctc_states = self.ctc_prefix_scorer.index_select_state(self.ctc_states, best)
+        scoring_ids = None
+        if self.pre_beam_size > 0:
+            scores[:, self.pad_token_id] = LOGZERO  # :325, before the candidates are drawn
+            scoring_ids = torch.sort(scores, dim=1, descending=True, stable=True).indices[:, : self.pre_beam_size].contiguous()
+        ctc_scores, self.ctc_states = self.ctc_prefix_scorer(input_ids, self.ctc_states, scoring_ids)
         s_np = scores.numpy()  # shares memory: the in-place scores[:, pad] = logzero reaches the caller
         assert s_np.flags.c_contiguous
         out = combine(s_np, ctc_scores.numpy(), self.pad_token_id, self.ctc_weight, self.apply_eos_space_trick,

@@ -20,6 +20,8 @@ Case kinds
   edge_*    : start == T-1, output_length >= T (early return :138-145), all-equal scores
               (token_scores == 0 -> logzero, :176), zero-length-padded utterances.
   decode_*  : 1-best sequences of the shared beam-search harness with the reference processor.
+  prebeam_* : the reference SCORER driven with ESPnet's pre-beam policy (scoring_ids = top-S decoder tokens per
+              hypothesis, states selected with source hypothesis * V + token): per-step replay and 1-best decodes.
 """
 import os
 import sys
@@ -247,9 +249,81 @@ def case_extend():
                         ext_r=ext[0].numpy(), x_after=scorer.x.numpy(), ts2=ts2.numpy(), r2=st2[0].numpy(), log_psi2=st2[1].numpy()))
 
 
+class ReferencePreBeamProcessor:
+    """The reference processor's arithmetic (ctc_scorer.py:324-332) around the UNMODIFIED reference scorer, with the two
+    things ESPnet's beam search does and the reference's processor does not: scoring_ids = top-S tokens of the decoder
+    scores (after scores[:, pad] = logzero), and index_select_state ids = source hypothesis * V + token when the loop
+    reports its beam indices (set_beam_idx).  use_beam_idx=False keeps the reference's token-only ids (:326-329)."""
+
+    def __init__(self, logits, lens, ctc_weight, W, S, use_beam_idx=True):
+        self.scorer = CTCPrefixScoreTH(torch.log_softmax(logits, -1), lens, BLANK, EOS, 0)
+        self.w, self.W, self.S, self.use_beam_idx = ctc_weight, W, S, use_beam_idx
+        self.states, self._best = None, None
+        self.trace = []
+
+    def set_beam_idx(self, beam_idx):
+        if self.use_beam_idx:
+            self._best = (beam_idx.view(-1, self.W) % self.W) * self.scorer.odim
+
+    def __call__(self, input_ids, scores):
+        scores[:, BLANK] = self.scorer.logzero
+        sel = None
+        if self.states is not None:
+            best = input_ids[:, -1].reshape(-1, self.W)
+            if self.use_beam_idx and self._best is not None:
+                best, self._best = best + self._best, None
+            sel = self.scorer.index_select_state(self.states, best)
+        ids = torch.sort(scores, dim=1, descending=True, stable=True).indices[:, : self.S].contiguous()
+        ctc, self.states = self.scorer(input_ids, sel, scoring_ids=ids)
+        out = (1 - self.w) * scores + self.w * ctc
+        self.trace.append(dict(ids=ids.numpy().copy(), ctc=ctc.numpy().copy(), out=out.numpy().copy(),
+                               log_psi=self.states[1].numpy().copy(),
+                               sel_r=None if sel is None else sel[0].numpy().copy(),
+                               sel_s=None if sel is None else sel[1][:, 0].numpy().copy()))
+        return out
+
+
+def case_prebeam():
+    # (1) per-step replay under the shared harness (records what the processor saw and returned at every step)
+    specs = [
+        # name, B, W, T, V, S, kind, ragged, use_beam_idx, seed, max_length
+        ("prebeam_w4_s6", 2, 4, 40, 48, 6, "peaky", True, True, 61, 14),
+        ("prebeam_w3_s40_v129", 2, 3, 30, 129, 40, "peaky", False, True, 62, 10),   # S > 32: two-list top-k
+        ("prebeam_w5_s8_tokens_only", 2, 5, 36, 64, 8, "peaky", True, False, 63, 12),  # the reference's hyp-0 selection
+        ("prebeam_w1_s5_flat", 3, 1, 25, 33, 5, "flat", True, True, 64, 10),
+    ]
+    for name, B, W, T, V, S, kind, ragged, ubi, seed, max_length in specs:
+        logits, lens, _ = make_encoder_logits(B, T, V, kind, ragged, seed=seed)
+        rec = dict(logits=logits.numpy(), lens=lens.numpy(), W=W, S=S, ctc_weight=0.3, use_beam_idx=ubi, seed=seed,
+                   max_length=max_length)
+        for dtype, suf in ((torch.float32, ""), (torch.float64, "_f64")):
+            proc = ReferencePreBeamProcessor(logits.to(dtype), lens.clone(), 0.3, W, S, ubi)
+            seen = []
+
+            def dec(ids, n, BW=B * W, V=V, s=seed, dtype=dtype, seen=seen):
+                seen.append(ids.numpy().copy())
+                return make_attention_scores(BW, V, n, seed=s, scale=0.5).to(dtype)
+
+            out = joint_beam_search(proc, dec, B, W, V, BOS, EOS, BLANK, max_length=max_length)
+            if suf == "":
+                rec.update(seq=out.sequences.numpy(), len=out.lengths.numpy(), score=out.scores.numpy(), steps=out.steps)
+                for n, ids in enumerate(seen):
+                    rec[f"input_ids_{n}"] = ids
+            for n, tr in enumerate(proc.trace):
+                for k, v in tr.items():
+                    if v is not None and (suf == "" or k != "ids"):
+                        rec[f"{k}_{n}{suf}"] = v
+        print(name, "steps", rec["steps"], "lens", rec["len"].tolist())
+        save(name, rec)
+
+
 if __name__ == "__main__":
+    if "--prebeam-only" in sys.argv:
+        case_prebeam()
+        sys.exit(0)
     case_steps()
     case_partial_and_select()
     case_edges()
     case_decode()
     case_extend()
+    case_prebeam()

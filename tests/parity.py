@@ -222,3 +222,69 @@ def replay_decode(be: Backend, blank=3, eos=1, bos=0):
         assert (to_np(out.lengths) == g[f"d{i}_len"]).all(), f"decode {i}: lengths differ"
         assert (to_np(out.sequences) == g[f"d{i}_seq"]).all(), f"decode {i}: 1-best token sequences differ"
         assert np.abs(to_np(out.scores) - g[f"d{i}_score"]).max() <= 1e-4
+
+
+PREBEAM_CASES = ["prebeam_w4_s6", "prebeam_w3_s40_v129", "prebeam_w5_s8_tokens_only", "prebeam_w1_s5_flat"]
+
+
+class _PreBeamChecker:
+    """Wraps a processor in pre-beam mode inside the shared harness and compares, at every step, what it was given and
+    what it returned with the golden trace of the reference scorer under the same policy (make_golden.case_prebeam)."""
+
+    def __init__(self, proc, g, name):
+        self.proc, self.g, self.name, self.n = proc, g, name, 0
+        self.worst = {}
+        self.use_beam_idx = getattr(proc, "use_beam_idx", False)
+        self._sel = None
+        scorer = proc.ctc_prefix_scorer
+        inner = scorer.index_select_state
+
+        def recording_select(state, best_ids, *a, **k):
+            self._sel = inner(state, best_ids, *a, **k)
+            return self._sel
+
+        scorer.index_select_state = recording_select
+
+    def set_beam_idx(self, beam_idx):
+        self.proc.set_beam_idx(beam_idx)
+
+    def _max(self, key, v):
+        self.worst[key] = max(self.worst.get(key, 0.0), v)
+
+    def __call__(self, input_ids, scores):
+        g, n, name = self.g, self.n, self.name
+        assert (to_np(input_ids) == g[f"input_ids_{n}"]).all(), f"{name} step {n}: the decode took a different path"
+        self._sel = None
+        out = self.proc(input_ids, scores)
+        self._max("out", assert_parity(out, g[f"out_{n}"], f"{name} step {n} processor out", ref64=g.get(f"out_{n}_f64")))
+        st = self.proc.ctc_states
+        self._max("log_psi", assert_parity(st[1], g[f"log_psi_{n}"], f"{name} step {n} log_psi", ref64=g.get(f"log_psi_{n}_f64")))
+        assert tuple(st[0].shape) == (self.proc.ctc_prefix_scorer.input_length, 2, input_ids.shape[0], int(g["S"]))
+        if n > 0:
+            assert self._sel is not None, f"{name} step {n}: no state selection happened"
+            self._max("sel_r", assert_parity(self._sel[0], g[f"sel_r_{n}"], f"{name} step {n} sel_r", ref64=g.get(f"sel_r_{n}_f64")))
+            self._max("sel_s", assert_parity(self._sel[1][:, 0], g[f"sel_s_{n}"], f"{name} step {n} sel_s",
+                                             ref64=g.get(f"sel_s_{n}_f64")))
+        self.n += 1
+        return out
+
+
+def replay_prebeam(make_processor, device, name, blank=3, eos=1, bos=0):
+    """make_processor(logits, lens, w, W, S, use_beam_idx) -> a processor in pre-beam mode on `device`."""
+    from huggingface_asr_b200.beam_search import joint_beam_search
+    from huggingface_asr_b200.synthetic import make_attention_scores
+
+    g = load(name)
+    W, S, seed = int(g["W"]), int(g["S"]), int(g["seed"])
+    logits = torch.from_numpy(g["logits"]).to(device)
+    lens = torch.from_numpy(g["lens"]).to(device)
+    B, T, V = logits.shape
+    proc = make_processor(logits.clone(), lens, float(g["ctc_weight"]), W, S, bool(g["use_beam_idx"]))
+    chk = _PreBeamChecker(proc, g, name)
+    out = joint_beam_search(chk, lambda ids, n: make_attention_scores(B * W, V, n, seed=seed, scale=0.5).to(device),
+                            B, W, V, bos, eos, blank, max_length=int(g["max_length"]), device=device)
+    assert out.steps == int(g["steps"])
+    assert (to_np(out.sequences) == g["seq"]).all(), f"{name}: 1-best token sequences differ"
+    assert (to_np(out.lengths) == g["len"]).all()
+    assert np.abs(to_np(out.scores) - g["score"]).max() <= 1e-4
+    return chk.worst

@@ -49,6 +49,15 @@ def test_oracle_decode_1best():
     parity.replay_decode(BE)
 
 
+@pytest.mark.parametrize("name", parity.PREBEAM_CASES)
+def test_oracle_prebeam_policy_vs_reference_scorer(name):
+    """ESPnet's pre-beam policy around the scorer (scoring_ids = top-S decoder tokens, hyp*V+tok state selection)."""
+    def mk(logits, lens, w, W, S, use_beam_idx):
+        return orc.OracleCTCRescorerLogitsProcessor(logits, lens, 3, 1, 0, w, W, pre_beam_size=S, use_beam_idx=use_beam_idx)
+
+    print(name, parity.replay_prebeam(mk, "cpu", name))
+
+
 def test_oracle_padded_posteriors_match_reference():
     g = parity.load("steps_peaky_ragged_w10")
     x = orc.log_softmax(g["logits"])

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--ol", type=int, default=20)
     ap.add_argument("--only", default="")
+    ap.add_argument("--pre-beam", type=int, default=32)
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     B, W, T, V = args.batch or cfg.B, cfg.W, cfg.T, cfg.V
@@ -60,6 +61,42 @@ def main():
             res[f"select {name}"] = timeit(lambda: sc.index_select_state(st, ids[:, -1].reshape(-1, W)))
         del proc, sc, st, sel
         torch.cuda.empty_cache()
+    if want("prebeam"):
+        S = args.pre_beam
+        res[f"init token-major (S={S})"] = timeit(lambda: CTCRescorerLogitsProcessor(logits, lens, BLANK, EOS, 0, 0.3, W, -1, False, 1.0,
+                                                                                     pre_beam_size=S), 5)
+        proc = CTCRescorerLogitsProcessor(logits, lens, BLANK, EOS, 0, 0.3, W, -1, False, 1.0, pre_beam_size=S)
+        sc = proc.ctc_prefix_scorer
+        ids0 = torch.zeros((BW, 1), dtype=torch.long, device=dev)
+        cid, cj = proc.score_candidates(ids0, att.clone())
+        st = proc.ctc_states
+        best = (torch.arange(W, device=dev).view(1, W) * V + cid.view(B, W, S)[:, :, 0]).contiguous()  # every hyp keeps its best token
+        sel = sc.index_select_state(st, best)
+        ids1 = torch.cat([ids0, cid[:, :1]], 1)
+        res["prebeam topk"] = timeit(lambda: proc._top_candidates(att), 20)
+        cid1, ca1 = proc._top_candidates(att)
+        res["prebeam score_candidates (unprepared: + k_prep_psi)"] = timeit(lambda: sc._score_candidates(ids1, sel, cid1, ca1, 0.3), 20)
+        res["prebeam select (stage + scan)"] = timeit(lambda: sc.index_select_state(st, best), 20)
+        res["prebeam dense __call__ (topk + score + to_dense)"] = timeit(lambda: (setattr(proc, "ctc_states", None), proc(ids0, att))[1], 20)
+        maxlen = 128
+        idc = torch.randint(5, V, (BW, maxlen), device=dev)
+        idn = torch.empty_like(idc)
+        bs = torch.randn(B, W, device=dev)
+        ps = torch.full((B, W), float("-inf"), device=dev)
+        pl = torch.zeros(B, W, dtype=torch.long, device=dev)
+        pq = torch.zeros(B, W, maxlen, dtype=torch.long, device=dev)
+        done = torch.zeros(B, dtype=torch.uint8, device=dev)
+        n = ctypes.c_size_t(0)
+        L.ctcps_beam_step_workspace_bytes(B, W, ctypes.byref(n))
+        ws = torch.zeros((n.value + 15) // 16 * 2, dtype=torch.int64, device=dev)
+        bo = torch.empty((B, W), dtype=torch.long, device=dev)
+        st_ = torch.cuda.current_stream().cuda_stream
+        res["prebeam beam_step_candidates"] = timeit(lambda: _lib.check(L.ctcps_beam_step_candidates(
+            cj.data_ptr(), cid.data_ptr(), S, bs.data_ptr(), idc.data_ptr(), idn.data_ptr(), maxlen, ol + 1, B, W, V, EOS, BLANK,
+            float(ol + 1), ps.data_ptr(), pl.data_ptr(), pq.data_ptr(), maxlen, done.data_ptr(), ws.data_ptr(), ws.numel() * 8, None, 0, 0,
+            bo.data_ptr(), st_), "beam_cand"), 20)
+        del proc, sc, st, sel
+        torch.cuda.empty_cache()
     if want("beam"):
         joint = torch.randn(BW, V, device=dev)
         maxlen = 128
@@ -77,7 +114,7 @@ def main():
         res["beam_step"] = timeit(lambda: _lib.check(L.ctcps_beam_step(joint.data_ptr(), bs.data_ptr(), idc.data_ptr(), idn.data_ptr(), maxlen,
                                                                        ol + 1, B, W, V, EOS, BLANK, float(ol + 1), ps.data_ptr(), pl.data_ptr(),
                                                                        pq.data_ptr(), maxlen, done.data_ptr(), ws.data_ptr(), ws.numel() * 8,
-                                                                       None, 0, 0, st), "beam"), 20)
+                                                                       None, 0, 0, None, st), "beam"), 20)
         res["torch topk(2W) of (B, W*V) for comparison"] = timeit(lambda: joint.view(B, W * V).topk(2 * W, dim=1), 20)
     for k, v in res.items():
         print(f"{k:48s} {v * 1e3:10.1f} us")
