@@ -269,8 +269,13 @@ class _PreBeamChecker:
         return out
 
 
-def replay_prebeam(make_processor, device, name, blank=3, eos=1, bos=0):
-    """make_processor(logits, lens, w, W, S, use_beam_idx) -> a processor in pre-beam mode on `device`."""
+def replay_prebeam(make_processor, device, name, blank=3, eos=1, bos=0, teacher_forced=False):
+    """make_processor(logits, lens, w, W, S, use_beam_idx) -> a processor in pre-beam mode on `device`.
+
+    teacher_forced: feed the golden input_ids of every step instead of letting the harness choose the beams.  Needed for
+    the token-only selection case on another device than the one that made the golden file: there a beam whose token
+    was not scored for hypothesis 0 gets s_prev = logzero, all its candidates score 3e9 (one fp32 ulp = 256) and tie
+    exactly, and torch.topk breaks exact ties differently on CPU and CUDA."""
     from huggingface_asr_b200.beam_search import joint_beam_search
     from huggingface_asr_b200.synthetic import make_attention_scores
 
@@ -281,6 +286,11 @@ def replay_prebeam(make_processor, device, name, blank=3, eos=1, bos=0):
     B, T, V = logits.shape
     proc = make_processor(logits.clone(), lens, float(g["ctc_weight"]), W, S, bool(g["use_beam_idx"]))
     chk = _PreBeamChecker(proc, g, name)
+    if teacher_forced:
+        assert not bool(g["use_beam_idx"])
+        for n in range(int(g["steps"])):
+            chk(torch.from_numpy(g[f"input_ids_{n}"]).to(device), make_attention_scores(B * W, V, n, seed=seed, scale=0.5).to(device))
+        return chk.worst
     out = joint_beam_search(chk, lambda ids, n: make_attention_scores(B * W, V, n, seed=seed, scale=0.5).to(device),
                             B, W, V, bos, eos, blank, max_length=int(g["max_length"]), device=device)
     assert out.steps == int(g["steps"])

@@ -23,7 +23,8 @@ def _proc(logits, lens, w, W, S, use_beam_idx, materialize=False, **kw):
 @pytest.mark.parametrize("name", parity.PREBEAM_CASES)
 @pytest.mark.parametrize("materialize", [False, True])
 def test_prebeam_vs_reference_golden(name, materialize):
-    worst = parity.replay_prebeam(lambda lg, ln, w, W, S, ubi: _proc(lg, ln, w, W, S, ubi, materialize), "cuda", name)
+    worst = parity.replay_prebeam(lambda lg, ln, w, W, S, ubi: _proc(lg, ln, w, W, S, ubi, materialize), "cuda", name,
+                                  teacher_forced=name.endswith("tokens_only"))
     print(name, "materialized" if materialize else "lazy", worst)
 
 
@@ -37,8 +38,8 @@ def test_sparse_fused_decode_vs_reference_golden(name):
     W, S, seed = int(g["W"]), int(g["S"]), int(g["seed"])
     logits, lens = torch.from_numpy(g["logits"]).cuda(), torch.from_numpy(g["lens"]).cuda()
     B, T, V = logits.shape
-    if S < 2:
-        pytest.skip("the sparse beam step needs S >= 2")
+    if not bool(g["use_beam_idx"]):
+        pytest.skip("token-only selection with candidates produces exact ties at 3e9 (see parity.replay_prebeam)")
     proc = _proc(logits, lens, float(g["ctc_weight"]), W, S, bool(g["use_beam_idx"]))
     out = joint_beam_search_fused(proc, lambda ids, n: make_attention_scores(B * W, V, n, seed=seed, scale=0.5).cuda(), B, W, V, BOS,
                                   EOS, BLANK, max_length=int(g["max_length"]), device="cuda")
