@@ -1,0 +1,199 @@
+"""The callers of the scorer, for transformers 5.x.
+
+The reference wires its processors into HF `generate()` in `JointCTCAttentionEncoderDecoder`
+(src/models/ctc_encoder_plus_autoregressive_decoder.py:360-482; copy: src/reguler/modeling_decred.py:434-482) against
+transformers 4.39.3, configures decoding through `GenerationConfigCustom` (src/trainers/train_enc_dec_asr.py:61-85) and
+reports decoding speed in `do_evaluate` / `do_generate` (src/utilities/general_utils.py:129-228).  This module restates
+those three pieces -- and only those -- for the transformers installed here (5.5), so a model class gets the sm_100a
+scorer by inheriting one mixin:
+
+    class MyASRModel(JointCTCAttentionGenerationMixin, SpeechEncoderDecoderModel): ...
+
+  * `JointCTCAttentionGenerationMixin._get_logits_processor`  (reference :360-404)
+  * `JointCTCAttentionGenerationMixin._reorder_cache`         not in the reference: hands HF's `beam_idx` to the processor
+                                                              (used only when the processor was built with use_beam_idx)
+  * `joint_ctc_generation_config`                             (GenerationConfigCustom, train_enc_dec_asr.py:61-85)
+  * `evaluate_decoding`                                       (do_evaluate's timing / tokens-per-second lines :150-164 and
+                                                              the WER that `compute_metrics` gets from jiwer)
+
+Models, trainers, datasets and tokenizers stay out of scope.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+from typing import Callable, Iterable, Sequence
+
+import torch
+from transformers import GenerationConfig, LogitsProcessorList
+
+from .decoding.ctc_scorer import CTCRescorerLogitsProcessor, LogSoftmaxProcessor
+
+
+def joint_ctc_generation_config(*, ctc_weight: float = 0.0, ctc_margin: int = 0, space_token_id: int = -1,
+                                apply_eos_space_trick: bool = False, eos_space_trick_weight: float = 1.0,
+                                ctc_pre_beam_size: int = 0, **generation_kwargs) -> GenerationConfig:
+    """GenerationConfig carrying the joint-decoding fields of the reference's GenerationConfigCustom
+    (train_enc_dec_asr.py:61-85; lm_weight / lm_model belong to the LM-fusion processor, out of scope) plus
+    `ctc_pre_beam_size` (N2, 0 = the reference's full-vocabulary scoring)."""
+    cfg = GenerationConfig(**generation_kwargs)
+    cfg.ctc_weight, cfg.ctc_margin, cfg.space_token_id = ctc_weight, ctc_margin, space_token_id
+    cfg.apply_eos_space_trick, cfg.eos_space_trick_weight = apply_eos_space_trick, eos_space_trick_weight
+    cfg.ctc_pre_beam_size = ctc_pre_beam_size
+    return cfg
+
+
+class JointCTCAttentionGenerationMixin:
+    """Generation hooks of JointCTCAttentionEncoderDecoder for transformers 5.x.
+
+    The model (or its `generate` override, reference :450-482) stores the CTC head's outputs of the current batch in
+    `self.encoder_logits` (B,T,V) -- un-expanded, one row per utterance -- and `self.encoder_output_lens` (B,) before
+    beam search starts (reference :406-418: `_prepare_encoder_decoder_kwargs_for_generation`); `set_ctc_inputs` does
+    that for callers that run the encoder themselves.
+    """
+
+    ctc_rescorer_cls = CTCRescorerLogitsProcessor  # tests substitute the CPU oracle's processor here
+    log_softmax_cls = LogSoftmaxProcessor
+    encoder_logits = None
+    encoder_output_lens = None
+    ctc_rescorer = None
+
+    def set_ctc_inputs(self, encoder_logits: torch.Tensor, encoder_output_lens: torch.Tensor) -> None:
+        self.encoder_logits, self.encoder_output_lens = encoder_logits, encoder_output_lens
+
+    def _get_logits_processor(self, generation_config, *args, **kwargs) -> LogitsProcessorList:
+        processors = super()._get_logits_processor(generation_config, *args, **kwargs)
+        if getattr(generation_config, "ctc_weight", 0) and generation_config.ctc_weight > 0:  # reference :382
+            if self.encoder_logits is None or self.encoder_output_lens is None:
+                raise ValueError("ctc_weight > 0 needs the CTC head outputs: call set_ctc_inputs(encoder_logits, encoder_output_lens) "
+                                 "(or store them in _prepare_encoder_decoder_kwargs_for_generation) before generate()")
+            if generation_config.num_beams <= 1:  # greedy search hands raw logits to the processors (:383-384)
+                processors.append(self.log_softmax_cls())
+            extra = {}
+            pre_beam = int(getattr(generation_config, "ctc_pre_beam_size", 0) or 0)
+            if pre_beam > 0:
+                extra["pre_beam_size"] = pre_beam
+            eos = generation_config.eos_token_id
+            if isinstance(eos, (list, tuple)):
+                eos = eos[0]
+            elif isinstance(eos, torch.Tensor):
+                eos = int(eos.flatten()[0])
+            self.ctc_rescorer = self.ctc_rescorer_cls(
+                self.encoder_logits,
+                self.encoder_output_lens,
+                generation_config.pad_token_id,
+                eos,
+                getattr(generation_config, "ctc_margin", 0),
+                generation_config.ctc_weight,
+                generation_config.num_beams,
+                getattr(generation_config, "space_token_id", -1),
+                getattr(generation_config, "apply_eos_space_trick", False),
+                getattr(generation_config, "eos_space_trick_weight", 1.0),
+                **extra,
+            )
+            processors.append(self.ctc_rescorer)
+        return processors
+
+    def _reorder_cache(self, past_key_values, beam_idx):
+        """HF beam search calls this with the rows the next step continues (global indices b*W + source beam).  The
+        reference's processor never sees them (it selects CTC states from token ids only, ctc_scorer.py:326-329); ours
+        uses them when it was built with use_beam_idx (always in pre-beam mode)."""
+        if self.ctc_rescorer is not None and hasattr(self.ctc_rescorer, "set_beam_idx"):
+            self.ctc_rescorer.set_beam_idx(beam_idx)
+        if hasattr(past_key_values, "reorder_cache"):
+            past_key_values.reorder_cache(beam_idx)
+        return past_key_values
+
+    @torch.no_grad()
+    def generate(self, *args, **kwargs):
+        try:
+            return super().generate(*args, **kwargs)
+        finally:  # reference :480-481: nothing of a batch survives its generate()
+            self.encoder_logits = None
+            self.encoder_output_lens = None
+            self.ctc_rescorer = None
+
+
+# ------------------------------------------------------------------------------------------------
+# evaluation driver
+# ------------------------------------------------------------------------------------------------
+def edit_distance(ref: Sequence, hyp: Sequence) -> int:
+    """Levenshtein distance between two token / word sequences (what jiwer computes for the reference's WER)."""
+    prev = list(range(len(hyp) + 1))
+    for i, r in enumerate(ref, 1):
+        cur = [i] + [0] * len(hyp)
+        for j, h in enumerate(hyp, 1):
+            cur[j] = min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (r != h))
+        prev = cur
+    return prev[-1]
+
+
+def error_rate(refs: Iterable[Sequence], hyps: Iterable[Sequence]) -> float:
+    """sum of edit distances / sum of reference lengths (WER over word lists, TER over token lists)."""
+    errs = n = 0
+    for r, h in zip(refs, hyps):
+        errs += edit_distance(r, h)
+        n += len(r)
+    return errs / max(n, 1)
+
+
+@dataclass
+class DecodingReport:
+    """What do_evaluate logs per split (general_utils.py:158-164), plus the error rate when references are given."""
+    utterances: int = 0
+    tokens_produced: int = 0
+    seconds: float = 0.0
+    error_rate: float | None = None
+    predictions: list = field(default_factory=list)
+
+    @property
+    def tokens_per_second(self) -> float:
+        return self.tokens_produced / self.seconds if self.seconds > 0 else float("nan")
+
+    @property
+    def utterances_per_second(self) -> float:
+        return self.utterances / self.seconds if self.seconds > 0 else float("nan")
+
+
+def evaluate_decoding(model, batches: Iterable[dict], generation_config: GenerationConfig, pad_token_id: int,
+                      decode: Callable[[list[int]], Sequence] | None = None,
+                      special_token_ids: Sequence[int] = ()) -> DecodingReport:
+    """Decode every batch with `model.generate` and report speed and error rate, like do_evaluate / do_generate.
+
+    A batch is a dict of `generate()` keyword arguments; the optional keys "labels" ((B,L) int64, pad- or -100-filled
+    references), "encoder_logits" and "encoder_output_lens" are consumed here: the latter two are handed to
+    `model.set_ctc_inputs` (a model that computes them itself in `_prepare_encoder_decoder_kwargs_for_generation`, like
+    the reference's, just omits them).  `decode` maps a list of token ids to the unit the error rate is counted in
+    (e.g. `lambda ids: tokenizer.decode(ids).split()` for WER); default: the token ids themselves.
+    Time is wall-clock around generate() with the device synchronised, as in the reference (:150-160)."""
+    rep = DecodingReport()
+    drop = set(special_token_ids) | {pad_token_id, -100}
+    refs, hyps = [], []
+    for batch in batches:
+        batch = dict(batch)
+        labels = batch.pop("labels", None)
+        enc_logits, enc_lens = batch.pop("encoder_logits", None), batch.pop("encoder_output_lens", None)
+        if enc_logits is not None:
+            model.set_ctc_inputs(enc_logits, enc_lens)
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = model.generate(generation_config=generation_config, **batch)
+        seqs = out.sequences if hasattr(out, "sequences") else out
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        rep.seconds += time.perf_counter() - t0
+        seqs = seqs.cpu()
+        rep.utterances += int(seqs.shape[0])
+        rep.tokens_produced += int((seqs != pad_token_id).sum())  # general_utils.py:158
+        for row in seqs.tolist():
+            ids = [t for t in row if t not in drop]
+            rep.predictions.append(ids)
+            hyps.append(decode(ids) if decode else ids)
+        if labels is not None:
+            for row in labels.cpu().tolist():
+                ids = [t for t in row if t not in drop]
+                refs.append(decode(ids) if decode else ids)
+    if refs:
+        rep.error_rate = error_rate(refs, hyps)
+    return rep
