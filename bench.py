@@ -31,7 +31,8 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-from huggingface_asr_b200.beam_search import joint_beam_search, joint_beam_search_fused  # noqa: E402
+from huggingface_asr_b200.beam_search import (joint_beam_search, joint_beam_search_fused, joint_beam_search_native,  # noqa: E402
+                                              resolve_score_timing)
 from huggingface_asr_b200.synthetic import BLANK, BOS, CONFIGS, EOS, SyntheticDecoder, make_encoder_logits  # noqa: E402
 
 METRIC = "utt/s beam-10 joint CTC/attn decode"
@@ -145,12 +146,17 @@ def run_ours(args):
         """Both legs for one state mode.  Returns a dict of raw measurements (max over ranks for the times)."""
         launches = [0]
         score_events = []
+        score_ms_native = []
 
         def decode(lg, ln, timing=None):
             proc = CTCRescorerLogitsProcessor(lg, ln, BLANK, EOS, 0, cfg.ctc_weight, W, -1, False, 1.0, materialize_state=materialize,
                                               pre_beam_size=pre_beam)
-            proc.ctc_prefix_scorer._timing = timing
-            if args.harness == "fused":
+            proc.ctc_prefix_scorer._timing = timing if (args.harness != "native" or materialize) else None
+            lag = (0 if materialize else 1) if args.done_check_lag is None else args.done_check_lag
+            if args.harness == "native" and not materialize:
+                out = joint_beam_search_native(proc, decoder, B, W, V, BOS, EOS, BLANK, max_length=MAX_LENGTH, device=dev,
+                                               done_check_lag=lag, score_timing=None if timing is None else score_ms_native)
+            elif args.harness in ("fused", "native"):
                 out = joint_beam_search_fused(proc, decoder, B, W, V, BOS, EOS, BLANK, max_length=MAX_LENGTH, device=dev,
                                               done_check_lag=(0 if materialize else 1) if args.done_check_lag is None else args.done_check_lag)
             else:
@@ -158,15 +164,16 @@ def run_ours(args):
             # our kernels: K-a (1) + initial state (1); per step: scoring kernel (1) [+ fused beam step (1)], plus its
             # preparation kernel (every step when materialised; first step only in lazy mode, where the select scan of
             # the previous step prepares it); all steps but the first: select (1 gather, or 2 for the lazy stage + scan)
-            beam = 1 if args.harness == "fused" else 0
+            beam = 0 if args.harness == "torch" else 1
+            native = 1 if (args.harness == "native" and not materialize) else 0  # the native step also selects after the last step
             if pre_beam:
                 # K-a + transpose + initial state; per step: top-S, candidate scores, [dense scatter when the harness is not
                 # sparse], [beam step]; first step: k_prep_psi; all steps but the first: select stage + scan
-                dense = 0 if (args.harness == "fused" and pre_beam >= 2) else 1
-                launches[0] += 3 + out.steps * (2 + dense + beam) + 1 + (out.steps - 1) * 2
+                dense = 0 if (args.harness != "torch" and pre_beam >= 2) else 1
+                launches[0] += 3 + out.steps * (2 + dense + beam) + 1 + (out.steps - 1 + native) * 2
             else:
                 launches[0] += (2 + out.steps * (1 + beam) + (out.steps if materialize else 1)
-                                + (out.steps - 1) * (1 if materialize else 2))
+                                + (out.steps - 1 + native) * (1 if materialize else 2))
             last_sequences[(materialize, pre_beam)] = out.sequences
             return out
 
@@ -191,7 +198,7 @@ def run_ours(args):
         clk = clocks.stop()
         ms = e0.elapsed_time(e1)
         n_launch = launches[0]
-        score_ms = [a.elapsed_time(b) for a, b in score_events]
+        score_ms = [a.elapsed_time(b) for a, b in score_events] + resolve_score_timing(score_ms_native)
         res = {"ms": ms, "launches": n_launch, "score_ms": sum(score_ms) / max(len(score_ms), 1), "n_score": len(score_ms),
                "decode_steps": steps_total / args.steps, "clocks": clk, "ms_e2e": float("nan")}
         if args.profile:
@@ -413,8 +420,10 @@ def main():
     ap.add_argument("--single-mode", action="store_true", help="measure only --state")
     ap.add_argument("--pre-beam", type=int, default=15,
                     help="also measure pre-beam decoding with this many candidates per hypothesis (0 = skip); reported under 'pre_beam'")
-    ap.add_argument("--harness", default="fused", choices=["fused", "torch"],
-                    help="beam update between processor calls: one ctcps_beam_step launch (default) or the torch restatement")
+    ap.add_argument("--harness", default="native", choices=["native", "fused", "torch"],
+                    help="decode loop: native = one ctcps_decode_step host call per step (default; lazy state -- the materialized mode "
+                         "falls back to fused), fused = processor call + one ctcps_beam_step launch per step from Python, "
+                         "torch = the torch restatement of the HF loop")
     ap.add_argument("--done-check-lag", type=int, default=None,
                     help="fused harness: steps the CPU may run ahead of the GPU (default: 0 materialized, 1 lazy)")
     ap.add_argument("--profile", action="store_true", help="for runs under ncu: honour a warm-up below 3 and skip the e2e/cpu legs (never a bench value)")

@@ -94,11 +94,35 @@ SIGNATURES = {
     "ctcps_score_candidates": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _f, _f, _p, _p, _p, _p, _sz, _i, _p],
     "ctcps_candidates_to_dense": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _i, _p, _p, _p, _p],
     "ctcps_select_lazy_candidates": [_p, _i, _p, _p, _p, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p],
+    "ctcps_async_create": [ctypes.POINTER(_p), ctypes.POINTER(_p), ctypes.POINTER(_p)],
+    "ctcps_async_destroy": [_p, _p, _p],
+    "ctcps_event_create": [ctypes.POINTER(_p)],
+    "ctcps_event_destroy": [_p],
+    "ctcps_event_elapsed_ms": [_p, _p, ctypes.POINTER(_f)],
+    "ctcps_decode_step": [_p, _p, _i, _p, _p, _p],
+    "ctcps_decode_finish": [_p, _p],
     "ctcps_beam_step_candidates": [_p, _p, _i, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i64, _p, _p, _sz, _p, _i,
                                    _i64, _p, _p],
     "ctcps_select": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p],
     "ctcps_eos_space_trick": [_p, _p, _p, _i, _i, _i, _i, _f, _p],
 }
+
+
+class DecodeSession(ctypes.Structure):
+    """ctcps_decode_session of include/ctcps.h (same field order and types)."""
+    _fields_ = [
+        ("B", ctypes.c_int32), ("W", ctypes.c_int32), ("T", ctypes.c_int32), ("V", ctypes.c_int32), ("S", ctypes.c_int32),
+        ("blank", ctypes.c_int32), ("eos", ctypes.c_int32), ("pad", ctypes.c_int32), ("use_beam_idx", ctypes.c_int32),
+        ("ldx", ctypes.c_int32), ("ldt", ctypes.c_int32), ("ring", ctypes.c_int32),
+        ("one_minus_w", _f), ("w", _f), ("length_penalty", _f),
+        ("x_logp", _p), ("x_vt", _p), ("blank_lp", _p), ("r0", _p),
+        ("r_sel", _p * 2), ("s_sel", _p * 2), ("last_ids", _p * 2), ("cand_ids", _p * 2), ("cand_att", _p * 2),
+        ("cand_log_psi", _p * 2), ("cand_joint", _p), ("log_psi", _p * 2), ("joint", _p),
+        ("score_ws", _p), ("score_ws_bytes", _sz),
+        ("beam_scores", _p), ("ids", _p * 2), ("ld_ids", _i64), ("pool_scores", _p), ("pool_lens", _p), ("pool_seqs", _p),
+        ("ld_pool", _i64), ("done", _p), ("beam_ws", _p), ("beam_ws_bytes", _sz), ("done_ring", _p), ("best_ids", _p),
+        ("side_stream", _p), ("ev_step", _p), ("ev_select", _p),
+    ]
 
 
 def lib() -> ctypes.CDLL:

@@ -209,3 +209,155 @@ def joint_beam_search_fused(processor: Callable, decoder_log_probs: Callable[[to
                 break
     return _finalize(ids[cur][:, :L], beam_scores, pool_scores, pool_seqs, pool_lens, done.bool(), B, W, max_length, pad,
                      length_penalty, steps)
+
+
+@torch.no_grad()
+def joint_beam_search_native(processor, decoder_log_probs: Callable[[torch.Tensor, int], torch.Tensor], batch: int, num_beams: int,
+                             vocab: int, bos: int, eos: int, pad: int, max_length: int = 512, length_penalty: float = 1.0,
+                             device: torch.device | str = "cuda", done_check_lag: int = 1, score_timing: list | None = None) -> BeamSearchOutput:
+    """joint_beam_search_fused with ONE host call per decode step (ctcps_decode_step): [top-S candidates,] prefix scoring +
+    joint combine, beam step and -- on a side stream, under the next decoder forward pass -- the lazy state selection.
+    Same kernels and results as the fused loop; the 5-10 ctypes / torch calls it makes per step cost more host time
+    than the ~150-500 us of GPU work they enqueue.
+
+    `processor` is a CTCRescorerLogitsProcessor in lazy-state mode (full vocabulary or pre-beam); the loop uses its
+    posteriors, weights and policy flags and keeps the CTC state itself (processor.ctc_states is not touched).
+    score_timing: a list that receives one (begin, end) CUDA-event pair per step, recorded around the step's scoring call;
+    resolve_score_timing(list) turns them into milliseconds after the caller has synchronised (bench.py's roofline)."""
+    import ctypes
+
+    from . import _lib
+
+    L_ = _lib.lib()
+    B, W, V = batch, num_beams, vocab
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError("joint_beam_search_native needs a CUDA device (there is no CPU path)")
+    sc = processor.ctc_prefix_scorer
+    if processor.materialize_state or processor.apply_eos_space_trick:
+        raise RuntimeError("the native decode loop runs the lazy-state scorer without the eos/space trick; use joint_beam_search_fused")
+    if sc.batch != B or sc.odim != V or processor.num_beams != W:
+        raise ValueError("processor and loop disagree on batch / vocabulary / beams")
+    S = int(processor.pre_beam_size)
+    if S == 1:
+        raise ValueError("pre_beam_size = 1 leaves fewer than 2W candidates: use 0 or >= 2")
+    T, BW = sc.input_length, B * W
+    NEG = float("-inf")
+    f32 = dict(dtype=torch.float32, device=dev)
+    i64 = dict(dtype=torch.long, device=dev)
+    with torch.cuda.device(dev):
+        ids = [torch.full((BW, max_length), pad, **i64) for _ in range(2)]
+        ids[0][:, 0] = bos
+        last = [torch.full((BW,), bos, **i64), torch.empty((BW,), **i64)]
+        beam_scores = torch.zeros(B, W, **f32)
+        beam_scores[:, 1:] = -1e9
+        pool_scores = torch.full((B, W), NEG, **f32)
+        pool_seqs = torch.full((B, W, max_length), pad, **i64)
+        pool_lens = torch.zeros(B, W, **i64)
+        done = torch.zeros(B, dtype=torch.uint8, device=dev)
+        nws = ctypes.c_size_t(0)
+        _lib.check(L_.ctcps_beam_step_workspace_bytes(B, W, ctypes.byref(nws)), "ctcps_beam_step_workspace_bytes")
+        beam_ws = torch.zeros((nws.value + 15) // 16 * 2, **i64)
+        r0 = sc.initial_state(W)
+        r_sel = [torch.empty((T, 2, BW), **f32) for _ in range(2)]
+        s_sel = [torch.empty((BW,), **f32) for _ in range(2)]
+        best_ids = torch.empty((B, W), **i64)
+        ws = sc._workspace(W, 0)
+        keep = [ids, last, beam_scores, pool_scores, pool_seqs, pool_lens, done, beam_ws, r0, r_sel, s_sel, best_ids, ws]
+        sess = _lib.DecodeSession()
+        sess.B, sess.W, sess.T, sess.V, sess.S = B, W, T, V, S
+        sess.blank, sess.eos, sess.pad = sc.blank, eos, pad
+        sess.use_beam_idx = int(bool(processor.use_beam_idx))
+        w = float(processor.ctc_weight)
+        sess.one_minus_w, sess.w, sess.length_penalty = 1.0 - w, w, float(length_penalty)
+        sess.ldx, sess.ldt = sc._ldx, sc._ldt
+        if S > 0:
+            sess.x_vt = sc._token_major().data_ptr()
+            cand_ids = [torch.empty((BW, S), **i64) for _ in range(2)]
+            cand_att = [torch.empty((BW, S), **f32) for _ in range(2)]
+            cand_lp = [torch.empty((BW, S), **f32) for _ in range(2)]
+            cand_joint = torch.empty((BW, S), **f32)
+            keep += [cand_ids, cand_att, cand_lp, cand_joint]
+            for k in range(2):
+                sess.cand_ids[k], sess.cand_att[k], sess.cand_log_psi[k] = cand_ids[k].data_ptr(), cand_att[k].data_ptr(), cand_lp[k].data_ptr()
+            sess.cand_joint = cand_joint.data_ptr()
+        else:
+            sess.x_logp = sc._frame_major().data_ptr()
+            log_psi = [torch.empty((BW, V), **f32) for _ in range(2)]
+            joint = torch.empty((BW, V), **f32)
+            keep += [log_psi, joint]
+            sess.log_psi[0], sess.log_psi[1], sess.joint = log_psi[0].data_ptr(), log_psi[1].data_ptr(), joint.data_ptr()
+        sess.blank_lp, sess.r0 = sc._blank_lp.data_ptr(), r0.data_ptr()
+        for k in range(2):
+            sess.r_sel[k], sess.s_sel[k], sess.last_ids[k], sess.ids[k] = r_sel[k].data_ptr(), s_sel[k].data_ptr(), last[k].data_ptr(), ids[k].data_ptr()
+        sess.score_ws, sess.score_ws_bytes = ws.data_ptr(), ws.numel()
+        sc._ws_gen += 1  # the loop overwrites the scorer's workspace
+        sess.beam_scores, sess.ld_ids = beam_scores.data_ptr(), max_length
+        sess.pool_scores, sess.pool_lens, sess.pool_seqs, sess.ld_pool = pool_scores.data_ptr(), pool_lens.data_ptr(), pool_seqs.data_ptr(), max_length
+        sess.done, sess.beam_ws, sess.beam_ws_bytes = done.data_ptr(), beam_ws.data_ptr(), beam_ws.numel() * 8
+        RING = 8
+        ring = torch.full((RING,), -1, dtype=torch.int64).pin_memory()
+        ring_np = ring.numpy()
+        sess.done_ring, sess.ring, sess.best_ids = ring.data_ptr(), RING, best_ids.data_ptr()
+        side, ev_a, ev_b = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(L_.ctcps_async_create(ctypes.byref(side), ctypes.byref(ev_a), ctypes.byref(ev_b)), "ctcps_async_create")
+        sess.side_stream, sess.ev_step, sess.ev_select = side, ev_a, ev_b
+        stream = torch.cuda.current_stream(dev)
+        timing_events = []
+        sref = ctypes.byref(sess)
+        cur, L, steps = 0, 1, 0
+        try:
+            while True:
+                log_probs = decoder_log_probs(ids[cur][:, :L], steps)
+                if not log_probs.is_contiguous() or log_probs.dtype != torch.float32:
+                    raise ValueError("the decoder must return contiguous float32 log-probs (BW,V)")
+                e0 = e1 = None
+                if score_timing is not None:
+                    e0, e1 = ctypes.c_void_p(), ctypes.c_void_p()
+                    _lib.check(L_.ctcps_event_create(ctypes.byref(e0)), "ctcps_event_create")
+                    _lib.check(L_.ctcps_event_create(ctypes.byref(e1)), "ctcps_event_create")
+                    timing_events.append((e0, e1))
+                _lib.check(L_.ctcps_decode_step(sref, log_probs.data_ptr(), steps, e0, e1, stream.cuda_stream), "ctcps_decode_step")
+                cur ^= 1
+                L += 1
+                steps += 1
+                if L >= max_length:
+                    break
+                look = steps - 1 - done_check_lag
+                if look >= 0:
+                    if done_check_lag == 0:
+                        stream.synchronize()
+                    else:  # the entry of an older step: wait (briefly) until the GPU has published it
+                        while int(ring_np[look % RING]) >> 32 != look:
+                            pass
+                    if (int(ring_np[look % RING]) & 0xFFFFFFFF) == B:
+                        break
+            out = _finalize(ids[cur][:, :L], beam_scores, pool_scores, pool_seqs, pool_lens, done.bool(), B, W, max_length, pad,
+                            length_penalty, steps)
+        finally:
+            # the selection of the last step may still run on the side stream and uses buffers this frame owns: order
+            # everything the caller enqueues next behind it (no host synchronisation)
+            L_.ctcps_decode_finish(sref, stream.cuda_stream)
+            if score_timing is not None:
+                score_timing.extend(timing_events)  # resolved by the caller with resolve_score_timing() once the work is done
+            L_.ctcps_async_destroy(side, ev_a, ev_b)
+            del keep
+    return out
+
+
+def resolve_score_timing(pairs) -> list:
+    """Milliseconds of the (begin, end) event pairs collected by joint_beam_search_native(score_timing=...); destroys the
+    events.  Call after the device has finished the decodes (torch.cuda.synchronize)."""
+    import ctypes
+
+    from . import _lib
+
+    L_ = _lib.lib()
+    out = []
+    ms = ctypes.c_float(0.0)
+    for e0, e1 in pairs:
+        if L_.ctcps_event_elapsed_ms(e0, e1, ctypes.byref(ms)) == 0:
+            out.append(ms.value)
+        L_.ctcps_event_destroy(e0)
+        L_.ctcps_event_destroy(e1)
+    return out

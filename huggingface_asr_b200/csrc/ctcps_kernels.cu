@@ -1148,6 +1148,7 @@ __device__ __forceinline__ void rank_select(const Cand *cands, int n, int K, flo
 template <int KL, bool SPARSE>
 __global__ void __launch_bounds__(BEAM_NT) k_beam_step(const float *__restrict__ joint, const int64_t *__restrict__ cand_ids, int S,
                                                        float *beam_scores, int64_t *__restrict__ best_ids_out,
+                                                       int64_t *__restrict__ last_ids_out,
                                                        const int64_t *__restrict__ ids_cur, int64_t *__restrict__ ids_next,
                                                        long long ld_ids, int L, int W, int V, int P, int eos, int pad,
                                                        float len_norm, float *pool_scores, int64_t *pool_lens,
@@ -1326,6 +1327,7 @@ __global__ void __launch_bounds__(BEAM_NT) k_beam_step(const float *__restrict__
             beam_scores[b * W + k] = ns[k];
             // what index_select_state wants (ESPnet ids: source hypothesis * V + token, :180-191)
             if (best_ids_out != nullptr) best_ids_out[b * W + k] = (long long)next_src_s[k] * V + next_tok_s[k];
+            if (last_ids_out != nullptr) last_ids_out[b * W + k] = next_tok_s[k];
         }
         done[b] = dn_new ? 1 : 0;
     }
@@ -1561,7 +1563,7 @@ int select_lazy_impl(const XView x, const float *blank_lp, const float *r_prev, 
 int beam_step_impl(const float *joint, const int64_t *cand_ids, int S, float *beam_scores, const int64_t *ids_cur, int64_t *ids_next,
                    int64_t ld_ids, int L, int B, int W, int V, int eos, int pad, float len_norm, float *pool_scores, int64_t *pool_lens,
                    int64_t *pool_seqs, int64_t ld_pool, unsigned char *done, void *workspace, size_t workspace_bytes,
-                   int64_t *done_ring, int ring, int64_t step_tag, int64_t *best_ids_out, cudaStream_t st) {
+                   int64_t *done_ring, int ring, int64_t step_tag, int64_t *best_ids_out, int64_t *last_ids_out, cudaStream_t st) {
     ARG_CHECK(joint && beam_scores && ids_cur && ids_next && pool_scores && pool_lens && pool_seqs && done && workspace,
               CTCPS_E_BADARG, "beam_step: null pointer");
     ARG_CHECK(B > 0 && W > 0 && V > 0 && L >= 1 && L < ld_ids && L - 1 <= ld_pool, CTCPS_E_BADARG, "beam_step: bad size");
@@ -1582,7 +1584,7 @@ int beam_step_impl(const float *joint, const int64_t *cand_ids, int S, float *be
         while (P > 1 && (long long)W * V / P < 4 * 2 * W) --P;  // keep slices much longer than K
     }
 #define CTCPS_BEAM_LAUNCH(KL, SP)                                                                                                  \
-    k_beam_step<KL, SP><<<B * P, BEAM_NT, 0, st>>>(joint, cand_ids, S, beam_scores, best_ids_out, ids_cur, ids_next, ld_ids, L, W, V, P, \
+    k_beam_step<KL, SP><<<B * P, BEAM_NT, 0, st>>>(joint, cand_ids, S, beam_scores, best_ids_out, last_ids_out, ids_cur, ids_next, ld_ids, L, W, V, P, \
                                                    eos, pad, len_norm, pool_scores, pool_lens, pool_seqs, ld_pool, done, part,      \
                                                    utt_ticket, ticket, (long long *)done_ring, ring, step_tag)
     if (cand_ids != nullptr) {
@@ -1855,7 +1857,7 @@ int ctcps_beam_step(const float *joint, float *beam_scores, const int64_t *ids_c
                     int64_t ld_pool, unsigned char *done, void *workspace, size_t workspace_bytes, int64_t *done_ring, int ring,
                     int64_t step_tag, int64_t *best_ids_out, void *stream) {
     return beam_step_impl(joint, nullptr, 0, beam_scores, ids_cur, ids_next, ld_ids, L, B, W, V, eos, pad, len_norm, pool_scores, pool_lens,
-                          pool_seqs, ld_pool, done, workspace, workspace_bytes, done_ring, ring, step_tag, best_ids_out,
+                          pool_seqs, ld_pool, done, workspace, workspace_bytes, done_ring, ring, step_tag, best_ids_out, nullptr,
                           (cudaStream_t)stream);
 }
 
@@ -1866,7 +1868,7 @@ int ctcps_beam_step_candidates(const float *cand_joint, const int64_t *cand_ids,
                                int64_t *best_ids_out, void *stream) {
     ARG_CHECK(cand_ids != nullptr && S >= 2, CTCPS_E_BADARG, "beam_step_candidates: need candidate ids and S >= 2");
     return beam_step_impl(cand_joint, cand_ids, S, beam_scores, ids_cur, ids_next, ld_ids, L, B, W, V, eos, pad, len_norm, pool_scores,
-                          pool_lens, pool_seqs, ld_pool, done, workspace, workspace_bytes, done_ring, ring, step_tag, best_ids_out,
+                          pool_lens, pool_seqs, ld_pool, done, workspace, workspace_bytes, done_ring, ring, step_tag, best_ids_out, nullptr,
                           (cudaStream_t)stream);
 }
 
@@ -1908,11 +1910,10 @@ int ctcps_prebeam_topk(float *att_scores, int BW, int V, int blank, int S, int64
     ARG_CHECK(att_scores && scoring_ids && cand_att && BW > 0 && V > 0, CTCPS_E_BADARG, "prebeam_topk: bad argument");
     ARG_CHECK(blank >= 0 && blank < V, CTCPS_E_BADARG, "prebeam_topk: blank id outside the vocabulary");
     ARG_CHECK(S >= 1 && S <= 64 && S <= V, CTCPS_E_TOOBIG, "prebeam_topk: need 1 <= S <= min(64, V)");
-    const int grid = (BW + 3) / 4;
     if (S <= 32)
-        k_prebeam_topk<1><<<grid, 128, 0, (cudaStream_t)stream>>>(att_scores, BW, V, blank, S, scoring_ids, cand_att);
+        k_prebeam_topk<1><<<BW, BEAM_NT, 0, (cudaStream_t)stream>>>(att_scores, V, blank, S, scoring_ids, cand_att);
     else
-        k_prebeam_topk<2><<<grid, 128, 0, (cudaStream_t)stream>>>(att_scores, BW, V, blank, S, scoring_ids, cand_att);
+        k_prebeam_topk<2><<<BW, BEAM_NT, 0, (cudaStream_t)stream>>>(att_scores, V, blank, S, scoring_ids, cand_att);
     return cuda_rc(cudaGetLastError());
 }
 
@@ -1986,6 +1987,109 @@ int ctcps_select_lazy_candidates(const float *x_vt, int ldt, const float *blank_
     const XView x = {x_vt, (long long)V * ldt, 1, (long long)ldt};
     return select_lazy_impl(x, blank_lp, r_prev, last_ids, ol, cand_log_psi, scoring_ids, S, best_ids, B, W, T, V, r_new, s_new,
                             next_workspace, next_workspace_bytes, (cudaStream_t)stream);
+}
+
+/* ---- native decode-step driver ----------------------------------------------------------------------------- */
+
+int ctcps_async_create(void **side_stream, void **ev_step, void **ev_select) {
+    ARG_CHECK(side_stream && ev_step && ev_select, CTCPS_E_BADARG, "async_create: null pointer");
+    cudaStream_t st;
+    cudaEvent_t a, b;
+    cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaEventCreateWithFlags(&a, cudaEventDisableTiming);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaEventCreateWithFlags(&b, cudaEventDisableTiming);
+    if (e != cudaSuccess) return (int)e;
+    *side_stream = st, *ev_step = a, *ev_select = b;
+    return 0;
+}
+
+int ctcps_async_destroy(void *side_stream, void *ev_step, void *ev_select) {
+    if (ev_step) cudaEventDestroy((cudaEvent_t)ev_step);
+    if (ev_select) cudaEventDestroy((cudaEvent_t)ev_select);
+    if (side_stream) cudaStreamDestroy((cudaStream_t)side_stream);
+    return 0;
+}
+
+int ctcps_event_create(void **event) {
+    ARG_CHECK(event != nullptr, CTCPS_E_BADARG, "event_create: null pointer");
+    cudaEvent_t e;
+    cudaError_t rc = cudaEventCreate(&e);
+    if (rc != cudaSuccess) return (int)rc;
+    *event = e;
+    return 0;
+}
+int ctcps_event_destroy(void *event) { return event ? cuda_rc(cudaEventDestroy((cudaEvent_t)event)) : 0; }
+int ctcps_event_elapsed_ms(void *begin, void *end, float *ms) {
+    ARG_CHECK(begin && end && ms, CTCPS_E_BADARG, "event_elapsed_ms: null pointer");
+    return cuda_rc(cudaEventElapsedTime(ms, (cudaEvent_t)begin, (cudaEvent_t)end));
+}
+
+int ctcps_decode_step(const ctcps_decode_session *s, float *att_scores, int step, void *ev_score_begin, void *ev_score_end,
+                      void *stream) {
+    ARG_CHECK(s != nullptr && att_scores != nullptr && step >= 0, CTCPS_E_BADARG, "decode_step: bad argument");
+    ARG_CHECK(s->S == 0 || s->S >= 2, CTCPS_E_BADARG, "decode_step: S must be 0 (full vocabulary) or >= 2");
+    cudaStream_t main_st = (cudaStream_t)stream;
+    cudaStream_t side = s->side_stream ? (cudaStream_t)s->side_stream : main_st;
+    const int cur = step & 1, nxt = cur ^ 1;
+    const int L = step + 1, ol = step;
+    const int B = s->B, W = s->W, T = s->T, V = s->V, S = s->S;
+    const float *r_prev = step == 0 ? s->r0 : s->r_sel[cur];
+    const float *s_prev = step == 0 ? nullptr : s->s_sel[cur];
+    const int prepared = (step > 0 && step <= T) ? 1 : 0;  // the select of the previous step prepared this step's workspace
+    const float len_norm = powf((float)L, s->length_penalty);
+    int rc;
+    if (S > 0) {  // the candidates do not depend on the CTC state: rank them while the select of the previous step still runs
+        rc = ctcps_prebeam_topk(att_scores, B * W, V, s->blank, S, s->cand_ids[cur], s->cand_att[cur], main_st);
+        if (rc) return rc;
+    }
+    if (step > 0 && side != main_st) {
+        cudaError_t e = cudaStreamWaitEvent(main_st, (cudaEvent_t)s->ev_select, 0);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (ev_score_begin) cudaEventRecord((cudaEvent_t)ev_score_begin, main_st);
+    if (S > 0) {
+        rc = ctcps_score_candidates(s->x_vt, s->ldt, r_prev, s_prev, s->last_ids[cur], ol, B, W, T, V, s->blank, s->cand_ids[cur], S,
+                                    s->cand_att[cur], s->one_minus_w, s->w, s->cand_log_psi[cur], nullptr, s->cand_joint, s->score_ws,
+                                    s->score_ws_bytes, prepared, main_st);
+    } else {
+        rc = ctcps_score_lazy(s->x_logp, s->ldx, s->blank_lp, r_prev, s_prev, 1, 0, s->last_ids[cur], ol, B, W, T, V, s->blank, att_scores,
+                              s->one_minus_w, s->w, s->log_psi[cur], nullptr, s->joint, s->score_ws, s->score_ws_bytes, prepared, main_st);
+    }
+    if (rc) return rc;
+    if (ev_score_end) cudaEventRecord((cudaEvent_t)ev_score_end, main_st);
+    rc = beam_step_impl(S > 0 ? s->cand_joint : s->joint, S > 0 ? s->cand_ids[cur] : nullptr, S, s->beam_scores, s->ids[cur], s->ids[nxt],
+                        s->ld_ids, L, B, W, V, s->eos, s->pad, len_norm, s->pool_scores, s->pool_lens, s->pool_seqs, s->ld_pool, s->done,
+                        s->beam_ws, s->beam_ws_bytes, s->done_ring, s->ring, (int64_t)step, s->best_ids, s->last_ids[nxt], main_st);
+    if (rc) return rc;
+    if (side != main_st) {
+        cudaError_t e = cudaEventRecord((cudaEvent_t)s->ev_step, main_st);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(side, (cudaEvent_t)s->ev_step, 0);
+        if (e != cudaSuccess) return (int)e;
+    }
+    // state of the next step: ESPnet ids (source hypothesis * V + token) or, like the reference's processor, tokens only
+    const int64_t *sel_ids = s->use_beam_idx ? s->best_ids : s->last_ids[nxt];
+    if (S > 0) {
+        rc = ctcps_select_lazy_candidates(s->x_vt, s->ldt, s->blank_lp, r_prev, s->last_ids[cur], ol, s->cand_ids[cur], S,
+                                          s->cand_log_psi[cur], sel_ids, B, W, T, V, s->r_sel[nxt], s->s_sel[nxt], s->score_ws,
+                                          s->score_ws_bytes, side);
+    } else {
+        rc = ctcps_select_lazy(s->x_logp, s->ldx, s->blank_lp, r_prev, s->last_ids[cur], ol, s->log_psi[cur], sel_ids, B, W, T, V,
+                               s->r_sel[nxt], s->s_sel[nxt], s->score_ws, s->score_ws_bytes, side);
+    }
+    if (rc) return rc;
+    if (side != main_st) {
+        cudaError_t e = cudaEventRecord((cudaEvent_t)s->ev_select, side);
+        if (e != cudaSuccess) return (int)e;
+    }
+    return 0;
+}
+
+int ctcps_decode_finish(const ctcps_decode_session *s, void *stream) {
+    ARG_CHECK(s != nullptr, CTCPS_E_BADARG, "decode_finish: null session");
+    if (s->side_stream == nullptr || s->side_stream == stream) return 0;
+    return cuda_rc(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)s->ev_select, 0));
 }
 
 }  // extern "C"

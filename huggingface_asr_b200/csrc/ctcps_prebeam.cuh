@@ -37,14 +37,17 @@ __global__ void __launch_bounds__(256) k_transpose_vt(const float *__restrict__ 
     }
 }
 
-// One warp per row of the decoder scores: sets scores[row, blank] = logzero in place (:325) and returns the S best
-// (score, id) pairs of the row, best first, equal scores by lower id (the order of warp_list_insert).
+// One CTA (4 warps) per row of the decoder scores: sets scores[row, blank] = logzero in place (:325) and returns the S
+// best (score, id) pairs of the row, best first, equal scores by lower id.  Each warp keeps the sorted top-S of its quarter
+// of the row in registers (warp_list_insert), the four lists are merged by rank counting in shared memory.
 template <int KL>
-__global__ void __launch_bounds__(128) k_prebeam_topk(float *att, int BW, int V, int blank, int S, int64_t *__restrict__ ids,
-                                                      float *__restrict__ cand_att) {
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= BW) return;
+__global__ void __launch_bounds__(BEAM_NT) k_prebeam_topk(float *att, int V, int blank, int S, int64_t *__restrict__ ids,
+                                                          float *__restrict__ cand_att) {
+    __shared__ Cand wl[BEAM_NW * BEAM_MAXK];
+    __shared__ Cand top[BEAM_MAXK];
+    __shared__ float kth[BEAM_NW];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int row = blockIdx.x;
     const float NEG = -INFINITY;
     float ls[KL];
     int li[KL];
@@ -53,14 +56,16 @@ __global__ void __launch_bounds__(128) k_prebeam_topk(float *att, int BW, int V,
     float thr = NEG;
     const int thr_lane = (S - 1) & 31, thr_list = (S - 1) >> 5;
     float *a = att + (size_t)row * V;
+    const int per_warp = (((V + BEAM_NW - 1) / BEAM_NW + 31) / 32) * 32;
+    const int s0 = min(V, wid * per_warp), e0 = min(V, s0 + per_warp);
     constexpr int U = 8;
-    for (int vb0 = 0; vb0 < V; vb0 += 32 * U) {
+    for (int vb0 = s0; vb0 < e0; vb0 += 32 * U) {
         float cu[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int i = vb0 + u * 32 + lane;
             // -inf (a token masked by another processor) still ranks, below everything finite, so that S ids always exist
-            cu[u] = i < V ? (i == blank ? LZ : fmaxf(a[i], -3.0e38f)) : NEG;
+            cu[u] = i < e0 ? (i == blank ? LZ : fmaxf(a[i], -3.0e38f)) : NEG;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -77,15 +82,24 @@ __global__ void __launch_bounds__(128) k_prebeam_topk(float *att, int BW, int V,
             }
         }
     }
-    if (lane == 0) a[blank] = LZ;
+    Cand *mine = wl + wid * BEAM_MAXK;
 #pragma unroll
-    for (int j = 0; j < KL; ++j) {
-        const int pos = j * 32 + lane;
-        if (pos < S) {
-            ids[(size_t)row * S + pos] = li[j];
-            cand_att[(size_t)row * S + pos] = li[j] == blank ? LZ : a[li[j]];
-        }
+    for (int j = 0; j < KL; ++j) mine[j * 32 + lane].s = ls[j], mine[j * 32 + lane].i = li[j];
+    if (KL == 1) mine[32 + lane].s = NEG, mine[32 + lane].i = 0x7fffffff;
+    if (lane == 0) kth[wid] = thr;
+    for (int k = tid; k < BEAM_MAXK; k += BEAM_NT) top[k].s = NEG, top[k].i = 0x7fffffff;
+    __syncthreads();
+    float bound = kth[0];
+    for (int q = 1; q < BEAM_NW; ++q) bound = fmaxf(bound, kth[q]);
+    rank_select(wl, BEAM_NW * BEAM_MAXK, S, bound, top);
+    __syncthreads();
+    if (tid < S) {
+        const int id = top[tid].i;
+        ids[(size_t)row * S + tid] = id;
+        cand_att[(size_t)row * S + tid] = id == blank ? LZ : a[id];
     }
+    __syncthreads();
+    if (tid == 0) a[blank] = LZ;
 }
 
 struct CandArgs {

@@ -194,6 +194,69 @@ int ctcps_beam_step_candidates(const float *cand_joint, const int64_t *cand_ids,
                                int64_t *best_ids_out, void *stream);
 
 /*
+ * Native decode-step driver: ONE host call enqueues a whole joint-decoding step -- [top-S candidates,] prefix scoring
+ * fused with the joint combine, the beam-search step, and (on a side stream, overlapping the caller's next decoder
+ * forward pass) the lazy state selection that also prepares the next scoring call.  It is what
+ * huggingface_asr_b200/beam_search.py::joint_beam_search_fused does with 5-10 ctypes / torch calls per step; at
+ * ~150 us of GPU work per step those calls were the bottleneck.  Same kernels, same results.
+ *
+ * The caller fills the session once per generate() (all buffers are the caller's; [2] = ping-pong by step parity) and
+ * calls ctcps_decode_step(session, decoder scores of this step, step) with step = 0, 1, 2, ...; before step 0:
+ * ids[0][:, 0] = bos, last_ids[0][:] = bos, beam_scores = {0, -1e9, ...}, pool_scores = -inf, done = 0, beam_ws zeroed.
+ * After step n the running hypotheses are ids[(n+1) & 1][:, :n+2].
+ */
+typedef struct ctcps_decode_session {
+    int32_t B, W, T, V;
+    int32_t S;             /* 0: full vocabulary, lazy state (ctcps_score_lazy); >= 2: pre-beam candidates */
+    int32_t blank, eos, pad;
+    int32_t use_beam_idx;  /* 1: select states with source hypothesis * V + token; 0: tokens only, like the reference (:326-329) */
+    int32_t ldx, ldt, ring;
+    float one_minus_w, w, length_penalty;
+    const float *x_logp;   /* (B,T,ldx), S == 0 */
+    const float *x_vt;     /* (B,V,ldt), S > 0 */
+    const float *blank_lp; /* (B,T) */
+    const float *r0;       /* (T,2,BW) ctcps_initial_state */
+    float *r_sel[2];       /* (T,2,BW) selected state */
+    float *s_sel[2];       /* (BW) */
+    int64_t *last_ids[2];  /* (BW) last token of every row */
+    int64_t *cand_ids[2];  /* (BW,S)   S > 0 */
+    float *cand_att[2];    /* (BW,S)   S > 0 */
+    float *cand_log_psi[2];/* (BW,S)   S > 0 */
+    float *cand_joint;     /* (BW,S)   S > 0 */
+    float *log_psi[2];     /* (BW,V)   S == 0 */
+    float *joint;          /* (BW,V)   S == 0 */
+    void *score_ws;        /* ctcps_workspace_bytes */
+    size_t score_ws_bytes;
+    float *beam_scores;    /* (B,W) */
+    int64_t *ids[2];       /* (BW, ld_ids) */
+    int64_t ld_ids;
+    float *pool_scores;    /* (B,W) */
+    int64_t *pool_lens;    /* (B,W) */
+    int64_t *pool_seqs;    /* (B,W,ld_pool) */
+    int64_t ld_pool;
+    unsigned char *done;   /* (B) */
+    void *beam_ws;         /* ctcps_beam_step_workspace_bytes, zeroed once */
+    size_t beam_ws_bytes;
+    int64_t *done_ring;    /* host-visible, `ring` entries, or NULL */
+    int64_t *best_ids;     /* (B,W) */
+    void *side_stream;     /* from ctcps_async_create; NULL: the selection runs on `stream` */
+    void *ev_step, *ev_select;
+} ctcps_decode_session;
+
+int ctcps_async_create(void **side_stream, void **ev_step, void **ev_select);
+int ctcps_async_destroy(void *side_stream, void *ev_step, void *ev_select);
+/* Timing events for callers without a CUDA runtime binding (bench.py times the scoring call inside a step with them). */
+int ctcps_event_create(void **event);
+int ctcps_event_destroy(void *event);
+int ctcps_event_elapsed_ms(void *begin, void *end, float *ms);
+/* ev_score_begin / ev_score_end (nullable): recorded on `stream` around the scoring call of the step. */
+int ctcps_decode_step(const ctcps_decode_session *s, float *att_scores, int step, void *ev_score_begin, void *ev_score_end,
+                      void *stream);
+/* After the last step: makes `stream` wait for the selection still running on the side stream, so that work enqueued on
+ * `stream` afterwards (e.g. freeing and reusing the session's buffers) is ordered behind it.  No host synchronisation. */
+int ctcps_decode_finish(const ctcps_decode_session *s, void *stream);
+
+/*
  * Optional eos/space trick of the processor (ctc_scorer.py:333-349), in place on `next`:
  * rows with argmax(att) == eos and argmax(ctc) == space and next[eos] < next[space] < k*next[eos]
  * get next[eos] *= k.

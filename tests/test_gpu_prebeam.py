@@ -171,3 +171,69 @@ def test_prebeam_argument_errors():
     p = _proc(logits.cuda(), lens.cuda(), 0.3, 3, 0, False)
     with pytest.raises(RuntimeError):
         p.score_candidates(torch.zeros((6, 1), dtype=torch.long, device="cuda"), torch.zeros((6, 40), device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------------
+# native decode-step driver (ctcps_decode_step): one host call per step, same kernels, same results
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", [n for n in parity.PREBEAM_CASES if not n.endswith("tokens_only")])
+@pytest.mark.parametrize("lag", [0, 1])
+def test_native_loop_prebeam_vs_reference_golden(name, lag):
+    from huggingface_asr_b200.beam_search import joint_beam_search_native
+    from huggingface_asr_b200.synthetic import make_attention_scores
+
+    g = parity.load(name)
+    W, S, seed = int(g["W"]), int(g["S"]), int(g["seed"])
+    logits, lens = torch.from_numpy(g["logits"]).cuda(), torch.from_numpy(g["lens"]).cuda()
+    B, T, V = logits.shape
+    proc = _proc(logits, lens, float(g["ctc_weight"]), W, S, True)
+    out = joint_beam_search_native(proc, lambda ids, n: make_attention_scores(B * W, V, n, seed=seed, scale=0.5).cuda(), B, W, V, BOS,
+                                   EOS, BLANK, max_length=int(g["max_length"]), device="cuda", done_check_lag=lag)
+    assert out.steps >= int(g["steps"]) and out.steps <= int(g["steps"]) + lag  # lag > 0 may run extra (frozen) steps
+    assert (out.sequences.cpu().numpy() == g["seq"]).all(), f"{name}: 1-best differs"
+    assert (out.lengths.cpu().numpy() == g["len"]).all()
+    assert np.abs(out.scores.cpu().numpy() - g["score"]).max() <= 1e-4
+
+
+def test_native_loop_full_vocabulary_vs_reference_golden():
+    """S = 0: the lazy full-vocabulary step (the bench line) through ctcps_decode_step gives the reference's 1-best."""
+    from huggingface_asr_b200.beam_search import joint_beam_search_native
+    from huggingface_asr_b200.decoding.ctc_scorer import CTCRescorerLogitsProcessor
+    from huggingface_asr_b200.synthetic import make_attention_scores
+
+    g = parity.load("decode_1best")
+    for i in range(3):
+        logits, lens = torch.from_numpy(g[f"d{i}_logits"]).cuda(), torch.from_numpy(g[f"d{i}_lens"]).cuda()
+        W, seed = int(g[f"d{i}_W"]), int(g[f"d{i}_seed"])
+        B, T, V = logits.shape
+        proc = CTCRescorerLogitsProcessor(logits, lens, BLANK, EOS, 0, 0.3, W, -1, False, 1.0, materialize_state=False)
+        timing = []
+        out = joint_beam_search_native(proc, lambda ids, n: make_attention_scores(B * W, V, n, seed=seed, scale=0.5).cuda(), B, W, V,
+                                       BOS, EOS, BLANK, max_length=int(g[f"d{i}_max_length"]), device="cuda", done_check_lag=0,
+                                       score_timing=timing)
+        assert out.steps == int(g[f"d{i}_steps"])
+        assert (out.sequences.cpu().numpy() == g[f"d{i}_seq"]).all(), f"decode {i}: 1-best differs from the reference"
+        assert np.abs(out.scores.cpu().numpy() - g[f"d{i}_score"]).max() <= 1e-4
+        from huggingface_asr_b200.beam_search import resolve_score_timing
+
+        torch.cuda.synchronize()
+        ms = resolve_score_timing(timing)
+        assert len(ms) == out.steps and all(m > 0 for m in ms)
+
+
+@pytest.mark.parametrize("S", [0, 15, 40])
+def test_native_loop_equals_fused_loop(S):
+    """Same kernels behind one host call per step: identical hypotheses, scores bit for bit, on a C1-like shape."""
+    from huggingface_asr_b200.beam_search import joint_beam_search_fused, joint_beam_search_native
+    from huggingface_asr_b200.synthetic import SyntheticDecoder, make_encoder_logits
+
+    B, W, T, V = 8, 10, 120, 5000
+    logits, lens, transcripts = make_encoder_logits(B, T, V, "peaky", True, seed=81)
+    dec = SyntheticDecoder(transcripts, W, V, 40, seed=3, device="cuda")
+    a = joint_beam_search_fused(_proc(logits.cuda(), lens.cuda(), 0.3, W, S, None), dec, B, W, V, BOS, EOS, BLANK, max_length=40,
+                                device="cuda")
+    b = joint_beam_search_native(_proc(logits.cuda(), lens.cuda(), 0.3, W, S, None), dec, B, W, V, BOS, EOS, BLANK, max_length=40,
+                                 device="cuda", done_check_lag=0)
+    assert a.steps == b.steps and torch.equal(a.sequences, b.sequences) and torch.equal(a.scores, b.scores)
+    want = torch.tensor([len(t) for t in transcripts])
+    assert (a.lengths.cpu() == want).all(), "the decode does not recover the planted transcripts"
