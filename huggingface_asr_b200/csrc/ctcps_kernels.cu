@@ -776,6 +776,7 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
 struct LazySel {
     long long hs;   // source hypothesis (global row) whose column of r is taken
     long long tok;  // token of that column
+    long long last; // the token the output hypothesis ends with (= tok unless it was not scored and lane 0 stands in)
     long long src;  // where s_new comes from: index into log_psi (BW,V) or, with candidates, cand_log_psi (BW,S); -1 = logzero
 };
 // cand_ids (BW,S) non-null = the step was scored on candidates only (ids unique per hypothesis): the lane is
@@ -787,6 +788,7 @@ __device__ __forceinline__ LazySel lazy_source(const int64_t *__restrict__ best_
     LazySel q;
     q.hs = flat / V;
     q.tok = flat - q.hs * V;
+    q.last = q.tok;
     q.src = flat;
     if (cand_ids != nullptr) {
         const int64_t *c = cand_ids + q.hs * S;
@@ -909,7 +911,7 @@ __global__ void __launch_bounds__(64) k_select_lazy_scan(const XView x, const fl
             for (int f = ol; f <= T - 2; ++f) {
                 const float a = r_new[((size_t)f * 2 + 0) * BW + j], c = r_new[((size_t)f * 2 + 1) * BW + j];
                 lbase[(size_t)(f + 1) * HWP] = expf(lse2_precise(a, c) - gm);
-                pc = fmaf(expf(c - gm), expf(x.at(j / W, f + 1, q.tok)), pc);
+                pc = fmaf(expf(c - gm), expf(x.at(j / W, f + 1, q.last)), pc);  // the NEXT step's last label is the real token
             }
         }
         Gmax[j] = gm;
@@ -1910,10 +1912,7 @@ int ctcps_prebeam_topk(float *att_scores, int BW, int V, int blank, int S, int64
     ARG_CHECK(att_scores && scoring_ids && cand_att && BW > 0 && V > 0, CTCPS_E_BADARG, "prebeam_topk: bad argument");
     ARG_CHECK(blank >= 0 && blank < V, CTCPS_E_BADARG, "prebeam_topk: blank id outside the vocabulary");
     ARG_CHECK(S >= 1 && S <= 64 && S <= V, CTCPS_E_TOOBIG, "prebeam_topk: need 1 <= S <= min(64, V)");
-    if (S <= 32)
-        k_prebeam_topk<1><<<BW, BEAM_NT, 0, (cudaStream_t)stream>>>(att_scores, V, blank, S, scoring_ids, cand_att);
-    else
-        k_prebeam_topk<2><<<BW, BEAM_NT, 0, (cudaStream_t)stream>>>(att_scores, V, blank, S, scoring_ids, cand_att);
+    k_prebeam_topk<<<BW, TOPK_NT, 0, (cudaStream_t)stream>>>(att_scores, V, blank, S, scoring_ids, cand_att);
     return cuda_rc(cudaGetLastError());
 }
 
