@@ -253,7 +253,12 @@ def run_ours(args):
         return res
 
     main_mode = args.state == "materialized"
-    res = measure(main_mode)
+    if args.state == "pre_beam":  # diagnostic / profiling runs of the N2 path only; the bench line is always a full-vocabulary mode
+        if not args.profile:
+            raise SystemExit("--state pre_beam is for --profile runs; the default run reports pre-beam under its own key")
+        res = measure(False, args.pre_beam)
+    else:
+        res = measure(main_mode)
     if args.profile:
         if rank == 0:
             emit({"profile_run": True, "state": args.state, "ms_per_step": res["ms"] / args.steps, "avg_score_ms": res["score_ms"]})
@@ -415,7 +420,7 @@ def main():
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=None, help="override utterances per GPU (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--state", default="lazy", choices=["materialized", "lazy"],
+    ap.add_argument("--state", default="lazy", choices=["materialized", "lazy", "pre_beam"],
                     help="state mode of the headline keys; the other mode is measured too and reported under its own key")
     ap.add_argument("--single-mode", action="store_true", help="measure only --state")
     ap.add_argument("--pre-beam", type=int, default=15,

@@ -1912,7 +1912,31 @@ int ctcps_prebeam_topk(float *att_scores, int BW, int V, int blank, int S, int64
     ARG_CHECK(att_scores && scoring_ids && cand_att && BW > 0 && V > 0, CTCPS_E_BADARG, "prebeam_topk: bad argument");
     ARG_CHECK(blank >= 0 && blank < V, CTCPS_E_BADARG, "prebeam_topk: blank id outside the vocabulary");
     ARG_CHECK(S >= 1 && S <= 64 && S <= V, CTCPS_E_TOOBIG, "prebeam_topk: need 1 <= S <= min(64, V)");
-    k_prebeam_topk<<<BW, TOPK_NT, 0, (cudaStream_t)stream>>>(att_scores, V, blank, S, scoring_ids, cand_att);
+    const size_t smem = (size_t)V * sizeof(unsigned);
+    ARG_CHECK(smem <= 200 * 1024, CTCPS_E_TOOBIG, "prebeam_topk: vocabulary too large for the shared-memory row (V <= 51200)");
+    const bool fast = (V & 3) == 0 && (V >> 2) <= TOPK_NT * TOPK_MAXU && (((uintptr_t)att_scores) & 15) == 0;
+    const int U = fast ? ((V >> 2) + TOPK_NT - 1) / TOPK_NT : 0;
+    cudaStream_t st = (cudaStream_t)stream;
+#define CTCPS_TOPK_LAUNCH(UU)                                                                                              \
+    do {                                                                                                                   \
+        if (smem > 40 * 1024) {                                                                                            \
+            cudaError_t e = cudaFuncSetAttribute(k_prebeam_topk<UU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+            if (e != cudaSuccess) return (int)e;                                                                           \
+        }                                                                                                                  \
+        k_prebeam_topk<UU><<<BW, TOPK_NT, smem, st>>>(att_scores, V, blank, S, scoring_ids, cand_att);                     \
+    } while (0)
+    switch (U) {
+        case 1: CTCPS_TOPK_LAUNCH(1); break;
+        case 2: CTCPS_TOPK_LAUNCH(2); break;
+        case 3: CTCPS_TOPK_LAUNCH(3); break;
+        case 4: CTCPS_TOPK_LAUNCH(4); break;
+        case 5: CTCPS_TOPK_LAUNCH(5); break;
+        case 6: CTCPS_TOPK_LAUNCH(6); break;
+        case 7: CTCPS_TOPK_LAUNCH(7); break;
+        case 8: CTCPS_TOPK_LAUNCH(8); break;
+        default: CTCPS_TOPK_LAUNCH(0); break;
+    }
+#undef CTCPS_TOPK_LAUNCH
     return cuda_rc(cudaGetLastError());
 }
 

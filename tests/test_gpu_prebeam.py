@@ -135,10 +135,17 @@ def test_prebeam_topk_matches_torch_sort():
 
     L = _lib.lib()
     g = torch.Generator().manual_seed(3)
-    for BW, V, S in [(37, 5000, 32), (5, 129, 40), (64, 1000, 1), (3, 70, 64)]:
+    # register fast path (V % 4 == 0, V <= 8192), general radix path (odd V, V > 8192), S up to 64
+    for BW, V, S in [(37, 5000, 32), (5, 129, 40), (64, 1000, 1), (3, 70, 64), (9, 5000, 64), (4, 9000, 15), (6, 8192, 20), (5, 64, 15)]:
         att = torch.randn(BW, V, generator=g).cuda()
         att[0, 5:9] = att[0, 4]          # ties: lower id first
         att[1 % BW, 10] = float("-inf")  # masked token
+        if BW > 2:
+            att[2] = -7.25               # a constant row: > TOPK_CAP elements at the threshold -> radix select, id order
+        if BW > 3:
+            att[3] = torch.log_softmax(torch.randn(V, generator=g) * 0.5, -1).round(decimals=1).cuda()  # heavy ties at the boundary
+        if BW > 4:
+            att[4, ::2] = 3.5            # half the row shares the best score
         ref = att.clone()
         ref[:, BLANK] = -1e10
         ids = torch.empty((BW, S), dtype=torch.long, device="cuda")
