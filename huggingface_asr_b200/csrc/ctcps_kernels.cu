@@ -863,43 +863,61 @@ __global__ void __launch_bounds__(64) k_select_lazy_scan(const XView x, const fl
         for (int te = 0; te <= ol && te < Tpad; ++te) lbase[(size_t)te * HWP] = 0.f;
         for (int te = T; te < Tpad; ++te) lbase[(size_t)te * HWP] = 0.f;
     }
-    // software pipeline: the loads of batch k+1 are in flight while the serial chain of batch k runs
-    constexpr int U = 8;
-    float ph[U], xv[U], bl[U];
-    auto load = [&](int t0, float (&a)[U], float (&c)[U], float (&d)[U]) {
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int t = min(t0 + u, T - 1);
-            a[u] = r_new[((size_t)t * 2 + 0) * BW + j];
-            c[u] = r_new[((size_t)t * 2 + 1) * BW + j];
-            d[u] = xb[t];
+    // One warp per scheduler at best (BW threads in all), so the time of this kernel is (instructions per frame) x (issue
+    // interval of a lone warp): running pointers instead of index arithmetic (the first version spent 3 of 4 instructions
+    // on 64-bit address math: 383 cycles per frame), no per-frame predicates (first frame peeled, full batches, scalar
+    // tail), and a software pipeline: the loads of batch k+1 are in flight while the serial chain of batch k runs.
+    const size_t st2 = 2 * (size_t)BW;  // floats between two frames of r_new
+    int t = start;
+    float *pt = r_new + (size_t)t * st2 + j;     // r_new[t, 0, j]; the blank plane is BW floats further
+    const float *pb = xb + t;
+    float *pl = NEXT ? lbase + (size_t)t * HWP : nullptr;
+    auto frame = [&](float ph_t, float xv_t, float bl_t, bool next) {
+        const float ls = lse2_fast(rn, rb);  // = r_sum[t-1], a by-product of the blank row
+        if (NEXT && next) {                  // frame f = t-1 of the next step's sums (f in [ol, T-2]), entry te = t
+            mx = fmaxf(mx, ls);
+            *pl = ex2_approx(fminf(ls - sj, 0.f) * LOG2E);
+            // last-label column: r_prev_blank[f] * p[f+1, tok]
+            pc = fmaf(ex2_approx(fminf(rb - sj, 0.f) * LOG2E), ex2_approx(xv_t * LOG2E), pc);
         }
+        const float nn = lse2_fast(rn, ph_t) + xv_t;
+        rn = nn;
+        rb = ls + bl_t;
+        pt[0] = rn;
+        pt[BW] = rb;
+        pt += st2;
+        if (NEXT) pl += HWP;
     };
-    load(start, ph, xv, bl);
-    for (int t0 = start; t0 < T; t0 += U) {
-        float ph2[U], xv2[U], bl2[U];
-        if (t0 + U < T) load(t0 + U, ph2, xv2, bl2);
+    if (ol >= 1 && t < T) {  // t - 1 = ol - 1 is not among the frames the next step sums over
+        frame(pt[0], pt[BW], *pb, false);
+        ++pb, ++t;
+    }
+    constexpr int U = 8;
+    if (t + U <= T) {
+        float ph[U], xv[U], bl[U];
+        auto load = [&](const float *p, const float *xbp, float (&a)[U], float (&c)[U], float (&d)[U]) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int t = t0 + u;
-            if (t < T) {
-                const float ls = lse2_fast(rn, rb);  // = r_sum[t-1], a by-product of the blank row
-                if (NEXT && t - 1 >= ol) {           // frame f = t-1 of the next step's sums (f in [ol, T-2]), entry te = t
-                    mx = fmaxf(mx, ls);
-                    lbase[(size_t)t * HWP] = ex2_approx(fminf(ls - sj, 0.f) * LOG2E);
-                    // last-label column: r_prev_blank[f] * p[f+1, tok]
-                    pc = fmaf(ex2_approx(fminf(rb - sj, 0.f) * LOG2E), ex2_approx(xv[u] * LOG2E), pc);
-                }
-                const float nn = lse2_fast(rn, ph[u]) + xv[u];
-                rn = nn;
-                rb = ls + bl[u];
-                r_new[((size_t)t * 2 + 0) * BW + j] = rn;
-                r_new[((size_t)t * 2 + 1) * BW + j] = rb;
+            for (int u = 0; u < U; ++u) {
+                a[u] = p[0];
+                c[u] = p[BW];
+                d[u] = xbp[u];
+                p += st2;
+            }
+        };
+        load(pt, pb, ph, xv, bl);
+        for (; t + U <= T; t += U, pb += U) {
+            float ph2[U], xv2[U], bl2[U];
+            const bool more = t + 2 * U <= T;
+            if (more) load(pt + U * st2, pb + U, ph2, xv2, bl2);
+#pragma unroll
+            for (int u = 0; u < U; ++u) frame(ph[u], xv[u], bl[u], true);
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) ph[u] = ph2[u], xv[u] = xv2[u], bl[u] = bl2[u];
             }
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) ph[u] = ph2[u], xv[u] = xv2[u], bl[u] = bl2[u];
     }
+    for (; t < T; ++t, ++pb) frame(pt[0], pt[BW], *pb, true);
     if (NEXT) {
         float gm = sj;
         // s_new is not a usable offset when it is not a prefix probability (finished beam: last label = pad, s_new = logzero)
@@ -1978,14 +1996,13 @@ int ctcps_score_candidates(const float *x_vt, int ldt, const float *r_prev, cons
     a.cand_att = cand_att, a.omw = one_minus_w, a.w = w, a.cand_log_psi = cand_log_psi, a.cand_ts = cand_token_scores;
     a.cand_joint = cand_joint, a.B = B, a.W = W, a.T = T, a.V = V, a.S = S, a.blank = blank, a.ol = ol, a.G = G, a.HW = HW, a.HWP = HWP;
     a.Tpad = Tpad;
-    const size_t smem = (size_t)4 * ldt * sizeof(float);
+    const size_t smem = (size_t)HW * ldt * sizeof(float);
     ARG_CHECK(smem <= 200 * 1024, CTCPS_E_TOOBIG, "score_candidates: T too large for the shared-memory stream");
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_psi_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    const long long items = BW * ((S + 31) / 32);
-    k_psi_cand<<<(unsigned)((items + 3) / 4), 128, smem, st>>>(a);
+    k_psi_cand<<<(unsigned)(B * G), 32 * HW, smem, st>>>(a);
     return cuda_rc(cudaGetLastError());
 }
 

@@ -10,8 +10,9 @@
 //   k_transpose_vt    (B,T,ldx) -> (B,V,ldt), once per generate()
 //   k_prebeam_topk    scores[:, pad] = logzero (:325) + top-S of every row of the decoder scores (radix select)
 //   k_psi_cand        log_psi / token score / joint score of the S candidates of every hypothesis: a dot product over t of
-//                     the per-hypothesis stream (the same `lin` workspace k_psi_full consumes) with exp(x_vt[b, v, :]) --
-//                     no recursion: in lazy-state mode the forward variables are only recomputed for the survivors
+//                     the per-hypothesis stream (the same `lin` workspace k_psi_full consumes) with exp(x_vt[b, v, :]),
+//                     one warp-wide coalesced row read per candidate -- no recursion: in lazy-state mode the forward
+//                     variables are only recomputed for the survivors
 //   k_cand_to_dense   the reference-shaped (BW,V) outputs for callers that need them (HF's beam search)
 //
 // The recursion itself (state of the W survivors) is k_select_lazy_* of ctcps_kernels.cu on the token-major view.
@@ -281,63 +282,94 @@ struct CandArgs {
     int B, W, T, V, S, blank, ol, G, HW, HWP, Tpad;
 };
 
-// Warp = (hypothesis h, chunk of 32 candidates).  The warp first copies the hypothesis' lin column into shared memory
-// (it is strided by HWP in the workspace), then every lane streams its token's time series with 128-bit loads:
-// acc = sum_t lin[t] * exp(x[t]), ONE accumulator walked in frame order -- the same operations in the same order as a
-// lane of k_psi_full, so a candidate's scores are bit-identical to the full-vocabulary step's.
-__global__ void __launch_bounds__(128) k_psi_cand(const CandArgs a) {
-    extern __shared__ __align__(16) float lin_s[];  // [warps per CTA][ldt]
+// CTA = (utterance b, hypothesis group g), one warp per hypothesis.  The group's lin block (Tpad x HWP, hypothesis
+// innermost in the workspace) is staged transposed into shared memory with coalesced loads; then the warp walks its S
+// candidates: the 32 lanes read a candidate's time series as consecutive 128-bit words (512 contiguous bytes per warp
+// request -- a thread-per-candidate mapping read 16 bytes from 15-32 different rows per request and ran at a third of the
+// speed, DRAM-pattern-bound), multiply with exp() against the lin column and reduce with shuffles.  The loads of several
+// candidates are in flight together.  Lane s finishes candidate s (epilogue shared with the full-vocabulary kernels).
+constexpr int CAND_UNROLL = 5;
+
+__global__ void __launch_bounds__(320) k_psi_cand(const CandArgs a) {
+    extern __shared__ __align__(16) float lin_s[];  // [HW][ldt]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int nchunk = (a.S + 31) >> 5;
-    const int item = blockIdx.x * (blockDim.x >> 5) + wid;
-    if (item >= a.B * a.W * nchunk) return;
-    const int h = item / nchunk, chunk = item - h * nchunk;
-    const int b = h / a.W, w = h - b * a.W;
-    const int g = w / a.HW, hh = w - g * a.HW;
-    float *ls = lin_s + (size_t)wid * a.ldt;
-    const float *lsrc = a.lin + ((size_t)(b * a.G + g) * a.Tpad) * a.HWP + hh;
-    for (int t = lane; t < a.ldt; t += 32) ls[t] = lsrc[(size_t)t * a.HWP];  // ldt <= Tpad; entries >= T are zero
-    __syncwarp();
-    const int s = chunk * 32 + lane;
-    if (s >= a.S) return;
-    const long long v = a.ids[(size_t)h * a.S + s];
-    const int start = a.ol > 1 ? a.ol : 1;
-    float acc = 0.f, x0 = LZ;
-    if (v >= 0 && v < a.V) {
-        const float4 *xr = reinterpret_cast<const float4 *>(a.xt + ((size_t)b * a.V + (size_t)v) * a.ldt);
-        const float4 *l4 = reinterpret_cast<const float4 *>(ls);
-        if (a.ol == 0) x0 = a.xt[((size_t)b * a.V + (size_t)v) * a.ldt];
-        const int q0 = (a.ol == 0 ? 0 : start) >> 2, q1 = a.ldt >> 2;
-        auto quad = [&](const float4 xv, const float4 l) {
-            acc = fmaf(l.x, ex2_approx(xv.x * LOG2E), acc);
-            acc = fmaf(l.y, ex2_approx(xv.y * LOG2E), acc);
-            acc = fmaf(l.z, ex2_approx(xv.z * LOG2E), acc);
-            acc = fmaf(l.w, ex2_approx(xv.w * LOG2E), acc);
-        };
-        constexpr int U = 8;  // 128-bit loads in flight per lane: the kernel is latency-bound (one wave of ~17 warps per SM)
-        int q = q0;
-        for (; q + U <= q1; q += U) {
-            float4 xv[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) xv[u] = __ldg(xr + q + u);
-#pragma unroll
-            for (int u = 0; u < U; ++u) quad(xv[u], l4[q + u]);
+    const int b = blockIdx.x / a.G, g = blockIdx.x - b * a.G;
+    const int nhyp = min(a.HW, a.W - g * a.HW);
+    const int ldt = a.ldt;
+    {   // stage: global (t, hh) -> shared [hh][t]
+        const float *src = a.lin + ((size_t)(b * a.G + g) * a.Tpad) * a.HWP;
+        const int n = ldt * a.HWP;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int t = i / a.HWP, hh = i - t * a.HWP;
+            if (hh < nhyp) lin_s[hh * ldt + t] = src[i];
         }
-        for (; q < q1; ++q) quad(__ldg(xr + q), l4[q]);
-        if (a.last_ids[h] == v) acc = a.psic[h];  // phi = r_prev blank there (:117-124)
     }
+    __syncthreads();
+    if (wid >= nhyp) return;
+    const int h = b * a.W + g * a.HW + wid;
+    const float4 *l4 = reinterpret_cast<const float4 *>(lin_s + wid * ldt);
+    const int start = a.ol > 1 ? a.ol : 1;
+    const int nq = ldt >> 2;                            // float4 per row
+    const int q_lo = ((a.ol == 0 ? 0 : start) >> 2);    // lin is zero before `start`
+    const long long last = a.last_ids[h];
+    const float gm = a.Gmax[h], pcl = a.psic[h];
+    const float sp_row = a.s_prev != nullptr ? a.s_prev[h] : 0.f;
+    const int64_t *ids = a.ids + (size_t)h * a.S;
+    const float *xb = a.xt + (size_t)b * a.V * ldt;
     EpiArgs e;
     e.Gmax = a.Gmax, e.s_prev = a.s_prev, e.s_rs = 1, e.s_cs = 0, e.att = nullptr, e.omw = a.omw, e.w = a.w;
     e.log_psi = nullptr, e.token_scores = nullptr, e.joint = nullptr, e.V = a.V, e.blank = a.blank, e.ol = a.ol;
-    const float sp_row = a.s_prev != nullptr ? a.s_prev[h] : 0.f;
-    const float av_in = a.cand_att != nullptr ? a.cand_att[(size_t)h * a.S + s] : 0.f;
-    float lp, ts, jt, av;
-    epi_lane(e, h, (int)v, acc, a.Gmax[h], x0, sp_row, av_in, lp, ts, jt, av);
-    if (!(v >= 0 && v < a.V)) lp = LZ, ts = LZ, jt = LZ;
-    const size_t o = (size_t)h * a.S + s;
-    a.cand_log_psi[o] = lp;
-    if (a.cand_ts != nullptr) a.cand_ts[o] = ts;
-    if (a.cand_joint != nullptr) a.cand_joint[o] = jt;
+
+    for (int s0 = 0; s0 < a.S; s0 += 32) {   // lane s - s0 finishes candidate s
+        float my_sum = 0.f, my_x0 = LZ;
+        const int s1 = min(a.S, s0 + 32);
+        for (int sb = s0; sb < s1; sb += CAND_UNROLL) {
+            float acc[CAND_UNROLL], x0[CAND_UNROLL];
+            long long v[CAND_UNROLL];
+#pragma unroll
+            for (int u = 0; u < CAND_UNROLL; ++u) {
+                acc[u] = 0.f, x0[u] = LZ;
+                v[u] = sb + u < s1 ? ids[sb + u] : -1;
+                if (v[u] >= a.V) v[u] = -1;
+            }
+            for (int q = q_lo + lane; q < nq; q += 32) {
+                const float4 l = l4[q];
+                float4 xv[CAND_UNROLL];
+#pragma unroll
+                for (int u = 0; u < CAND_UNROLL; ++u)
+                    xv[u] = v[u] >= 0 ? __ldg(reinterpret_cast<const float4 *>(xb + (size_t)v[u] * ldt) + q) : make_float4(LZ, LZ, LZ, LZ);
+#pragma unroll
+                for (int u = 0; u < CAND_UNROLL; ++u) {
+                    if (q == 0) x0[u] = xv[u].x;
+                    acc[u] = fmaf(l.x, ex2_approx(xv[u].x * LOG2E), acc[u]);
+                    acc[u] = fmaf(l.y, ex2_approx(xv[u].y * LOG2E), acc[u]);
+                    acc[u] = fmaf(l.z, ex2_approx(xv[u].z * LOG2E), acc[u]);
+                    acc[u] = fmaf(l.w, ex2_approx(xv[u].w * LOG2E), acc[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < CAND_UNROLL; ++u) {
+                const float tot = warp_sum(acc[u]);
+                const float first = __shfl_sync(0xffffffffu, x0[u], 0);  // x[b, 0, v]: lane 0 holds q = 0 when q_lo == 0
+                if (lane == sb + u - s0) my_sum = tot, my_x0 = first;
+            }
+        }
+        const int s = s0 + lane;
+        if (s < s1) {
+            const long long vv = ids[s];
+            const bool ok = vv >= 0 && vv < a.V;
+            float S_lin = my_sum;
+            if (ok && last == vv) S_lin = pcl;  // phi = r_prev blank there (:117-124)
+            const float av_in = a.cand_att != nullptr ? a.cand_att[(size_t)h * a.S + s] : 0.f;
+            float lp, ts, jt, av;
+            epi_lane(e, h, (int)vv, S_lin, gm, a.ol == 0 ? my_x0 : LZ, sp_row, av_in, lp, ts, jt, av);
+            if (!ok) lp = LZ, ts = LZ, jt = LZ;
+            const size_t o = (size_t)h * a.S + s;
+            a.cand_log_psi[o] = lp;
+            if (a.cand_ts != nullptr) a.cand_ts[o] = ts;
+            if (a.cand_joint != nullptr) a.cand_joint[o] = jt;
+        }
+    }
 }
 
 // `start > end` early return of the reference (:138-145) for the candidate path: everything logzero.

@@ -108,9 +108,9 @@ def test_prebeam_decode_vs_oracle(B, W, T, V, S):
     assert (of.scores.cpu() - oc.scores).abs().max() <= 1e-4
 
 
-def test_candidate_scores_are_bitwise_those_of_the_full_vocabulary_step():
-    """k_psi_cand walks one accumulator in frame order like a lane of k_psi_full: on the same state the joint scores of the
-    candidates are bit-identical to the full-vocabulary lazy step's, at the first step and after a state selection."""
+def test_candidate_scores_equal_those_of_the_full_vocabulary_step():
+    """On the same state the joint scores of the candidates are those of the full-vocabulary lazy step (same lin stream, same
+    posteriors; only the order of the sum over frames differs: warp-wide tree here, frame order there): <= 2e-5."""
     from huggingface_asr_b200.decoding.ctc_scorer import CTCRescorerLogitsProcessor
     from huggingface_asr_b200.synthetic import make_attention_scores
 
@@ -124,7 +124,9 @@ def test_candidate_scores_are_bitwise_those_of_the_full_vocabulary_step():
         jf = full(ids, att.clone())
         cid, cj = cand.score_candidates(ids, att.clone())
         assert cid.shape == (B * W, S) and (cid.sort(1).values[:, 1:] != cid.sort(1).values[:, :-1]).all(), "ids not unique"
-        assert torch.equal(jf.gather(1, cid), cj), f"step {n}: candidate joint scores are not bit-identical"
+        ref = jf.gather(1, cid)
+        fin = ref > -1e9
+        assert bool((cj[~fin] <= -1e9).all()) and float((cj[fin] - ref[fin]).abs().max()) <= 2e-5, f"step {n}"
         # both continue with tokens that hypothesis 0 of the utterance scored (the token-only selection reads its column)
         nxt = cid.view(B, W, S)[:, 0, :W].reshape(-1, 1)
         ids = torch.cat([ids, nxt], 1)
