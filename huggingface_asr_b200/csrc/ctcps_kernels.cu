@@ -1996,13 +1996,14 @@ int ctcps_score_candidates(const float *x_vt, int ldt, const float *r_prev, cons
     a.cand_att = cand_att, a.omw = one_minus_w, a.w = w, a.cand_log_psi = cand_log_psi, a.cand_ts = cand_token_scores;
     a.cand_joint = cand_joint, a.B = B, a.W = W, a.T = T, a.V = V, a.S = S, a.blank = blank, a.ol = ol, a.G = G, a.HW = HW, a.HWP = HWP;
     a.Tpad = Tpad;
-    const size_t smem = (size_t)HW * ldt * sizeof(float);
+    const int hper = (HW + CAND_SPLIT - 1) / CAND_SPLIT;  // hypotheses (= warps) per CTA
+    const size_t smem = (size_t)hper * ldt * sizeof(float);
     ARG_CHECK(smem <= 200 * 1024, CTCPS_E_TOOBIG, "score_candidates: T too large for the shared-memory stream");
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(k_psi_cand, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    k_psi_cand<<<(unsigned)(B * G), 32 * HW, smem, st>>>(a);
+    k_psi_cand<<<(unsigned)(B * G * CAND_SPLIT), 32 * hper, smem, st>>>(a);
     return cuda_rc(cudaGetLastError());
 }
 

@@ -288,25 +288,49 @@ struct CandArgs {
 // request -- a thread-per-candidate mapping read 16 bytes from 15-32 different rows per request and ran at a third of the
 // speed, DRAM-pattern-bound), multiply with exp() against the lin column and reduce with shuffles.  The loads of several
 // candidates are in flight together.  Lane s finishes candidate s (epilogue shared with the full-vocabulary kernels).
-constexpr int CAND_UNROLL = 5;
+constexpr int CAND_CU = 4;      // candidates whose row reads are in flight together
+constexpr int CAND_QMAX = 3;    // 512-byte row segments per candidate in flight (covers T <= 384 in one trip)
+constexpr int CAND_SPLIT = 2;   // CTAs per (utterance, hypothesis group): 512 CTAs of 5 warps at C2 instead of 256 of 10
 
 __global__ void __launch_bounds__(320) k_psi_cand(const CandArgs a) {
-    extern __shared__ __align__(16) float lin_s[];  // [HW][ldt]
+    extern __shared__ __align__(16) float lin_s[];  // [hypotheses of this CTA][ldt]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int b = blockIdx.x / a.G, g = blockIdx.x - b * a.G;
-    const int nhyp = min(a.HW, a.W - g * a.HW);
+    const int part = blockIdx.x % CAND_SPLIT;
+    const int bg = blockIdx.x / CAND_SPLIT;
+    const int b = bg / a.G, g = bg - b * a.G;
+    const int nhyp_g = min(a.HW, a.W - g * a.HW);            // hypotheses of the group
+    const int hper = (a.HW + CAND_SPLIT - 1) / CAND_SPLIT;   // hypotheses per CTA (= warps per CTA)
+    const int hh0 = part * hper;
+    const int nhyp = max(0, min(hper, nhyp_g - hh0));
     const int ldt = a.ldt;
-    {   // stage: global (t, hh) -> shared [hh][t]
-        const float *src = a.lin + ((size_t)(b * a.G + g) * a.Tpad) * a.HWP;
-        const int n = ldt * a.HWP;
-        for (int i = threadIdx.x; i < n; i += blockDim.x) {
-            const int t = i / a.HWP, hh = i - t * a.HWP;
-            if (hh < nhyp) lin_s[hh * ldt + t] = src[i];
+    {   // stage: global (t, hh) -> shared [hh - hh0][t], 128-bit loads, all of a thread's loads in flight together
+        const float4 *src = reinterpret_cast<const float4 *>(a.lin + ((size_t)(b * a.G + g) * a.Tpad) * a.HWP);
+        const int n4 = (ldt * a.HWP) >> 2;  // HWP % 4 == 0
+        for (int i0 = 0; i0 < n4; i0 += blockDim.x * 4) {
+            float4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + k * blockDim.x + threadIdx.x;
+                if (i < n4) v[k] = src[i];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + k * blockDim.x + threadIdx.x;
+                if (i < n4) {
+                    const int e0 = i * 4, t = e0 / a.HWP, hq = e0 - t * a.HWP;  // 4 consecutive hypotheses of frame t
+                    const float x[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int hh = hq + j - hh0;
+                        if (hh >= 0 && hh < nhyp) lin_s[hh * ldt + t] = x[j];
+                    }
+                }
+            }
         }
     }
     __syncthreads();
     if (wid >= nhyp) return;
-    const int h = b * a.W + g * a.HW + wid;
+    const int h = b * a.W + g * a.HW + hh0 + wid;
     const float4 *l4 = reinterpret_cast<const float4 *>(lin_s + wid * ldt);
     const int start = a.ol > 1 ? a.ol : 1;
     const int nq = ldt >> 2;                            // float4 per row
@@ -319,36 +343,45 @@ __global__ void __launch_bounds__(320) k_psi_cand(const CandArgs a) {
     EpiArgs e;
     e.Gmax = a.Gmax, e.s_prev = a.s_prev, e.s_rs = 1, e.s_cs = 0, e.att = nullptr, e.omw = a.omw, e.w = a.w;
     e.log_psi = nullptr, e.token_scores = nullptr, e.joint = nullptr, e.V = a.V, e.blank = a.blank, e.ol = a.ol;
+    const float4 lz4 = make_float4(LZ, LZ, LZ, LZ);
 
     for (int s0 = 0; s0 < a.S; s0 += 32) {   // lane s - s0 finishes candidate s
         float my_sum = 0.f, my_x0 = LZ;
         const int s1 = min(a.S, s0 + 32);
-        for (int sb = s0; sb < s1; sb += CAND_UNROLL) {
-            float acc[CAND_UNROLL], x0[CAND_UNROLL];
-            long long v[CAND_UNROLL];
+        for (int sb = s0; sb < s1; sb += CAND_CU) {
+            float acc[CAND_CU], x0[CAND_CU];
+            const float4 *row[CAND_CU];
 #pragma unroll
-            for (int u = 0; u < CAND_UNROLL; ++u) {
+            for (int u = 0; u < CAND_CU; ++u) {
                 acc[u] = 0.f, x0[u] = LZ;
-                v[u] = sb + u < s1 ? ids[sb + u] : -1;
-                if (v[u] >= a.V) v[u] = -1;
+                long long v = sb + u < s1 ? ids[sb + u] : -1;
+                if (v >= a.V) v = -1;
+                row[u] = v >= 0 ? reinterpret_cast<const float4 *>(xb + (size_t)v * ldt) : nullptr;
             }
-            for (int q = q_lo + lane; q < nq; q += 32) {
-                const float4 l = l4[q];
-                float4 xv[CAND_UNROLL];
+            for (int qb = q_lo; qb < nq; qb += 32 * CAND_QMAX) {
+                float4 l[CAND_QMAX], xv[CAND_CU][CAND_QMAX];
 #pragma unroll
-                for (int u = 0; u < CAND_UNROLL; ++u)
-                    xv[u] = v[u] >= 0 ? __ldg(reinterpret_cast<const float4 *>(xb + (size_t)v[u] * ldt) + q) : make_float4(LZ, LZ, LZ, LZ);
+                for (int k = 0; k < CAND_QMAX; ++k) {
+                    const int q = qb + k * 32 + lane;
+                    l[k] = q < nq ? l4[q] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int u = 0; u < CAND_UNROLL; ++u) {
-                    if (q == 0) x0[u] = xv[u].x;
-                    acc[u] = fmaf(l.x, ex2_approx(xv[u].x * LOG2E), acc[u]);
-                    acc[u] = fmaf(l.y, ex2_approx(xv[u].y * LOG2E), acc[u]);
-                    acc[u] = fmaf(l.z, ex2_approx(xv[u].z * LOG2E), acc[u]);
-                    acc[u] = fmaf(l.w, ex2_approx(xv[u].w * LOG2E), acc[u]);
+                    for (int u = 0; u < CAND_CU; ++u) xv[u][k] = (q < nq && row[u] != nullptr) ? __ldg(row[u] + q) : lz4;
+                }
+#pragma unroll
+                for (int k = 0; k < CAND_QMAX; ++k) {
+                    const int q = qb + k * 32 + lane;
+#pragma unroll
+                    for (int u = 0; u < CAND_CU; ++u) {
+                        if (q == 0) x0[u] = xv[u][k].x;
+                        acc[u] = fmaf(l[k].x, ex2_approx(xv[u][k].x * LOG2E), acc[u]);
+                        acc[u] = fmaf(l[k].y, ex2_approx(xv[u][k].y * LOG2E), acc[u]);
+                        acc[u] = fmaf(l[k].z, ex2_approx(xv[u][k].z * LOG2E), acc[u]);
+                        acc[u] = fmaf(l[k].w, ex2_approx(xv[u][k].w * LOG2E), acc[u]);
+                    }
                 }
             }
 #pragma unroll
-            for (int u = 0; u < CAND_UNROLL; ++u) {
+            for (int u = 0; u < CAND_CU; ++u) {
                 const float tot = warp_sum(acc[u]);
                 const float first = __shfl_sync(0xffffffffu, x0[u], 0);  // x[b, 0, v]: lane 0 holds q = 0 when q_lo == 0
                 if (lane == sb + u - s0) my_sum = tot, my_x0 = first;
