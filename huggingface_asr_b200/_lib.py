@@ -101,6 +101,7 @@ SIGNATURES = {
     "ctcps_event_elapsed_ms": [_p, _p, ctypes.POINTER(_f)],
     "ctcps_decode_step": [_p, _p, _i, _p, _p, _p],
     "ctcps_decode_finish": [_p, _p],
+    "ctcps_split_tf32": [_p, _i64, _i, _i, _p, _p],
     "ctcps_beam_step_candidates": [_p, _p, _i, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i64, _p, _p, _sz, _p, _i,
                                    _i64, _p, _p],
     "ctcps_select": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p],

@@ -2133,4 +2133,11 @@ int ctcps_decode_finish(const ctcps_decode_session *s, void *stream) {
     return cuda_rc(cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)s->ev_select, 0));
 }
 
+int ctcps_split_tf32(const float *x, int64_t n, int d, int weight_order, float *out, void *stream) {
+    ARG_CHECK(x && out && n > 0 && d > 0, CTCPS_E_BADARG, "split_tf32: bad argument");
+    ARG_CHECK((d & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)out)) & 15) == 0, CTCPS_E_ALIGN, "split_tf32: d must be a multiple of 4, pointers 16-byte aligned");
+    k_split_tf32<<<grid_for((size_t)n * (d >> 2), 256), 256, 0, (cudaStream_t)stream>>>(x, n, d, weight_order, out);
+    return cuda_rc(cudaGetLastError());
+}
+
 }  // extern "C"

@@ -348,15 +348,16 @@ __global__ void __launch_bounds__(320) k_psi_cand(const CandArgs a) {
     for (int s0 = 0; s0 < a.S; s0 += 32) {   // lane s - s0 finishes candidate s
         float my_sum = 0.f, my_x0 = LZ;
         const int s1 = min(a.S, s0 + 32);
+        long long my_id = s0 + lane < s1 ? ids[s0 + lane] : -1;  // one coalesced read; batches take their ids by shuffle
+        if (my_id >= a.V) my_id = -1;
         for (int sb = s0; sb < s1; sb += CAND_CU) {
             float acc[CAND_CU], x0[CAND_CU];
             const float4 *row[CAND_CU];
 #pragma unroll
             for (int u = 0; u < CAND_CU; ++u) {
                 acc[u] = 0.f, x0[u] = LZ;
-                long long v = sb + u < s1 ? ids[sb + u] : -1;
-                if (v >= a.V) v = -1;
-                row[u] = v >= 0 ? reinterpret_cast<const float4 *>(xb + (size_t)v * ldt) : nullptr;
+                const long long v = __shfl_sync(0xffffffffu, my_id, (sb + u - s0) & 31);  // -1 past the last candidate
+                row[u] = (sb + u < s1 && v >= 0) ? reinterpret_cast<const float4 *>(xb + (size_t)v * ldt) : nullptr;
             }
             for (int qb = q_lo; qb < nq; qb += 32 * CAND_QMAX) {
                 float4 l[CAND_QMAX], xv[CAND_CU][CAND_QMAX];
@@ -389,8 +390,8 @@ __global__ void __launch_bounds__(320) k_psi_cand(const CandArgs a) {
         }
         const int s = s0 + lane;
         if (s < s1) {
-            const long long vv = ids[s];
-            const bool ok = vv >= 0 && vv < a.V;
+            const long long vv = my_id;
+            const bool ok = vv >= 0;
             float S_lin = my_sum;
             if (ok && last == vv) S_lin = pcl;  // phi = r_prev blank there (:117-124)
             const float av_in = a.cand_att != nullptr ? a.cand_att[(size_t)h * a.S + s] : 0.f;
@@ -441,5 +442,35 @@ __global__ void __launch_bounds__(256) k_cand_to_dense(const float *__restrict__
         if (log_psi != nullptr) log_psi[o + v] = cand_log_psi[c];
         if (token_scores != nullptr) token_scores[o + v] = cand_ts[c];
         if (joint != nullptr) joint[o + v] = cand_joint[c];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// N4 (the step before the path): the CTC head's GEMM at fp32 accuracy on the TF32 tensor cores.  logits = h W^T is
+// computed as ONE TF32 GEMM over operands split into TF32-exact parts and stacked along K:
+//   h' = [h_hi | h_hi | h_lo] (n, 3d),  W' = [W_hi | W_lo | W_hi] (V, 3d),  h' W'^T = h_hi W_hi + h_hi W_lo + h_lo W_hi
+// with x_hi = tf32(x) (round to nearest) and x_lo = x - x_hi (exact in fp32); the dropped h_lo W_lo term is 2^-22
+// relative, fp32 accumulation.  This kernel does the split; the GEMM itself is a plain library call (cuBLAS).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_split_tf32(const float *__restrict__ x, long long n, int d, int weight_order, float *__restrict__ out) {
+    const long long total = n * (long long)(d >> 2);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / (d >> 2);
+        const int c = (int)(i - r * (d >> 2)) * 4;
+        const float4 v = *reinterpret_cast<const float4 *>(x + r * d + c);
+        const float in[4] = {v.x, v.y, v.z, v.w};
+        float hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            unsigned t;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(in[j]));
+            hi[j] = __uint_as_float(t);
+            lo[j] = in[j] - hi[j];
+        }
+        const float4 h4 = make_float4(hi[0], hi[1], hi[2], hi[3]), l4 = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        float *o = out + r * 3 * d + c;
+        *reinterpret_cast<float4 *>(o) = h4;
+        *reinterpret_cast<float4 *>(o + d) = weight_order ? l4 : h4;
+        *reinterpret_cast<float4 *>(o + 2 * d) = weight_order ? h4 : l4;
     }
 }

@@ -596,6 +596,13 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
         self.eos_space_trick_weight = eos_space_trick_weight
         self.debug = debug
 
+    @classmethod
+    def from_encoder_hidden_states(cls, hidden_states: torch.FloatTensor, ctc_head, encoder_output_lens, *args, **kwargs):
+        """take the encoder's last hidden states (B,T,d) and its CTC head (ctc_head.CTCHead) instead of the
+        (B,T,V) logits -- a tenth of the bytes -- and compute the logits here (TF32x3 tensor-core GEMM, fp32 accuracy).
+        The remaining arguments are those of the constructor after `encoder_output_lens`."""
+        return cls(ctc_head(hidden_states), encoder_output_lens, *args, **kwargs)
+
     # -- state selection ----------------------------------------------------------------------------------
     def set_beam_idx(self, beam_idx: torch.LongTensor) -> None:
         """Tell the processor which rows of the previous step the current rows continue (HF's `beam_idx`, global row

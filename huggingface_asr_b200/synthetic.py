@@ -92,6 +92,39 @@ def make_encoder_logits(B: int, T: int, V: int, kind: str = "peaky", ragged: boo
     return logits.to(device), lens.to(device), transcripts
 
 
+def make_encoder_hidden(B: int, T: int, V: int, d: int = 512, kind: str = "peaky", ragged: bool = False, seed: int = 20240,
+                        boost: float = 8.0):
+    """Encoder hidden states + CTC head for the N4 boundary: returns (hidden (B,T,d), weight (V,d), bias (V), lens, transcripts)
+    such that hidden @ weight.T + bias looks like make_encoder_logits' output: N(0,1) noise plus `boost` at the aligned label.
+    The head rows have unit norm, the hidden state of a frame is noise + boost * (row of its label)."""
+    gen = torch.Generator().manual_seed(seed)
+    weight = torch.randn(V, d, generator=gen, dtype=torch.float32)
+    weight = weight / weight.norm(dim=1, keepdim=True)
+    bias = 0.1 * torch.randn(V, generator=gen, dtype=torch.float32)
+    hidden = torch.randn(B, T, d, generator=gen, dtype=torch.float32)
+    lens = make_lengths(B, T, ragged, gen)
+    transcripts = []
+    if kind == "peaky":
+        for b in range(B):
+            L = int(lens[b])
+            U = max(1, L // 8)
+            labels = torch.randint(5, V, (U,), generator=gen).tolist() + [EOS]
+            n = len(labels)
+            if L - 2 >= n:
+                pos = torch.randperm(L - 2, generator=gen)[:n].sort().values + 1
+            else:
+                labels = labels[: max(1, L - 2)]
+                n = len(labels)
+                pos = torch.arange(1, n + 1)
+            target = torch.full((T,), BLANK, dtype=torch.long)
+            target[pos] = torch.tensor(labels)
+            hidden[b] += boost * weight[target]
+            transcripts.append(labels)
+    else:
+        transcripts = [[] for _ in range(B)]
+    return hidden, weight, bias, lens, transcripts
+
+
 def make_attention_scores(BW: int, V: int, step: int, seed: int = 7, device: str | torch.device = "cpu",
                           scale: float = 2.0) -> torch.Tensor:
     """Scorer-only stand-in for the attention decoder: log_softmax(scale * N(0,1)), (BW,V)."""

@@ -1,0 +1,72 @@
+"""GPU: N4 -- the CTC head GEMM at fp32 accuracy on the TF32 tensor cores (operand split + one stacked-K GEMM), and the
+processor built from encoder hidden states.  Run on the B200 box with -m gpu."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+BLANK, EOS, BOS = 3, 1, 0
+
+
+def test_split_is_exact():
+    from huggingface_asr_b200.ctc_head import split_tf32
+
+    g = torch.Generator().manual_seed(1)
+    x = (torch.randn(37, 64, generator=g) * torch.logspace(-6, 6, 64)).cuda()
+    a, w = split_tf32(x, False), split_tf32(x, True)
+    hi, lo = a[:, :64], a[:, 128:]
+    assert torch.equal(a[:, 64:128], hi) and torch.equal(w[:, :64], hi) and torch.equal(w[:, 64:128], lo) and torch.equal(w[:, 128:], hi)
+    assert bool(((hi.view(torch.int32) & 0x1FFF) == 0).all()), "hi must be exactly representable in TF32"
+    assert torch.equal(hi + lo, x), "hi + lo must reproduce x exactly"
+    assert float((lo.abs() / x.abs()).max()) <= 2.0 ** -11
+
+
+def test_head_has_fp32_accuracy_where_single_pass_tf32_does_not():
+    from huggingface_asr_b200.ctc_head import CTCHead
+    from huggingface_asr_b200.synthetic import make_encoder_hidden
+
+    hidden, weight, bias, _, _ = make_encoder_hidden(8, 120, 5000, 512, seed=5)
+    ref = (hidden.double().reshape(-1, 512) @ weight.double().t() + bias.double()).view(8, 120, 5000)
+    head = CTCHead(weight.cuda(), bias.cuda())
+    out = head(hidden.cuda()).cpu().double()
+    err3 = float((out - ref).abs().max())
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    err_fp32 = float((torch.addmm(bias.cuda(), hidden.cuda().view(-1, 512), weight.cuda().t()).cpu().double().view_as(ref) - ref).abs().max())
+    torch.backends.cuda.matmul.allow_tf32 = True
+    err1 = float((torch.addmm(bias.cuda(), hidden.cuda().view(-1, 512), weight.cuda().t()).cpu().double().view_as(ref) - ref).abs().max())
+    torch.backends.cuda.matmul.allow_tf32 = prev
+    print(f"max |logit error| vs fp64: split-TF32 {err3:.2e}, fp32 SGEMM {err_fp32:.2e}, single-pass TF32 {err1:.2e}")
+    assert err3 <= 2e-5, "the split GEMM must be as accurate as an fp32 GEMM"
+    assert err3 <= 4 * err_fp32 + 1e-6
+    assert err1 > 1e-4, "single-pass TF32 should miss the tolerance (else this test does not exercise the tensor-core path)"
+
+
+def test_processor_from_hidden_states_matches_the_oracle():
+    from huggingface_asr_b200.beam_search import joint_beam_search, joint_beam_search_native
+    from huggingface_asr_b200.ctc_head import CTCHead
+    from huggingface_asr_b200.decoding.ctc_scorer import CTCRescorerLogitsProcessor
+    from huggingface_asr_b200.synthetic import SyntheticDecoder, make_encoder_hidden
+    from oracle import oracle as orc
+    import parity
+
+    B, W, T, V, d = 4, 10, 96, 1000, 256
+    hidden, weight, bias, lens, transcripts = make_encoder_hidden(B, T, V, d, ragged=True, seed=6)
+    logits_ref = (hidden.double().reshape(-1, d) @ weight.double().t() + bias.double()).view(B, T, V).float()
+    head = CTCHead(weight.cuda(), bias.cuda())
+    proc = CTCRescorerLogitsProcessor.from_encoder_hidden_states(hidden.cuda(), head, lens.cuda(), BLANK, EOS, 0, 0.3, W, -1, False, 1.0)
+    cpu = orc.OracleCTCRescorerLogitsProcessor(logits_ref.clone(), lens.clone(), BLANK, EOS, 0, 0.3, W)
+    ids = torch.full((B * W, 1), BOS, dtype=torch.long)
+    att = torch.log_softmax(torch.randn(B * W, V, generator=torch.Generator().manual_seed(2)), -1)
+    parity.assert_parity(proc(ids.cuda(), att.cuda()), cpu(ids, att.clone()), "joint scores from hidden states")
+    dec_g = SyntheticDecoder(transcripts, W, V, 40, seed=3, device="cuda")
+    dec_c = SyntheticDecoder(transcripts, W, V, 40, seed=3, device="cpu")
+    # the CPU and CUDA generators differ, so give both decoders the same noise
+    dec_c.pool = [p.cpu() for p in dec_g.pool]
+    out_g = joint_beam_search_native(CTCRescorerLogitsProcessor.from_encoder_hidden_states(hidden.cuda(), head, lens.cuda(), BLANK, EOS, 0,
+                                                                                           0.3, W, -1, False, 1.0),
+                                     dec_g, B, W, V, BOS, EOS, BLANK, max_length=40, device="cuda", done_check_lag=0)
+    out_c = joint_beam_search(orc.OracleCTCRescorerLogitsProcessor(logits_ref.clone(), lens.clone(), BLANK, EOS, 0, 0.3, W), dec_c,
+                              B, W, V, BOS, EOS, BLANK, max_length=40)
+    assert out_g.steps == out_c.steps and (out_g.sequences.cpu() == out_c.sequences).all()
+    assert (out_g.lengths.cpu() == torch.tensor([len(t) - 1 for t in transcripts])).all()
