@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(TOPK_NT, TOPK_U <= 5 ? 4 : 3) k_prebeam_topk(f
                     cand_att[(size_t)row * S + rank] = me.s;
                 }
             }
-            if (tid == 0) a[blank] = LZ;
+            if (tid == 0 && blank >= 0) a[blank] = LZ;
             return;
         }
         // too many elements share the top scores (e.g. a constant row): hand the row to the radix select
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(TOPK_NT, TOPK_U <= 5 ? 4 : 3) k_prebeam_topk(f
     __syncthreads();
     topk_radix(sh, keys, V, S);
     topk_emit(sh, S, row, ids, cand_att);
-    if (tid == 0) a[blank] = LZ;
+    if (tid == 0 && blank >= 0) a[blank] = LZ;
 }
 
 struct CandArgs {
