@@ -165,7 +165,10 @@ def run_ours(args):
             # our kernels: K-a (1) + initial state (1); per step: scoring kernel (1) [+ fused beam step (1)], plus its
             # preparation kernel (every step when materialised; first step only in lazy mode, where the select scan of
             # the previous step prepares it); all steps but the first: select (1 gather, or 2 for the lazy stage + scan)
-            beam = 0 if args.harness == "torch" else 1
+            # beam step: the candidate kernel alone (pre-beam), or -- dense scores whose rows fit the register top-k -- the
+            # per-row top-2W kernel + the candidate kernel
+            two_kernel = not pre_beam and V % 4 == 0 and V <= 8192
+            beam = 0 if args.harness == "torch" else (2 if two_kernel else 1)
             native = 1 if (args.harness == "native" and not materialize) else 0  # the native step also selects after the last step
             if pre_beam:
                 # K-a + transpose + initial state; per step: top-S, candidate scores, [dense scatter when the harness is not
