@@ -448,9 +448,11 @@ __global__ void __launch_bounds__(256) k_cand_to_dense(const float *__restrict__
 // ------------------------------------------------------------------------------------------
 // N4 (the step before the path): the CTC head's GEMM at fp32 accuracy on the TF32 tensor cores.  logits = h W^T is
 // computed as ONE TF32 GEMM over operands split into TF32-exact parts and stacked along K:
-//   h' = [h_hi | h_hi | h_lo] (n, 3d),  W' = [W_hi | W_lo | W_hi] (V, 3d),  h' W'^T = h_hi W_hi + h_hi W_lo + h_lo W_hi
+//   h' = [h_hi | h_lo | h_hi] (n, 3d),  W' = [W_lo | W_hi | W_hi] (V, 3d),  h' W'^T = h_hi W_lo + h_lo W_hi + h_hi W_hi
 // with x_hi = tf32(x) (round to nearest) and x_lo = x - x_hi (exact in fp32); the dropped h_lo W_lo term is 2^-22
-// relative, fp32 accumulation.  This kernel does the split; the GEMM itself is a plain library call (cuBLAS).
+// relative, fp32 accumulation.  The two small cross terms come FIRST along K: the tensor cores' accumulator rounds toward
+// zero at every k-step, a bias proportional to the running sum, so the large hi*hi part should pass through as few
+// k-steps as possible.  This kernel does the split; the GEMM itself is a plain library call (cuBLAS).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_split_tf32(const float *__restrict__ x, long long n, int d, int weight_order, float *__restrict__ out) {
     const long long total = n * (long long)(d >> 2);
@@ -469,8 +471,8 @@ __global__ void __launch_bounds__(256) k_split_tf32(const float *__restrict__ x,
         }
         const float4 h4 = make_float4(hi[0], hi[1], hi[2], hi[3]), l4 = make_float4(lo[0], lo[1], lo[2], lo[3]);
         float *o = out + r * 3 * d + c;
-        *reinterpret_cast<float4 *>(o) = h4;
-        *reinterpret_cast<float4 *>(o + d) = weight_order ? l4 : h4;
-        *reinterpret_cast<float4 *>(o + 2 * d) = weight_order ? h4 : l4;
+        *reinterpret_cast<float4 *>(o) = weight_order ? l4 : h4;
+        *reinterpret_cast<float4 *>(o + d) = weight_order ? h4 : l4;
+        *reinterpret_cast<float4 *>(o + 2 * d) = h4;
     }
 }

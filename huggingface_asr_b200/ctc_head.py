@@ -4,8 +4,8 @@ In the reference the head is the stock `Wav2Vec2ForCTC.lm_head` Linear (src/regu
 SGEMM of (B*T, d) x (d, V) on the CUDA cores (C2: 0.49 TFLOP, ~7 ms on a B200) whose (B,T,V) output the processor then
 log-softmaxes.  A single-pass TF32 GEMM would be 10x faster but misses the 1e-4 log-space tolerance of the path
 (10-bit mantissas).  Here both operands are split into TF32-exact high and low parts by `ctcps_split_tf32` and stacked
-along K, so ONE TF32 GEMM with fp32 accumulation computes hi*hi + hi*lo + lo*hi -- fp32 accuracy (the dropped lo*lo
-term is 2^-22 relative) at a third of the TF32 rate.  The GEMM itself is a plain library call (cuBLAS through
+along K, so ONE TF32 GEMM with fp32 accumulation computes hi*lo + lo*hi + hi*hi -- the dropped lo*lo term is 2^-22
+relative -- at a third of the TF32 rate.  The GEMM itself is a plain library call (cuBLAS through
 torch.addmm, bias in its epilogue); the log-softmax + padding that follows is K-a (`ctcps_init`).
 
 Status: N4 is only started -- fusing the bias / row-max / sum-exp epilogue into a hand-written tcgen05 GEMM (so that the
@@ -35,7 +35,7 @@ def _tf32_matmul():
 
 
 def split_tf32(x: torch.Tensor, weight_order: bool) -> torch.Tensor:
-    """(n,d) fp32 -> (n,3d): [hi | hi | lo] for activations, [hi | lo | hi] for weights (see ctcps_split_tf32)."""
+    """(n,d) fp32 -> (n,3d): [hi | lo | hi] for activations, [lo | hi | hi] for weights (see ctcps_split_tf32)."""
     if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or not x.is_contiguous():
         raise ValueError("split_tf32 needs a contiguous 2-D float32 CUDA tensor")
     n, d = x.shape

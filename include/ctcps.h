@@ -267,8 +267,8 @@ int ctcps_eos_space_trick(const float *att_scores, const float *ctc_scores, floa
 /*
  * N4 (the step before the path): operand split for the CTC head's GEMM (Wav2Vec2ForCTC.lm_head, src/reguler/
  * e_branchformer.py:245-252) at fp32 accuracy on the TF32 tensor cores.  x (n,d) -> out (n,3d):
- * weight_order = 0: [hi | hi | lo] (activations), 1: [hi | lo | hi] (weights); hi = tf32(x) rounded to nearest,
- * lo = x - hi.  out_h out_W^T = hi hi + hi lo + lo hi in one TF32 GEMM with fp32 accumulation.
+ * weight_order = 0: [hi | lo | hi] (activations), 1: [lo | hi | hi] (weights); hi = tf32(x) rounded to nearest,
+ * lo = x - hi.  out_h out_W^T = hi lo + lo hi + hi hi in one TF32 GEMM with fp32 accumulation (small terms first).
  */
 int ctcps_split_tf32(const float *x, int64_t n, int d, int weight_order, float *out, void *stream);
 

@@ -14,8 +14,8 @@ def test_split_is_exact():
     g = torch.Generator().manual_seed(1)
     x = (torch.randn(37, 64, generator=g) * torch.logspace(-6, 6, 64)).cuda()
     a, w = split_tf32(x, False), split_tf32(x, True)
-    hi, lo = a[:, :64], a[:, 128:]
-    assert torch.equal(a[:, 64:128], hi) and torch.equal(w[:, :64], hi) and torch.equal(w[:, 64:128], lo) and torch.equal(w[:, 128:], hi)
+    hi, lo = a[:, :64], a[:, 64:128]
+    assert torch.equal(a[:, 128:], hi) and torch.equal(w[:, :64], lo) and torch.equal(w[:, 64:128], hi) and torch.equal(w[:, 128:], hi)
     assert bool(((hi.view(torch.int32) & 0x1FFF) == 0).all()), "hi must be exactly representable in TF32"
     assert torch.equal(hi + lo, x), "hi + lo must reproduce x exactly"
     assert float((lo.abs() / x.abs()).max()) <= 2.0 ** -11
@@ -37,11 +37,11 @@ def test_head_has_fp32_accuracy_where_single_pass_tf32_does_not():
     err1 = float((torch.addmm(bias.cuda(), hidden.cuda().view(-1, 512), weight.cuda().t()).cpu().double().view_as(ref) - ref).abs().max())
     torch.backends.cuda.matmul.allow_tf32 = prev
     print(f"max |logit error| vs fp64: split-TF32 {err3:.2e}, fp32 SGEMM {err_fp32:.2e}, single-pass TF32 {err1:.2e}")
-    # The products are exact (hi*hi, hi*lo, lo*hi cover 22 mantissa bits); what remains is the tensor cores' accumulator, which
-    # rounds toward zero at every k-step: a bias of a few tens of fp32 ulps on the largest logits (|z| ~ 10 -> <= 1e-4), where an
-    # SGEMM's round-to-nearest errors average out to ~1e-5.  (A hand-written kernel can promote partial sums to fp32 registers
-    # every few k-steps; with a library GEMM the accumulator is what it is.)
-    assert err3 <= 1e-4, "the split GEMM must stay within the path's tolerance"
+    # The products are exact (hi*lo, lo*hi, hi*hi cover 22 mantissa bits); what remains is the tensor cores' accumulator, which
+    # rounds toward zero at every k-step -- a bias proportional to the running sum.  With the small cross terms first along K the
+    # large hi*hi part passes through 64 k-steps instead of 192: 1.8e-5 measured (7.6e-5 with hi*hi first; fp32 SGEMM 1.05e-5).
+    assert err3 <= 3e-5, "the split GEMM must be as accurate as an fp32 GEMM to within a small factor"
+    assert err3 <= 3 * err_fp32
     assert err1 > 10 * err3, "single-pass TF32 should be far worse (else this test does not exercise the split)"
 
 
