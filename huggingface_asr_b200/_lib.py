@@ -90,6 +90,7 @@ SIGNATURES = {
     "ctcps_beam_step": [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i64, _p, _p, _sz, _p, _i, _i64, _p, _p],
     "ctcps_padded_lt": [_i],
     "ctcps_transpose_vt": [_p, _i, _i, _i, _i, _p, _i, _p],
+    "ctcps_init_vt": [_p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p],
     "ctcps_prebeam_topk": [_p, _i, _i, _i, _i, _p, _p, _p],
     "ctcps_score_candidates": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _f, _f, _p, _p, _p, _p, _sz, _i, _p],
     "ctcps_candidates_to_dense": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _i, _p, _p, _p, _p],
@@ -101,6 +102,7 @@ SIGNATURES = {
     "ctcps_event_elapsed_ms": [_p, _p, ctypes.POINTER(_f)],
     "ctcps_decode_step": [_p, _p, _i, _p, _p, _p],
     "ctcps_decode_finish": [_p, _p],
+    "ctcps_decode_session_size": [],
     "ctcps_split_tf32": [_p, _i64, _i, _i, _p, _p],
     "ctcps_beam_step_candidates": [_p, _p, _i, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i64, _p, _p, _sz, _p, _i,
                                    _i64, _p, _p],
@@ -135,7 +137,10 @@ def lib() -> ctypes.CDLL:
         for name, argtypes in SIGNATURES.items():
             fn = getattr(L, name)
             fn.argtypes = argtypes
-            fn.restype = ctypes.c_char_p if name == "ctcps_error_string" else ctypes.c_int
+            fn.restype = (ctypes.c_char_p if name == "ctcps_error_string" else
+                          ctypes.c_size_t if name == "ctcps_decode_session_size" else ctypes.c_int)
+        if L.ctcps_decode_session_size() != ctypes.sizeof(DecodeSession):
+            raise CtcpsError("DecodeSession (huggingface_asr_b200/_lib.py) does not mirror ctcps_decode_session (include/ctcps.h)")
         _lib = L
     return _lib
 

@@ -165,6 +165,18 @@ class CTCPrefixScoreTH(object):
         self.end_frames = lens - 1  # :47
         self._lens = lens.to(device=self.device, dtype=torch.long).contiguous()
         ldx = L.ctcps_padded_ld(V)
+        self._ldx = ldx
+        self._xt, self._ldt = None, L.ctcps_padded_lt(T)
+        if token_major and apply_log_softmax:
+            # K-a straight into the token-major layout (one pass over HBM); the frame-major copy is rebuilt on demand
+            with torch.cuda.device(self.device):
+                self._blank_lp = torch.empty((B, T), dtype=torch.float32, device=self.device)
+                self._xt = torch.empty((B, V, self._ldt), dtype=torch.float32, device=self.device)
+                _lib.check(L.ctcps_init_vt(_ptr(x), V, _ptr(self._lens), B, T, V, self.blank, 1, _ptr(self._xt), self._ldt,
+                                           _ptr(self._blank_lp), _stream(self.device)), "ctcps_init_vt")
+            self._x = None
+            self._finish_setup(margin)
+            return
         with torch.cuda.device(self.device):
             self._blank_lp = torch.empty((B, T), dtype=torch.float32, device=self.device)
             if apply_log_softmax or ldx != V:
@@ -177,8 +189,6 @@ class CTCPrefixScoreTH(object):
                                         _stream(self.device)), "ctcps_init")
             _lib.check(L.ctcps_init(_ptr(x), V, _ptr(self._lens), B, T, V, self.blank, int(apply_log_softmax),
                                     _ptr(self._x), ldx, _ptr(self._blank_lp), _stream(self.device)), "ctcps_init")
-        self._ldx = ldx
-        self._xt, self._ldt = None, L.ctcps_padded_lt(T)
         if token_major:
             with torch.cuda.device(self.device):
                 self._xt = torch.empty((B, V, self._ldt), dtype=torch.float32, device=self.device)
@@ -186,6 +196,10 @@ class CTCPrefixScoreTH(object):
                            "ctcps_transpose_vt")
             if self._x is not x:
                 self._x = None  # rebuilt on demand by _frame_major()
+        self._finish_setup(margin)
+
+    def _finish_setup(self, margin):
+        B, T, V = self.batch, self.input_length, self.odim
         self._ws = None
         self._ws_key = None
         self._ws_gen = 0  # bumped by every call that overwrites the workspace

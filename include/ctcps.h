@@ -160,6 +160,9 @@ int ctcps_beam_step(const float *joint, float *beam_scores, const int64_t *ids_c
  */
 int ctcps_padded_lt(int T);
 int ctcps_transpose_vt(const float *x_logp, int ldx, int B, int T, int V, float *x_vt, int ldt, void *stream);
+/* K-a (ctcps_init: ctc_scorer.py:279, :39-46) writing the token-major layout directly, one pass over HBM. */
+int ctcps_init_vt(const float *logits, int ld_in, const int64_t *lens, int B, int T, int V, int blank, int apply_log_softmax,
+                  float *x_vt, int ldt, float *blank_lp, void *stream);
 
 /* scores[:, blank] = logzero in place (:325), then the S best (id, score) of every row, best first, ties by lower id. */
 int ctcps_prebeam_topk(float *att_scores, int BW, int V, int blank, int S, int64_t *scoring_ids, float *cand_att, void *stream);
@@ -243,6 +246,8 @@ typedef struct ctcps_decode_session {
     void *ev_step, *ev_select;
 } ctcps_decode_session;
 
+/* sizeof(ctcps_decode_session) as this library was compiled: lets a binding check its mirror of the struct. */
+size_t ctcps_decode_session_size(void);
 int ctcps_async_create(void **side_stream, void **ev_step, void **ev_select);
 int ctcps_async_destroy(void *side_stream, void *ev_step, void *ev_select);
 /* Timing events for callers without a CUDA runtime binding (bench.py times the scoring call inside a step with them). */

@@ -56,6 +56,33 @@ def test_argument_errors_are_reported_before_any_launch():
                                  None, None, None, None, 0, None), "ctcps_score")
 
 
+def test_argument_errors_of_the_pre_beam_and_step_entry_points():
+    """Same for the N2 / N4 / native-step entry points: every one validates on the host before it launches anything."""
+    import ctypes
+
+    from huggingface_asr_b200 import _lib
+
+    L = _lib.lib()
+    assert L.ctcps_padded_lt(373) == 376 and L.ctcps_padded_lt(376) == 376
+    assert L.ctcps_transpose_vt(None, 8, 1, 4, 8, None, 4, None) == -1
+    assert L.ctcps_prebeam_topk(None, 4, 8, 3, 2, None, None, None) == -1
+    assert L.ctcps_score_candidates(None, 4, None, None, None, 0, 1, 1, 4, 8, 3, None, 2, None, 0.7, 0.3, None, None, None, None, 0, 0,
+                                    None) == -1
+    assert L.ctcps_candidates_to_dense(None, None, None, None, None, None, 1, 8, 2, 0.7, 0.3, 0, 4, None, None, None, None) == -1
+    assert L.ctcps_select_lazy_candidates(None, 4, None, None, None, 0, None, 2, None, None, 1, 1, 4, 8, None, None, None, 0, None) == -1
+    assert L.ctcps_beam_step_candidates(None, None, 1, None, None, None, 8, 1, 1, 1, 8, 1, 3, 1.0, None, None, None, 8, None, None, 0,
+                                        None, 0, 0, None, None) == -1
+    assert L.ctcps_split_tf32(None, 4, 8, 0, None, None) == -1
+    assert L.ctcps_decode_step(None, None, 0, None, None, None) == -1
+    sess = _lib.DecodeSession()
+    sess.S = 1  # neither full vocabulary nor >= 2 candidates
+    dummy = ctypes.c_float(0.0)
+    assert L.ctcps_decode_step(ctypes.byref(sess), ctypes.byref(dummy), 0, None, None, None) == -1
+    assert L.ctcps_decode_finish(None, None) == -1
+    # the session struct mirrors the C declaration (a mismatch would shift every pointer)
+    assert ctypes.sizeof(_lib.DecodeSession) == L.ctcps_decode_session_size()
+
+
 def test_cuda_library_is_sm_100a_with_tma():
     from huggingface_asr_b200 import _lib
 
