@@ -90,7 +90,6 @@ SIGNATURES = {
     "ctcps_beam_step": [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i64, _p, _p, _sz, _p, _i, _i64, _p, _p],
     "ctcps_padded_lt": [_i],
     "ctcps_transpose_vt": [_p, _i, _i, _i, _i, _p, _i, _p],
-    "ctcps_init_vt": [_p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p],
     "ctcps_prebeam_topk": [_p, _i, _i, _i, _i, _p, _p, _p],
     "ctcps_score_candidates": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _f, _f, _p, _p, _p, _p, _sz, _i, _p],
     "ctcps_candidates_to_dense": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _i, _p, _p, _p, _p],

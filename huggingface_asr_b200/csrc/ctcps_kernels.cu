@@ -1894,34 +1894,21 @@ int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const 
     a.ol = ol;
     a.G = G;
     a.Tpad = Tpad;
-    // Tile width: 512 tokens (128 threads, 4 resident CTAs per SM) for large problems; small ones (C1, C3, C4: fewer than two
-    // tiles per resident CTA, so the persistent grid would run one almost empty second round) take 256-token tiles with 8
-    // resident CTAs per SM -- twice the tiles, each half the work, which halves the cost of the wave quantisation.
-    int sms = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long tiles512 = (long long)B * G * ((V + 511) / 512);
-    const bool narrow = tiles512 < 2ll * sms * 4;
-#define CTCPS_PSI_LAUNCH(HWv, HWPv)                                                        \
-    do {                                                                                   \
-        if (narrow) {                                                                      \
-            a.nvt = (V + 255) / 256;                                                       \
-            return launch_psi_full<HWv, HWPv, 64, 8>(tm, a, st);                           \
-        }                                                                                  \
-        a.nvt = (V + 511) / 512;                                                           \
-        return launch_psi_full<HWv, HWPv, 128, 4>(tm, a, st);                              \
-    } while (0)
+    // (256-token tiles with 8 resident CTAs per SM were tried for the small shapes, C1 / C3 / C4: same time -- a tile is a serial
+    // chain of T/8 TMA chunks of ~1.3 us each, so halving its width halves nothing; those shapes need the frame range split
+    // across CTAs, which is future work.)
+    constexpr int NT = 128;
+    a.nvt = (V + NT * 4 - 1) / (NT * 4);
     switch (HW) {
-        case 1: CTCPS_PSI_LAUNCH(1, 4);
-        case 2: CTCPS_PSI_LAUNCH(2, 4);
-        case 3: CTCPS_PSI_LAUNCH(3, 4);
-        case 4: CTCPS_PSI_LAUNCH(4, 4);
-        case 5: CTCPS_PSI_LAUNCH(5, 8);
-        case 6: CTCPS_PSI_LAUNCH(6, 8);
-        case 8: CTCPS_PSI_LAUNCH(8, 8);
-        default: CTCPS_PSI_LAUNCH(10, 12);
+        case 1: return launch_psi_full<1, 4, NT, 4>(tm, a, st);
+        case 2: return launch_psi_full<2, 4, NT, 4>(tm, a, st);
+        case 3: return launch_psi_full<3, 4, NT, 4>(tm, a, st);
+        case 4: return launch_psi_full<4, 4, NT, 4>(tm, a, st);
+        case 5: return launch_psi_full<5, 8, NT, 4>(tm, a, st);
+        case 6: return launch_psi_full<6, 8, NT, 4>(tm, a, st);
+        case 8: return launch_psi_full<8, 8, NT, 4>(tm, a, st);
+        default: return launch_psi_full<10, 12, NT, 4>(tm, a, st);
     }
-#undef CTCPS_PSI_LAUNCH
 }
 
 int ctcps_select_lazy(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const int64_t *last_ids, int ol,
@@ -1993,19 +1980,6 @@ int ctcps_transpose_vt(const float *x_logp, int ldx, int B, int T, int V, float 
     ARG_CHECK(B < 65536 && (ldt + 31) / 32 < 65536, CTCPS_E_TOOBIG, "transpose_vt: B or T too large for one launch");
     const dim3 grid((V + 31) / 32, (ldt + 31) / 32, B);
     k_transpose_vt<<<grid, 256, 0, (cudaStream_t)stream>>>(x_logp, ldx, T, V, x_vt, ldt);
-    return cuda_rc(cudaGetLastError());
-}
-
-int ctcps_init_vt(const float *logits, int ld_in, const int64_t *lens, int B, int T, int V, int blank, int apply_log_softmax,
-                  float *x_vt, int ldt, float *blank_lp, void *stream) {
-    ARG_CHECK(logits && x_vt && B > 0 && T > 0 && V > 0, CTCPS_E_BADARG, "init_vt: null pointer or non-positive size");
-    ARG_CHECK(blank >= 0 && blank < V, CTCPS_E_BADARG, "init_vt: blank id outside the vocabulary");
-    ARG_CHECK(ld_in >= V, CTCPS_E_BADARG, "init_vt: row stride smaller than V");
-    ARG_CHECK(ldt >= T && (ldt & 3) == 0 && (((uintptr_t)x_vt) & 15) == 0, CTCPS_E_ALIGN,
-              "init_vt: ldt must be a multiple of 4 and >= T, x_vt 16-byte aligned");
-    ARG_CHECK(B < 65536, CTCPS_E_TOOBIG, "init_vt: B too large for one launch");
-    const dim3 grid((ldt + KIV_TB - 1) / KIV_TB, B);
-    k_init_vt<<<grid, 256, 0, (cudaStream_t)stream>>>(logits, ld_in, lens, T, V, blank, apply_log_softmax, x_vt, ldt, blank_lp);
     return cuda_rc(cudaGetLastError());
 }
 

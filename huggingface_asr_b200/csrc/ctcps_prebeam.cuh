@@ -7,8 +7,9 @@
 // With S candidates instead of V tokens per hypothesis a decode step has BW*S lanes (C2: 82 k instead of 12.8 M), so
 // the layout that serves it is token-major: x_vt (B, V, ldt), a token's time series contiguous, and the kernels are
 //
-//   k_init_vt         K-a writing the token-major layout directly (log-softmax + padding + blank column + transpose)
-//   k_transpose_vt    (B,T,ldx) -> (B,V,ldt) for a scorer that already holds frame-major posteriors
+//   k_transpose_vt    (B,T,ldx) -> (B,V,ldt), once per generate() (a K-a that writes the token-major layout directly --
+//                     warp-per-row reductions + warp-private transpose tiles -- measured 1.30 ms against 0.60 + 0.74 ms for
+//                     k_init + this kernel, and was not kept)
 //   k_prebeam_topk    scores[:, pad] = logzero (:325) + top-S of every row of the decoder scores (radix select)
 //   k_psi_cand        log_psi / token score / joint score of the S candidates of every hypothesis: a dot product over t of
 //                     the per-hypothesis stream (the same `lin` workspace k_psi_full consumes) with exp(x_vt[b, v, :]),
@@ -36,85 +37,6 @@ __global__ void __launch_bounds__(256) k_transpose_vt(const float *__restrict__ 
     for (int k = 0; k < 4; ++k) {
         const int v = v0 + ty + k * 8, t = t0 + tx;
         if (v < V && t < ldt) dst[(size_t)v * ldt + t] = tile[tx][ty + k * 8];
-    }
-}
-
-// K-a for the token-major layout in one pass over HBM: log-softmax + length padding + blank column + transpose.
-// CTA = (utterance b, 32 consecutive frames).  Phase A: each warp reduces 4 of the rows (max, then sum of exp; the second
-// sweep hits L1).  Phase B: the CTA re-reads its 32 rows (L2-resident: 640 KB just read) in 32x32 tiles, normalises and
-// writes them transposed, 128 contiguous bytes per (token, 32 frames).  HBM traffic: logits once, x_vt once -- the
-// two-kernel version (k_init then k_transpose_vt) moved the posteriors three more times (1.32 ms at C2).
-constexpr int KIV_TB = 32;
-__global__ void __launch_bounds__(256) k_init_vt(const float *__restrict__ in, int ld_in, const int64_t *__restrict__ lens, int T, int V,
-                                                 int blank, int apply, float *__restrict__ xt, int ldt, float *__restrict__ blank_lp) {
-    __shared__ float row_m[KIV_TB], row_ls[KIV_TB];
-    __shared__ int row_kind[KIV_TB];  // 0 = beyond T (zero fill), 1 = padded frame (:39-42), 2 = regular
-    __shared__ float tile[32][33];
-    const int b = blockIdx.y, t0 = blockIdx.x * KIV_TB;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    long long len = T;
-    if (lens != nullptr) {
-        const long long lraw = lens[b];
-        len = lraw < 0 ? lraw + T : lraw;  // python slice x[i, l:, :]
-        if (len < 0) len = 0;
-        if (lraw >= T) len = T;
-    }
-    const float *src = in + (size_t)b * T * ld_in;
-    const bool vec = (V & 3) == 0 && (ld_in & 3) == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0;
-    for (int r = wid; r < KIV_TB; r += 8) {
-        const int t = t0 + r;
-        int kind = 2;
-        float m = 0.f, ls = 0.f;
-        if (t >= T) kind = 0;
-        else if (t >= len) kind = 1;
-        else if (apply) {
-            const float *row = src + (size_t)t * ld_in;
-            m = -INFINITY;
-            if (vec) {
-                const float4 *r4 = reinterpret_cast<const float4 *>(row);
-                for (int q = lane; q < (V >> 2); q += 32) {
-                    const float4 v = r4[q];
-                    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
-                }
-                m = warp_max(m);
-                float sacc = 0.f;
-                for (int q = lane; q < (V >> 2); q += 32) {
-                    const float4 v = r4[q];
-                    sacc += expf(v.x - m) + expf(v.y - m) + expf(v.z - m) + expf(v.w - m);
-                }
-                ls = logf(warp_sum(sacc));
-            } else {
-                for (int v = lane; v < V; v += 32) m = fmaxf(m, row[v]);
-                m = warp_max(m);
-                float sacc = 0.f;
-                for (int v = lane; v < V; v += 32) sacc += expf(row[v] - m);
-                ls = logf(warp_sum(sacc));
-            }
-        }
-        if (lane == 0) row_m[r] = m, row_ls[r] = ls, row_kind[r] = kind;
-    }
-    __syncthreads();
-    float *dst = xt + (size_t)b * V * ldt;
-    for (int v0 = 0; v0 < V; v0 += 32) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int r = wid + k * 8, t = t0 + r, v = v0 + lane;
-            float o = 0.f;
-            if (v < V) {
-                const int kind = row_kind[r];
-                if (kind == 2) o = (src[(size_t)t * ld_in + v] - row_m[r]) - row_ls[r];
-                else if (kind == 1) o = (v == blank) ? 0.f : LZ;
-                if (kind != 0 && v == blank && blank_lp != nullptr) blank_lp[(size_t)b * T + t] = o;
-            }
-            tile[r][lane] = o;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int v = v0 + wid + k * 8, t = t0 + lane;
-            if (v < V && t < ldt) dst[(size_t)v * ldt + t] = tile[lane][wid + k * 8];
-        }
-        __syncthreads();
     }
 }
 

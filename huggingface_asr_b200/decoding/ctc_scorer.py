@@ -167,16 +167,6 @@ class CTCPrefixScoreTH(object):
         ldx = L.ctcps_padded_ld(V)
         self._ldx = ldx
         self._xt, self._ldt = None, L.ctcps_padded_lt(T)
-        if token_major and apply_log_softmax:
-            # K-a straight into the token-major layout (one pass over HBM); the frame-major copy is rebuilt on demand
-            with torch.cuda.device(self.device):
-                self._blank_lp = torch.empty((B, T), dtype=torch.float32, device=self.device)
-                self._xt = torch.empty((B, V, self._ldt), dtype=torch.float32, device=self.device)
-                _lib.check(L.ctcps_init_vt(_ptr(x), V, _ptr(self._lens), B, T, V, self.blank, 1, _ptr(self._xt), self._ldt,
-                                           _ptr(self._blank_lp), _stream(self.device)), "ctcps_init_vt")
-            self._x = None
-            self._finish_setup(margin)
-            return
         with torch.cuda.device(self.device):
             self._blank_lp = torch.empty((B, T), dtype=torch.float32, device=self.device)
             if apply_log_softmax or ldx != V:

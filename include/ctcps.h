@@ -160,9 +160,6 @@ int ctcps_beam_step(const float *joint, float *beam_scores, const int64_t *ids_c
  */
 int ctcps_padded_lt(int T);
 int ctcps_transpose_vt(const float *x_logp, int ldx, int B, int T, int V, float *x_vt, int ldt, void *stream);
-/* K-a (ctcps_init: ctc_scorer.py:279, :39-46) writing the token-major layout directly, one pass over HBM. */
-int ctcps_init_vt(const float *logits, int ld_in, const int64_t *lens, int B, int T, int V, int blank, int apply_log_softmax,
-                  float *x_vt, int ldt, float *blank_lp, void *stream);
 
 /* scores[:, blank] = logzero in place (:325), then the S best (id, score) of every row, best first, ties by lower id. */
 int ctcps_prebeam_topk(float *att_scores, int BW, int V, int blank, int S, int64_t *scoring_ids, float *cand_att, void *stream);

@@ -168,24 +168,10 @@ def test_token_major_layout_round_trips():
     a = CTCPrefixScoreTH.from_logits(logits.cuda(), lens.cuda(), BLANK, EOS)
     b = CTCPrefixScoreTH.from_logits(logits.cuda(), lens.cuda(), BLANK, EOS, token_major=True)
     assert b._x is None and b._xt.shape == (B, V, b._ldt) and b._ldt % 4 == 0
-    # k_init_vt reduces a row per warp, k_init per CTA: same formula, different summation order -> last-ulp differences
-    fin = a._x[:, :, :V] > -1e9
-    assert bool(((b._xt[:, :, :T].transpose(1, 2) > -1e9) == fin).all())
-    assert float((b._xt[:, :, :T].transpose(1, 2)[fin] - a._x[:, :, :V][fin]).abs().max()) <= 4e-6
+    assert torch.equal(b._xt[:, :, :T].transpose(1, 2), a._x[:, :, :V])
     assert bool((b._xt[:, :, T:] == 0).all())
-    assert torch.equal(a._blank_lp > -1e9, b._blank_lp > -1e9) and float((a._blank_lp - b._blank_lp).abs().max()) <= 4e-6
-    assert float((a.x - b.x)[a.x > -1e9].abs().max()) <= 4e-6  # rebuilt frame-major copy
-    # the two-kernel route (frame-major first, then ctcps_transpose_vt) is an exact copy
-    assert torch.equal(a._token_major()[:, :, :T].transpose(1, 2), a._x[:, :, :V])
-    # V % 4 != 0, ragged lengths incl. a zero-length utterance
-    lg, ln, _ = _seeded(3, 2, 41, 33, seed=75)
-    ln[1] = 0
-    c = CTCPrefixScoreTH.from_logits(lg.cuda(), ln.cuda(), BLANK, EOS)
-    d = CTCPrefixScoreTH.from_logits(lg.cuda(), ln.cuda(), BLANK, EOS, token_major=True)
-    fin = c._x[:, :, :33] > -1e9
-    got = d._xt[:, :, :41].transpose(1, 2)
-    assert bool(((got > -1e9) == fin).all()) and float((got[fin] - c._x[:, :, :33][fin]).abs().max()) <= 4e-6
-    assert float((c._blank_lp - d._blank_lp).abs().max()) <= 4e-6
+    assert torch.equal(a.x, b.x)  # rebuilt frame-major copy
+    assert torch.equal(a._token_major(), b._xt)
 
 
 def test_prebeam_argument_errors():
