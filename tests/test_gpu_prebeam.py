@@ -247,3 +247,83 @@ def test_native_loop_equals_fused_loop(S):
     assert a.steps == b.steps and torch.equal(a.sequences, b.sequences) and torch.equal(a.scores, b.scores)
     want = torch.tensor([len(t) - 1 for t in transcripts])  # hypotheses are stored without their eos
     assert (a.lengths.cpu() == want).all(), "the decode does not recover the planted transcripts"
+
+
+def test_prebeam_edge_shapes_vs_oracle():
+    """Shapes that take the other code paths: V % 4 != 0 (radix top-k, scalar loads), S = 64 (two candidate passes per warp),
+    W = 20 (two hypothesis groups), T > 384 (several row segments per candidate), ragged lengths with a very short utterance."""
+    from huggingface_asr_b200.beam_search import joint_beam_search, joint_beam_search_native
+    from huggingface_asr_b200.synthetic import make_attention_scores, make_encoder_logits
+    from oracle import oracle as orc
+
+    B, W, T, V, S = 2, 20, 520, 203, 64
+    logits, lens, _ = make_encoder_logits(B, T, V, "peaky", True, seed=91)
+    lens[1] = 7
+    cpu = orc.OracleCTCRescorerLogitsProcessor(logits.clone(), lens.clone(), BLANK, EOS, 0, 0.3, W, pre_beam_size=S)
+    trace = []
+
+    class Rec:
+        use_beam_idx = True
+
+        def set_beam_idx(self, bi):
+            cpu.set_beam_idx(bi)
+
+        def __call__(self, ids, scores):
+            out = cpu(ids, scores)
+            trace.append((ids.clone(), out.clone()))
+            return out
+
+    def att(dev):
+        return lambda ids, n: make_attention_scores(B * W, V, n, seed=19, scale=0.5).to(dev)
+
+    oc = joint_beam_search(Rec(), att("cpu"), B, W, V, BOS, EOS, BLANK, max_length=12)
+    gpu = _proc(logits.cuda(), lens.cuda(), 0.3, W, S, True)
+    step = [0]
+
+    class Chk:
+        use_beam_idx = True
+
+        def set_beam_idx(self, bi):
+            gpu.set_beam_idx(bi)
+
+        def __call__(self, ids, scores):
+            ref_ids, ref_out = trace[step[0]]
+            assert (ids.cpu() == ref_ids).all(), f"step {step[0]}: decode diverged"
+            out = gpu(ids, scores)
+            parity.assert_parity(out, ref_out, f"step {step[0]} joint")
+            step[0] += 1
+            return out
+
+    og = joint_beam_search(Chk(), att("cuda"), B, W, V, BOS, EOS, BLANK, max_length=12, device="cuda")
+    assert og.steps == oc.steps and (og.sequences.cpu() == oc.sequences).all()
+    on = joint_beam_search_native(_proc(logits.cuda(), lens.cuda(), 0.3, W, S, True), att("cuda"), B, W, V, BOS, EOS, BLANK,
+                                  max_length=12, device="cuda", done_check_lag=0)
+    assert on.steps == oc.steps and (on.sequences.cpu() == oc.sequences).all()
+    assert (on.scores.cpu() - oc.scores).abs().max() <= 1e-4
+
+
+def test_prebeam_prefix_longer_than_the_utterance():
+    """output_length > T: the reference returns logzero everywhere (:138-145); the candidate path must do the same, and the
+    steps around it (start == T - 1, start == T) must match the oracle."""
+    from huggingface_asr_b200.synthetic import make_attention_scores, make_encoder_logits
+    from oracle import oracle as orc
+
+    B, W, T, V, S = 1, 3, 6, 24, 5
+    logits, lens, _ = make_encoder_logits(B, T, V, "flat", False, seed=92)
+    cpu = orc.OracleCTCRescorerLogitsProcessor(logits.clone(), lens.clone(), BLANK, EOS, 0, 0.3, W, pre_beam_size=S)
+    gpu = _proc(logits.cuda(), lens.cuda(), 0.3, W, S, True)
+    ids = torch.full((B * W, 1), BOS, dtype=torch.long)
+    g = torch.Generator().manual_seed(1)
+    for n in range(T + 3):
+        a = make_attention_scores(B * W, V, n, seed=23, scale=0.5)
+        oc = cpu(ids, a.clone())
+        og = gpu(ids.cuda(), a.cuda())
+        parity.assert_parity(og, oc, f"prefix length {n}")
+        parity.assert_parity(gpu.ctc_states[1], cpu.ctc_states[1], f"log_psi at prefix length {n}")
+        # every beam keeps its own best-scored candidate (never eos / blank): beam_idx = identity
+        tok = torch.sort(a, dim=1, descending=True, stable=True).indices
+        nxt = torch.stack([next(t for t in row.tolist() if t not in (EOS, BLANK)) * torch.ones((), dtype=torch.long) for row in tok])
+        bi = torch.arange(B * W)
+        cpu.set_beam_idx(bi)
+        gpu.set_beam_idx(bi.cuda())
+        ids = torch.cat([ids, nxt.view(-1, 1)], 1)
