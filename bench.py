@@ -115,6 +115,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", 0))
     dev = torch.device(f"cuda:{local}")
     torch.cuda.set_device(dev)
+    numa = bind_to_gpu_numa_node(local) if world > 1 and not args.no_numa_bind else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -382,7 +383,7 @@ def run_ours(args):
                        "ctc_weight": cfg.ctc_weight, "logits": cfg.kind, "state": args.state, "harness": args.harness,
                        "decode_steps_per_utterance_batch": m["decode_steps_per_utterance_batch"],
                        "attention_scores": "SyntheticDecoder: log_softmax(noise + 10*onehot(transcript[n])) (the decoder is model code outside the path)",
-                       "max_length": MAX_LENGTH,
+                       "max_length": MAX_LENGTH, "numa_bound_cpus": None if numa is None else len(numa),
                        "l2": "inputs exceed L2: posteriors are 1.9 GB and (materialized) every scorer launch writes 8*T*BW*V bytes of state"},
             "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "roofline": m["roofline"], "clocks": m["clocks"],
         }
@@ -422,6 +423,28 @@ def run_ours(args):
         emit(line)
     if dist is not None:
         dist.destroy_process_group()
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs NVML reports as local to its GPU BEFORE it allocates pinned memory (first touch puts the
+    staging buffers on that NUMA node): with several ranks per host, H2D copies from one socket's memory cap the whole job.
+    Returns the CPU list, or None when NVML / sched_setaffinity is unavailable."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
 
 
 def load_traffic(kernel):
@@ -522,6 +545,7 @@ def main():
                     help="fused harness: steps the CPU may run ahead of the GPU (default: 0 materialized, 1 lazy)")
     ap.add_argument("--hidden-dim", type=int, default=512,
                     help="also measure end to end from encoder hidden states of this width (N4 boundary; 0 = skip)")
+    ap.add_argument("--no-numa-bind", action="store_true", help="multi-rank runs: do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--profile", action="store_true", help="for runs under ncu: honour a warm-up below 3 and skip the e2e/cpu legs (never a bench value)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -114,3 +114,52 @@ def test_full_size_decode_lazy_equals_materialised_and_transcript():
     assert (outs[0].scores - outs[1].scores).abs().max().item() <= 1e-4
     for i in range(B):
         assert outs[0].sequences[i, : outs[0].lengths[i]].tolist() == tr[i][:-1]
+
+
+def test_full_size_c2_decodes_native_loop_prebeam_and_hidden_states():
+    """The bench workload (C2: 256 x 15 s, beam 10, 5000 tokens, ragged) through the native loop: full vocabulary, pre-beam
+    S = 15 and the N4 boundary (encoder hidden states -> CTC head on the tensor cores) all recover the planted transcripts,
+    and pre-beam agrees with the full-vocabulary 1-best; sample rows of the candidate scores equal the oracle's."""
+    from huggingface_asr_b200.beam_search import joint_beam_search_native
+    from huggingface_asr_b200.ctc_head import CTCHead
+    from huggingface_asr_b200.decoding.ctc_scorer import CTCRescorerLogitsProcessor
+    from huggingface_asr_b200.synthetic import BLANK, BOS, CONFIGS, EOS, SyntheticDecoder, make_attention_scores, make_encoder_hidden
+    from oracle import oracle as orc
+
+    cfg = CONFIGS["C2"]
+    B, W, T, V = cfg.B, cfg.W, cfg.T, cfg.V
+    _need(12)
+    hidden, weight, bias, lens, tr = make_encoder_hidden(B, T, V, 512, "peaky", True, seed=4242)
+    head = CTCHead(weight.cuda(), bias.cuda())
+    logits = head(hidden.cuda())
+    dec = SyntheticDecoder(tr, W, V, 128, seed=1, device="cuda")
+    want = [t[:-1] for t in tr]
+
+    def run(**kw):
+        proc = CTCRescorerLogitsProcessor(logits, lens.cuda(), BLANK, EOS, 0, cfg.ctc_weight, W, -1, False, 1.0, **kw)
+        return joint_beam_search_native(proc, dec, B, W, V, BOS, EOS, BLANK, max_length=128, device="cuda")
+
+    full, pre = run(), run(pre_beam_size=15)
+    for out in (full, pre):
+        for i in range(B):
+            assert out.sequences[i, : out.lengths[i]].tolist() == want[i]
+    assert torch.equal(full.sequences, pre.sequences)
+    assert (full.scores - pre.scores).abs().max().item() <= 1e-4
+
+    # candidate scores of three utterances of the full batch vs the oracle run on those three (first two steps)
+    sample = [0, B // 2, B - 1]
+    rows = torch.tensor([b * W + w for b in sample for w in range(W)])
+    gpu = CTCRescorerLogitsProcessor(logits, lens.cuda(), BLANK, EOS, 0, 0.3, W, -1, False, 1.0, pre_beam_size=15)
+    cpu = orc.OracleCTCRescorerLogitsProcessor(logits[sample].cpu(), lens[sample].clone(), BLANK, EOS, 0, 0.3, W, pre_beam_size=15)
+    ids = torch.zeros((B * W, 1), dtype=torch.long)
+    for n in range(2):
+        att = make_attention_scores(B * W, V, n, seed=8, scale=0.5)
+        og = gpu(ids.cuda(), att.cuda())
+        oc = cpu(ids[rows], att[rows].clone())
+        parity.assert_parity(og[rows.cuda()], oc, f"C2 pre-beam step {n} joint vs oracle")
+        # every beam continues with its own best candidate
+        nxt = og.argmax(dim=1).cpu()
+        bi = torch.arange(B * W)
+        gpu.set_beam_idx(bi.cuda())
+        cpu.set_beam_idx(torch.arange(len(rows)))
+        ids = torch.cat([ids, nxt.view(-1, 1)], 1)
