@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ctcps.h"
@@ -1894,9 +1895,9 @@ int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const 
     a.ol = ol;
     a.G = G;
     a.Tpad = Tpad;
-    // (256-token tiles with 8 resident CTAs per SM were tried for the small shapes, C1 / C3 / C4: same time -- a tile is a serial
-    // chain of T/8 TMA chunks of ~1.3 us each, so halving its width halves nothing; those shapes need the frame range split
-    // across CTAs, which is future work.)
+    // 256-token tiles (64 threads, 8 resident CTAs per SM) were measured and not kept: no gain for the small shapes (C1 / C3 /
+    // C4 -- a tile is a serial chain of T/8 TMA chunks, halving its width halves nothing; they need the frame range split across
+    // CTAs) and 4 % slower at C2 (0.371 vs 0.356 ms).
     constexpr int NT = 128;
     a.nvt = (V + NT * 4 - 1) / (NT * 4);
     switch (HW) {

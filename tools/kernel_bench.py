@@ -13,10 +13,28 @@ from huggingface_asr_b200.synthetic import BLANK, CONFIGS, EOS, make_encoder_log
 
 
 def timeit(fn, n=10, warm=3):
+    """Device time per call in ms.  The calls are captured into ONE CUDA graph and the graph is replayed, so that the host
+    cost of a call (ctypes + torch.empty: 20-60 us, more than most of these kernels take) is not what gets measured; calls
+    that cannot be captured fall back to eager launches (then small numbers are host-bound)."""
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(n):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    except Exception as exc:  # noqa: BLE001
+        print(f"  (graph capture failed: {type(exc).__name__}; eager timing)")
+        torch.cuda.synchronize()
     e0.record()
     for _ in range(n):
         fn()
@@ -94,7 +112,7 @@ def main():
         res["prebeam beam_step_candidates"] = timeit(lambda: _lib.check(L.ctcps_beam_step_candidates(
             cj.data_ptr(), cid.data_ptr(), S, bs.data_ptr(), idc.data_ptr(), idn.data_ptr(), maxlen, ol + 1, B, W, V, EOS, BLANK,
             float(ol + 1), ps.data_ptr(), pl.data_ptr(), pq.data_ptr(), maxlen, done.data_ptr(), ws.data_ptr(), ws.numel() * 8, None, 0, 0,
-            bo.data_ptr(), st_), "beam_cand"), 20)
+            bo.data_ptr(), torch.cuda.current_stream().cuda_stream), "beam_cand"), 20)
         del proc, sc, st, sel
         torch.cuda.empty_cache()
     if want("beam"):
@@ -114,7 +132,7 @@ def main():
         res["beam_step"] = timeit(lambda: _lib.check(L.ctcps_beam_step(joint.data_ptr(), bs.data_ptr(), idc.data_ptr(), idn.data_ptr(), maxlen,
                                                                        ol + 1, B, W, V, EOS, BLANK, float(ol + 1), ps.data_ptr(), pl.data_ptr(),
                                                                        pq.data_ptr(), maxlen, done.data_ptr(), ws.data_ptr(), ws.numel() * 8,
-                                                                       None, 0, 0, None, st), "beam"), 20)
+                                                                       None, 0, 0, None, torch.cuda.current_stream().cuda_stream), "beam"), 20)
         res["torch topk(2W) of (B, W*V) for comparison"] = timeit(lambda: joint.view(B, W * V).topk(2 * W, dim=1), 20)
     for k, v in res.items():
         print(f"{k:48s} {v * 1e3:10.1f} us")
