@@ -184,8 +184,11 @@ def run_ours(args):
 
         # clocks are sampled from the warm-up on (same load as the timed steps), so that short timed regions still
         # get enough nvidia-smi samples; the sampler stops right after the timed region
+        # rank 0 only: eight nvidia-smi pollers contend for the driver with the launch path of every rank (the pre-beam leg,
+        # ~5 launches per 200 us step, dropped from 24 k to 6 k utt/s per GPU at N = 8 with one poller per rank)
         clocks = ClockSampler(local)
-        clocks.start()
+        if rank == 0:
+            clocks.start()
         for _ in range(warm):
             decode(logits_d, lens_d)
         sync_all()
