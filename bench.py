@@ -74,11 +74,20 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            # nvidia-smi needs 0.1-1 s to initialise NVML, during which it holds driver locks that stall kernel launches:
+            # wait for its first sample so that this happens before the warm-up, not inside a short timed region
+            t0 = time.perf_counter()
+            while not self.lines and time.perf_counter() - t0 < 5.0 and self.proc.poll() is None:
+                time.sleep(0.01)
         except Exception:
             self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln)
 
     def stop(self):
         if self.proc is None:
@@ -529,7 +538,7 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
