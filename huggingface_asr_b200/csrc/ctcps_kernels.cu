@@ -344,18 +344,27 @@ __device__ __forceinline__ void epi_lane(const EpiArgs &e, int h, int v, float S
     jt_out = __fadd_rn(__fmul_rn(e.omw, av), __fmul_rn(e.w, ts));
 }
 
+// The loop over the hypotheses is deliberately NOT unrolled: with HW = 10 the unrolled body (40 lanes of logf / expf /
+// branches) was 13 k SASS instructions = 200 KB, far beyond the instruction caches, and every warp streamed it from L2
+// once per tile -- ncu: 35 % of the stall samples of the lazy kernel at C1 were `no_instruction`, a fixed ~25 us per
+// launch.  The sums live in registers, which cannot be indexed by a loop variable, so each iteration works on row 0 and
+// then shifts the rows down by one (4*(HW-1) register moves).
 template <int HW>
-__device__ __forceinline__ void epilogue_tile(const EpiArgs &e, const float (&S)[HW][4], const float (&x0)[4], int h0, int nhyp,
+__device__ __forceinline__ void epilogue_tile(const EpiArgs &e, const float (&S_in)[HW][4], const float (&x0)[4], int h0, int nhyp,
                                               int v0) {
     const int V = e.V;
     if (v0 >= V) return;
     const bool vec = ((V & 3) == 0);  // then v0 + 3 < V and every row start is 16-byte aligned
     const bool has_att = e.att != nullptr;
+    float S[HW][4];
+#pragma unroll
+    for (int hh = 0; hh < HW; ++hh)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) S[hh][j] = S_in[hh][j];
     float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
     if (vec && has_att) nxt = *reinterpret_cast<const float4 *>(e.att + (size_t)h0 * V + v0);
-#pragma unroll
-    for (int hh = 0; hh < HW; ++hh) {
-        if (hh >= nhyp) break;
+#pragma unroll 1
+    for (int hh = 0; hh < nhyp; ++hh) {
         const int h = h0 + hh;
         const float gm = e.Gmax[h];
         const float sp_row = (e.s_prev != nullptr && e.s_cs == 0) ? e.s_prev[(long long)h * e.s_rs] : 0.f;
@@ -366,7 +375,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs &e, const float (&S)
             const float av_in[4] = {cur.x, cur.y, cur.z, cur.w};
             float lp[4], ts[4], jt[4], av[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) epi_lane(e, h, v0 + j, S[hh][j], gm, x0[j], sp_row, av_in[j], lp[j], ts[j], jt[j], av[j]);
+            for (int j = 0; j < 4; ++j) epi_lane(e, h, v0 + j, S[0][j], gm, x0[j], sp_row, av_in[j], lp[j], ts[j], jt[j], av[j]);
             *reinterpret_cast<float4 *>(e.log_psi + o) = make_float4(lp[0], lp[1], lp[2], lp[3]);
             if (e.token_scores != nullptr) *reinterpret_cast<float4 *>(e.token_scores + o) = make_float4(ts[0], ts[1], ts[2], ts[3]);
             if (has_att) {
@@ -374,12 +383,14 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs &e, const float (&S)
                 if (e.blank >= v0 && e.blank < v0 + 4) e.att[(size_t)h * V + e.blank] = LZ;  // scores[:, pad] = logzero in place
             }
         } else {
-#pragma unroll
+#pragma unroll 1
             for (int j = 0; j < 4; ++j) {
                 const int v = v0 + j;
-                if (v >= V) continue;
+                if (v >= V) break;
                 float lp, ts, jt, av;
-                epi_lane(e, h, v, S[hh][j], gm, x0[j], sp_row, has_att ? e.att[o + j] : 0.f, lp, ts, jt, av);
+                const float sj = j == 0 ? S[0][0] : (j == 1 ? S[0][1] : (j == 2 ? S[0][2] : S[0][3]));
+                const float xj = j == 0 ? x0[0] : (j == 1 ? x0[1] : (j == 2 ? x0[2] : x0[3]));
+                epi_lane(e, h, v, sj, gm, xj, sp_row, has_att ? e.att[o + j] : 0.f, lp, ts, jt, av);
                 e.log_psi[o + j] = lp;
                 if (e.token_scores != nullptr) e.token_scores[o + j] = ts;
                 if (has_att) {
@@ -388,6 +399,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs &e, const float (&S)
                 }
             }
         }
+#pragma unroll
+        for (int i = 0; i + 1 < HW; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) S[i][j] = S[i + 1][j];
     }
 }
 
@@ -594,6 +609,13 @@ struct PsiArgs {
     float omw, w;
     float *log_psi, *token_scores, *joint;
     int B, W, T, V, blank, ol, G, Tpad, nvt;
+    // frame-split kernel only
+    const float *x;        // the (B,T,ldx) posteriors the tensor map describes (first-frame term of step 0)
+    int ldx;
+    int nfull;             // whole tiles per CTA (tiles i, i+grid, ...), before its piece of the split phase
+    int q;                 // chunks per CTA in the split phase
+    float4 *part;          // [grid][2][HW][NT] parked partial sums
+    unsigned int *ticket;  // [tiles] contributors that have parked their piece; zero between launches
 };
 
 template <int HWP, int NT>
@@ -766,6 +788,192 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
         e.Gmax = a.Gmax, e.s_prev = a.s_prev, e.s_rs = a.s_rs, e.s_cs = a.s_cs, e.att = a.att, e.omw = a.omw, e.w = a.w;
         e.log_psi = a.log_psi, e.token_scores = a.token_scores, e.joint = a.joint, e.V = V, e.blank = a.blank, e.ol = a.ol;
         epilogue_tile<HW>(e, acc, x0, h0, nhyp, v0);
+    }
+}
+
+// Frame-split ("stream-K") variant of k_psi_full.  CTA i first walks `nfull` WHOLE tiles i, i+grid, ... exactly like
+// k_psi_full (neighbouring CTAs read neighbouring column segments of the same frames: the DRAM-friendly order).  The
+// ntiles % grid tiles that would otherwise form a last, mostly empty wave (C3: 48 of 640 tiles on 592 resident CTAs; C1:
+// all 160) are not handed out whole: their chunks form one flat sequence (tile-major) that is cut into equal ranges of
+// `q` chunks, one per CTA, so every CTA streams the same number of bytes whatever the shape.
+// A tile whose chunks straddle several CTAs is finished by whichever of them arrives last: partial sums are additive
+// in the linear domain; every contributor parks its registers in `part` (slot 1 = the piece that holds the tile's first
+// chunk, slot 0 = any later piece; a CTA has at most one of each) and takes a ticket; the last one adds the pieces in
+// chunk order -- a fixed order, so results do not depend on arrival -- and runs the shared epilogue.  The first-frame
+// term of the first step (:158,165) is read from global memory by the finisher instead of from the staged chunk.
+template <int HW, int HWP, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_psi_split(const __grid_constant__ CUtensorMap tmx, const PsiArgs a) {
+    using Smem = PsiSmem<HWP, NT>;
+    constexpr int VTILE = Smem::VTILE;
+    constexpr int NBOX = Smem::NBOX;
+    constexpr int NWARP = NT / 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
+    __shared__ int s_last;
+    const int tid = threadIdx.x;
+    const int T = a.T, V = a.V, W = a.W;
+    const int start = a.ol > 1 ? a.ol : 1;
+    const int c0 = (a.ol == 0 ? 0 : start) / TT;
+    const int cN = (T - 1) / TT;
+    const int nchunk = cN - c0 + 1;
+    const int ntiles = a.B * a.nvt * a.G;
+    const int kfull = a.nfull * nchunk;               // items of the whole-tile phase
+    const int rem_tile0 = a.nfull * (int)gridDim.x;   // first tile of the split phase
+    const long long nrem = (long long)(ntiles - rem_tile0) * nchunk;
+    const long long i0 = (long long)blockIdx.x * a.q;  // this CTA's range of the split phase: [i0, i0 + q) clipped to nrem
+    const int nsplit = i0 >= nrem ? 0 : (int)((i0 + a.q <= nrem ? i0 + a.q : nrem) - i0);
+    const int nitems = kfull + nsplit;
+    constexpr uint32_t STAGE_BYTES = TT * VTILE * 4 + TT * HWP * 4;
+
+    auto decode_tile = [&](int tile, int &b, int &vt, int &g) {
+        g = tile % a.G;
+        tile /= a.G;
+        vt = tile % a.nvt;
+        b = tile / a.nvt;
+    };
+    auto locate = [&](int k, int &tile, int &ci) {  // item k of this CTA -> (tile, chunk index within the tile)
+        if (k < kfull) {
+            const int r = k / nchunk;
+            tile = (int)blockIdx.x + r * (int)gridDim.x;
+            ci = k - r * nchunk;
+        } else {
+            const long long it = i0 + (k - kfull);
+            const int r = (int)(it / nchunk);
+            tile = rem_tile0 + r;
+            ci = (int)(it - (long long)r * nchunk);
+        }
+    };
+    auto issue = [&](int k) {
+        int tile, ci, b, vt, g;
+        locate(k, tile, ci);
+        const int c = c0 + ci;
+        decode_tile(tile, b, vt, g);
+        const int s = k % NS;
+        mbar_expect_tx(&sm.full[s], STAGE_BYTES);
+#pragma unroll
+        for (int bx = 0; bx < NBOX; ++bx) tma_load_2d(&sm.xs[s][bx][0][0], &tmx, vt * VTILE + bx * BOXC, b * T + c * TT, &sm.full[s]);
+        bulk_load_1d(&sm.lin[s][0][0], a.lin + ((size_t)(b * a.G + g) * a.Tpad + (size_t)c * TT) * HWP, TT * HWP * 4, &sm.full[s]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(&sm.full[s], 1), mbar_init(&sm.empty[s], NWARP);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int k = 0; k < nitems && k < NS; ++k) issue(k);
+    }
+    __syncthreads();
+
+    const int bx = (tid * 4) / BOXC, col = (tid * 4) % BOXC;
+    int k = 0;
+    while (k < nitems) {
+        int tile, ci;
+        locate(k, tile, ci);
+        const int ci_begin = ci;
+        const int ci_end = min(nchunk, ci + (nitems - k));
+        int b, vt, g;
+        decode_tile(tile, b, vt, g);
+        unsigned long long acc2[HW][2];  // (token 0, token 1), (token 2, token 3) packed for FFMA2
+#pragma unroll
+        for (int hh = 0; hh < HW; ++hh) acc2[hh][0] = acc2[hh][1] = 0ull;
+
+        for (; ci < ci_end; ++ci, ++k) {
+            const int s = k % NS;
+            mbar_wait(&sm.full[s], (uint32_t)((k / NS) & 1));
+#pragma unroll
+            for (int tt = 0; tt < TT; ++tt) {
+                const float4 xv4 = *reinterpret_cast<const float4 *>(&sm.xs[s][bx][tt][col]);
+                const unsigned long long p01 = pack2(ex2_approx(xv4.x * LOG2E), ex2_approx(xv4.y * LOG2E));
+                const unsigned long long p23 = pack2(ex2_approx(xv4.z * LOG2E), ex2_approx(xv4.w * LOG2E));
+                float l[HWP];
+#pragma unroll
+                for (int qd = 0; qd < HWP / 4; ++qd) {
+                    const float4 l4 = *reinterpret_cast<const float4 *>(&sm.lin[s][tt][qd * 4]);
+                    l[qd * 4 + 0] = l4.x, l[qd * 4 + 1] = l4.y, l[qd * 4 + 2] = l4.z, l[qd * 4 + 3] = l4.w;
+                }
+#pragma unroll
+                for (int hh = 0; hh < HW; ++hh) {
+                    const unsigned long long ll = pack2(l[hh], l[hh]);
+                    acc2[hh][0] = ffma2(ll, p01, acc2[hh][0]);
+                    acc2[hh][1] = ffma2(ll, p23, acc2[hh][1]);
+                }
+            }
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&sm.empty[s]);
+            if (tid == 0 && k + NS < nitems) {  // refill the stage just released, once every warp is done with it
+                mbar_wait(&sm.empty[s], (uint32_t)((k / NS) & 1));
+                issue(k + NS);
+            }
+        }
+
+        float acc[HW][4];
+#pragma unroll
+        for (int hh = 0; hh < HW; ++hh) {
+            unpack2(acc2[hh][0], acc[hh][0], acc[hh][1]);
+            unpack2(acc2[hh][1], acc[hh][2], acc[hh][3]);
+        }
+        bool finish = true;
+        if (!(ci_begin == 0 && ci_end == nchunk)) {  // a piece of a tile: park it, the last contributor adds the pieces up
+            const long long t0 = (long long)(tile - rem_tile0) * nchunk;
+            const int c_first = (int)(t0 / a.q), c_last = (int)((t0 + nchunk - 1) / a.q);
+            float4 *mine = a.part + ((size_t)((int)blockIdx.x * 2 + (ci_begin == 0 ? 1 : 0)) * HW) * NT + tid;
+#pragma unroll
+            for (int hh = 0; hh < HW; ++hh) __stcg(mine + (size_t)hh * NT, make_float4(acc[hh][0], acc[hh][1], acc[hh][2], acc[hh][3]));
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) {
+                const unsigned int prev = atomicAdd(a.ticket + tile, 1u);
+                s_last = (prev == (unsigned int)(c_last - c_first)) ? 1 : 0;
+                if (s_last) a.ticket[tile] = 0u;  // self-cleaning: the next launch finds zeros
+            }
+            __syncthreads();
+            finish = s_last != 0;
+            if (finish) {
+                __threadfence();
+                float tot[HW][4];
+#pragma unroll
+                for (int hh = 0; hh < HW; ++hh)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) tot[hh][j] = 0.f;
+                // every piece, its own included, comes back from L2 in chunk order: a branch-free loop whose loads overlap
+#pragma unroll 2
+                for (int c = c_first; c <= c_last; ++c) {
+                    const float4 *piece = a.part + ((size_t)(c * 2 + (c == c_first ? 1 : 0)) * HW) * NT + tid;
+#pragma unroll
+                    for (int hh = 0; hh < HW; ++hh) {
+                        const float4 p = __ldcg(piece + (size_t)hh * NT);
+                        tot[hh][0] += p.x, tot[hh][1] += p.y, tot[hh][2] += p.z, tot[hh][3] += p.w;
+                    }
+                }
+#pragma unroll
+                for (int hh = 0; hh < HW; ++hh)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[hh][j] = tot[hh][j];
+            }
+        }
+        if (finish) {
+            const int v0 = vt * VTILE + tid * 4;
+            const int h0 = b * W + g * HW;
+            const int nhyp = min(HW, W - g * HW);
+            float x0[4] = {LZ, LZ, LZ, LZ};
+            if (a.ol == 0 && v0 < V) {  // r[0,0] = x_[0,0] enters log_psi as its own term (:158,165)
+                const float4 xv4 = __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)b * T * a.ldx + v0));
+                x0[0] = xv4.x, x0[1] = xv4.y, x0[2] = xv4.z, x0[3] = xv4.w;
+            }
+            // the column of each hypothesis' last label sums r_prev_blank instead of r_sum: take it from k_prep_psi
+#pragma unroll
+            for (int hh = 0; hh < HW; ++hh) {
+                if (hh < nhyp) {
+                    const int cj = (int)(a.last_ids[h0 + hh] - (long long)v0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (cj == j) acc[hh][j] = a.psic[h0 + hh];
+                }
+            }
+            EpiArgs e;
+            e.Gmax = a.Gmax, e.s_prev = a.s_prev, e.s_rs = a.s_rs, e.s_cs = a.s_cs, e.att = a.att, e.omw = a.omw, e.w = a.w;
+            e.log_psi = a.log_psi, e.token_scores = a.token_scores, e.joint = a.joint, e.V = V, e.blank = a.blank, e.ol = a.ol;
+            epilogue_tile<HW>(e, acc, x0, h0, nhyp, v0);
+        }
     }
 }
 
@@ -1457,10 +1665,13 @@ void pick_hw_psi(int W, int *HW, int *HWP, int *G) {
     *HWP = (best + 3) & ~3;
     *G = (W + best - 1) / best;
 }
+constexpr int PSI_NT = 128;         // threads of the lazy scoring kernels (512-token tiles)
+constexpr int PSI_MIN_Q = 8;          // fewest chunks a CTA of k_psi_split is given
+constexpr int PSI_MAX_GRID = 640;   // >= 148 SMs x 4 resident CTAs; bounds the parked partial sums of k_psi_split
 struct WorkspaceLazy {
-    size_t lin_off, lin_bytes, g_off, c_off, total;
+    size_t lin_off, lin_bytes, g_off, c_off, part_off, ticket_off, ticket_bytes, total;
 };
-WorkspaceLazy plan_workspace_lazy(int B, int T, int W) {
+WorkspaceLazy plan_workspace_lazy(int B, int T, int W, int V) {
     int HW, HWP, G;
     pick_hw_psi(W, &HW, &HWP, &G);
     WorkspaceLazy ws;
@@ -1469,7 +1680,12 @@ WorkspaceLazy plan_workspace_lazy(int B, int T, int W) {
     ws.g_off = (ws.lin_bytes + 255) & ~(size_t)255;
     const size_t gb = ((size_t)B * W * sizeof(float) + 255) & ~(size_t)255;
     ws.c_off = ws.g_off + gb;
-    ws.total = ws.c_off + gb;
+    ws.part_off = ws.c_off + gb;
+    const size_t pb = (size_t)PSI_MAX_GRID * 2 * HW * PSI_NT * sizeof(float4);
+    ws.ticket_off = ws.part_off + pb;
+    const int nvt = (V + PSI_NT * 4 - 1) / (PSI_NT * 4);
+    ws.ticket_bytes = ((size_t)B * nvt * G * sizeof(unsigned int) + 255) & ~(size_t)255;
+    ws.total = ws.ticket_off + ws.ticket_bytes;
     return ws;
 }
 
@@ -1536,6 +1752,50 @@ int launch_psi_full(const CUtensorMap &tm, const PsiArgs &a, cudaStream_t st) {
     return cuda_rc(cudaGetLastError());
 }
 
+// Frame-split launch: grid = resident CTAs (<= PSI_MAX_GRID); floor(tiles / grid) whole tiles per CTA, the chunks of the
+// remaining tiles in equal ranges of q.
+template <int HW, int HWP, int NT, int MINB>
+int launch_psi_split(const CUtensorMap &tm, PsiArgs a, cudaStream_t st) {
+    using Smem = PsiSmem<HWP, NT>;
+    static_assert(NT == PSI_NT, "workspace plan assumes PSI_NT threads");
+    auto kern = k_psi_split<HW, HWP, NT, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+    if (e != cudaSuccess) return (int)e;
+    static int slots = 0;  // resident CTAs on the whole device for this instantiation (same on every B200 of a box)
+    if (slots == 0) {
+        int per_sm = 0, dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, sizeof(Smem));
+        if (e != cudaSuccess) return (int)e;
+        slots = sms * (per_sm < 1 ? 1 : per_sm);
+        if (slots > PSI_MAX_GRID) slots = PSI_MAX_GRID;
+    }
+    const int start = a.ol > 1 ? a.ol : 1;
+    const int nchunk = (a.T - 1) / TT - (a.ol == 0 ? 0 : start) / TT + 1;
+    const long long ntiles = (long long)a.B * a.nvt * a.G;
+    long long grid = slots;
+    a.nfull = (int)(ntiles / slots);
+    const long long nrem = (ntiles - (long long)a.nfull * slots) * nchunk;  // chunks of the split phase
+    long long q = (nrem + slots - 1) / slots;
+    if (q < PSI_MIN_Q) q = PSI_MIN_Q;  // pieces shorter than the pipeline depth only add merge traffic
+    a.q = (int)q;
+    if (a.nfull == 0) grid = (nrem + q - 1) / q;  // fewer tiles than resident CTAs: only CTAs that get a piece
+    kern<<<(unsigned)grid, NT, sizeof(Smem), st>>>(tm, a);
+    return cuda_rc(cudaGetLastError());
+}
+
+// 0 = whole tiles on one CTA (k_psi_full, the default: fastest on every BASELINE shape), 1 = k_psi_split;
+// ctcps_set_psi_split / CTCPS_PSI_SPLIT, for A/B runs and tests
+int g_psi_split = -1;
+int psi_split_mode() {
+    if (g_psi_split < 0) {
+        const char *ev = getenv("CTCPS_PSI_SPLIT");
+        g_psi_split = (ev != nullptr && ev[0] == '1') ? 1 : 0;
+    }
+    return g_psi_split;
+}
+
 int encode_x_map(CUtensorMap *tm, const float *x_logp, int ldx, int B, int T, int V) {
     EncodeTiledFn enc = get_encode();
     ARG_CHECK(enc != nullptr, CTCPS_E_NODRIVER, "cuTensorMapEncodeTiled not found");
@@ -1566,7 +1826,7 @@ int select_lazy_impl(const XView x, const float *blank_lp, const float *r_prev, 
     if (next_workspace != nullptr && ol + 1 <= T) {  // also prepare the next scoring call (it may then pass workspace_prepared = 1)
         int HW, HWP, G;
         pick_hw_psi(W, &HW, &HWP, &G);
-        const WorkspaceLazy ws = plan_workspace_lazy(B, T, W);
+        const WorkspaceLazy ws = plan_workspace_lazy(B, T, W, V);
         ARG_CHECK(next_workspace_bytes >= ws.total, CTCPS_E_WORKSPACE, "select_lazy: workspace too small");
         ARG_CHECK((((uintptr_t)next_workspace) & 255) == 0, CTCPS_E_ALIGN, "select_lazy: workspace must be 256-byte aligned");
         float *lin = reinterpret_cast<float *>((char *)next_workspace + ws.lin_off);
@@ -1695,11 +1955,17 @@ const char *ctcps_error_string(int code) {
 // 6.5 TB/s with 256-byte-aligned rows and at 5.3 TB/s with rows that are only 32-byte aligned (ld = 5000).
 int ctcps_padded_ld(int n) { return (n + 63) & ~63; }
 
+int ctcps_set_psi_split(int mode) {
+    const int prev = psi_split_mode();
+    if (mode == 0 || mode == 1) g_psi_split = mode;
+    return prev;
+}
+
 int ctcps_workspace_bytes(int B, int T, int V, int W, int S, size_t *out_bytes) {
     (void)V;
     (void)S;
     ARG_CHECK(out_bytes != nullptr && B > 0 && T > 0 && W > 0, CTCPS_E_BADARG, "workspace_bytes: bad sizes");
-    const size_t a = plan_workspace(B, T, W).total, l = plan_workspace_lazy(B, T, W).total;
+    const size_t a = plan_workspace(B, T, W).total, l = plan_workspace_lazy(B, T, W, V).total;
     *out_bytes = a > l ? a : l;
     return 0;
 }
@@ -1859,7 +2125,7 @@ int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const 
     }
     int HW, HWP, G;
     pick_hw_psi(W, &HW, &HWP, &G);
-    const WorkspaceLazy ws = plan_workspace_lazy(B, T, W);
+    const WorkspaceLazy ws = plan_workspace_lazy(B, T, W, V);
     ARG_CHECK(workspace != nullptr && workspace_bytes >= ws.total, CTCPS_E_WORKSPACE, "score_lazy: workspace too small");
     ARG_CHECK((((uintptr_t)workspace) & 255) == 0, CTCPS_E_ALIGN, "score_lazy: workspace must be 256-byte aligned");
     float *lin = reinterpret_cast<float *>((char *)workspace + ws.lin_off);
@@ -1895,11 +2161,31 @@ int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const 
     a.ol = ol;
     a.G = G;
     a.Tpad = Tpad;
-    // 256-token tiles (64 threads, 8 resident CTAs per SM) were measured and not kept: no gain for the small shapes (C1 / C3 /
-    // C4 -- a tile is a serial chain of T/8 TMA chunks, halving its width halves nothing; they need the frame range split across
-    // CTAs) and 4 % slower at C2 (0.371 vs 0.356 ms).
-    constexpr int NT = 128;
+    // 256-token tiles (64 threads, 8 resident CTAs per SM) were measured and not kept: no gain for the small shapes (a tile
+    // is a serial chain of T/8 TMA chunks, halving its width halves nothing) and 4 % slower at C2 (0.371 vs 0.356 ms).
+    // What the small shapes need is the frame range split across CTAs: k_psi_split.
+    constexpr int NT = PSI_NT;
     a.nvt = (V + NT * 4 - 1) / (NT * 4);
+    a.x = x_logp;
+    a.ldx = ldx;
+    a.q = 0;
+    a.part = reinterpret_cast<float4 *>((char *)workspace + ws.part_off);
+    a.ticket = reinterpret_cast<unsigned int *>((char *)workspace + ws.ticket_off);
+    if (psi_split_mode()) {
+        // tickets are self-cleaning, but the workspace is caller memory of unknown content on its first use
+        cudaError_t me = cudaMemsetAsync(a.ticket, 0, ws.ticket_bytes, st);
+        if (me != cudaSuccess) return (int)me;
+        switch (HW) {
+            case 1: return launch_psi_split<1, 4, NT, 4>(tm, a, st);
+            case 2: return launch_psi_split<2, 4, NT, 4>(tm, a, st);
+            case 3: return launch_psi_split<3, 4, NT, 4>(tm, a, st);
+            case 4: return launch_psi_split<4, 4, NT, 4>(tm, a, st);
+            case 5: return launch_psi_split<5, 8, NT, 4>(tm, a, st);
+            case 6: return launch_psi_split<6, 8, NT, 4>(tm, a, st);
+            case 8: return launch_psi_split<8, 8, NT, 4>(tm, a, st);
+            default: return launch_psi_split<10, 12, NT, 4>(tm, a, st);
+        }
+    }
     switch (HW) {
         case 1: return launch_psi_full<1, 4, NT, 4>(tm, a, st);
         case 2: return launch_psi_full<2, 4, NT, 4>(tm, a, st);
@@ -2013,7 +2299,7 @@ int ctcps_score_candidates(const float *x_vt, int ldt, const float *r_prev, cons
     }
     int HW, HWP, G;
     pick_hw_psi(W, &HW, &HWP, &G);
-    const WorkspaceLazy ws = plan_workspace_lazy(B, T, W);
+    const WorkspaceLazy ws = plan_workspace_lazy(B, T, W, V);
     ARG_CHECK(workspace != nullptr && workspace_bytes >= ws.total, CTCPS_E_WORKSPACE, "score_candidates: workspace too small");
     ARG_CHECK((((uintptr_t)workspace) & 255) == 0, CTCPS_E_ALIGN, "score_candidates: workspace must be 256-byte aligned");
     float *lin = reinterpret_cast<float *>((char *)workspace + ws.lin_off);

@@ -48,6 +48,13 @@ const char *ctcps_error_string(int code);
  * 256-byte rows; any multiple of 4 is accepted by ctcps_score). */
 int ctcps_padded_ld(int n);
 
+/* Work distribution of the lazy scoring kernel (ctcps_score_lazy): 0 (default) = one CTA per whole tile (k_psi_full);
+ * 1 (env CTCPS_PSI_SPLIT=1) = the tiles of the last, partial wave are split along the frame axis across all resident CTAs
+ * and the pieces merged in a fixed order (k_psi_split).  Same results up to the order of an fp32 sum.  Measured on B200
+ * the split is not faster on any BASELINE shape, so it is opt-in.  Returns the previous mode; any
+ * other argument only queries.  Process-wide; meant for A/B measurements and tests. */
+int ctcps_set_psi_split(int mode);
+
 /* Bytes of scratch ctcps_score needs for these sizes. */
 int ctcps_workspace_bytes(int B, int T, int V, int W, int S, size_t *out_bytes);
 
