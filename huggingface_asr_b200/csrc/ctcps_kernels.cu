@@ -363,11 +363,21 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs &e, const float (&S_
         for (int j = 0; j < 4; ++j) S[hh][j] = S_in[hh][j];
     float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
     if (vec && has_att) nxt = *reinterpret_cast<const float4 *>(e.att + (size_t)h0 * V + v0);
+    // per-hypothesis scalars of the whole tile requested up front (one load latency instead of one per iteration: the
+    // stores of an iteration may alias them as far as the compiler knows); they ride the same shift as the sums
+    float gmv[HW], spv[HW];
+    const bool row_sp = e.s_prev != nullptr && e.s_cs == 0;
+#pragma unroll
+    for (int hh = 0; hh < HW; ++hh) {
+        const int h = h0 + (hh < nhyp ? hh : 0);
+        gmv[hh] = e.Gmax[h];
+        spv[hh] = row_sp ? e.s_prev[(long long)h * e.s_rs] : 0.f;
+    }
 #pragma unroll 1
     for (int hh = 0; hh < nhyp; ++hh) {
         const int h = h0 + hh;
-        const float gm = e.Gmax[h];
-        const float sp_row = (e.s_prev != nullptr && e.s_cs == 0) ? e.s_prev[(long long)h * e.s_rs] : 0.f;
+        const float gm = gmv[0];
+        const float sp_row = spv[0];
         const size_t o = (size_t)h * V + v0;
         if (vec) {
             const float4 cur = nxt;
@@ -400,9 +410,11 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs &e, const float (&S_
             }
         }
 #pragma unroll
-        for (int i = 0; i + 1 < HW; ++i)
+        for (int i = 0; i + 1 < HW; ++i) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) S[i][j] = S[i + 1][j];
+            gmv[i] = gmv[i + 1], spv[i] = spv[i + 1];
+        }
     }
 }
 
