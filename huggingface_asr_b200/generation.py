@@ -9,7 +9,8 @@ scorer by inheriting one mixin:
 
     class MyASRModel(JointCTCAttentionGenerationMixin, SpeechEncoderDecoderModel): ...
 
-  * `JointCTCAttentionGenerationMixin._get_logits_processor`  (reference :360-404)
+  * `JointCTCAttentionGenerationMixin._get_logits_processor`  (reference :360-404, incl. the LM shallow-fusion processor
+                                                              :398-404, here with a KV cache: decoding/shallow_fusion.py)
   * `JointCTCAttentionGenerationMixin._reorder_cache`         not in the reference: hands HF's `beam_idx` to the processor
                                                               (used only when the processor was built with use_beam_idx)
   * `joint_ctc_generation_config`                             (GenerationConfigCustom, train_enc_dec_asr.py:61-85)
@@ -28,18 +29,22 @@ import torch
 from transformers import GenerationConfig, LogitsProcessorList
 
 from .decoding.ctc_scorer import CTCRescorerLogitsProcessor, LogSoftmaxProcessor
+from .decoding.shallow_fusion import LMRescorerLogitsProcessor
 
 
 def joint_ctc_generation_config(*, ctc_weight: float = 0.0, ctc_margin: int = 0, space_token_id: int = -1,
                                 apply_eos_space_trick: bool = False, eos_space_trick_weight: float = 1.0,
-                                ctc_pre_beam_size: int = 0, **generation_kwargs) -> GenerationConfig:
+                                ctc_pre_beam_size: int = 0, lm_weight: float = 0.0, **generation_kwargs) -> GenerationConfig:
     """GenerationConfig carrying the joint-decoding fields of the reference's GenerationConfigCustom
-    (train_enc_dec_asr.py:61-85; lm_weight / lm_model belong to the LM-fusion processor, out of scope) plus
-    `ctc_pre_beam_size` (N2, 0 = the reference's full-vocabulary scoring)."""
+    (train_enc_dec_asr.py:61-85) plus `ctc_pre_beam_size` (N2, 0 = the reference's full-vocabulary scoring).
+    The reference also stores the language model itself in the config (`lm_model`, :73); `generate()` deep-copies its
+    config, so here the LM is handed to the model with `set_lm_model` and only `lm_weight` travels in the config (a
+    config that does carry `lm_model` is honoured too)."""
     cfg = GenerationConfig(**generation_kwargs)
     cfg.ctc_weight, cfg.ctc_margin, cfg.space_token_id = ctc_weight, ctc_margin, space_token_id
     cfg.apply_eos_space_trick, cfg.eos_space_trick_weight = apply_eos_space_trick, eos_space_trick_weight
     cfg.ctc_pre_beam_size = ctc_pre_beam_size
+    cfg.lm_weight = lm_weight
     return cfg
 
 
@@ -54,12 +59,20 @@ class JointCTCAttentionGenerationMixin:
 
     ctc_rescorer_cls = CTCRescorerLogitsProcessor  # tests substitute the CPU oracle's processor here
     log_softmax_cls = LogSoftmaxProcessor
+    lm_rescorer_cls = LMRescorerLogitsProcessor
     encoder_logits = None
     encoder_output_lens = None
     ctc_rescorer = None
+    lm_rescorer = None
+    external_lm = None
 
     def set_ctc_inputs(self, encoder_logits: torch.Tensor, encoder_output_lens: torch.Tensor) -> None:
         self.encoder_logits, self.encoder_output_lens = encoder_logits, encoder_output_lens
+
+    def set_lm_model(self, lm_model) -> None:
+        """The external causal LM for shallow fusion (reference: `generation_config.lm_model`, train_enc_dec_asr.py:73).
+        Stored outside the module tree on purpose: it is not a sub-module of the ASR model."""
+        object.__setattr__(self, "external_lm", lm_model)
 
     def _get_logits_processor(self, generation_config, *args, **kwargs) -> LogitsProcessorList:
         processors = super()._get_logits_processor(generation_config, *args, **kwargs)
@@ -92,6 +105,12 @@ class JointCTCAttentionGenerationMixin:
                 **extra,
             )
             processors.append(self.ctc_rescorer)
+        if getattr(generation_config, "lm_weight", 0) and generation_config.lm_weight > 0:  # reference :398-404
+            lm = getattr(generation_config, "lm_model", None) or self.external_lm
+            if lm is None:
+                raise ValueError("If `lm_weight` is specified, make sure that `lm_model` is defined.")
+            self.lm_rescorer = self.lm_rescorer_cls(generation_config.lm_weight, lm, device=self.device)
+            processors.append(self.lm_rescorer)
         return processors
 
     def _reorder_cache(self, past_key_values, beam_idx):
@@ -100,6 +119,8 @@ class JointCTCAttentionGenerationMixin:
         uses them when it was built with use_beam_idx (always in pre-beam mode)."""
         if self.ctc_rescorer is not None and hasattr(self.ctc_rescorer, "set_beam_idx"):
             self.ctc_rescorer.set_beam_idx(beam_idx)
+        if self.lm_rescorer is not None and hasattr(self.lm_rescorer, "set_beam_idx"):
+            self.lm_rescorer.set_beam_idx(beam_idx)
         if hasattr(past_key_values, "reorder_cache"):
             past_key_values.reorder_cache(beam_idx)
         return past_key_values
@@ -112,6 +133,7 @@ class JointCTCAttentionGenerationMixin:
             self.encoder_logits = None
             self.encoder_output_lens = None
             self.ctc_rescorer = None
+            self.lm_rescorer = None
 
 
 # ------------------------------------------------------------------------------------------------

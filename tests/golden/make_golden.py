@@ -20,6 +20,8 @@ Case kinds
   edge_*    : start == T-1, output_length >= T (early return :138-145), all-equal scores
               (token_scores == 0 -> logzero, :176), zero-length-padded utterances.
   decode_*  : 1-best sequences of the shared beam-search harness with the reference processor.
+  lm_fusion_*: the reference's LMRescorerLogitsProcessor (shallow_fussion.py, full-prefix LM forward per step) with a small
+              random GPT-2 (weights stored in the fixture), over a beam search that reorders hypotheses and a greedy decode.
   prebeam_* : the reference SCORER driven with ESPnet's pre-beam policy (scoring_ids = top-S decoder tokens per
               hypothesis, states selected with source hypothesis * V + token): per-step replay and 1-best decodes.
 """
@@ -317,9 +319,58 @@ def case_prebeam():
         save(name, rec)
 
 
+def tiny_gpt2(vocab, seed):
+    """A small random GPT-2 LM; its weights are stored in the fixture, so the test does not depend on torch's initialiser."""
+    from transformers import GPT2Config, GPT2LMHeadModel
+
+    torch.manual_seed(seed)
+    cfg = GPT2Config(vocab_size=vocab, n_positions=64, n_embd=32, n_layer=2, n_head=4, bos_token_id=BOS, eos_token_id=EOS,
+                     resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+    lm = GPT2LMHeadModel(cfg).eval()
+    with torch.no_grad():  # the default init gives a nearly uniform LM; make it opinionated
+        for p_ in lm.parameters():
+            p_.mul_(6.0)
+    return lm
+
+
+def case_lm_fusion():
+    """LMRescorerLogitsProcessor (src/decoding/shallow_fussion.py:5-58), the reference's full-prefix version, replayed over a
+    beam search that reorders and duplicates hypotheses (B=3, W=4) and over a greedy decode (W=1)."""
+    from decoding.shallow_fussion import LMRescorerLogitsProcessor  # the reference
+
+    for name, B, W, n_steps in (("lm_fusion_w4", 3, 4, 9), ("lm_fusion_w1", 2, 1, 6)):
+        V = 48
+        lm = tiny_gpt2(V, seed=11)
+        proc = LMRescorerLogitsProcessor(0.5, lm, torch.device("cpu"))
+        rec = {"n_steps": n_steps, "B": B, "W": W, "V": V, "lm_weight": 0.5}
+        for k, v in lm.state_dict().items():
+            rec["lm." + k] = v.numpy().copy()
+        input_ids = torch.full((B * W, 1), BOS, dtype=torch.long)
+        beam_scores = torch.zeros(B, W)
+        beam_scores[:, 1:] = -1e9
+        for n in range(n_steps):
+            att = make_attention_scores(B * W, V, n, seed=21, scale=0.5)
+            with torch.no_grad():
+                out = proc(input_ids, att.clone())
+            rec[f"input_ids_{n}"] = input_ids.numpy().copy()
+            rec[f"att_{n}"] = att.numpy().copy()
+            rec[f"out_{n}"] = out.numpy().copy()
+            cand = (out + beam_scores.view(-1, 1)).view(B, W * V)
+            top, idx = cand.topk(W, dim=1)
+            src, tok = idx // V, idx % V
+            beam_idx = (src + (torch.arange(B) * W).view(B, 1)).view(-1)
+            rec[f"beam_idx_{n}"] = beam_idx.numpy().copy()
+            input_ids = torch.cat([input_ids[beam_idx], tok.view(-1, 1)], dim=1)
+            beam_scores = top
+        save(name, rec)
+
+
 if __name__ == "__main__":
     if "--prebeam-only" in sys.argv:
         case_prebeam()
+        sys.exit(0)
+    if "--lm-only" in sys.argv:
+        case_lm_fusion()
         sys.exit(0)
     case_steps()
     case_partial_and_select()
@@ -327,3 +378,4 @@ if __name__ == "__main__":
     case_decode()
     case_extend()
     case_prebeam()
+    case_lm_fusion()
