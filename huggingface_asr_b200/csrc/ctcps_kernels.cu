@@ -361,8 +361,15 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs &e, const float (&S_
     for (int hh = 0; hh < HW; ++hh)
 #pragma unroll
         for (int j = 0; j < 4; ++j) S[hh][j] = S_in[hh][j];
-    float4 nxt = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (vec && has_att) nxt = *reinterpret_cast<const float4 *>(e.att + (size_t)h0 * V + v0);
+    // attention rows of the next EPI_AHEAD hypotheses in flight (ncu at C1, a lone warp per scheduler: with one row
+    // ahead an iteration of ~600 cycles waited ~1400 for its row -- 39 % of the kernel's samples were in this loop)
+    constexpr int EPI_AHEAD = HW < 4 ? HW : 4;
+    float4 attv[EPI_AHEAD];
+#pragma unroll
+    for (int i = 0; i < EPI_AHEAD; ++i) {
+        attv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec && has_att && i < nhyp) attv[i] = *reinterpret_cast<const float4 *>(e.att + (size_t)(h0 + i) * V + v0);
+    }
     // per-hypothesis scalars of the whole tile requested up front (one load latency instead of one per iteration: the
     // stores of an iteration may alias them as far as the compiler knows); they ride the same shift as the sums
     float gmv[HW], spv[HW];
@@ -380,8 +387,11 @@ __device__ __forceinline__ void epilogue_tile(const EpiArgs &e, const float (&S_
         const float sp_row = spv[0];
         const size_t o = (size_t)h * V + v0;
         if (vec) {
-            const float4 cur = nxt;
-            if (has_att && hh + 1 < nhyp) nxt = *reinterpret_cast<const float4 *>(e.att + o + V);  // next hyp's row, one ahead
+            const float4 cur = attv[0];
+#pragma unroll
+            for (int i = 0; i + 1 < EPI_AHEAD; ++i) attv[i] = attv[i + 1];
+            if (has_att && hh + EPI_AHEAD < nhyp)  // the row EPI_AHEAD hypotheses ahead
+                attv[EPI_AHEAD - 1] = *reinterpret_cast<const float4 *>(e.att + o + (size_t)EPI_AHEAD * V);
             const float av_in[4] = {cur.x, cur.y, cur.z, cur.w};
             float lp[4], ts[4], jt[4], av[4];
 #pragma unroll
