@@ -79,6 +79,7 @@ SIGNATURES = {
     "ctcps_error_string": [_i],
     "ctcps_padded_ld": [_i],
     "ctcps_set_psi_split": [_i],
+    "ctcps_set_select_pscan": [_i],
     "ctcps_workspace_bytes": [_i, _i, _i, _i, _i, ctypes.POINTER(_sz)],
     "ctcps_init": [_p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p],
     "ctcps_log_softmax": [_p, _i, _p, _i, _i, _i, _p],

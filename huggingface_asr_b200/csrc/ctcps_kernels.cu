@@ -1169,6 +1169,169 @@ __global__ void __launch_bounds__(64) k_select_lazy_scan(const XView x, const fl
 }
 
 // ------------------------------------------------------------------------------------------
+// Time-parallel variant of k_select_lazy_scan (opt-in: CTCPS_SELECT_PSCAN=1 / ctcps_set_select_pscan(1)).
+// The recursion is an affine map in the (logsumexp, +) semiring,
+//     rn' = lse(rn + xv, ph + xv)        rb' = lse(rn + bl, rb + bl)
+// with five live coefficients (A_nn, A_bn, A_bb, c_n, c_b: rn never depends on rb), and affine maps compose
+// associatively.  A WARP owns one output hypothesis: lane l composes the maps of its block of F = ceil((T-start)/32)
+// frames (depth F), a 5-level warp scan of the 32 block maps gives every lane its incoming state, and the lane replays
+// its block with the same `frame` arithmetic as the sequential kernel (depth F): 2F + 6 dependent logsumexp levels
+// instead of T.  Everything stays in the log domain with the finite logzero, so there is no dynamic-range problem.
+// Results differ from the sequential kernel only by the rounding of the block-entry states (numpy emulation against the
+// reference's fp64 run: tools/pscan_prototype.py).  A CTA holds PS_H hypotheses; their staged columns of r_new (T,2,BW)
+// go through shared memory so that global accesses stay coalesced across hypotheses; in shared memory a column is
+// hypothesis-major with an odd hypothesis stride and an odd per-lane block stride (conflict-free on both sides).
+// ------------------------------------------------------------------------------------------
+constexpr int PS_H = 16;  // hypotheses (warps) per CTA
+
+struct AffMap {
+    float ann, abn, abb, cn, cb;
+};
+__device__ __forceinline__ AffMap aff_compose(const AffMap &m2, const AffMap &m1) {  // m2 after m1
+    AffMap r;
+    r.ann = m2.ann + m1.ann;
+    r.abn = lse2_fast(m2.abn + m1.ann, m2.abb + m1.abn);
+    r.abb = m2.abb + m1.abb;
+    r.cn = lse2_fast(m2.ann + m1.cn, m2.cn);
+    r.cb = lse2_fast(lse2_fast(m2.abn + m1.cn, m2.abb + m1.cb), m2.cb);
+    return r;
+}
+__device__ __forceinline__ AffMap aff_shfl_up(const AffMap &m, int d) {
+    AffMap r;
+    r.ann = __shfl_up_sync(0xffffffffu, m.ann, d);
+    r.abn = __shfl_up_sync(0xffffffffu, m.abn, d);
+    r.abb = __shfl_up_sync(0xffffffffu, m.abb, d);
+    r.cn = __shfl_up_sync(0xffffffffu, m.cn, d);
+    r.cb = __shfl_up_sync(0xffffffffu, m.cb, d);
+    return r;
+}
+
+template <bool NEXT>
+__global__ void __launch_bounds__(PS_H * 32) k_select_lazy_pscan(const XView x, const float *__restrict__ blank_lp, int ol,
+                                                                 const float *__restrict__ log_psi,
+                                                                 const int64_t *__restrict__ best_ids,
+                                                                 const int64_t *__restrict__ cand_ids, int S, int B, int W, int T,
+                                                                 int V, float *r_new, float *__restrict__ s_new,
+                                                                 float *__restrict__ lin, float *__restrict__ Gmax,
+                                                                 float *__restrict__ psic, int HW, int HWP, int G, int Tpad, int F,
+                                                                 int Fo, int HS) {
+    extern __shared__ float ps_sm[];  // [PS_H][HS]: hypothesis jj, plane k, lane block l, offset i at jj*HS + k*32*Fo + l*Fo + i
+    const int BW = B * W;
+    const int j0 = blockIdx.x * PS_H;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int start = ol > 1 ? ol : 1;
+    const int n = T - start;  // frames the recursion walks: t = start .. T-1 (n >= 1, checked by the host)
+    const size_t st2 = 2 * (size_t)BW;
+
+    // P0: staged columns (phi[t-1] in plane 0, x[t, tok] in plane 1) of this CTA's hypotheses, coalesced across hypotheses
+    for (int idx = tid; idx < n * 2 * PS_H; idx += PS_H * 32) {
+        const int jj = idx % PS_H, row = idx / PS_H;  // row = (t - start) * 2 + k
+        const int k = row & 1, tr = row >> 1;
+        const int l = tr / F, i = tr - l * F;
+        float v = LZ;
+        if (j0 + jj < BW) v = r_new[(size_t)(start * 2 + row) * BW + j0 + jj];
+        ps_sm[jj * HS + k * 32 * Fo + l * Fo + i] = v;
+    }
+    __syncthreads();
+
+    const int j = j0 + w;
+    const bool active = j < BW;  // warp-uniform
+    float sj = LZ, gm_mx = -INFINITY, pc = 0.f;
+    float *lbase = nullptr;
+    LazySel q;
+    q.hs = 0, q.tok = 0, q.last = 0, q.src = -1;
+    if (active) {
+        q = lazy_source(best_ids, cand_ids, S, j, W, V);
+        sj = q.src < 0 ? LZ : log_psi[q.src];
+        if (lane == 0) s_new[j] = sj;  // :193
+        const float *xb = blank_lp + (size_t)(j / W) * T;
+        float *col = ps_sm + w * HS;
+        const int lo = lane * F, hi = min(n, lo + F);  // this lane's frames, relative to `start`
+        // P1: the map of this lane's block
+        AffMap m;
+        m.ann = 0.f, m.abn = LZ, m.abb = 0.f, m.cn = LZ, m.cb = LZ;
+        for (int i = 0; lo + i < hi; ++i) {
+            const float ph = col[lane * Fo + i], xv = col[32 * Fo + lane * Fo + i], bl = xb[start + lo + i];
+            const float abn = bl + lse2_fast(m.ann, m.abn);
+            const float cb = bl + lse2_fast(m.cn, m.cb);
+            m.cn = xv + lse2_fast(m.cn, ph);
+            m.ann = xv + m.ann;
+            m.abb = bl + m.abb;
+            m.abn = abn;
+            m.cb = cb;
+        }
+        // P2: inclusive scan over the lanes, then one step up = the map of everything before this lane's block
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const AffMap up = aff_shfl_up(m, d);
+            if (lane >= d) m = aff_compose(m, up);
+        }
+        AffMap e = aff_shfl_up(m, 1);
+        if (lane == 0) e.ann = 0.f, e.abn = LZ, e.abb = 0.f, e.cn = LZ, e.cb = LZ;
+        const float rn0 = (ol == 0) ? r_new[j] : LZ, rb0 = LZ;
+        float rn = lse2_fast(e.ann + rn0, e.cn);
+        float rb = lse2_fast(lse2_fast(e.abn + rn0, e.abb + rb0), e.cb);
+        // P3: replay the block (same arithmetic per frame as k_select_lazy_scan) and the by-products of the NEXT scoring call
+        if (NEXT) {
+            const int wv = j % W;
+            lbase = lin + ((size_t)((j / W) * G + wv / HW) * Tpad) * HWP + (wv % HW);
+            for (int te = lane; te <= ol && te < Tpad; te += 32) lbase[(size_t)te * HWP] = 0.f;
+            for (int te = T + lane; te < Tpad; te += 32) lbase[(size_t)te * HWP] = 0.f;
+        }
+        for (int i = 0; lo + i < hi; ++i) {
+            const int t = start + lo + i;
+            const float ph = col[lane * Fo + i], xv = col[32 * Fo + lane * Fo + i], bl = xb[t];
+            const float ls = lse2_fast(rn, rb);  // = r_sum[t-1]
+            if (NEXT && !(ol >= 1 && t == start)) {  // frame f = t-1 of the next step's sums (f in [ol, T-2]), entry te = t
+                gm_mx = fmaxf(gm_mx, ls);
+                lbase[(size_t)t * HWP] = ex2_approx(fminf(ls - sj, 0.f) * LOG2E);
+                pc = fmaf(ex2_approx(fminf(rb - sj, 0.f) * LOG2E), ex2_approx(xv * LOG2E), pc);
+            }
+            rn = lse2_fast(rn, ph) + xv;
+            rb = ls + bl;
+            col[lane * Fo + i] = rn;
+            col[32 * Fo + lane * Fo + i] = rb;
+        }
+    }
+    __syncthreads();
+    // P4: the new forward variables back to r_new, coalesced across hypotheses
+    for (int idx = tid; idx < n * 2 * PS_H; idx += PS_H * 32) {
+        const int jj = idx % PS_H, row = idx / PS_H;
+        const int k = row & 1, tr = row >> 1;
+        const int l = tr / F, i = tr - l * F;
+        if (j0 + jj < BW) r_new[(size_t)(start * 2 + row) * BW + j0 + jj] = ps_sm[jj * HS + k * 32 * Fo + l * Fo + i];
+    }
+    if (NEXT && active) {
+        const float mx = warp_max(gm_mx);
+        pc = warp_sum(pc);
+        float gm = sj;
+        // same fallback as the sequential kernel: s_new is not a usable offset for a finished beam or when every summed frame
+        // lies far below it -- redo the stream against max_t r_sum (rare; the lanes share the frames)
+        if (!(sj > -1e9f) || mx < sj - 60.f) {
+            gm = mx > -INFINITY ? mx : 0.f;
+            pc = 0.f;
+            const float *col = ps_sm + w * HS;
+            for (int f = ol + lane; f <= T - 2; f += 32) {
+                float a, c;
+                if (f >= start) {
+                    const int tr = f - start, l = tr / F, i = tr - l * F;
+                    a = col[l * Fo + i], c = col[32 * Fo + l * Fo + i];
+                } else {  // f = 0 with ol = 0: the staged frame 0 was not touched by the scan
+                    a = r_new[(size_t)f * st2 + j], c = r_new[(size_t)f * st2 + BW + j];
+                }
+                lbase[(size_t)(f + 1) * HWP] = expf(lse2_precise(a, c) - gm);
+                pc = fmaf(expf(c - gm), expf(x.at(j / W, f + 1, q.last)), pc);
+            }
+            pc = warp_sum(pc);
+        }
+        if (lane == 0) {
+            Gmax[j] = gm;
+            psic[j] = pc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // K-b partial scoring: one thread per (hyp, candidate) lane.  ~V/S times less work than the full
 // path; written for fidelity (libm-grade exp/log, running-max logsumexp), not for the roofline.
 // ------------------------------------------------------------------------------------------
@@ -1807,6 +1970,17 @@ int launch_psi_split(const CUtensorMap &tm, PsiArgs a, cudaStream_t st) {
     return cuda_rc(cudaGetLastError());
 }
 
+// 0 = one thread per hypothesis walks T frames (k_select_lazy_scan, the default), 1 = time-parallel warp per hypothesis
+// (k_select_lazy_pscan); ctcps_set_select_pscan / CTCPS_SELECT_PSCAN
+int g_select_pscan = -1;
+int select_pscan_mode() {
+    if (g_select_pscan < 0) {
+        const char *ev = getenv("CTCPS_SELECT_PSCAN");
+        g_select_pscan = (ev != nullptr && ev[0] == '1') ? 1 : 0;
+    }
+    return g_select_pscan;
+}
+
 // 0 = whole tiles on one CTA (k_psi_full, the default: fastest on every BASELINE shape), 1 = k_psi_split;
 // ctcps_set_psi_split / CTCPS_PSI_SPLIT, for A/B runs and tests
 int g_psi_split = -1;
@@ -1845,7 +2019,37 @@ int select_lazy_impl(const XView x, const float *blank_lp, const float *r_prev, 
     const int BW = B * W;
     const dim3 grid((BW + 127) / 128, (T + LAZY_TC - 1) / LAZY_TC);
     k_select_lazy_stage<<<grid, 128, 0, st>>>(x, r_prev, last_ids, ol, best_ids, cand_ids, S, B, W, T, V, r_new);
-    if (next_workspace != nullptr && ol + 1 <= T) {  // also prepare the next scoring call (it may then pass workspace_prepared = 1)
+    // opt-in time-parallel scan: needs at least one frame to walk and a tile of PS_H columns that fits shared memory
+    const int ps_start = ol > 1 ? ol : 1;
+    const int ps_n = T - ps_start;
+    const int ps_F = (ps_n + 31) / 32, ps_Fo = ps_F | 1, ps_HS = 2 * 32 * ps_Fo + 1;
+    const size_t ps_smem = (size_t)PS_H * ps_HS * sizeof(float);
+    const bool pscan = select_pscan_mode() && ps_n >= 1 && ps_smem <= 200 * 1024;
+    if (pscan) {
+        cudaError_t e = cudaSuccess;
+        if (ps_smem > 48 * 1024) {
+            e = cudaFuncSetAttribute(k_select_lazy_pscan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_smem);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_select_lazy_pscan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ps_smem);
+            if (e != cudaSuccess) return (int)e;
+        }
+    }
+    if (pscan && next_workspace != nullptr && ol + 1 <= T) {
+        int HW, HWP, G;
+        pick_hw_psi(W, &HW, &HWP, &G);
+        const WorkspaceLazy ws = plan_workspace_lazy(B, T, W, V);
+        ARG_CHECK(next_workspace_bytes >= ws.total, CTCPS_E_WORKSPACE, "select_lazy: workspace too small");
+        ARG_CHECK((((uintptr_t)next_workspace) & 255) == 0, CTCPS_E_ALIGN, "select_lazy: workspace must be 256-byte aligned");
+        float *lin = reinterpret_cast<float *>((char *)next_workspace + ws.lin_off);
+        float *Gmax = reinterpret_cast<float *>((char *)next_workspace + ws.g_off);
+        float *psic = reinterpret_cast<float *>((char *)next_workspace + ws.c_off);
+        k_select_lazy_pscan<true><<<(BW + PS_H - 1) / PS_H, PS_H * 32, ps_smem, st>>>(x, blank_lp, ol, scores, best_ids, cand_ids, S, B, W, T, V,
+                                                                                  r_new, s_new, lin, Gmax, psic, HW, HWP, G, tpad_of(T),
+                                                                                  ps_F, ps_Fo, ps_HS);
+    } else if (pscan) {
+        k_select_lazy_pscan<false><<<(BW + PS_H - 1) / PS_H, PS_H * 32, ps_smem, st>>>(x, blank_lp, ol, scores, best_ids, cand_ids, S, B, W, T, V,
+                                                                                   r_new, s_new, nullptr, nullptr, nullptr, 1, 4, 1, 0, ps_F,
+                                                                                   ps_Fo, ps_HS);
+    } else if (next_workspace != nullptr && ol + 1 <= T) {  // also prepare the next scoring call (it may then pass workspace_prepared = 1)
         int HW, HWP, G;
         pick_hw_psi(W, &HW, &HWP, &G);
         const WorkspaceLazy ws = plan_workspace_lazy(B, T, W, V);
@@ -1976,6 +2180,12 @@ const char *ctcps_error_string(int code) {
 // 64 floats = 256 B: measured on B200 (tools/membw2.py, profiles/r1_write_pattern.md) the store stream of r runs at
 // 6.5 TB/s with 256-byte-aligned rows and at 5.3 TB/s with rows that are only 32-byte aligned (ld = 5000).
 int ctcps_padded_ld(int n) { return (n + 63) & ~63; }
+
+int ctcps_set_select_pscan(int mode) {
+    const int prev = select_pscan_mode();
+    if (mode == 0 || mode == 1) g_select_pscan = mode;
+    return prev;
+}
 
 int ctcps_set_psi_split(int mode) {
     const int prev = psi_split_mode();

@@ -55,6 +55,14 @@ int ctcps_padded_ld(int n);
  * other argument only queries.  Process-wide; meant for A/B measurements and tests. */
 int ctcps_set_psi_split(int mode);
 
+/* Lazy state selection (ctcps_select_lazy, ctcps_select_lazy_candidates): 0 (default) = one thread per surviving column walks
+ * the T frames of the recursion (k_select_lazy_scan); 1 (env CTCPS_SELECT_PSCAN=1) = a warp per column, time-parallel: the
+ * recursion is an affine map in the (logsumexp, +) semiring, lanes compose the maps of their blocks of frames, a warp scan
+ * hands every lane its incoming state (k_select_lazy_pscan; 2*ceil(T/32) + 6 dependent logsumexp levels instead of T).
+ * Same results up to fp32 rounding of the block-entry states (<= 1e-4 in log space; tools/pscan_prototype.py).
+ * Returns the previous mode; any other argument only queries.  Process-wide. */
+int ctcps_set_select_pscan(int mode);
+
 /* Bytes of scratch ctcps_score needs for these sizes. */
 int ctcps_workspace_bytes(int B, int T, int V, int W, int S, size_t *out_bytes);
 
