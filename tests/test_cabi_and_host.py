@@ -148,3 +148,19 @@ def test_reference_frame_counts():
 
     assert [frames_for_seconds(s) for s in (10, 15, 30)] == [248, 373, 748]
     assert [frames_for_seconds(s, 1) for s in (10, 15, 30)] == [250, 375, 750]
+
+
+def test_ab_switches_query_set_restore():
+    """ctcps_set_psi_split / ctcps_set_select_pscan: any argument other than 0 / 1 only queries; both default to the validated kernels."""
+    from huggingface_asr_b200 import _lib
+
+    L = _lib.lib()
+    for fn in (L.ctcps_set_psi_split, L.ctcps_set_select_pscan):
+        prev = fn(-1)
+        assert prev in (0, 1)
+        assert fn(1) == prev and fn(7) == 1 and fn(0) == 1 and fn(-1) == 0
+        fn(prev)
+    import os
+
+    if "CTCPS_PSI_SPLIT" not in os.environ and "CTCPS_SELECT_PSCAN" not in os.environ:
+        assert L.ctcps_set_psi_split(-1) == 0 and L.ctcps_set_select_pscan(-1) == 0
