@@ -166,7 +166,8 @@ def run_ours(args):
             lag = (0 if materialize else 1) if args.done_check_lag is None else args.done_check_lag
             if args.harness == "native" and not materialize:
                 out = joint_beam_search_native(proc, decoder, B, W, V, BOS, EOS, BLANK, max_length=MAX_LENGTH, device=dev,
-                                               done_check_lag=lag, score_timing=None if timing is None else score_ms_native)
+                                               done_check_lag=lag, score_timing=None if timing is None else score_ms_native,
+                                               fuse_topk=not args.no_fuse_topk)
             elif args.harness in ("fused", "native"):
                 out = joint_beam_search_fused(proc, decoder, B, W, V, BOS, EOS, BLANK, max_length=MAX_LENGTH, device=dev,
                                               done_check_lag=(0 if materialize else 1) if args.done_check_lag is None else args.done_check_lag)
@@ -178,8 +179,10 @@ def run_ours(args):
             # beam step: the candidate kernel alone (pre-beam), or -- dense scores whose rows fit the register top-k -- the
             # per-row top-2W kernel + the candidate kernel
             two_kernel = not pre_beam and V % 4 == 0 and V <= 8192
-            beam = 0 if args.harness == "torch" else (2 if two_kernel else 1)
             native = 1 if (args.harness == "native" and not materialize) else 0  # the native step also selects after the last step
+            # native full-vocabulary loop: the scoring kernel ranks its tiles itself, the beam step is the list merge alone
+            fused_topk = bool(native and not pre_beam and not args.no_fuse_topk and V % 4 == 0)
+            beam = 0 if args.harness == "torch" else (1 if fused_topk else (2 if two_kernel else 1))
             if pre_beam:
                 # K-a + transpose + initial state; per step: top-S, candidate scores, [dense scatter when the harness is not
                 # sparse], [beam step]; first step: k_prep_psi; all steps but the first: select stage + scan
@@ -557,6 +560,8 @@ def main():
                     help="fused harness: steps the CPU may run ahead of the GPU (default: 0 materialized, 1 lazy)")
     ap.add_argument("--hidden-dim", type=int, default=512,
                     help="also measure end to end from encoder hidden states of this width (N4 boundary; 0 = skip)")
+    ap.add_argument("--no-fuse-topk", action="store_true",
+                    help="native loop: write the dense joint scores and rank them in a second kernel (the round-1 step) instead of the fused per-tile top-2W")
     ap.add_argument("--no-numa-bind", action="store_true", help="multi-rank runs: do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--profile", action="store_true", help="for runs under ncu: honour a warm-up below 3 and skip the e2e/cpu legs (never a bench value)")
     args = ap.parse_args()

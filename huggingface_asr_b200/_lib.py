@@ -78,7 +78,6 @@ SIGNATURES = {
     "ctcps_version": [],
     "ctcps_error_string": [_i],
     "ctcps_padded_ld": [_i],
-    "ctcps_set_psi_split": [_i],
     "ctcps_set_select_pscan": [_i],
     "ctcps_workspace_bytes": [_i, _i, _i, _i, _i, ctypes.POINTER(_sz)],
     "ctcps_init": [_p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p],
@@ -88,6 +87,10 @@ SIGNATURES = {
                     _p, _sz, _p],
     "ctcps_score_lazy": [_p, _i, _p, _p, _p, _i64, _i64, _p, _i, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _sz, _i, _p],
     "ctcps_select_lazy": [_p, _i, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p],
+    "ctcps_topk_lists_shape": [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)],
+    "ctcps_score_lazy_topk": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _sz, _i, _p],
+    "ctcps_beam_step_lists": [_p, _i, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i64, _p, _p, _sz, _p, _i, _i64, _p, _p,
+                              _p, _p, _p],
     "ctcps_beam_step_workspace_bytes": [_i, _i, ctypes.POINTER(_sz)],
     "ctcps_beam_step": [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i64, _p, _p, _sz, _p, _i, _i64, _p, _p],
     "ctcps_padded_lt": [_i],
@@ -126,6 +129,7 @@ class DecodeSession(ctypes.Structure):
         ("beam_scores", _p), ("ids", _p * 2), ("ld_ids", _i64), ("pool_scores", _p), ("pool_lens", _p), ("pool_seqs", _p),
         ("ld_pool", _i64), ("done", _p), ("beam_ws", _p), ("beam_ws_bytes", _sz), ("done_ring", _p), ("best_ids", _p),
         ("side_stream", _p), ("ev_step", _p), ("ev_select", _p),
+        ("tile_lists", _p), ("tag_base", _i64),
     ]
 
 

@@ -125,6 +125,61 @@ def joint_beam_search(processor: Callable, decoder_log_probs: Callable[[torch.Te
     return _finalize(input_ids, beam_scores, pool_scores, pool_seqs, pool_lens, done, B, W, max_length, pad, length_penalty, steps)
 
 
+_RING = 8
+_decode_serial = [0]
+
+
+def _next_tag_base() -> int:
+    """Serial number of a decode, shifted above the step bits: the beam-step kernels publish ((tag_base + step) << 32 | #done)
+    into the pinned ring, so an entry written late by an EARLIER decode (whose ring block the pinned allocator may have
+    handed to this one) can never be mistaken for this decode's."""
+    _decode_serial[0] = (_decode_serial[0] + 1) % (1 << 14)
+    return _decode_serial[0] << 16  # a multiple of the ring size: the slot of a step is still step % ring
+
+
+_rings: dict = {}
+
+
+def _ring_for(device):
+    """The pinned done-ring of (device, host thread): persistent, so a step kernel that the host ran ahead of (done_check_lag)
+    never writes into memory that has been handed to somebody else after the decode returned; stale entries carry the
+    serial number of their decode and never match."""
+    import threading
+
+    key = (str(device), threading.get_ident())
+    ring = _rings.get(key)
+    if ring is None:
+        ring = torch.full((_RING,), -1, dtype=torch.int64).pin_memory()
+        _rings[key] = ring
+    return ring
+
+
+def _wait_ring(ring_np, tag: int, stream, what: str, timeout_s: float = 120.0) -> int:
+    """Spin until the ring slot of `tag` carries it; returns the number of finished utterances.  A kernel that faulted or
+    never ran would leave the host spinning for ever: the stream is polled, and an idle stream without the entry (or a
+    deadline) raises instead."""
+    import time
+
+    slot = tag % _RING
+    t0 = None
+    spins = 0
+    while True:
+        v = int(ring_np[slot])
+        if v >> 32 == tag:
+            return v & 0xFFFFFFFF
+        spins += 1
+        if spins % 4096 == 0:
+            if stream.query():  # everything enqueued has finished (or failed: query raises) and the entry is still missing
+                v = int(ring_np[slot])
+                if v >> 32 == tag:
+                    return v & 0xFFFFFFFF
+                raise RuntimeError(f"{what}: the beam step of tag {tag} finished without publishing its done count")
+            now = time.perf_counter()
+            t0 = t0 or now
+            if now - t0 > timeout_s:
+                raise RuntimeError(f"{what}: no done count from the GPU after {timeout_s:.0f} s (tag {tag})")
+
+
 @torch.no_grad()
 def joint_beam_search_fused(processor: Callable, decoder_log_probs: Callable[[torch.Tensor, int], torch.Tensor], batch: int,
                             num_beams: int, vocab: int, bos: int, eos: int, pad: int, max_length: int = 512,
@@ -160,9 +215,10 @@ def joint_beam_search_fused(processor: Callable, decoder_log_probs: Callable[[to
     nws = ctypes.c_size_t(0)
     _lib.check(L_.ctcps_beam_step_workspace_bytes(B, W, ctypes.byref(nws)), "ctcps_beam_step_workspace_bytes")
     ws = torch.zeros((nws.value + 15) // 16 * 2, dtype=torch.int64, device=dev)  # zeroed: holds the arrival tickets
-    RING = 8
-    ring = torch.full((RING,), -1, dtype=torch.int64).pin_memory()
+    RING = _RING
+    ring = _ring_for(dev)
     ring_np = ring.numpy()
+    tag_base = _next_tag_base()
     stream = torch.cuda.current_stream(dev)
     prefetch = getattr(processor, "prefetch_state", None)
     wants_best = bool(getattr(processor, "use_beam_idx", False)) and prefetch is not None
@@ -175,7 +231,7 @@ def joint_beam_search_fused(processor: Callable, decoder_log_probs: Callable[[to
         log_probs = decoder_log_probs(input_ids, steps)
         common = (beam_scores.data_ptr(), ids[cur].data_ptr(), ids[1 - cur].data_ptr(), max_length, L, B, W, V, eos, pad,
                   float(L) ** length_penalty, pool_scores.data_ptr(), pool_lens.data_ptr(), pool_seqs.data_ptr(), max_length,
-                  done.data_ptr(), ws.data_ptr(), ws.numel() * 8, ring.data_ptr(), RING, steps,
+                  done.data_ptr(), ws.data_ptr(), ws.numel() * 8, ring.data_ptr(), RING, tag_base + steps,
                   None if best_ids is None else best_ids.data_ptr(), stream.cuda_stream)
         if sparse:
             cand_ids, cand_joint = processor.score_candidates(input_ids, log_probs)
@@ -202,10 +258,8 @@ def joint_beam_search_fused(processor: Callable, decoder_log_probs: Callable[[to
         if look >= 0:
             if done_check_lag == 0:
                 stream.synchronize()
-            else:  # the entry of an older step: wait (briefly) until the GPU has published it
-                while int(ring_np[look % RING]) >> 32 != look:
-                    pass
-            if (int(ring_np[look % RING]) & 0xFFFFFFFF) == B:
+            # the entry of an older step: wait (briefly) until the GPU has published it
+            if _wait_ring(ring_np, tag_base + look, stream, "joint_beam_search_fused") == B:
                 break
     return _finalize(ids[cur][:, :L], beam_scores, pool_scores, pool_seqs, pool_lens, done.bool(), B, W, max_length, pad,
                      length_penalty, steps)
@@ -214,7 +268,8 @@ def joint_beam_search_fused(processor: Callable, decoder_log_probs: Callable[[to
 @torch.no_grad()
 def joint_beam_search_native(processor, decoder_log_probs: Callable[[torch.Tensor, int], torch.Tensor], batch: int, num_beams: int,
                              vocab: int, bos: int, eos: int, pad: int, max_length: int = 512, length_penalty: float = 1.0,
-                             device: torch.device | str = "cuda", done_check_lag: int = 1, score_timing: list | None = None) -> BeamSearchOutput:
+                             device: torch.device | str = "cuda", done_check_lag: int = 1, score_timing: list | None = None,
+                             fuse_topk: bool = True) -> BeamSearchOutput:
     """joint_beam_search_fused with ONE host call per decode step (ctcps_decode_step): [top-S candidates,] prefix scoring +
     joint combine, beam step and -- on a side stream, under the next decoder forward pass -- the lazy state selection.
     Same kernels and results as the fused loop; the 5-10 ctypes / torch calls it makes per step cost more host time
@@ -222,6 +277,8 @@ def joint_beam_search_native(processor, decoder_log_probs: Callable[[torch.Tenso
 
     `processor` is a CTCRescorerLogitsProcessor in lazy-state mode (full vocabulary or pre-beam); the loop uses its
     posteriors, weights and policy flags and keeps the CTC state itself (processor.ctc_states is not touched).
+    fuse_topk (full vocabulary only): rank the candidates inside the scoring kernel's epilogue (per-tile top-2W lists merged
+    by the beam step) instead of writing the (BW,V) joint scores and ranking them in a second kernel; same results bit for bit.
     score_timing: a list that receives one (begin, end) CUDA-event pair per step, recorded around the step's scoring call;
     resolve_score_timing(list) turns them into milliseconds after the caller has synchronised (bench.py's roofline)."""
     import ctypes
@@ -271,6 +328,7 @@ def joint_beam_search_native(processor, decoder_log_probs: Callable[[torch.Tenso
         w = float(processor.ctc_weight)
         sess.one_minus_w, sess.w, sess.length_penalty = 1.0 - w, w, float(length_penalty)
         sess.ldx, sess.ldt = sc._ldx, sc._ldt
+        fused_topk = S == 0 and fuse_topk and V % 4 == 0 and pad == sc.blank and 2 * W <= 64 and W <= 32
         if S > 0:
             sess.x_vt = sc._token_major().data_ptr()
             cand_ids = [torch.empty((BW, S), **i64) for _ in range(2)]
@@ -283,10 +341,25 @@ def joint_beam_search_native(processor, decoder_log_probs: Callable[[torch.Tenso
             sess.cand_joint = cand_joint.data_ptr()
         else:
             sess.x_logp = sc._frame_major().data_ptr()
-            log_psi = [torch.empty((BW, V), **f32) for _ in range(2)]
-            joint = torch.empty((BW, V), **f32)
-            keep += [log_psi, joint]
-            sess.log_psi[0], sess.log_psi[1], sess.joint = log_psi[0].data_ptr(), log_psi[1].data_ptr(), joint.data_ptr()
+            if fused_topk:
+                nl, kk = ctypes.c_int(0), ctypes.c_int(0)
+                _lib.check(L_.ctcps_topk_lists_shape(B, W, V, ctypes.byref(nl), ctypes.byref(kk)), "ctcps_topk_lists_shape")
+                fused_topk = nl.value * kk.value <= 1024
+            if fused_topk:
+                # fused scoring + per-tile top-2W: no (BW,V) tensor per step, only the candidate lists (and, for the reference's
+                # token-only state selection, the log_psi row of hypothesis 0 of every utterance)
+                tile_lists = torch.empty((B, nl.value, kk.value, 4), **f32)
+                keep.append(tile_lists)
+                sess.tile_lists = tile_lists.data_ptr()
+                if not processor.use_beam_idx:
+                    lp0 = torch.empty((B, V), **f32)
+                    keep.append(lp0)
+                    sess.log_psi[0] = lp0.data_ptr()
+            if not fused_topk or max_length - 1 > T:  # the dense step (also taken once a prefix outgrows the utterance, ol > T)
+                log_psi = [torch.empty((BW, V), **f32) for _ in range(2)]
+                joint = torch.empty((BW, V), **f32)
+                keep += [log_psi, joint]
+                sess.log_psi[0], sess.log_psi[1], sess.joint = log_psi[0].data_ptr(), log_psi[1].data_ptr(), joint.data_ptr()
         sess.blank_lp, sess.r0 = sc._blank_lp.data_ptr(), r0.data_ptr()
         for k in range(2):
             sess.r_sel[k], sess.s_sel[k], sess.last_ids[k], sess.ids[k] = r_sel[k].data_ptr(), s_sel[k].data_ptr(), last[k].data_ptr(), ids[k].data_ptr()
@@ -295,10 +368,11 @@ def joint_beam_search_native(processor, decoder_log_probs: Callable[[torch.Tenso
         sess.beam_scores, sess.ld_ids = beam_scores.data_ptr(), max_length
         sess.pool_scores, sess.pool_lens, sess.pool_seqs, sess.ld_pool = pool_scores.data_ptr(), pool_lens.data_ptr(), pool_seqs.data_ptr(), max_length
         sess.done, sess.beam_ws, sess.beam_ws_bytes = done.data_ptr(), beam_ws.data_ptr(), beam_ws.numel() * 8
-        RING = 8
-        ring = torch.full((RING,), -1, dtype=torch.int64).pin_memory()
+        RING = _RING
+        ring = _ring_for(dev)
         ring_np = ring.numpy()
-        sess.done_ring, sess.ring, sess.best_ids = ring.data_ptr(), RING, best_ids.data_ptr()
+        tag_base = _next_tag_base()
+        sess.done_ring, sess.ring, sess.best_ids, sess.tag_base = ring.data_ptr(), RING, best_ids.data_ptr(), tag_base
         side, ev_a, ev_b = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
         _lib.check(L_.ctcps_async_create(ctypes.byref(side), ctypes.byref(ev_a), ctypes.byref(ev_b)), "ctcps_async_create")
         sess.side_stream, sess.ev_step, sess.ev_select = side, ev_a, ev_b
@@ -327,10 +401,7 @@ def joint_beam_search_native(processor, decoder_log_probs: Callable[[torch.Tenso
                 if look >= 0:
                     if done_check_lag == 0:
                         stream.synchronize()
-                    else:  # the entry of an older step: wait (briefly) until the GPU has published it
-                        while int(ring_np[look % RING]) >> 32 != look:
-                            pass
-                    if (int(ring_np[look % RING]) & 0xFFFFFFFF) == B:
+                    if _wait_ring(ring_np, tag_base + look, stream, "joint_beam_search_native") == B:
                         break
             out = _finalize(ids[cur][:, :L], beam_scores, pool_scores, pool_seqs, pool_lens, done.bool(), B, W, max_length, pad,
                             length_penalty, steps)

@@ -612,392 +612,7 @@ __global__ void __launch_bounds__(NT, MINB) k_score_full(const __grid_constant__
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// Lazy-state variant of K-b ("survivor recompute"): log_psi -- and with it the token
-// and joint scores -- depends only on phi = f(r_prev) and x, NOT on the new forward variables r.  The only
-// consumer of r is index_select_state, which keeps W columns per utterance out of W*V.  So in lazy mode the
-// (T,2,BW,V) state is never written: k_psi_full computes the scores (reads x once: 4*T*B*V bytes instead of
-// writing 8*T*BW*V), and k_select_lazy re-runs the recursion for the BW surviving (hyp, token) columns only.
-// Results are identical to the materialising kernels (same operations in the same order per lane).
-// ------------------------------------------------------------------------------------------
-struct PsiArgs {
-    const float *lin;    // (B*G, Tpad, HWP) exp(r_sum[t-1] - Gm), zero outside the summed range
-    const float *Gmax;   // (BW)
-    const float *psic;   // (BW) linear-domain sum for the column of the last label (phi = r_prev blank there)
-    const float *s_prev;
-    long long s_rs, s_cs;
-    const int64_t *last_ids;
-    float *att;
-    float omw, w;
-    float *log_psi, *token_scores, *joint;
-    int B, W, T, V, blank, ol, G, Tpad, nvt;
-    // frame-split kernel only
-    const float *x;        // the (B,T,ldx) posteriors the tensor map describes (first-frame term of step 0)
-    int ldx;
-    int nfull;             // whole tiles per CTA (tiles i, i+grid, ...), before its piece of the split phase
-    int q;                 // chunks per CTA in the split phase
-    float4 *part;          // [grid][2][HW][NT] parked partial sums
-    unsigned int *ticket;  // [tiles] contributors that have parked their piece; zero between launches
-};
-
-template <int HWP, int NT>
-struct PsiSmem {
-    static constexpr int VTILE = NT * 4;
-    static constexpr int NBOX = VTILE / BOXC;
-    alignas(128) float xs[NS][NBOX][TT][BOXC];
-    alignas(16) float lin[NS][TT][HWP];
-    alignas(8) uint64_t full[NS];
-    alignas(8) uint64_t empty[NS];
-};
-
-// one warp per (padded) hypothesis: lin stream, Gmax and the last-label column sum
-__global__ void __launch_bounds__(128) k_prep_psi(const float *__restrict__ r_prev, const XView x,
-                                                  const int64_t *__restrict__ last_ids, int B, int W, int T, int V, int HW,
-                                                  int HWP, int G, int start, int Tpad, float *__restrict__ lin,
-                                                  float *__restrict__ Gmax, float *__restrict__ psic) {
-    const int lane = threadIdx.x & 31;
-    const int hp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (hp >= B * G * HWP) return;
-    const int BW = B * W;
-    const int b = hp / (G * HWP);
-    const int rem = hp - b * (G * HWP);
-    const int g = rem / HWP, hh = rem - g * HWP;
-    const int w = g * HW + hh;
-    const bool valid = hh < HW && w < W;
-    const int h = b * W + w;
-    float gm = -INFINITY;
-    if (valid)
-        for (int t = lane; t < T; t += 32)
-            if (t >= start - 1 && t <= T - 2)
-                gm = fmaxf(gm, lse2_precise(r_prev[((size_t)t * 2 + 0) * BW + h], r_prev[((size_t)t * 2 + 1) * BW + h]));
-    gm = warp_max(gm);
-    if (!(gm > -INFINITY)) gm = 0.f;
-    float *base = lin + ((size_t)(b * G + g) * Tpad) * HWP + hh;
-    long long c = valid ? last_ids[h] : -1;
-    if (c < 0 || c >= V) c = -1;
-    float sc = 0.f;
-    for (int te = lane; te < Tpad; te += 32) {
-        float e = 0.f;
-        const int f = te - 1;
-        if (valid && f >= start - 1 && f <= T - 2) {
-            const float a = r_prev[((size_t)f * 2 + 0) * BW + h], cb = r_prev[((size_t)f * 2 + 1) * BW + h];
-            e = expf(lse2_precise(a, cb) - gm);
-            if (c >= 0) sc += expf(cb - gm) * expf(x.at(b, te, c));
-        }
-        base[(size_t)te * HWP] = e;
-    }
-    sc = warp_sum(sc);
-    if (valid && lane == 0) {
-        Gmax[h] = gm;
-        psic[h] = sc;
-    }
-}
-
-// Persistent kernel: grid = #SMs x resident CTAs, CTA i walks tiles i, i+grid, ... (tile = (utterance, 512-token
-// tile, hyp group)).  The chunks of all its tiles form one flat sequence that thread 0 keeps NS-1 stages ahead of the
-// consumers with TMA; stages are handed back through `empty` mbarriers (one arrival per warp), so warps never meet at
-// a CTA-wide barrier inside the stream.  The lin stream is zero outside the summed frame range, which makes the inner
-// loop branch-free: 8 frames x (1 LDS.128 of x, 4 ex2, HWP/4 LDS.128 of lin, 4*HW FFMA).
-template <int HW, int HWP, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ CUtensorMap tmx, const PsiArgs a) {
-    using Smem = PsiSmem<HWP, NT>;
-    constexpr int VTILE = Smem::VTILE;
-    constexpr int NBOX = Smem::NBOX;
-    constexpr int NWARP = NT / 32;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-    const int tid = threadIdx.x;
-    const int T = a.T, V = a.V, W = a.W;
-    const int start = a.ol > 1 ? a.ol : 1;
-    const int c0 = (a.ol == 0 ? 0 : start) / TT;
-    const int cN = (T - 1) / TT;
-    const int nchunk = cN - c0 + 1;
-    const int ntiles = a.B * a.nvt * a.G;
-    const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int nitems = my_tiles * nchunk;
-    constexpr uint32_t STAGE_BYTES = TT * VTILE * 4 + TT * HWP * 4;
-
-    auto decode_tile = [&](int tile, int &b, int &vt, int &g) {
-        g = tile % a.G;
-        tile /= a.G;
-        vt = tile % a.nvt;
-        b = tile / a.nvt;
-    };
-    auto issue = [&](int k) {  // item k = (k / nchunk)-th tile of this CTA, chunk c0 + k % nchunk
-        int b, vt, g;
-        decode_tile((int)blockIdx.x + (k / nchunk) * (int)gridDim.x, b, vt, g);
-        const int c = c0 + k % nchunk;
-        const int s = k % NS;
-        mbar_expect_tx(&sm.full[s], STAGE_BYTES);
-#pragma unroll
-        for (int bx = 0; bx < NBOX; ++bx) tma_load_2d(&sm.xs[s][bx][0][0], &tmx, vt * VTILE + bx * BOXC, b * T + c * TT, &sm.full[s]);
-        bulk_load_1d(&sm.lin[s][0][0], a.lin + ((size_t)(b * a.G + g) * a.Tpad + (size_t)c * TT) * HWP, TT * HWP * 4, &sm.full[s]);
-    };
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NS; ++s) mbar_init(&sm.full[s], 1), mbar_init(&sm.empty[s], NWARP);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int k = 0; k < nitems && k < NS; ++k) issue(k);
-    }
-    __syncthreads();
-
-    const int bx = (tid * 4) / BOXC, col = (tid * 4) % BOXC;
-    int k = 0;
-    for (int ti = 0; ti < my_tiles; ++ti) {
-        int b, vt, g;
-        decode_tile((int)blockIdx.x + ti * (int)gridDim.x, b, vt, g);
-        unsigned long long acc2[HW][2];  // (token 0, token 1), (token 2, token 3) packed for FFMA2
-        float x0[4];
-#pragma unroll
-        for (int hh = 0; hh < HW; ++hh) acc2[hh][0] = acc2[hh][1] = 0ull;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) x0[j] = LZ;
-
-        for (int ci = 0; ci < nchunk; ++ci, ++k) {
-            const int s = k % NS;
-            mbar_wait(&sm.full[s], (uint32_t)((k / NS) & 1));
-            if (a.ol == 0 && ci == 0) {  // r[0,0] = x_[0,0] enters log_psi as its own term (:158,165)
-                const float4 xv4 = *reinterpret_cast<const float4 *>(&sm.xs[s][bx][0][col]);
-                x0[0] = xv4.x, x0[1] = xv4.y, x0[2] = xv4.z, x0[3] = xv4.w;
-            }
-#pragma unroll
-            for (int tt = 0; tt < TT; ++tt) {
-                const float4 xv4 = *reinterpret_cast<const float4 *>(&sm.xs[s][bx][tt][col]);
-                const unsigned long long p01 = pack2(ex2_approx(xv4.x * LOG2E), ex2_approx(xv4.y * LOG2E));
-                const unsigned long long p23 = pack2(ex2_approx(xv4.z * LOG2E), ex2_approx(xv4.w * LOG2E));
-                float l[HWP];
-#pragma unroll
-                for (int q = 0; q < HWP / 4; ++q) {
-                    const float4 l4 = *reinterpret_cast<const float4 *>(&sm.lin[s][tt][q * 4]);
-                    l[q * 4 + 0] = l4.x, l[q * 4 + 1] = l4.y, l[q * 4 + 2] = l4.z, l[q * 4 + 3] = l4.w;
-                }
-#pragma unroll
-                for (int hh = 0; hh < HW; ++hh) {
-                    const unsigned long long ll = pack2(l[hh], l[hh]);
-                    acc2[hh][0] = ffma2(ll, p01, acc2[hh][0]);
-                    acc2[hh][1] = ffma2(ll, p23, acc2[hh][1]);
-                }
-            }
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&sm.empty[s]);
-            if (tid == 0 && k + NS < nitems) {  // refill the stage just released, once every warp is done with it
-                mbar_wait(&sm.empty[s], (uint32_t)((k / NS) & 1));
-                issue(k + NS);
-            }
-        }
-
-        const int v0 = vt * VTILE + tid * 4;
-        const int h0 = b * W + g * HW;
-        const int nhyp = min(HW, W - g * HW);
-        float acc[HW][4];
-#pragma unroll
-        for (int hh = 0; hh < HW; ++hh) {
-            unpack2(acc2[hh][0], acc[hh][0], acc[hh][1]);
-            unpack2(acc2[hh][1], acc[hh][2], acc[hh][3]);
-        }
-        // the column of each hypothesis' last label sums r_prev_blank instead of r_sum: take it from k_prep_psi
-#pragma unroll
-        for (int hh = 0; hh < HW; ++hh) {
-            if (hh < nhyp) {
-                const int cj = (int)(a.last_ids[h0 + hh] - (long long)v0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (cj == j) acc[hh][j] = a.psic[h0 + hh];
-            }
-        }
-        EpiArgs e;
-        e.Gmax = a.Gmax, e.s_prev = a.s_prev, e.s_rs = a.s_rs, e.s_cs = a.s_cs, e.att = a.att, e.omw = a.omw, e.w = a.w;
-        e.log_psi = a.log_psi, e.token_scores = a.token_scores, e.joint = a.joint, e.V = V, e.blank = a.blank, e.ol = a.ol;
-        epilogue_tile<HW>(e, acc, x0, h0, nhyp, v0);
-    }
-}
-
-// Frame-split ("stream-K") variant of k_psi_full.  CTA i first walks `nfull` WHOLE tiles i, i+grid, ... exactly like
-// k_psi_full (neighbouring CTAs read neighbouring column segments of the same frames: the DRAM-friendly order).  The
-// ntiles % grid tiles that would otherwise form a last, mostly empty wave (C3: 48 of 640 tiles on 592 resident CTAs; C1:
-// all 160) are not handed out whole: their chunks form one flat sequence (tile-major) that is cut into equal ranges of
-// `q` chunks, one per CTA, so every CTA streams the same number of bytes whatever the shape.
-// A tile whose chunks straddle several CTAs is finished by whichever of them arrives last: partial sums are additive
-// in the linear domain; every contributor parks its registers in `part` (slot 1 = the piece that holds the tile's first
-// chunk, slot 0 = any later piece; a CTA has at most one of each) and takes a ticket; the last one adds the pieces in
-// chunk order -- a fixed order, so results do not depend on arrival -- and runs the shared epilogue.  The first-frame
-// term of the first step (:158,165) is read from global memory by the finisher instead of from the staged chunk.
-template <int HW, int HWP, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_psi_split(const __grid_constant__ CUtensorMap tmx, const PsiArgs a) {
-    using Smem = PsiSmem<HWP, NT>;
-    constexpr int VTILE = Smem::VTILE;
-    constexpr int NBOX = Smem::NBOX;
-    constexpr int NWARP = NT / 32;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(smem_raw);
-    __shared__ int s_last;
-    const int tid = threadIdx.x;
-    const int T = a.T, V = a.V, W = a.W;
-    const int start = a.ol > 1 ? a.ol : 1;
-    const int c0 = (a.ol == 0 ? 0 : start) / TT;
-    const int cN = (T - 1) / TT;
-    const int nchunk = cN - c0 + 1;
-    const int ntiles = a.B * a.nvt * a.G;
-    const int kfull = a.nfull * nchunk;               // items of the whole-tile phase
-    const int rem_tile0 = a.nfull * (int)gridDim.x;   // first tile of the split phase
-    const long long nrem = (long long)(ntiles - rem_tile0) * nchunk;
-    const long long i0 = (long long)blockIdx.x * a.q;  // this CTA's range of the split phase: [i0, i0 + q) clipped to nrem
-    const int nsplit = i0 >= nrem ? 0 : (int)((i0 + a.q <= nrem ? i0 + a.q : nrem) - i0);
-    const int nitems = kfull + nsplit;
-    constexpr uint32_t STAGE_BYTES = TT * VTILE * 4 + TT * HWP * 4;
-
-    auto decode_tile = [&](int tile, int &b, int &vt, int &g) {
-        g = tile % a.G;
-        tile /= a.G;
-        vt = tile % a.nvt;
-        b = tile / a.nvt;
-    };
-    auto locate = [&](int k, int &tile, int &ci) {  // item k of this CTA -> (tile, chunk index within the tile)
-        if (k < kfull) {
-            const int r = k / nchunk;
-            tile = (int)blockIdx.x + r * (int)gridDim.x;
-            ci = k - r * nchunk;
-        } else {
-            const long long it = i0 + (k - kfull);
-            const int r = (int)(it / nchunk);
-            tile = rem_tile0 + r;
-            ci = (int)(it - (long long)r * nchunk);
-        }
-    };
-    auto issue = [&](int k) {
-        int tile, ci, b, vt, g;
-        locate(k, tile, ci);
-        const int c = c0 + ci;
-        decode_tile(tile, b, vt, g);
-        const int s = k % NS;
-        mbar_expect_tx(&sm.full[s], STAGE_BYTES);
-#pragma unroll
-        for (int bx = 0; bx < NBOX; ++bx) tma_load_2d(&sm.xs[s][bx][0][0], &tmx, vt * VTILE + bx * BOXC, b * T + c * TT, &sm.full[s]);
-        bulk_load_1d(&sm.lin[s][0][0], a.lin + ((size_t)(b * a.G + g) * a.Tpad + (size_t)c * TT) * HWP, TT * HWP * 4, &sm.full[s]);
-    };
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < NS; ++s) mbar_init(&sm.full[s], 1), mbar_init(&sm.empty[s], NWARP);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int k = 0; k < nitems && k < NS; ++k) issue(k);
-    }
-    __syncthreads();
-
-    const int bx = (tid * 4) / BOXC, col = (tid * 4) % BOXC;
-    int k = 0;
-    while (k < nitems) {
-        int tile, ci;
-        locate(k, tile, ci);
-        const int ci_begin = ci;
-        const int ci_end = min(nchunk, ci + (nitems - k));
-        int b, vt, g;
-        decode_tile(tile, b, vt, g);
-        unsigned long long acc2[HW][2];  // (token 0, token 1), (token 2, token 3) packed for FFMA2
-#pragma unroll
-        for (int hh = 0; hh < HW; ++hh) acc2[hh][0] = acc2[hh][1] = 0ull;
-
-        for (; ci < ci_end; ++ci, ++k) {
-            const int s = k % NS;
-            mbar_wait(&sm.full[s], (uint32_t)((k / NS) & 1));
-#pragma unroll
-            for (int tt = 0; tt < TT; ++tt) {
-                const float4 xv4 = *reinterpret_cast<const float4 *>(&sm.xs[s][bx][tt][col]);
-                const unsigned long long p01 = pack2(ex2_approx(xv4.x * LOG2E), ex2_approx(xv4.y * LOG2E));
-                const unsigned long long p23 = pack2(ex2_approx(xv4.z * LOG2E), ex2_approx(xv4.w * LOG2E));
-                float l[HWP];
-#pragma unroll
-                for (int qd = 0; qd < HWP / 4; ++qd) {
-                    const float4 l4 = *reinterpret_cast<const float4 *>(&sm.lin[s][tt][qd * 4]);
-                    l[qd * 4 + 0] = l4.x, l[qd * 4 + 1] = l4.y, l[qd * 4 + 2] = l4.z, l[qd * 4 + 3] = l4.w;
-                }
-#pragma unroll
-                for (int hh = 0; hh < HW; ++hh) {
-                    const unsigned long long ll = pack2(l[hh], l[hh]);
-                    acc2[hh][0] = ffma2(ll, p01, acc2[hh][0]);
-                    acc2[hh][1] = ffma2(ll, p23, acc2[hh][1]);
-                }
-            }
-            __syncwarp();
-            if ((tid & 31) == 0) mbar_arrive(&sm.empty[s]);
-            if (tid == 0 && k + NS < nitems) {  // refill the stage just released, once every warp is done with it
-                mbar_wait(&sm.empty[s], (uint32_t)((k / NS) & 1));
-                issue(k + NS);
-            }
-        }
-
-        float acc[HW][4];
-#pragma unroll
-        for (int hh = 0; hh < HW; ++hh) {
-            unpack2(acc2[hh][0], acc[hh][0], acc[hh][1]);
-            unpack2(acc2[hh][1], acc[hh][2], acc[hh][3]);
-        }
-        bool finish = true;
-        if (!(ci_begin == 0 && ci_end == nchunk)) {  // a piece of a tile: park it, the last contributor adds the pieces up
-            const long long t0 = (long long)(tile - rem_tile0) * nchunk;
-            const int c_first = (int)(t0 / a.q), c_last = (int)((t0 + nchunk - 1) / a.q);
-            float4 *mine = a.part + ((size_t)((int)blockIdx.x * 2 + (ci_begin == 0 ? 1 : 0)) * HW) * NT + tid;
-#pragma unroll
-            for (int hh = 0; hh < HW; ++hh) __stcg(mine + (size_t)hh * NT, make_float4(acc[hh][0], acc[hh][1], acc[hh][2], acc[hh][3]));
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) {
-                const unsigned int prev = atomicAdd(a.ticket + tile, 1u);
-                s_last = (prev == (unsigned int)(c_last - c_first)) ? 1 : 0;
-                if (s_last) a.ticket[tile] = 0u;  // self-cleaning: the next launch finds zeros
-            }
-            __syncthreads();
-            finish = s_last != 0;
-            if (finish) {
-                __threadfence();
-                float tot[HW][4];
-#pragma unroll
-                for (int hh = 0; hh < HW; ++hh)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) tot[hh][j] = 0.f;
-                // every piece, its own included, comes back from L2 in chunk order: a branch-free loop whose loads overlap
-#pragma unroll 2
-                for (int c = c_first; c <= c_last; ++c) {
-                    const float4 *piece = a.part + ((size_t)(c * 2 + (c == c_first ? 1 : 0)) * HW) * NT + tid;
-#pragma unroll
-                    for (int hh = 0; hh < HW; ++hh) {
-                        const float4 p = __ldcg(piece + (size_t)hh * NT);
-                        tot[hh][0] += p.x, tot[hh][1] += p.y, tot[hh][2] += p.z, tot[hh][3] += p.w;
-                    }
-                }
-#pragma unroll
-                for (int hh = 0; hh < HW; ++hh)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) acc[hh][j] = tot[hh][j];
-            }
-        }
-        if (finish) {
-            const int v0 = vt * VTILE + tid * 4;
-            const int h0 = b * W + g * HW;
-            const int nhyp = min(HW, W - g * HW);
-            float x0[4] = {LZ, LZ, LZ, LZ};
-            if (a.ol == 0 && v0 < V) {  // r[0,0] = x_[0,0] enters log_psi as its own term (:158,165)
-                const float4 xv4 = __ldg(reinterpret_cast<const float4 *>(a.x + (size_t)b * T * a.ldx + v0));
-                x0[0] = xv4.x, x0[1] = xv4.y, x0[2] = xv4.z, x0[3] = xv4.w;
-            }
-            // the column of each hypothesis' last label sums r_prev_blank instead of r_sum: take it from k_prep_psi
-#pragma unroll
-            for (int hh = 0; hh < HW; ++hh) {
-                if (hh < nhyp) {
-                    const int cj = (int)(a.last_ids[h0 + hh] - (long long)v0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (cj == j) acc[hh][j] = a.psic[h0 + hh];
-                }
-            }
-            EpiArgs e;
-            e.Gmax = a.Gmax, e.s_prev = a.s_prev, e.s_rs = a.s_rs, e.s_cs = a.s_cs, e.att = a.att, e.omw = a.omw, e.w = a.w;
-            e.log_psi = a.log_psi, e.token_scores = a.token_scores, e.joint = a.joint, e.V = V, e.blank = a.blank, e.ol = a.ol;
-            epilogue_tile<HW>(e, acc, x0, h0, nhyp, v0);
-        }
-    }
-}
+#include "ctcps_psi.cuh"
 
 // Lazy index_select_state: re-run the forward recursion of the PREVIOUS step for the surviving (hyp, token)
 // column of every output hypothesis j -- exactly the lane k_score_full would have written to r[:, :, hyp, tok].
@@ -1072,15 +687,16 @@ __global__ void __launch_bounds__(64) k_select_lazy_scan(const XView x, const fl
                                                          const float *__restrict__ log_psi,  // (BW,V), or (BW,S) with cand_ids
                                                          const int64_t *__restrict__ best_ids,
                                                          const int64_t *__restrict__ cand_ids, int S, int B, int W, int T, int V,
-                                                         float *r_new, float *__restrict__ s_new, float *__restrict__ lin,
+                                                         float *r_new, float *s_new, float *__restrict__ lin,
                                                          float *__restrict__ Gmax, float *__restrict__ psic, int HW, int HWP, int G,
                                                          int Tpad) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int BW = B * W;
     if (j >= BW) return;
     const LazySel q = lazy_source(best_ids, cand_ids, S, j, W, V);
-    const float sj = q.src < 0 ? LZ : log_psi[q.src];
-    s_new[j] = sj;  // :193
+    // log_psi == nullptr: the fused beam step (k_beam_merge) has already written the prefix scores of the new rows into s_new
+    const float sj = log_psi == nullptr ? s_new[j] : (q.src < 0 ? LZ : log_psi[q.src]);
+    if (log_psi != nullptr) s_new[j] = sj;  // :193
     const int start = ol > 1 ? ol : 1;
     const float *xb = blank_lp + (size_t)(j / W) * T;
     float rn = (ol == 0) ? r_new[j] : LZ, rb = LZ;
@@ -1169,7 +785,7 @@ __global__ void __launch_bounds__(64) k_select_lazy_scan(const XView x, const fl
 }
 
 // ------------------------------------------------------------------------------------------
-// Time-parallel variant of k_select_lazy_scan (opt-in: CTCPS_SELECT_PSCAN=1 / ctcps_set_select_pscan(1)).
+// Time-parallel variant of k_select_lazy_scan (the default; CTCPS_SELECT_PSCAN=0 / ctcps_set_select_pscan(0) selects the sequential one).
 // The recursion is an affine map in the (logsumexp, +) semiring,
 //     rn' = lse(rn + xv, ph + xv)        rb' = lse(rn + bl, rb + bl)
 // with five live coefficients (A_nn, A_bn, A_bb, c_n, c_b: rn never depends on rb), and affine maps compose
@@ -1211,7 +827,7 @@ __global__ void __launch_bounds__(PS_H * 32) k_select_lazy_pscan(const XView x, 
                                                                  const float *__restrict__ log_psi,
                                                                  const int64_t *__restrict__ best_ids,
                                                                  const int64_t *__restrict__ cand_ids, int S, int B, int W, int T,
-                                                                 int V, float *r_new, float *__restrict__ s_new,
+                                                                 int V, float *r_new, float *s_new,
                                                                  float *__restrict__ lin, float *__restrict__ Gmax,
                                                                  float *__restrict__ psic, int HW, int HWP, int G, int Tpad, int F,
                                                                  int Fo, int HS) {
@@ -1242,8 +858,8 @@ __global__ void __launch_bounds__(PS_H * 32) k_select_lazy_pscan(const XView x, 
     q.hs = 0, q.tok = 0, q.last = 0, q.src = -1;
     if (active) {
         q = lazy_source(best_ids, cand_ids, S, j, W, V);
-        sj = q.src < 0 ? LZ : log_psi[q.src];
-        if (lane == 0) s_new[j] = sj;  // :193
+        sj = log_psi == nullptr ? s_new[j] : (q.src < 0 ? LZ : log_psi[q.src]);  // nullptr: written by the fused beam step
+        if (lane == 0 && log_psi != nullptr) s_new[j] = sj;  // :193
         const float *xb = blank_lp + (size_t)(j / W) * T;
         float *col = ps_sm + w * HS;
         const int lo = lane * F, hi = min(n, lo + F);  // this lane's frames, relative to `start`
@@ -1364,9 +980,16 @@ __global__ void __launch_bounds__(128) k_score_partial(const float *__restrict__
     const int64_t c = last_ids[h];
     const bool last = (c >= 0 && c < V) ? (idmap[(size_t)h * V + c] == s) : false;  // :117-121
     const int start = ol > 1 ? ol : 1;
-    const float *xr = x + (size_t)b * T * ldx + v;
     const size_t plane = (size_t)BW * ldr, frame = 2 * plane;
     float *rp = r + (size_t)h * ldr + s;
+    if (v < 0 || v >= V) {  // the reference raises an IndexError here; never read outside the posteriors: the lane is logzero
+        for (int t = 0; t < T; ++t) {
+            rp[(size_t)t * frame] = LZ;
+            rp[(size_t)t * frame + plane] = LZ;
+        }
+        return;
+    }
+    const float *xr = x + (size_t)b * T * ldx + v;
     for (int t = 0; t < start && t < T; ++t) {
         rp[(size_t)t * frame] = LZ;
         rp[(size_t)t * frame + plane] = LZ;
@@ -1554,6 +1177,210 @@ __device__ __forceinline__ void rank_select(const Cand *cands, int n, int K, flo
     }
 }
 
+// Phases 4-6 of a beam step, shared by k_beam_step and k_beam_merge: given the utterance's K = 2W best candidates (sorted,
+// top[r].i = source hypothesis * V + token, sentinel entries have i = INT_MAX), finalise eos candidates ranked inside the
+// top W into the finished pool, choose the W continuing beams, test `done`, write the reordered + extended rows, and let
+// the last CTA of the grid publish (step, #done utterances) to host-visible memory.
+// Warp 0 does the bookkeeping with ballots and prefix counts (round 1 ran it serially on one thread: ~1500 dependent
+// instructions behind a CTA barrier); lane r owns candidates r and r + 32 and pool slot r.
+struct BeamOut {
+    float *beam_scores;
+    int64_t *best_ids_out, *last_ids_out;
+    const int64_t *ids_cur;
+    int64_t *ids_next;
+    long long ld_ids;
+    float *pool_scores;
+    int64_t *pool_lens, *pool_seqs;
+    long long ld_pool;
+    unsigned char *done;
+    unsigned int *ticket;
+    long long *done_ring;
+    int ring;
+    long long step_tag;
+    // fused scoring only: prefix score of every row of the next step (what index_select_state would read, :193)
+    float *s_next;           // (BW) or null
+    const float *top_lp;     // shared memory: log_psi of top[r] (selection by source hypothesis * V + token), or null
+    const float *log_psi0;   // (B,V) log_psi of hypothesis 0 of every utterance (the reference's token-only selection), or null
+};
+
+struct BeamShared {
+    int job_src[32], job_dst[32], n_pool_jobs;
+    int next_tok[32], next_src[32], next_rank[32];
+    float next_score[32];
+    unsigned int last;
+    int tot;
+};
+
+__device__ __forceinline__ void beam_bookkeep(const Cand *top, BeamShared &bs, const BeamOut &o, int b, int nB, int L, int W, int V, int eos,
+                                              int pad, float len_norm) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int K = 2 * W;
+    const float NEG = -INFINITY;
+    if (tid < 32) {
+        const float inv_norm = 1.0f / len_norm;  // torch divides a tensor by a scalar as a * (1 / scalar)
+        const bool dn = o.done[b] != 0;
+        float cs[2];
+        int csrc[2], ctok[2];
+        bool cok[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const int r = lane + 32 * q;
+            cok[q] = r < K && top[r].i != 0x7fffffff;
+            const int i = cok[q] ? top[r].i : 0;
+            cs[q] = cok[q] ? top[r].s : NEG;
+            csrc[q] = i / V;
+            ctok[q] = i - csrc[q] * V;
+        }
+        float ps = lane < W ? o.pool_scores[(size_t)b * W + lane] : INFINITY;  // pool slot `lane`
+        int my_job_src = -1;
+        // eos candidates ranked inside the top W are finalised, in rank order (W <= 32: they all live in q = 0)
+        unsigned eos_mask = __ballot_sync(0xffffffffu, cok[0] && lane < W && ctok[0] == eos && !dn && cs[0] > NEG);
+        while (eos_mask) {
+            const int r = __ffs(eos_mask) - 1;
+            eos_mask &= eos_mask - 1;
+            const float fs = __shfl_sync(0xffffffffu, cs[0], r) * inv_norm;
+            const int fsrc = __shfl_sync(0xffffffffu, csrc[0], r);
+            float wv = ps;  // the worst slot, lowest index on ties
+            int wi = lane;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, wv, d);
+                const int oi = __shfl_xor_sync(0xffffffffu, wi, d);
+                if (ov < wv || (ov == wv && oi < wi)) wv = ov, wi = oi;
+            }
+            if (fs > wv && lane == wi) ps = fs, my_job_src = fsrc;  // a later candidate may overwrite a slot filled in this same step
+        }
+        const bool has_job = lane < W && my_job_src >= 0;
+        if (has_job) {
+            o.pool_scores[(size_t)b * W + lane] = ps;
+            o.pool_lens[(size_t)b * W + lane] = L - 1;
+        }
+        const unsigned job_mask = __ballot_sync(0xffffffffu, has_job);
+        if (has_job) {
+            const int jq = __popc(job_mask & ((1u << lane) - 1u));
+            bs.job_src[jq] = my_job_src, bs.job_dst[jq] = lane;
+        }
+        if (lane == 0) bs.n_pool_jobs = __popc(job_mask);
+        // the first W non-eos candidates continue: candidate (lane, q) goes to position = number of continuing candidates before it
+        const unsigned m0 = __ballot_sync(0xffffffffu, cok[0] && ctok[0] != eos);
+        const unsigned m1 = __ballot_sync(0xffffffffu, cok[1] && ctok[1] != eos);
+        const int n0 = __popc(m0), ncont = n0 + __popc(m1);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const unsigned m = q == 0 ? m0 : m1;
+            const int pos = (q == 0 ? 0 : n0) + __popc(m & ((1u << lane) - 1u));
+            if (((m >> lane) & 1u) && pos < W)
+                bs.next_score[pos] = cs[q], bs.next_tok[pos] = ctok[q], bs.next_src[pos] = csrc[q], bs.next_rank[pos] = lane + 32 * q;
+        }
+        __syncwarp();
+        float ns = NEG;
+        int ntok = pad, nsrc = 0, nrank = -1;
+        if (lane < W && lane < ncont) ns = bs.next_score[lane], ntok = bs.next_tok[lane], nsrc = bs.next_src[lane], nrank = bs.next_rank[lane];
+        // done test of the utterance (BeamHypotheses.is_done, early_stopping = False)
+        const bool full = __all_sync(0xffffffffu, ps > NEG);
+        float worst = ps;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) worst = fminf(worst, __shfl_xor_sync(0xffffffffu, worst, d));
+        const float top0 = top[0].i != 0x7fffffff ? top[0].s : NEG;
+        const bool dn_new = dn || (full && worst >= top0 * inv_norm);
+        __syncwarp();
+        if (lane < W) {
+            if (dn_new) ns = 0.f, ntok = pad, nsrc = 0, nrank = -1;
+            o.beam_scores[b * W + lane] = ns;
+            // what index_select_state wants (ESPnet ids: source hypothesis * V + token, :180-191)
+            if (o.best_ids_out != nullptr) o.best_ids_out[b * W + lane] = (long long)nsrc * V + ntok;
+            if (o.last_ids_out != nullptr) o.last_ids_out[b * W + lane] = ntok;
+            if (o.s_next != nullptr) {
+                float sv = LZ;  // a pad row: log_psi[:, blank] = logzero (:173; the fused path requires pad == blank)
+                if (o.log_psi0 != nullptr) sv = o.log_psi0[(size_t)b * V + ntok];
+                else if (nrank >= 0) sv = o.top_lp[nrank];
+                o.s_next[b * W + lane] = sv;
+            }
+            bs.next_tok[lane] = ntok, bs.next_src[lane] = nsrc;
+        }
+        if (lane == 0) o.done[b] = dn_new ? 1 : 0;
+    }
+    __syncthreads();
+
+    // ---- copies: finished prefixes into the pool, reordered + extended rows into ids_next ----------
+    const int nt = blockDim.x;
+    for (int q = 0; q < bs.n_pool_jobs; ++q) {
+        const int64_t *src = o.ids_cur + ((size_t)b * W + bs.job_src[q]) * o.ld_ids + 1;  // drop bos
+        int64_t *dst = o.pool_seqs + ((size_t)b * W + bs.job_dst[q]) * o.ld_pool;
+        for (int k = tid; k < L - 1; k += nt) dst[k] = src[k];
+    }
+    for (int w = 0; w < W; ++w) {
+        const int64_t *src = o.ids_cur + ((size_t)b * W + bs.next_src[w]) * o.ld_ids;
+        int64_t *dst = o.ids_next + ((size_t)b * W + w) * o.ld_ids;
+        for (int k = tid; k < L; k += nt) dst[k] = src[k];
+        if (tid == 0) dst[L] = bs.next_tok[w];
+    }
+
+    // ---- the last utterance to finish its step publishes (step, #done utterances) to host-visible memory
+    if (o.done_ring != nullptr) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) bs.last = (atomicAdd(o.ticket, 1u) == (unsigned)(nB - 1)) ? 1u : 0u, bs.tot = 0;
+        __syncthreads();
+        if (bs.last) {
+            int cnt = 0;
+            for (int k = tid; k < nB; k += nt) cnt += ((volatile unsigned char *)o.done)[k] ? 1 : 0;
+            atomicAdd(&bs.tot, cnt);
+            __syncthreads();
+            if (tid == 0) {
+                *o.ticket = 0;
+                o.done_ring[o.step_tag % o.ring] = (o.step_tag << 32) | (long long)bs.tot;
+                __threadfence_system();
+            }
+        }
+    }
+}
+
+// Beam step over the per-tile candidate lists of the fused scoring kernel (k_psi_full<TOPK>): one CTA per utterance merges
+// its nlists sorted lists of K = 2W (key = joint + running beam score, dense index, log_psi) into the K best and does the
+// bookkeeping.  Every list is sorted, so its K-th key bounds the merge from below: entries under the largest such bound
+// cannot be among the K best.
+constexpr int MERGE_MAX = 1024;  // candidates of an utterance held in shared memory
+__global__ void __launch_bounds__(BEAM_NT) k_beam_merge(const float4 *__restrict__ lists, int nlists, int L, int W, int V, int eos, int pad,
+                                                        float len_norm, BeamOut o) {
+    __shared__ float4 cands[MERGE_MAX];
+    __shared__ Cand top[BEAM_MAXK];
+    __shared__ float top_lp[BEAM_MAXK];
+    __shared__ float bound_s[BEAM_NT / 32];
+    __shared__ BeamShared bs;
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int K = 2 * W, n = nlists * K;
+    const float NEG = -INFINITY;
+    const float4 *src = lists + (size_t)b * n;
+    float bnd = NEG;
+    for (int q = tid; q < n; q += BEAM_NT) {
+        const float4 c = src[q];
+        cands[q] = c;
+        if ((q % K) == K - 1 && __float_as_int(c.y) != 0x7fffffff) bnd = fmaxf(bnd, c.x);
+    }
+    for (int k = tid; k < BEAM_MAXK; k += BEAM_NT) top[k].s = NEG, top[k].i = 0x7fffffff, top_lp[k] = LZ;
+    bnd = warp_max(bnd);
+    if (lane == 0) bound_s[wid] = bnd;
+    __syncthreads();
+    float bound = bound_s[0];
+#pragma unroll
+    for (int q = 1; q < BEAM_NT / 32; ++q) bound = fmaxf(bound, bound_s[q]);
+    for (int q = tid; q < n; q += BEAM_NT) {
+        const float4 me = cands[q];
+        const int mi = __float_as_int(me.y);
+        if (mi == 0x7fffffff || me.x < bound) continue;
+        int rank = 0;
+        for (int p = 0; p < n; ++p) {
+            const float4 c = cands[p];
+            rank += (__float_as_int(c.y) != 0x7fffffff && cand_beats(c.x, __float_as_int(c.y), me.x, mi)) ? 1 : 0;
+        }
+        if (rank < K) top[rank].s = me.x, top[rank].i = mi, top_lp[rank] = me.z;
+    }
+    __syncthreads();
+    o.top_lp = top_lp;
+    beam_bookkeep(top, bs, o, b, (int)gridDim.x, L, W, V, eos, pad, len_norm);
+}
+
 // grid = B * P: CTA (b, p) reduces slice p of the W*V candidates of utterance b to its K best, the last CTA of the
 // utterance to arrive (ticket) merges the P partial lists and does the bookkeeping and the copies.
 // SPARSE: the candidates are the S pre-beam tokens of each hypothesis, `joint` is (BW,S) and cand_ids (BW,S) names them;
@@ -1572,7 +1399,7 @@ __global__ void __launch_bounds__(BEAM_NT) k_beam_step(const float *__restrict__
     __shared__ Cand wl[BEAM_MAXP * BEAM_MAXK];  // per-warp lists (phase 1), then the P partial lists (phase 2)
     __shared__ Cand top[BEAM_MAXK];             // sorted result of a rank_select
     __shared__ float kth[BEAM_MAXP];
-    __shared__ int job_src[32], job_dst[32], n_pool_jobs, next_tok_s[32], next_src_s[32];
+    __shared__ BeamShared bs;
     __shared__ unsigned int is_last;
     const int b = blockIdx.x / P, p = blockIdx.x - b * P;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1694,93 +1521,14 @@ __global__ void __launch_bounds__(BEAM_NT) k_beam_step(const float *__restrict__
         __syncthreads();
     }
 
-    // ---- 4. bookkeeping (serial, tiny) ------------------------------------------------------------------
-    if (tid == 0) {
-        utt_ticket[b] = 0;
-        const float inv_norm = 1.0f / len_norm;  // torch divides a tensor by a scalar as a * (1 / scalar)
-        const bool dn = done[b] != 0;
-        float *ps = pool_scores + (size_t)b * W;
-        int njobs = 0;
-        for (int r = 0; r < W; ++r) {  // eos candidates ranked inside the top W are finalised
-            const int tok = top[r].i % V;
-            if (tok == eos && !dn && top[r].s > NEG) {
-                const float fs = top[r].s * inv_norm;
-                int slot = 0;
-                float worst = ps[0];
-                for (int k = 1; k < W; ++k)
-                    if (ps[k] < worst) worst = ps[k], slot = k;
-                if (fs > worst) {
-                    ps[slot] = fs;
-                    pool_lens[(size_t)b * W + slot] = L - 1;
-                    int jq = -1;  // a later candidate may overwrite a slot filled in this same step
-                    for (int q = 0; q < njobs; ++q)
-                        if (job_dst[q] == slot) jq = q;
-                    if (jq < 0) jq = njobs++;
-                    job_src[jq] = top[r].i / V;
-                    job_dst[jq] = slot;
-                }
-            }
-        }
-        n_pool_jobs = njobs;
-        int o = 0;
-        float ns[32];
-        for (int r = 0; r < K && o < W; ++r) {  // the first W non-eos candidates continue
-            const int tok = top[r].i % V;
-            if (tok != eos) ns[o] = top[r].s, next_tok_s[o] = tok, next_src_s[o] = top[r].i / V, ++o;
-        }
-        for (; o < W; ++o) ns[o] = NEG, next_tok_s[o] = pad, next_src_s[o] = 0;
-        bool full = true;
-        float worst = INFINITY;
-        for (int k = 0; k < W; ++k) {
-            full = full && ps[k] > NEG;
-            worst = fminf(worst, ps[k]);
-        }
-        const bool dn_new = dn || (full && worst >= top[0].s * inv_norm);
-        for (int k = 0; k < W; ++k) {
-            if (dn_new) ns[k] = 0.f, next_tok_s[k] = pad, next_src_s[k] = 0;
-            beam_scores[b * W + k] = ns[k];
-            // what index_select_state wants (ESPnet ids: source hypothesis * V + token, :180-191)
-            if (best_ids_out != nullptr) best_ids_out[b * W + k] = (long long)next_src_s[k] * V + next_tok_s[k];
-            if (last_ids_out != nullptr) last_ids_out[b * W + k] = next_tok_s[k];
-        }
-        done[b] = dn_new ? 1 : 0;
-    }
-    __syncthreads();
-
-    // ---- 5. copies: finished prefixes into the pool, reordered + extended rows into ids_next ----------
-    for (int q = 0; q < n_pool_jobs; ++q) {
-        const int64_t *src = ids_cur + ((size_t)b * W + job_src[q]) * ld_ids + 1;  // drop bos
-        int64_t *dst = pool_seqs + ((size_t)b * W + job_dst[q]) * ld_pool;
-        for (int k = tid; k < L - 1; k += BEAM_NT) dst[k] = src[k];
-    }
-    for (int o = 0; o < W; ++o) {
-        const int64_t *src = ids_cur + ((size_t)b * W + next_src_s[o]) * ld_ids;
-        int64_t *dst = ids_next + ((size_t)b * W + o) * ld_ids;
-        for (int k = tid; k < L; k += BEAM_NT) dst[k] = src[k];
-        if (tid == 0) dst[L] = next_tok_s[o];
-    }
-
-    // ---- 6. the last utterance to finish its step publishes (step, #done utterances) to host-visible memory
-    if (done_ring != nullptr) {
-        const int B = gridDim.x / P;
-        __shared__ unsigned int last;
-        __shared__ int tot;
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) last = (atomicAdd(ticket, 1u) == (unsigned)(B - 1)) ? 1u : 0u, tot = 0;
-        __syncthreads();
-        if (last) {
-            int cnt = 0;
-            for (int k = tid; k < B; k += BEAM_NT) cnt += ((volatile unsigned char *)done)[k] ? 1 : 0;
-            atomicAdd(&tot, cnt);
-            __syncthreads();
-            if (tid == 0) {
-                *ticket = 0;
-                done_ring[step_tag % ring] = (step_tag << 32) | (long long)tot;
-                __threadfence_system();
-            }
-        }
-    }
+    // ---- 4.-6. bookkeeping, copies, done ring ---------------------------------------------------------
+    if (tid == 0) utt_ticket[b] = 0;
+    BeamOut o;
+    o.beam_scores = beam_scores, o.best_ids_out = best_ids_out, o.last_ids_out = last_ids_out, o.ids_cur = ids_cur, o.ids_next = ids_next;
+    o.ld_ids = ld_ids, o.pool_scores = pool_scores, o.pool_lens = pool_lens, o.pool_seqs = pool_seqs, o.ld_pool = ld_pool, o.done = done;
+    o.ticket = ticket, o.done_ring = done_ring, o.ring = ring, o.step_tag = step_tag;
+    o.s_next = nullptr, o.top_lp = nullptr, o.log_psi0 = nullptr;
+    beam_bookkeep(top, bs, o, b, (int)gridDim.x / P, L, W, V, eos, pad, len_norm);
 }
 
 #include "ctcps_prebeam.cuh"
@@ -1837,26 +1585,31 @@ Workspace plan_workspace(int B, int T, int W) {
     return ws;
 }
 
-// lazy mode: hyps per thread of k_psi_full and the padded width of its lin stream
+// lazy mode: hypotheses per thread of k_psi_full (even: packed FMAs pair two hypotheses) and the padded width of its lin
+// stream.  Up to 20 hypotheses in one group (W = 20 reads and exponentiates its x tile once); wider beams are split into
+// the group size with the fewest padded lanes.
 void pick_hw_psi(int W, int *HW, int *HWP, int *G) {
-    static const int cand[] = {10, 8, 6, 5, 4, 3, 2, 1};
-    int best = 1, best_pad = 1 << 30;
-    for (int hw : cand) {
-        const int g = (W + hw - 1) / hw;
-        const int pad = g * hw - W;
-        if (pad < best_pad) best = hw, best_pad = pad;
+    static const int cand[] = {20, 16, 12, 10, 8, 6, 4, 2};
+    int best = 2;
+    if (W <= 20) {
+        for (int hw : cand)
+            if (hw >= W) best = hw;  // the smallest group that holds every hypothesis
+    } else {
+        int best_pad = 1 << 30;
+        for (int hw : cand) {
+            const int pad = ((W + hw - 1) / hw) * hw - W;
+            if (pad < best_pad) best = hw, best_pad = pad;  // ties: the widest group (listed first)
+        }
     }
     *HW = best;
     *HWP = (best + 3) & ~3;
     *G = (W + best - 1) / best;
 }
-constexpr int PSI_NT = 128;         // threads of the lazy scoring kernels (512-token tiles)
-constexpr int PSI_MIN_Q = 8;          // fewest chunks a CTA of k_psi_split is given
-constexpr int PSI_MAX_GRID = 640;   // >= 148 SMs x 4 resident CTAs; bounds the parked partial sums of k_psi_split
 struct WorkspaceLazy {
-    size_t lin_off, lin_bytes, g_off, c_off, part_off, ticket_off, ticket_bytes, total;
+    size_t lin_off, lin_bytes, g_off, c_off, total;
 };
 WorkspaceLazy plan_workspace_lazy(int B, int T, int W, int V) {
+    (void)V;
     int HW, HWP, G;
     pick_hw_psi(W, &HW, &HWP, &G);
     WorkspaceLazy ws;
@@ -1865,12 +1618,7 @@ WorkspaceLazy plan_workspace_lazy(int B, int T, int W, int V) {
     ws.g_off = (ws.lin_bytes + 255) & ~(size_t)255;
     const size_t gb = ((size_t)B * W * sizeof(float) + 255) & ~(size_t)255;
     ws.c_off = ws.g_off + gb;
-    ws.part_off = ws.c_off + gb;
-    const size_t pb = (size_t)PSI_MAX_GRID * 2 * HW * PSI_NT * sizeof(float4);
-    ws.ticket_off = ws.part_off + pb;
-    const int nvt = (V + PSI_NT * 4 - 1) / (PSI_NT * 4);
-    ws.ticket_bytes = ((size_t)B * nvt * G * sizeof(unsigned int) + 255) & ~(size_t)255;
-    ws.total = ws.ticket_off + ws.ticket_bytes;
+    ws.total = ws.c_off + gb;
     return ws;
 }
 
@@ -1884,20 +1632,43 @@ int cuda_rc(cudaError_t e) { return e == cudaSuccess ? 0 : (int)e; }
         }                                                    \
     } while (0)
 
+// SM count of the CURRENT device, cached per device ordinal (a process may drive several GPUs).
+constexpr int MAX_DEVICES = 64;
+int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+int sm_count() {
+    static int cache[MAX_DEVICES] = {0};
+    const int dev = current_device();
+    if (dev >= 0 && dev < MAX_DEVICES && cache[dev] > 0) return cache[dev];
+    int sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    if (dev >= 0 && dev < MAX_DEVICES) cache[dev] = sms;
+    return sms;
+}
+
 int grid_for(size_t n, int block) {
     size_t g = (n + block - 1) / block;
-    const size_t cap = 148 * 32;
+    const size_t cap = (size_t)sm_count() * 32;
     return (int)(g < cap ? (g ? g : 1) : cap);
 }
 
+// Resident CTAs of a kernel instantiation on the whole current device; one cache slot per (instantiation, device).
 template <typename K>
-int resident_ctas(K kern, int nthreads, size_t smem, int *out) {
-    int per_sm = 0, dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+int resident_slots(K kern, int nthreads, size_t smem, int *slots_cache /* [MAX_DEVICES] */, int *out) {
+    const int dev = current_device();
+    if (dev >= 0 && dev < MAX_DEVICES && slots_cache[dev] > 0) {
+        *out = slots_cache[dev];
+        return 0;
+    }
+    int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthreads, smem);
     if (e != cudaSuccess) return (int)e;
-    *out = sms * (per_sm < 1 ? 1 : per_sm);
+    const int slots = sm_count() * (per_sm < 1 ? 1 : per_sm);
+    if (dev >= 0 && dev < MAX_DEVICES) slots_cache[dev] = slots;
+    *out = slots;
     return 0;
 }
 
@@ -1915,84 +1686,76 @@ int launch_score_full(const CUtensorMap &tm, const ScoreArgs &a, cudaStream_t st
     return cuda_rc(cudaGetLastError());
 }
 
-template <int HW, int HWP, int NT, int MINB>
+template <int HW, int HWP, int NT, int MINB, int NSTAGE, bool TOPK>
 int launch_psi_full(const CUtensorMap &tm, const PsiArgs &a, cudaStream_t st) {
-    using Smem = PsiSmem<HWP, NT>;
-    auto kern = k_psi_full<HW, HWP, NT, MINB>;
+    using Smem = PsiSmemAll<HW, HWP, NT, NSTAGE, TOPK>;
+    auto kern = k_psi_full<HW, HWP, NT, MINB, NSTAGE, TOPK>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
     if (e != cudaSuccess) return (int)e;
     const long long ntiles = (long long)a.B * a.nvt * a.G;
-    static int slots = 0;  // resident CTAs on the whole device for this instantiation (same on every B200 of a box)
-    if (slots == 0) {
-        int per_sm = 0, dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, sizeof(Smem));
-        if (e != cudaSuccess) return (int)e;
-        slots = sms * (per_sm < 1 ? 1 : per_sm);
-    }
+    static int slots_cache[MAX_DEVICES] = {0};
+    int slots = 0;
+    const int rc = resident_slots(kern, NT, sizeof(Smem), slots_cache, &slots);
+    if (rc) return rc;
     long long grid = slots;
     if (grid > ntiles) grid = ntiles;
     kern<<<(unsigned)grid, NT, sizeof(Smem), st>>>(tm, a);
     return cuda_rc(cudaGetLastError());
 }
 
-// Frame-split launch: grid = resident CTAs (<= PSI_MAX_GRID); floor(tiles / grid) whole tiles per CTA, the chunks of the
-// remaining tiles in equal ranges of q.
-template <int HW, int HWP, int NT, int MINB>
-int launch_psi_split(const CUtensorMap &tm, PsiArgs a, cudaStream_t st) {
-    using Smem = PsiSmem<HWP, NT>;
-    static_assert(NT == PSI_NT, "workspace plan assumes PSI_NT threads");
-    auto kern = k_psi_split<HW, HWP, NT, MINB>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-    if (e != cudaSuccess) return (int)e;
-    static int slots = 0;  // resident CTAs on the whole device for this instantiation (same on every B200 of a box)
-    if (slots == 0) {
-        int per_sm = 0, dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, sizeof(Smem));
-        if (e != cudaSuccess) return (int)e;
-        slots = sms * (per_sm < 1 ? 1 : per_sm);
-        if (slots > PSI_MAX_GRID) slots = PSI_MAX_GRID;
+// HW <= 10: 4 CTAs per SM (128 registers) with a 3-stage ring; wider groups: 3 CTAs per SM (168 registers), 4 stages.
+template <bool TOPK>
+int dispatch_psi_full(int HW, const CUtensorMap &tm, const PsiArgs &a, cudaStream_t st) {
+    constexpr int NT = PSI_NT;
+    switch (HW) {
+        case 2: return launch_psi_full<2, 4, NT, 4, 3, TOPK>(tm, a, st);
+        case 4: return launch_psi_full<4, 4, NT, 4, 3, TOPK>(tm, a, st);
+        case 6: return launch_psi_full<6, 8, NT, 4, 3, TOPK>(tm, a, st);
+        case 8: return launch_psi_full<8, 8, NT, 4, 3, TOPK>(tm, a, st);
+        case 10: return launch_psi_full<10, 12, NT, 4, 3, TOPK>(tm, a, st);
+        case 12: return launch_psi_full<12, 12, NT, 3, 4, TOPK>(tm, a, st);
+        case 16: return launch_psi_full<16, 16, NT, 3, 4, TOPK>(tm, a, st);
+        default: return launch_psi_full<20, 20, NT, 3, 4, TOPK>(tm, a, st);
     }
-    const int start = a.ol > 1 ? a.ol : 1;
-    const int nchunk = (a.T - 1) / TT - (a.ol == 0 ? 0 : start) / TT + 1;
-    const long long ntiles = (long long)a.B * a.nvt * a.G;
-    long long grid = slots;
-    a.nfull = (int)(ntiles / slots);
-    const long long nrem = (ntiles - (long long)a.nfull * slots) * nchunk;  // chunks of the split phase
-    long long q = (nrem + slots - 1) / slots;
-    if (q < PSI_MIN_Q) q = PSI_MIN_Q;  // pieces shorter than the pipeline depth only add merge traffic
-    a.q = (int)q;
-    if (a.nfull == 0) grid = (nrem + q - 1) / q;  // fewer tiles than resident CTAs: only CTAs that get a piece
-    kern<<<(unsigned)grid, NT, sizeof(Smem), st>>>(tm, a);
-    return cuda_rc(cudaGetLastError());
 }
 
-// 0 = one thread per hypothesis walks T frames (k_select_lazy_scan, the default), 1 = time-parallel warp per hypothesis
-// (k_select_lazy_pscan); ctcps_set_select_pscan / CTCPS_SELECT_PSCAN
+// 1 = time-parallel warp per hypothesis (k_select_lazy_pscan, the default since it passed its fp64-adjudicated hardware
+// gate and measured faster on every BASELINE shape: profiles/r2a_pscan_gate.md), 0 = one thread per hypothesis walks the
+// T frames (k_select_lazy_scan); ctcps_set_select_pscan / CTCPS_SELECT_PSCAN
 int g_select_pscan = -1;
 int select_pscan_mode() {
     if (g_select_pscan < 0) {
         const char *ev = getenv("CTCPS_SELECT_PSCAN");
-        g_select_pscan = (ev != nullptr && ev[0] == '1') ? 1 : 0;
+        g_select_pscan = (ev != nullptr && ev[0] == '0') ? 0 : 1;
     }
     return g_select_pscan;
 }
 
-// 0 = whole tiles on one CTA (k_psi_full, the default: fastest on every BASELINE shape), 1 = k_psi_split;
-// ctcps_set_psi_split / CTCPS_PSI_SPLIT, for A/B runs and tests
-int g_psi_split = -1;
-int psi_split_mode() {
-    if (g_psi_split < 0) {
-        const char *ev = getenv("CTCPS_PSI_SPLIT");
-        g_psi_split = (ev != nullptr && ev[0] == '1') ? 1 : 0;
-    }
-    return g_psi_split;
-}
-
+// The descriptor only depends on (pointer, ldx, B*T, V): a decode makes one scoring call per output token on the same
+// posteriors, so the last few descriptors are kept per host thread instead of calling the driver every step.
+struct MapCacheEntry {
+    const float *p;
+    int ldx, rows, V;
+    CUtensorMap tm;
+};
+int encode_x_map_uncached(CUtensorMap *tm, const float *x_logp, int ldx, int B, int T, int V);
 int encode_x_map(CUtensorMap *tm, const float *x_logp, int ldx, int B, int T, int V) {
+    constexpr int N = 4;
+    thread_local MapCacheEntry cache[N] = {};
+    thread_local int next = 0;
+    const int rows = B * T;
+    for (int i = 0; i < N; ++i)
+        if (cache[i].p == x_logp && cache[i].ldx == ldx && cache[i].rows == rows && cache[i].V == V) {
+            *tm = cache[i].tm;
+            return 0;
+        }
+    const int rc = encode_x_map_uncached(tm, x_logp, ldx, B, T, V);
+    if (rc) return rc;
+    cache[next].p = x_logp, cache[next].ldx = ldx, cache[next].rows = rows, cache[next].V = V, cache[next].tm = *tm;
+    next = (next + 1) % N;
+    return 0;
+}
+int encode_x_map_uncached(CUtensorMap *tm, const float *x_logp, int ldx, int B, int T, int V) {
     EncodeTiledFn enc = get_encode();
     ARG_CHECK(enc != nullptr, CTCPS_E_NODRIVER, "cuTensorMapEncodeTiled not found");
     cuuint64_t dims[2] = {(cuuint64_t)V, (cuuint64_t)B * T};
@@ -2014,12 +1777,13 @@ int encode_x_map(CUtensorMap *tm, const float *x_logp, int ldx, int B, int T, in
 int select_lazy_impl(const XView x, const float *blank_lp, const float *r_prev, const int64_t *last_ids, int ol, const float *scores,
                      const int64_t *cand_ids, int S, const int64_t *best_ids, int B, int W, int T, int V, float *r_new, float *s_new,
                      void *next_workspace, size_t next_workspace_bytes, cudaStream_t st) {
-    ARG_CHECK(blank_lp && r_prev && last_ids && scores && best_ids && r_new && s_new, CTCPS_E_BADARG, "select_lazy: null pointer");
+    ARG_CHECK(blank_lp && r_prev && last_ids && best_ids && r_new && s_new, CTCPS_E_BADARG, "select_lazy: null pointer");
+    ARG_CHECK(scores != nullptr || cand_ids == nullptr, CTCPS_E_BADARG, "select_lazy: candidate selection needs the candidate scores");
     ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0, CTCPS_E_BADARG, "select_lazy: bad size");
     const int BW = B * W;
     const dim3 grid((BW + 127) / 128, (T + LAZY_TC - 1) / LAZY_TC);
     k_select_lazy_stage<<<grid, 128, 0, st>>>(x, r_prev, last_ids, ol, best_ids, cand_ids, S, B, W, T, V, r_new);
-    // opt-in time-parallel scan: needs at least one frame to walk and a tile of PS_H columns that fits shared memory
+    // time-parallel scan: needs at least one frame to walk and a tile of PS_H columns that fits shared memory
     const int ps_start = ol > 1 ? ol : 1;
     const int ps_n = T - ps_start;
     const int ps_F = (ps_n + 31) / 32, ps_Fo = ps_F | 1, ps_HS = 2 * 32 * ps_Fo + 1;
@@ -2139,7 +1903,7 @@ int beam_step_impl(const float *joint, const int64_t *cand_ids, int S, float *be
     }
     int P = 1;
     if (cand_ids == nullptr) {
-        P = (148 * 8 + B - 1) / B;  // about 8 CTAs of 128 threads per SM in one wave
+        P = (sm_count() * 8 + B - 1) / B;  // about 8 CTAs of 128 threads per SM in one wave
         P = P < 1 ? 1 : (P > BEAM_MAXP ? BEAM_MAXP : P);
         while (P > 1 && (long long)W * V / P < 4 * 2 * W) --P;  // keep slices much longer than K
     }
@@ -2184,12 +1948,6 @@ int ctcps_padded_ld(int n) { return (n + 63) & ~63; }
 int ctcps_set_select_pscan(int mode) {
     const int prev = select_pscan_mode();
     if (mode == 0 || mode == 1) g_select_pscan = mode;
-    return prev;
-}
-
-int ctcps_set_psi_split(int mode) {
-    const int prev = psi_split_mode();
-    if (mode == 0 || mode == 1) g_psi_split = mode;
     return prev;
 }
 
@@ -2284,21 +2042,10 @@ int ctcps_score(const float *x_logp, int ldx, const float *blank_lp, const float
         k_prep<<<(warps + 3) / 4, 128, 0, st>>>(r_prev, blank_lp, B, W, T, HW, G, start, Tpad, aux, Gmax);
     }
 
-    EncodeTiledFn enc = get_encode();
-    ARG_CHECK(enc != nullptr, CTCPS_E_NODRIVER, "score: cuTensorMapEncodeTiled not found");
     CUtensorMap tm;
     {
-        cuuint64_t dims[2] = {(cuuint64_t)V, (cuuint64_t)B * T};
-        cuuint64_t strides[1] = {(cuuint64_t)ldx * sizeof(float)};
-        cuuint32_t box[2] = {(cuuint32_t)BOXC, (cuuint32_t)TT};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(x_logp), dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (cr != CUDA_SUCCESS) {
-            snprintf(g_errbuf, sizeof(g_errbuf), "cuTensorMapEncodeTiled failed with CUresult %d", (int)cr);
-            return CTCPS_E_NODRIVER;
-        }
+        const int rc_map = encode_x_map(&tm, x_logp, ldx, B, T, V);
+        if (rc_map) return rc_map;
     }
     ScoreArgs a;
     a.aux = aux;
@@ -2336,25 +2083,11 @@ int ctcps_score(const float *x_logp, int ldx, const float *blank_lp, const float
     return rc;
 }
 
-int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const float *s_prev,
-                     int64_t s_row_stride, int64_t s_col_stride, const int64_t *last_ids, int ol, int B, int W, int T, int V,
-                     int blank, float *att_scores, float one_minus_w, float w, float *log_psi, float *token_scores,
-                     float *joint, void *workspace, size_t workspace_bytes, int workspace_prepared, void *stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    (void)blank_lp;
-    ARG_CHECK(x_logp && r_prev && last_ids && log_psi, CTCPS_E_BADARG, "score_lazy: null pointer");
-    ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0, CTCPS_E_BADARG, "score_lazy: non-positive size");
-    ARG_CHECK(blank >= 0 && blank < V, CTCPS_E_BADARG, "score_lazy: blank id outside the vocabulary");
-    ARG_CHECK(att_scores == nullptr || joint != nullptr, CTCPS_E_BADARG, "score_lazy: att_scores given without joint output");
-    ARG_CHECK(ldx >= V && (ldx & 3) == 0 && (((uintptr_t)x_logp) & 15) == 0, CTCPS_E_ALIGN, "score_lazy: ldx must be a multiple of 4 and x_logp 16-byte aligned");
-    const long long BW = (long long)B * W;
-    ARG_CHECK(BW * (long long)V < (1ll << 31) && (long long)B * T < (1ll << 31), CTCPS_E_TOOBIG, "score_lazy: BW*V or B*T exceeds 2^31");
-    const int start = ol > 1 ? ol : 1;
-    if (start > T) {  // ctc_scorer.py:138-145
-        k_finalize<<<grid_for((size_t)BW * V, 256), 256, 0, st>>>(log_psi, s_prev, s_row_stride, s_col_stride, att_scores,
-                                                                 one_minus_w, w, (int)BW, V, blank, token_scores, joint, 1);
-        return cuda_rc(cudaGetLastError());
-    }
+// shared body of ctcps_score_lazy (dense outputs) and ctcps_score_lazy_topk (per-tile candidate lists)
+static int score_lazy_impl(const float *x_logp, int ldx, const float *r_prev, const float *s_prev, int64_t s_row_stride,
+                           int64_t s_col_stride, const int64_t *last_ids, int ol, int B, int W, int T, int V, int blank,
+                           float *att_scores, float one_minus_w, float w, float *log_psi, float *token_scores, float *joint,
+                           const PsiTopk *tk, void *workspace, size_t workspace_bytes, int workspace_prepared, cudaStream_t st) {
     int HW, HWP, G;
     pick_hw_psi(W, &HW, &HWP, &G);
     const WorkspaceLazy ws = plan_workspace_lazy(B, T, W, V);
@@ -2364,6 +2097,7 @@ int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const 
     float *Gmax = reinterpret_cast<float *>((char *)workspace + ws.g_off);
     float *psic = reinterpret_cast<float *>((char *)workspace + ws.c_off);
     const int Tpad = tpad_of(T);
+    const int start = ol > 1 ? ol : 1;
     if (!workspace_prepared) {  // else ctcps_select_lazy already wrote lin / Gmax / psic for this very call
         const int warps = B * G * HWP;
         k_prep_psi<<<(warps + 3) / 4, 128, 0, st>>>(r_prev, XView{x_logp, (long long)T * ldx, (long long)ldx, 1}, last_ids, B, W, T, V, HW, HWP, G, start, Tpad, lin, Gmax, psic);
@@ -2393,47 +2127,79 @@ int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const 
     a.ol = ol;
     a.G = G;
     a.Tpad = Tpad;
-    // 256-token tiles (64 threads, 8 resident CTAs per SM) were measured and not kept: no gain for the small shapes (a tile
-    // is a serial chain of T/8 TMA chunks, halving its width halves nothing) and 4 % slower at C2 (0.371 vs 0.356 ms).
-    // What the small shapes need is the frame range split across CTAs: k_psi_split.
-    constexpr int NT = PSI_NT;
-    a.nvt = (V + NT * 4 - 1) / (NT * 4);
-    a.x = x_logp;
-    a.ldx = ldx;
-    a.q = 0;
-    a.part = reinterpret_cast<float4 *>((char *)workspace + ws.part_off);
-    a.ticket = reinterpret_cast<unsigned int *>((char *)workspace + ws.ticket_off);
-    if (psi_split_mode()) {
-        // tickets are self-cleaning, but the workspace is caller memory of unknown content on its first use
-        cudaError_t me = cudaMemsetAsync(a.ticket, 0, ws.ticket_bytes, st);
-        if (me != cudaSuccess) return (int)me;
-        switch (HW) {
-            case 1: return launch_psi_split<1, 4, NT, 4>(tm, a, st);
-            case 2: return launch_psi_split<2, 4, NT, 4>(tm, a, st);
-            case 3: return launch_psi_split<3, 4, NT, 4>(tm, a, st);
-            case 4: return launch_psi_split<4, 4, NT, 4>(tm, a, st);
-            case 5: return launch_psi_split<5, 8, NT, 4>(tm, a, st);
-            case 6: return launch_psi_split<6, 8, NT, 4>(tm, a, st);
-            case 8: return launch_psi_split<8, 8, NT, 4>(tm, a, st);
-            default: return launch_psi_split<10, 12, NT, 4>(tm, a, st);
-        }
+    // 256-token tiles (64 threads, 8 resident CTAs per SM) were measured in round 1 and not kept: no gain for the small
+    // shapes (a tile is a serial chain of T/8 TMA chunks, halving its width halves nothing) and 4 % slower at C2; neither
+    // was splitting the frame range of the last wave's tiles across CTAs (k_psi_split, removed in round 2: not faster on
+    // any BASELINE shape, profiles/r1x_kernels_ncu.md section 3).
+    a.nvt = (V + PSI_NT * 4 - 1) / (PSI_NT * 4);
+    a.tk.beam_scores = nullptr, a.tk.lists = nullptr, a.tk.log_psi0 = nullptr, a.tk.K = 0;
+    if (tk != nullptr) {
+        a.tk = *tk;
+        return dispatch_psi_full<true>(HW, tm, a, st);
     }
-    switch (HW) {
-        case 1: return launch_psi_full<1, 4, NT, 4>(tm, a, st);
-        case 2: return launch_psi_full<2, 4, NT, 4>(tm, a, st);
-        case 3: return launch_psi_full<3, 4, NT, 4>(tm, a, st);
-        case 4: return launch_psi_full<4, 4, NT, 4>(tm, a, st);
-        case 5: return launch_psi_full<5, 8, NT, 4>(tm, a, st);
-        case 6: return launch_psi_full<6, 8, NT, 4>(tm, a, st);
-        case 8: return launch_psi_full<8, 8, NT, 4>(tm, a, st);
-        default: return launch_psi_full<10, 12, NT, 4>(tm, a, st);
+    return dispatch_psi_full<false>(HW, tm, a, st);
+}
+
+int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const float *s_prev,
+                     int64_t s_row_stride, int64_t s_col_stride, const int64_t *last_ids, int ol, int B, int W, int T, int V,
+                     int blank, float *att_scores, float one_minus_w, float w, float *log_psi, float *token_scores,
+                     float *joint, void *workspace, size_t workspace_bytes, int workspace_prepared, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    (void)blank_lp;
+    ARG_CHECK(x_logp && r_prev && last_ids && log_psi, CTCPS_E_BADARG, "score_lazy: null pointer");
+    ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0, CTCPS_E_BADARG, "score_lazy: non-positive size");
+    ARG_CHECK(blank >= 0 && blank < V, CTCPS_E_BADARG, "score_lazy: blank id outside the vocabulary");
+    ARG_CHECK(att_scores == nullptr || joint != nullptr, CTCPS_E_BADARG, "score_lazy: att_scores given without joint output");
+    ARG_CHECK(ldx >= V && (ldx & 3) == 0 && (((uintptr_t)x_logp) & 15) == 0, CTCPS_E_ALIGN, "score_lazy: ldx must be a multiple of 4 and x_logp 16-byte aligned");
+    const long long BW = (long long)B * W;
+    ARG_CHECK(BW * (long long)V < (1ll << 31) && (long long)B * T < (1ll << 31), CTCPS_E_TOOBIG, "score_lazy: BW*V or B*T exceeds 2^31");
+    const int start = ol > 1 ? ol : 1;
+    if (start > T) {  // ctc_scorer.py:138-145
+        k_finalize<<<grid_for((size_t)BW * V, 256), 256, 0, st>>>(log_psi, s_prev, s_row_stride, s_col_stride, att_scores,
+                                                                 one_minus_w, w, (int)BW, V, blank, token_scores, joint, 1);
+        return cuda_rc(cudaGetLastError());
     }
+    return score_lazy_impl(x_logp, ldx, r_prev, s_prev, s_row_stride, s_col_stride, last_ids, ol, B, W, T, V, blank, att_scores,
+                           one_minus_w, w, log_psi, token_scores, joint, nullptr, workspace, workspace_bytes, workspace_prepared, st);
+}
+
+int ctcps_topk_lists_shape(int B, int W, int V, int *lists_per_utterance, int *K) {
+    ARG_CHECK(lists_per_utterance && K && B > 0 && W > 0 && V > 0, CTCPS_E_BADARG, "topk_lists_shape: bad argument");
+    int HW, HWP, G;
+    pick_hw_psi(W, &HW, &HWP, &G);
+    *lists_per_utterance = ((V + PSI_NT * 4 - 1) / (PSI_NT * 4)) * G;
+    *K = 2 * W;
+    return 0;
+}
+
+int ctcps_score_lazy_topk(const float *x_logp, int ldx, const float *r_prev, const float *s_prev, const int64_t *last_ids, int ol,
+                          int B, int W, int T, int V, int blank, const float *att_scores, float one_minus_w, float w,
+                          const float *beam_scores, float *tile_lists, float *log_psi_hyp0, void *workspace,
+                          size_t workspace_bytes, int workspace_prepared, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ARG_CHECK(x_logp && r_prev && last_ids && att_scores && beam_scores && tile_lists, CTCPS_E_BADARG, "score_lazy_topk: null pointer");
+    ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0, CTCPS_E_BADARG, "score_lazy_topk: non-positive size");
+    ARG_CHECK(blank >= 0 && blank < V, CTCPS_E_BADARG, "score_lazy_topk: blank id outside the vocabulary");
+    ARG_CHECK((V & 3) == 0 && ldx >= V && (ldx & 3) == 0 && ((((uintptr_t)x_logp) | ((uintptr_t)att_scores) | ((uintptr_t)tile_lists)) & 15) == 0 &&
+                  (log_psi_hyp0 == nullptr || (((uintptr_t)log_psi_hyp0) & 15) == 0),
+              CTCPS_E_ALIGN, "score_lazy_topk: V and ldx must be multiples of 4, pointers 16-byte aligned");
+    ARG_CHECK(2 * W <= BEAM_MAXK, CTCPS_E_TOOBIG, "score_lazy_topk: num_beams > 32 is not supported");
+    const long long BW = (long long)B * W;
+    ARG_CHECK(BW * (long long)V < (1ll << 31) && (long long)B * T < (1ll << 31), CTCPS_E_TOOBIG, "score_lazy_topk: BW*V or B*T exceeds 2^31");
+    ARG_CHECK(ol <= T, CTCPS_E_BADARG, "score_lazy_topk: prefix longer than the utterance (use ctcps_score_lazy: every score is logzero)");
+    PsiTopk tk;
+    tk.beam_scores = beam_scores;
+    tk.lists = reinterpret_cast<float4 *>(tile_lists);
+    tk.log_psi0 = log_psi_hyp0;
+    tk.K = 2 * W;
+    return score_lazy_impl(x_logp, ldx, r_prev, s_prev, 1, 0, last_ids, ol, B, W, T, V, blank, const_cast<float *>(att_scores), one_minus_w, w,
+                           nullptr, nullptr, nullptr, &tk, workspace, workspace_bytes, workspace_prepared, st);
 }
 
 int ctcps_select_lazy(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const int64_t *last_ids, int ol,
                       const float *log_psi, const int64_t *best_ids, int B, int W, int T, int V, float *r_new, float *s_new,
                       void *next_workspace, size_t next_workspace_bytes, void *stream) {
-    ARG_CHECK(x_logp && log_psi, CTCPS_E_BADARG, "select_lazy: null pointer");
+    ARG_CHECK(x_logp != nullptr, CTCPS_E_BADARG, "select_lazy: null pointer");
     ARG_CHECK(T > 0 && V > 0 && ldx >= V, CTCPS_E_BADARG, "select_lazy: bad size");
     const XView x = {x_logp, (long long)T * ldx, (long long)ldx, 1};
     return select_lazy_impl(x, blank_lp, r_prev, last_ids, ol, log_psi, nullptr, 0, best_ids, B, W, T, V, r_new, s_new, next_workspace,
@@ -2466,6 +2232,32 @@ int ctcps_beam_step_candidates(const float *cand_joint, const int64_t *cand_ids,
     return beam_step_impl(cand_joint, cand_ids, S, beam_scores, ids_cur, ids_next, ld_ids, L, B, W, V, eos, pad, len_norm, pool_scores,
                           pool_lens, pool_seqs, ld_pool, done, workspace, workspace_bytes, done_ring, ring, step_tag, best_ids_out, nullptr,
                           (cudaStream_t)stream);
+}
+
+int ctcps_beam_step_lists(const float *tile_lists, int lists_per_utterance, float *beam_scores, const int64_t *ids_cur, int64_t *ids_next,
+                          int64_t ld_ids, int L, int B, int W, int V, int eos, int pad, float len_norm, float *pool_scores,
+                          int64_t *pool_lens, int64_t *pool_seqs, int64_t ld_pool, unsigned char *done, void *workspace,
+                          size_t workspace_bytes, int64_t *done_ring, int ring, int64_t step_tag, int64_t *best_ids_out,
+                          int64_t *last_ids_out, float *s_next, const float *log_psi_hyp0, void *stream) {
+    ARG_CHECK(tile_lists && beam_scores && ids_cur && ids_next && pool_scores && pool_lens && pool_seqs && done && workspace,
+              CTCPS_E_BADARG, "beam_step_lists: null pointer");
+    ARG_CHECK(B > 0 && W > 0 && V > 0 && L >= 1 && L < ld_ids && L - 1 <= ld_pool && lists_per_utterance > 0, CTCPS_E_BADARG,
+              "beam_step_lists: bad size");
+    ARG_CHECK(2 * W <= BEAM_MAXK && W <= 32 && (long long)lists_per_utterance * 2 * W <= MERGE_MAX, CTCPS_E_TOOBIG,
+              "beam_step_lists: num_beams > 32 or more than 1024 candidates per utterance");
+    ARG_CHECK((((uintptr_t)tile_lists) & 15) == 0, CTCPS_E_ALIGN, "beam_step_lists: tile_lists must be 16-byte aligned");
+    ARG_CHECK(done_ring == nullptr || ring > 0, CTCPS_E_BADARG, "beam_step_lists: done_ring without ring size");
+    const BeamWorkspace bw = plan_beam_workspace(B, W);
+    ARG_CHECK(workspace_bytes >= bw.total, CTCPS_E_WORKSPACE, "beam_step_lists: workspace too small");
+    unsigned int *utt_ticket = reinterpret_cast<unsigned int *>((char *)workspace + bw.ticket_off);
+    BeamOut o;
+    o.beam_scores = beam_scores, o.best_ids_out = best_ids_out, o.last_ids_out = last_ids_out, o.ids_cur = ids_cur, o.ids_next = ids_next;
+    o.ld_ids = ld_ids, o.pool_scores = pool_scores, o.pool_lens = pool_lens, o.pool_seqs = pool_seqs, o.ld_pool = ld_pool, o.done = done;
+    o.ticket = utt_ticket + B, o.done_ring = (long long *)done_ring, o.ring = ring, o.step_tag = step_tag;
+    o.s_next = s_next, o.top_lp = nullptr, o.log_psi0 = log_psi_hyp0;
+    k_beam_merge<<<B, BEAM_NT, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(tile_lists), lists_per_utterance, L, W, V, eos, pad,
+                                                         len_norm, o);
+    return cuda_rc(cudaGetLastError());
 }
 
 int ctcps_select(const float *r, int ldr, const float *log_psi, const int64_t *best_ids, const int64_t *scoring_idmap, int B,
@@ -2641,11 +2433,45 @@ int ctcps_decode_step(const ctcps_decode_session *s, float *att_scores, int step
         if (e != cudaSuccess) return (int)e;
     }
     if (ev_score_begin) cudaEventRecord((cudaEvent_t)ev_score_begin, main_st);
+    // Fused scoring + per-tile top-2W (full vocabulary): no (BW,V) tensor is written; the beam step merges the tile lists and
+    // hands the prefix scores of the new rows straight to the state selection.
+    int nlists = 0, Klist = 0;
+    if (S == 0) ctcps_topk_lists_shape(B, W, V, &nlists, &Klist);
+    const bool fused = S == 0 && s->tile_lists != nullptr && (V & 3) == 0 && ol <= T && s->pad == s->blank && 2 * W <= BEAM_MAXK &&
+                       W <= 32 && (long long)nlists * Klist <= MERGE_MAX && (s->use_beam_idx || s->log_psi[0] != nullptr);
+    const int64_t tag = s->tag_base + (int64_t)step;
+    if (fused) {
+        float *lp0 = s->use_beam_idx ? nullptr : s->log_psi[0];
+        rc = ctcps_score_lazy_topk(s->x_logp, s->ldx, r_prev, s_prev, s->last_ids[cur], ol, B, W, T, V, s->blank, att_scores, s->one_minus_w,
+                                   s->w, s->beam_scores, s->tile_lists, lp0, s->score_ws, s->score_ws_bytes, prepared, main_st);
+        if (rc) return rc;
+        if (ev_score_end) cudaEventRecord((cudaEvent_t)ev_score_end, main_st);
+        rc = ctcps_beam_step_lists(s->tile_lists, nlists, s->beam_scores, s->ids[cur], s->ids[nxt], s->ld_ids, L, B, W, V, s->eos, s->pad,
+                                   len_norm, s->pool_scores, s->pool_lens, s->pool_seqs, s->ld_pool, s->done, s->beam_ws, s->beam_ws_bytes,
+                                   s->done_ring, s->ring, tag, s->best_ids, s->last_ids[nxt], s->s_sel[nxt], lp0, main_st);
+        if (rc) return rc;
+        if (side != main_st) {
+            cudaError_t e = cudaEventRecord((cudaEvent_t)s->ev_step, main_st);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(side, (cudaEvent_t)s->ev_step, 0);
+            if (e != cudaSuccess) return (int)e;
+        }
+        const int64_t *sel = s->use_beam_idx ? s->best_ids : s->last_ids[nxt];
+        rc = ctcps_select_lazy(s->x_logp, s->ldx, s->blank_lp, r_prev, s->last_ids[cur], ol, nullptr, sel, B, W, T, V, s->r_sel[nxt],
+                               s->s_sel[nxt], s->score_ws, s->score_ws_bytes, side);
+        if (rc) return rc;
+        if (side != main_st) {
+            cudaError_t e = cudaEventRecord((cudaEvent_t)s->ev_select, side);
+            if (e != cudaSuccess) return (int)e;
+        }
+        return 0;
+    }
     if (S > 0) {
         rc = ctcps_score_candidates(s->x_vt, s->ldt, r_prev, s_prev, s->last_ids[cur], ol, B, W, T, V, s->blank, s->cand_ids[cur], S,
                                     s->cand_att[cur], s->one_minus_w, s->w, s->cand_log_psi[cur], nullptr, s->cand_joint, s->score_ws,
                                     s->score_ws_bytes, prepared, main_st);
     } else {
+        ARG_CHECK(s->joint != nullptr && s->log_psi[0] != nullptr && s->log_psi[1] != nullptr, CTCPS_E_BADARG,
+                  "decode_step: this step needs the dense (BW,V) buffers (joint, log_psi[2]) of the session");
         rc = ctcps_score_lazy(s->x_logp, s->ldx, s->blank_lp, r_prev, s_prev, 1, 0, s->last_ids[cur], ol, B, W, T, V, s->blank, att_scores,
                               s->one_minus_w, s->w, s->log_psi[cur], nullptr, s->joint, s->score_ws, s->score_ws_bytes, prepared, main_st);
     }
@@ -2653,7 +2479,7 @@ int ctcps_decode_step(const ctcps_decode_session *s, float *att_scores, int step
     if (ev_score_end) cudaEventRecord((cudaEvent_t)ev_score_end, main_st);
     rc = beam_step_impl(S > 0 ? s->cand_joint : s->joint, S > 0 ? s->cand_ids[cur] : nullptr, S, s->beam_scores, s->ids[cur], s->ids[nxt],
                         s->ld_ids, L, B, W, V, s->eos, s->pad, len_norm, s->pool_scores, s->pool_lens, s->pool_seqs, s->ld_pool, s->done,
-                        s->beam_ws, s->beam_ws_bytes, s->done_ring, s->ring, (int64_t)step, s->best_ids, s->last_ids[nxt], main_st);
+                        s->beam_ws, s->beam_ws_bytes, s->done_ring, s->ring, tag, s->best_ids, s->last_ids[nxt], main_st);
     if (rc) return rc;
     if (side != main_st) {
         cudaError_t e = cudaEventRecord((cudaEvent_t)s->ev_step, main_st);

@@ -1,0 +1,480 @@
+// ctcps_psi.cuh -- the lazy-state scoring kernel (K-b without the state write) and its fused per-tile top-2W epilogue.
+// Included by ctcps_kernels.cu inside its anonymous namespace (one translation unit, one library).
+//
+// Lazy-state variant of K-b ("survivor recompute"): log_psi -- and with it the token and joint
+// scores -- depends only on phi = f(r_prev) and x, NOT on the new forward variables r (ctc_scorer.py:154,164-167).  The
+// only consumer of r is index_select_state, which keeps W columns per utterance out of W*V.  So in lazy mode the
+// (T,2,BW,V) state is never written: k_psi_full computes the scores (reads x once: 4*T*B*V bytes instead of writing
+// 8*T*BW*V), and k_select_lazy_* re-runs the recursion for the BW surviving (hyp, token) columns only.
+//
+//   psi[h, v] = sum_t lin[t, h] * exp(x[t, b, v]),   lin[t, h] = exp(r_sum[t-1, h] - G_h)  (zero outside the summed frames)
+//
+// is a skinny (W x T) x (T x V) product per utterance with exp() applied on the fly to the streamed operand; it is bound
+// by reading x once from HBM, so it stays on the FP32 pipes (the 1e-4 log-space tolerance needs the fp32 mantissa).
+//
+// Round-2 structure (what changed against round 1 and why, profiles/r2*_psi_ncu.md):
+//   * packed FMAs pair two HYPOTHESES of one token (acc = (h0, h1) += (lin_h0, lin_h1) * (p, p)): the lin pairs come out
+//     of shared memory already packed (LDS.128 = two pairs) and only the 4 token probabilities are duplicated per frame,
+//     instead of one register move per hypothesis (10 at W = 10, 20 at W = 20);
+//   * up to 20 hypotheses per thread: a W = 20 tile is no longer processed by two hypothesis groups that each re-read the
+//     x tile from L2 and recompute exp(x) (round 1: C4 was MUFU / issue-bound at 0.46 of the HBM peak);
+//   * the warp that releases a pipeline stage LAST (a shared-memory ticket) refills it with TMA at once; round 1 made
+//     thread 0 both compute and issue, so a refill waited until warp 0 had finished its own chunk, and it paid three
+//     integer divisions per chunk -- the tile decode now happens once per tile;
+//   * TOPK mode (native decode loop): the epilogue ranks the tile's 512 x HW joint scores (+ running beam scores) and
+//     publishes the tile's best 2W candidates; (BW,V) joint / log_psi tensors are never written or re-read, and the
+//     separate per-row top-2W kernel of round 1 disappears.  The beam step merges nvt x G short sorted lists.
+
+struct PsiTopk {
+    const float *beam_scores;  // (BW) running beam scores, added to the joint scores for ranking
+    float4 *lists;             // [B][nvt*G][K]: (key, dense index hyp*V+tok as int bits, log_psi, 0), best first
+    float *log_psi0;           // (B,V) log_psi row of hypothesis 0 of every utterance (token-only state selection), or null
+    int K;                     // 2W
+};
+
+struct PsiArgs {
+    const float *lin;    // (B*G, Tpad, HWP) exp(r_sum[t-1] - Gm), zero outside the summed range
+    const float *Gmax;   // (BW)
+    const float *psic;   // (BW) linear-domain sum for the column of the last label (phi = r_prev blank there)
+    const float *s_prev;
+    long long s_rs, s_cs;
+    const int64_t *last_ids;
+    float *att;
+    float omw, w;
+    float *log_psi, *token_scores, *joint;
+    int B, W, T, V, blank, ol, G, Tpad, nvt;
+    PsiTopk tk;
+};
+
+constexpr int PSI_NT = 128;      // threads of the lazy scoring kernel (512-token tiles)
+constexpr int PSI_TOPK_CAP = 256;  // elements of a tile at or above the threshold that the exact ranking takes
+
+template <int HWP, int NT, int NSTAGE>
+struct PsiSmem {
+    static constexpr int VTILE = NT * 4;
+    static constexpr int NBOX = VTILE / BOXC;
+    alignas(128) float xs[NSTAGE][NBOX][TT][BOXC];
+    alignas(16) float lin[NSTAGE][TT][HWP];
+    alignas(8) uint64_t full[NSTAGE];
+    unsigned int released[NSTAGE];  // warps that have finished reading the stage (monotone ticket)
+};
+
+// one warp per (padded) hypothesis: lin stream, Gmax and the last-label column sum
+__global__ void __launch_bounds__(128) k_prep_psi(const float *__restrict__ r_prev, const XView x,
+                                                  const int64_t *__restrict__ last_ids, int B, int W, int T, int V, int HW,
+                                                  int HWP, int G, int start, int Tpad, float *__restrict__ lin,
+                                                  float *__restrict__ Gmax, float *__restrict__ psic) {
+    const int lane = threadIdx.x & 31;
+    const int hp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (hp >= B * G * HWP) return;
+    const int BW = B * W;
+    const int b = hp / (G * HWP);
+    const int rem = hp - b * (G * HWP);
+    const int g = rem / HWP, hh = rem - g * HWP;
+    const int w = g * HW + hh;
+    const bool valid = hh < HW && w < W;
+    const int h = b * W + w;
+    float gm = -INFINITY;
+    if (valid)
+        for (int t = lane; t < T; t += 32)
+            if (t >= start - 1 && t <= T - 2)
+                gm = fmaxf(gm, lse2_precise(r_prev[((size_t)t * 2 + 0) * BW + h], r_prev[((size_t)t * 2 + 1) * BW + h]));
+    gm = warp_max(gm);
+    if (!(gm > -INFINITY)) gm = 0.f;
+    float *base = lin + ((size_t)(b * G + g) * Tpad) * HWP + hh;
+    long long c = valid ? last_ids[h] : -1;
+    if (c < 0 || c >= V) c = -1;
+    float sc = 0.f;
+    for (int te = lane; te < Tpad; te += 32) {
+        float e = 0.f;
+        const int f = te - 1;
+        if (valid && f >= start - 1 && f <= T - 2) {
+            const float a = r_prev[((size_t)f * 2 + 0) * BW + h], cb = r_prev[((size_t)f * 2 + 1) * BW + h];
+            e = expf(lse2_precise(a, cb) - gm);
+            if (c >= 0) sc += expf(cb - gm) * expf(x.at(b, te, c));
+        }
+        base[(size_t)te * HWP] = e;
+    }
+    sc = warp_sum(sc);
+    if (valid && lane == 0) {
+        Gmax[h] = gm;
+        psic[h] = sc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// TOPK epilogue: the tile's K best (joint score + running beam score) out of 512 tokens x HW hypotheses, ranked exactly
+// by (score descending, dense index ascending) -- the order of the beam step (and of torch.topk on distinct scores).
+//
+//   pass 1  per hypothesis (rolled loop, one row of the sums at a time like epilogue_tile): log_psi, token score, joint
+//           score, key = joint + beam score; the sums are replaced by log_psi (the rows rotate through position 0, so
+//           after HW iterations they are back in place); every thread keeps the max of its keys;
+//   tau     = the K-th largest of the NT thread maxima (rank counting over shared memory): at least K elements of the
+//           tile are >= tau, so the K best are, and only a few dozen elements in all;
+//   pass 2  recomputes the keys from the stored log_psi (same operations, bit-identical) and appends the elements >= tau
+//           to a shared list, which is then ranked exactly by counting.
+// A tile where more than PSI_TOPK_CAP elements reach tau (fewer than K threads hold a valid score, or a constant row)
+// falls back to K rounds of block-wide argmax over the recomputed keys.  Invalid positions (v >= V, padded hypotheses)
+// never enter; a list with fewer than K valid entries is closed with (-inf, INT_MAX) sentinels.
+// ------------------------------------------------------------------------------------------
+struct PsiTopkSmem {
+    float tmax[PSI_NT];
+    float4 cand[PSI_TOPK_CAP];
+    float4 red[PSI_NT / 32];
+    float4 winner;
+    float tau;
+    unsigned int n_cand;
+};
+
+template <int HW, int NWARP, bool TOPK>
+struct PsiTopkScratch {};
+template <int HW, int NWARP>
+struct PsiTopkScratch<HW, NWARP, true> {
+    PsiTopkSmem t;
+    float scal[NWARP * 3 * HW];  // per warp: Gmax, s_prev, beam score of the tile's hypotheses
+};
+template <int HW, int HWP, int NT, int NSTAGE, bool TOPK>
+struct PsiSmemAll {
+    PsiSmem<HWP, NT, NSTAGE> pipe;
+    PsiTopkScratch<HW, NT / 32, TOPK> topk;
+};
+
+__device__ __forceinline__ bool key_beats(float s1, int i1, float s2, int i2) { return s1 > s2 || (s1 == s2 && i1 < i2); }
+
+// second half of epi_lane: log_psi -> token score -> joint score (:175-176, :325, :332)
+__device__ __forceinline__ float joint_of(const EpiArgs &e, int v, float lp, float sp, float av) {
+    float ts = lp - sp;
+    if (ts == 0.f) ts = LZ;
+    if (v == e.blank) av = LZ;
+    return __fadd_rn(__fmul_rn(e.omw, av), __fmul_rn(e.w, ts));
+}
+// first half: linear-domain sum -> log_psi (:164-173)
+__device__ __forceinline__ float log_psi_of(const EpiArgs &e, int v, float S, float gm, float x0) {
+    float lp = gm + logf(S);
+    if (!(lp > LZ)) lp = LZ;
+    if (e.ol == 0) lp = lse2_precise(lp, x0);
+    if (v == e.blank) lp = LZ;
+    return lp;
+}
+
+template <int HW>
+__device__ __forceinline__ void epilogue_topk(const EpiArgs &e, const PsiTopk &tk, PsiTopkSmem &ts, float (&S)[HW][4], const float (&x0)[4],
+                                              int b, int hrow0 /* global row of the tile's first hypothesis */,
+                                              int w0 /* its index inside the utterance */, int nhyp, int v0,
+                                              float4 *__restrict__ list_out, float *scal /* this warp's [3][HW] shared scratch */) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int V = e.V, K = tk.K;
+    const bool col_ok = v0 < V;  // V % 4 == 0 on this path: the thread's 4 tokens are valid together
+    const float NEG = -INFINITY;
+    // per-hypothesis scalars of the tile, staged by each warp for itself (no CTA barrier; read back as LDS broadcasts)
+    if (lane < HW) {
+        const int h = hrow0 + (lane < nhyp ? lane : 0);
+        scal[0 * HW + lane] = e.Gmax[h];
+        scal[1 * HW + lane] = e.s_prev != nullptr ? e.s_prev[(long long)h * e.s_rs] : 0.f;
+        scal[2 * HW + lane] = tk.beam_scores[h];
+    }
+    if (tid == 0) ts.n_cand = 0;
+    __syncwarp();
+
+    constexpr int AHEAD = HW < 4 ? HW : 4;
+    float4 attv[AHEAD];
+    auto att_row = [&](int hh) {
+        return (col_ok && hh < nhyp) ? __ldg(reinterpret_cast<const float4 *>(e.att + (size_t)(hrow0 + hh) * V + v0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    // ---- pass 1: sums -> log_psi (kept in S), thread max of the keys ---------------------------------------------
+    float mx = NEG;
+#pragma unroll
+    for (int i = 0; i < AHEAD; ++i) attv[i] = att_row(i);
+#pragma unroll 1
+    for (int hh = 0; hh < HW; ++hh) {
+        const float gm = scal[0 * HW + hh], sp = scal[1 * HW + hh], bm = scal[2 * HW + hh];
+        const float4 cur = attv[0];
+#pragma unroll
+        for (int i = 0; i + 1 < AHEAD; ++i) attv[i] = attv[i + 1];
+        attv[AHEAD - 1] = att_row(hh + AHEAD);
+        const float av[4] = {cur.x, cur.y, cur.z, cur.w};
+        float lp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            lp[j] = log_psi_of(e, v0 + j, S[0][j], gm, x0[j]);
+            const float key = joint_of(e, v0 + j, lp[j], sp, av[j]) + bm;
+            if (col_ok && hh < nhyp) mx = fmaxf(mx, key);
+        }
+        if (tk.log_psi0 != nullptr && w0 + hh == 0 && col_ok)
+            *reinterpret_cast<float4 *>(tk.log_psi0 + (size_t)b * V + v0) = make_float4(lp[0], lp[1], lp[2], lp[3]);
+#pragma unroll
+        for (int i = 0; i + 1 < HW; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) S[i][j] = S[i + 1][j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) S[HW - 1][j] = lp[j];
+    }
+    // ---- tau: the K-th largest thread maximum ------------------------------------------------------------------
+    ts.tmax[tid] = mx;
+    __syncthreads();
+    {
+        int rank = 0;
+#pragma unroll 4
+        for (int o = 0; o < PSI_NT; o += 4) {
+            const float4 m4 = *reinterpret_cast<const float4 *>(&ts.tmax[o]);
+            rank += key_beats(m4.x, o + 0, mx, tid) ? 1 : 0;
+            rank += key_beats(m4.y, o + 1, mx, tid) ? 1 : 0;
+            rank += key_beats(m4.z, o + 2, mx, tid) ? 1 : 0;
+            rank += key_beats(m4.w, o + 3, mx, tid) ? 1 : 0;
+        }
+        if (rank == K - 1) ts.tau = mx;  // ranks are unique (ties broken by thread id): exactly one writer
+    }
+    __syncthreads();
+    const float tau = ts.tau;
+    // ---- pass 2: elements >= tau into the shared list (keys recomputed from log_psi: same operations, same bits) ----
+#pragma unroll
+    for (int i = 0; i < AHEAD; ++i) attv[i] = att_row(i);
+#pragma unroll 1
+    for (int hh = 0; hh < HW; ++hh) {
+        const float sp = scal[1 * HW + hh], bm = scal[2 * HW + hh];
+        const float4 cur = attv[0];
+#pragma unroll
+        for (int i = 0; i + 1 < AHEAD; ++i) attv[i] = attv[i + 1];
+        attv[AHEAD - 1] = att_row(hh + AHEAD);
+        const float av[4] = {cur.x, cur.y, cur.z, cur.w};
+        float lp[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            lp[j] = S[0][j];
+            const float key = joint_of(e, v0 + j, lp[j], sp, av[j]) + bm;
+            if (col_ok && hh < nhyp && key >= tau) {
+                const unsigned pos = atomicAdd(&ts.n_cand, 1u);
+                if (pos < PSI_TOPK_CAP) ts.cand[pos] = make_float4(key, __int_as_float((w0 + hh) * V + v0 + j), lp[j], 0.f);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i + 1 < HW; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) S[i][j] = S[i + 1][j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) S[HW - 1][j] = lp[j];
+    }
+    __syncthreads();
+    const unsigned nc = ts.n_cand;
+    const float4 sentinel = make_float4(NEG, __int_as_float(0x7fffffff), LZ, 0.f);
+    if (nc <= PSI_TOPK_CAP) {
+        for (unsigned q = tid; q < nc; q += PSI_NT) {
+            const float4 me = ts.cand[q];
+            int rank = 0;
+            for (unsigned o = 0; o < nc; ++o) {
+                const float4 c = ts.cand[o];
+                rank += key_beats(c.x, __float_as_int(c.y), me.x, __float_as_int(me.y)) ? 1 : 0;
+            }
+            if (rank < K) list_out[rank] = me;
+        }
+        for (int r = (int)nc + tid; r < K; r += PSI_NT) list_out[r] = sentinel;
+        __syncthreads();  // the list and the counters are reused by the next tile
+        return;
+    }
+    // ---- fallback: K rounds of block-wide argmax over the keys that come after the previous winner -------------
+    float pk = INFINITY;
+    int pi = -1;
+    for (int r = 0; r < K; ++r) {
+        float bk = NEG, bl = LZ;
+        int bi = 0x7fffffff;
+#pragma unroll 1
+        for (int hh = 0; hh < HW; ++hh) {
+            const float sp = scal[1 * HW + hh], bm = scal[2 * HW + hh];
+            const float4 cur = att_row(hh);
+            const float av[4] = {cur.x, cur.y, cur.z, cur.w};
+            float lp[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                lp[j] = S[0][j];
+                const float key = joint_of(e, v0 + j, lp[j], sp, av[j]) + bm;
+                const int idx = (w0 + hh) * V + v0 + j;
+                if (col_ok && hh < nhyp && key_beats(pk, pi, key, idx) && (bi == 0x7fffffff || key_beats(key, idx, bk, bi)))
+                    bk = key, bi = idx, bl = lp[j];
+            }
+#pragma unroll
+            for (int i = 0; i + 1 < HW; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) S[i][j] = S[i + 1][j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) S[HW - 1][j] = lp[j];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ok = __shfl_xor_sync(0xffffffffu, bk, o), ol = __shfl_xor_sync(0xffffffffu, bl, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (oi != 0x7fffffff && (bi == 0x7fffffff || key_beats(ok, oi, bk, bi))) bk = ok, bi = oi, bl = ol;
+        }
+        if (lane == 0) ts.red[wid] = make_float4(bk, __int_as_float(bi), bl, 0.f);
+        __syncthreads();
+        if (tid == 0) {
+            float4 best = ts.red[0];
+            for (int q = 1; q < PSI_NT / 32; ++q) {
+                const float4 c = ts.red[q];
+                const int ci = __float_as_int(c.y), bi2 = __float_as_int(best.y);
+                if (ci != 0x7fffffff && (bi2 == 0x7fffffff || key_beats(c.x, ci, best.x, bi2))) best = c;
+            }
+            if (__float_as_int(best.y) == 0x7fffffff) best = sentinel;
+            ts.winner = best;
+            list_out[r] = best;
+        }
+        __syncthreads();
+        const float4 wv = ts.winner;
+        pk = wv.x, pi = __float_as_int(wv.y);
+        if (pi == 0x7fffffff) {  // nothing left: close the list
+            for (int q = r + 1 + tid; q < K; q += PSI_NT) list_out[q] = sentinel;
+            break;
+        }
+    }
+    __syncthreads();
+}
+
+// Persistent kernel: grid = #SMs x resident CTAs, CTA i walks tiles i, i+grid, ... (tile = (utterance, 512-token tile,
+// hypothesis group)).  The chunks of all its tiles form one flat sequence kept NSTAGE stages ahead of the consumers with
+// TMA: a stage is refilled by whichever warp is the last to finish reading it (ticket in shared memory), so a refill
+// never waits for a particular warp and the warps of a CTA never meet at a CTA-wide barrier inside the stream.  The lin
+// stream is zero outside the summed frame range, which makes the inner loop branch-free:
+//   8 frames x (1 LDS.128 of x, 4 FMUL + 4 ex2, 4 MOV, HWP/4 LDS.128 of lin, 2*HW FFMA2).
+template <int HW, int HWP, int NT, int MINB, int NSTAGE, bool TOPK>
+__global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ CUtensorMap tmx, const PsiArgs a) {
+    static_assert(HW % 2 == 0 && HW <= HWP && HWP % 4 == 0, "hypotheses are processed in pairs");
+    static_assert(!TOPK || NT == PSI_NT, "the top-k scratch is sized for PSI_NT threads");
+    using Smem = PsiSmem<HWP, NT, NSTAGE>;
+    using SmemAll = PsiSmemAll<HW, HWP, NT, NSTAGE, TOPK>;
+    constexpr int VTILE = Smem::VTILE;
+    constexpr int NBOX = Smem::NBOX;
+    constexpr int NWARP = NT / 32;
+    constexpr int HP = HW / 2;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SmemAll &sma = *reinterpret_cast<SmemAll *>(smem_raw);
+    Smem &sm = sma.pipe;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    (void)wid;
+    const int T = a.T, V = a.V, W = a.W;
+    const int start = a.ol > 1 ? a.ol : 1;
+    const int c0 = (a.ol == 0 ? 0 : start) / TT;
+    const int cN = (T - 1) / TT;
+    const int nchunk = cN - c0 + 1;
+    const int ntiles = a.B * a.nvt * a.G;
+    const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int nitems = my_tiles * nchunk;
+    constexpr uint32_t STAGE_BYTES = TT * VTILE * 4 + TT * HWP * 4;
+
+    auto decode_tile = [&](int tile, int &b, int &vt, int &g) {
+        g = tile % a.G;
+        tile /= a.G;
+        vt = tile % a.nvt;
+        b = tile / a.nvt;
+    };
+    auto issue = [&](int b, int vt, int g, int ci, int s) {  // chunk c0 + ci of tile (b, vt, g) into stage s
+        const int c = c0 + ci;
+        mbar_expect_tx(&sm.full[s], STAGE_BYTES);
+#pragma unroll
+        for (int bx = 0; bx < NBOX; ++bx) tma_load_2d(&sm.xs[s][bx][0][0], &tmx, vt * VTILE + bx * BOXC, b * T + c * TT, &sm.full[s]);
+        bulk_load_1d(&sm.lin[s][0][0], a.lin + ((size_t)(b * a.G + g) * a.Tpad + (size_t)c * TT) * HWP, TT * HWP * 4, &sm.full[s]);
+    };
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&sm.full[s], 1), sm.released[s] = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int k = 0; k < nitems && k < NSTAGE; ++k) {  // prologue: the first NSTAGE chunks of this CTA's sequence
+            int b, vt, g;
+            decode_tile((int)blockIdx.x + (k / nchunk) * (int)gridDim.x, b, vt, g);
+            issue(b, vt, g, k % nchunk, k);
+        }
+    }
+    __syncthreads();
+
+    const int bx = (tid * 4) / BOXC, col = (tid * 4) % BOXC;
+    int k = 0;
+    for (int ti = 0; ti < my_tiles; ++ti) {
+        int b, vt, g;
+        decode_tile((int)blockIdx.x + ti * (int)gridDim.x, b, vt, g);
+        // where chunk ci + NSTAGE of this tile lives: the same tile, or one of the next tiles of this CTA (decoded once per
+        // tile by the lane that issues, not once per chunk)
+        int nb = b, nvt_ = vt, ng = g, n_ti = ti;  // tile that the look-ahead currently points into
+        unsigned long long acc2[HP][4];  // (hyp 2p, hyp 2p+1) of token j, packed for FFMA2
+        float x0[4];
+#pragma unroll
+        for (int hp = 0; hp < HP; ++hp)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc2[hp][j] = 0ull;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x0[j] = LZ;
+
+        for (int ci = 0; ci < nchunk; ++ci, ++k) {
+            const int s = k % NSTAGE;
+            mbar_wait(&sm.full[s], (uint32_t)((k / NSTAGE) & 1));
+            if (a.ol == 0 && ci == 0) {  // r[0,0] = x_[0,0] enters log_psi as its own term (:158,165)
+                const float4 xv4 = *reinterpret_cast<const float4 *>(&sm.xs[s][bx][0][col]);
+                x0[0] = xv4.x, x0[1] = xv4.y, x0[2] = xv4.z, x0[3] = xv4.w;
+            }
+#pragma unroll
+            for (int tt = 0; tt < TT; ++tt) {
+                const float4 xv4 = *reinterpret_cast<const float4 *>(&sm.xs[s][bx][tt][col]);
+                unsigned long long pp[4];
+                {
+                    const float p0 = ex2_approx(xv4.x * LOG2E), p1 = ex2_approx(xv4.y * LOG2E);
+                    const float p2 = ex2_approx(xv4.z * LOG2E), p3 = ex2_approx(xv4.w * LOG2E);
+                    pp[0] = pack2(p0, p0), pp[1] = pack2(p1, p1), pp[2] = pack2(p2, p2), pp[3] = pack2(p3, p3);
+                }
+                unsigned long long lp2[HWP / 2];
+#pragma unroll
+                for (int q = 0; q < HWP / 4; ++q) {
+                    const ulonglong2 l2 = *reinterpret_cast<const ulonglong2 *>(&sm.lin[s][tt][q * 4]);
+                    lp2[q * 2 + 0] = l2.x, lp2[q * 2 + 1] = l2.y;
+                }
+#pragma unroll
+                for (int hp = 0; hp < HP; ++hp)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc2[hp][j] = ffma2(lp2[hp], pp[j], acc2[hp][j]);
+            }
+            // release the stage; the last warp to do so refills it with the chunk NSTAGE ahead in this CTA's sequence
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                const unsigned prev = atomicAdd(&sm.released[s], 1u);
+                if ((prev % NWARP) == NWARP - 1 && k + NSTAGE < nitems) {
+                    __threadfence_block();
+                    int nci = ci + NSTAGE;
+                    int t2 = ti;
+                    while (nci >= nchunk) nci -= nchunk, ++t2;
+                    if (t2 != n_ti) {
+                        n_ti = t2;
+                        decode_tile((int)blockIdx.x + t2 * (int)gridDim.x, nb, nvt_, ng);
+                    }
+                    issue(nb, nvt_, ng, nci, s);
+                }
+            }
+        }
+
+        const int v0 = vt * VTILE + tid * 4;
+        const int w0 = g * HW;
+        const int h0 = b * W + w0;
+        const int nhyp = min(HW, W - w0);
+        float acc[HW][4];
+#pragma unroll
+        for (int hp = 0; hp < HP; ++hp)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) unpack2(acc2[hp][j], acc[2 * hp][j], acc[2 * hp + 1][j]);
+        // the column of each hypothesis' last label sums r_prev_blank instead of r_sum: take it from k_prep_psi
+#pragma unroll
+        for (int hh = 0; hh < HW; ++hh) {
+            if (hh < nhyp) {
+                const int cj = (int)(a.last_ids[h0 + hh] - (long long)v0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (cj == j) acc[hh][j] = a.psic[h0 + hh];
+            }
+        }
+        EpiArgs e;
+        e.Gmax = a.Gmax, e.s_prev = a.s_prev, e.s_rs = a.s_rs, e.s_cs = a.s_cs, e.att = a.att, e.omw = a.omw, e.w = a.w;
+        e.log_psi = a.log_psi, e.token_scores = a.token_scores, e.joint = a.joint, e.V = V, e.blank = a.blank, e.ol = a.ol;
+        if constexpr (TOPK) {
+            float4 *list_out = a.tk.lists + ((size_t)(b * a.nvt + vt) * a.G + g) * a.tk.K;
+            epilogue_topk<HW>(e, a.tk, sma.topk.t, acc, x0, b, h0, w0, nhyp, v0, list_out, sma.topk.scal + wid * 3 * HW);
+        } else {
+            epilogue_tile<HW>(e, acc, x0, h0, nhyp, v0);
+        }
+    }
+}

@@ -142,6 +142,10 @@ class CTCPrefixScoreTH(object):
         F.log_softmax(encoder_logits) (reference :278-284) in one pass, leaving `logits` untouched.
         token_major=True keeps the posteriors as (B,V,ldt) -- a token's time series contiguous -- which is the layout the
         pre-beam (candidate) kernels gather from; the frame-major copy is then rebuilt only if a full-vocabulary call needs it."""
+        if isinstance(logits, torch.Tensor) and logits.is_floating_point() and logits.dtype != torch.float32:
+            # the reference log-softmaxes whatever dtype the encoder produced (fp16 / bf16 under autocast); the fused
+            # K-a writes a new fp32 buffer anyway, so half-precision encoder outputs are upcast instead of rejected
+            logits = logits.float()
         _require_cuda_f32(logits, "encoder_logits", 3)
         self = cls.__new__(cls)
         self._setup(logits.contiguous(), xlens, blank, eos, margin, apply_log_softmax=True, token_major=token_major)
@@ -577,8 +581,10 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
         super().__init__()
         self.pad_token_id = pad_token_id
         self.pre_beam_size = int(pre_beam_size)
-        if self.pre_beam_size < 0 or self.pre_beam_size > 64:
-            raise ValueError("pre_beam_size must be in [0, 64]")
+        if self.pre_beam_size < 0 or self.pre_beam_size > 64 or self.pre_beam_size == 1:
+            # beam search draws 2W candidates out of the W * S scored ones: S = 1 leaves fewer than 2W, and the unscored
+            # tokens it would then pick select lane 0 with a logzero prefix score -- every later state would be garbage
+            raise ValueError("pre_beam_size must be 0 (full vocabulary) or in [2, 64] (W * S >= 2W candidates are needed)")
         self.ctc_prefix_scorer = CTCPrefixScoreTH.from_logits(encoder_logits, encoder_output_lens, pad_token_id, eos_token_id,
                                                               ctc_margin, token_major=self.pre_beam_size > 0)
         if materialize_state is None:
@@ -589,6 +595,7 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
         self.ctc_weight = ctc_weight
         self.ctc_states = None
         self._best_ids = None    # (B,W) ids for the next index_select_state, from set_beam_idx()
+        self._prev_ids = None    # input_ids of the previous call: parents are recovered from them when nobody reports beam indices
         self._prefetched = None  # (last-token tensor, selected state, event) produced by prefetch_state()
         self._side_stream = None
         self._prefetch_bufs = None
@@ -624,7 +631,31 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
         if self.use_beam_idx and self._best_ids is not None:
             ids, self._best_ids = self._best_ids + last, None
             return ids
+        if self.use_beam_idx and self.ctc_states is not None:
+            # Nobody called set_beam_idx() (HF generate() without a KV cache never calls _reorder_cache; a custom loop may
+            # not forward beam_idx).  In pre-beam mode a token is only scored for the hypothesis that proposed it, so the
+            # reference's token-only selection would read a column that was never computed: recover every row's parent
+            # by matching its prefix against the rows of the previous call, or refuse.
+            parents = self._parents_by_prefix(input_ids)
+            return parents * self.ctc_prefix_scorer.odim + last
         return last
+
+    def _parents_by_prefix(self, input_ids):
+        """(B,W) index of the hypothesis of the previous call that every current row extends (first match inside its own
+        utterance; rows with equal prefixes carry equal states).  Raises when the previous ids are unknown."""
+        prev = self._prev_ids
+        W = self.num_beams
+        if prev is None or prev.shape[0] != input_ids.shape[0] or prev.shape[1] != input_ids.shape[1] - 1:
+            raise RuntimeError("use_beam_idx is set but no beam indices were supplied for this step (call set_beam_idx(beam_idx) from "
+                               "the model's _reorder_cache, or prefetch_state(..., best_ids)) and the rows of the previous call are "
+                               "not available to recover them from")
+        L1 = prev.shape[1]
+        cur = input_ids[:, :L1].reshape(-1, W, 1, L1)
+        old = prev.reshape(-1, 1, W, L1)
+        eq = (cur == old).all(dim=-1)                      # (B, W_cur, W_prev)
+        found = eq.any(dim=-1)
+        # a row whose prefix matches nothing (cannot happen under beam search) falls back to hypothesis 0 like the reference
+        return torch.where(found, eq.to(torch.uint8).argmax(dim=-1), torch.zeros_like(found, dtype=torch.long))
 
     def _select(self, input_ids):
         if self._prefetched is not None:
@@ -650,6 +681,8 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
         sc = self.ctc_prefix_scorer
         work = self._check_scores(scores)
         self._select(input_ids)
+        if self.use_beam_idx:
+            self._prev_ids = input_ids
         need_ts = self.apply_eos_space_trick or self.debug
         if self.pre_beam_size > 0:
             ctc_scores, next_token_scores = self._call_pre_beam(input_ids, work, need_ts)
@@ -715,6 +748,8 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
         if work is not scores:
             raise ValueError("scores must be contiguous")
         self._select(input_ids)
+        if self.use_beam_idx:
+            self._prev_ids = input_ids
         ids, cand_att = self._top_candidates(work)
         _, _, cand_joint, self.ctc_states, _ = self.ctc_prefix_scorer._score_candidates(input_ids, self.ctc_states, ids, cand_att,
                                                                                       self.ctc_weight)

@@ -59,6 +59,34 @@ def assert_parity(new, ref, what="", atol=ATOL, rtol=RTOL, ref64=None):
     return float(err.max()) if err.size else 0.0
 
 
+def f64_errors(new, ref64):
+    """|new - fp64 run| on the finite class of the fp64 run (zero elsewhere); the logzero / +1e9 classes are checked."""
+    a, r = to_np(new).astype(np.float64), to_np(ref64).astype(np.float64)
+    assert a.shape == r.shape, f"shape {a.shape} vs {r.shape}"
+    assert not np.isnan(a).any(), "NaN in output"
+    assert (a[r <= LZ_CLASS] <= LZ_CLASS).all(), "logzero class not preserved against the fp64 run"
+    assert (a[r >= -LZ_CLASS] >= -LZ_CLASS).all(), "+1e9 class not preserved against the fp64 run"
+    return np.abs(a - r) * (np.abs(r) < -LZ_CLASS)
+
+
+def assert_no_further_from_fp64(new, yardstick, ref64, what="", floor=ATOL, factor=2.0):
+    """Two fp32 evaluation orders of the same recursion (e.g. the sequential and the time-parallel state selection) are
+    adjudicated by an fp64 run of the reference algorithm: `new` may be at most max(floor, factor x the worst error of
+    `yardstick`) away from fp64.  Returns (worst error of new, worst error of the yardstick)."""
+    e_new, e_yard = f64_errors(new, ref64), f64_errors(yardstick, ref64)
+    bound = max(floor, factor * float(e_yard.max()) if e_yard.size else 0.0)
+    assert (e_new.max() if e_new.size else 0.0) <= bound, (f"{what}: {e_new.max():.3e} from fp64, the yardstick implementation is "
+                                                           f"{e_yard.max():.3e} from it (bound {bound:.3e})")
+    return float(e_new.max()) if e_new.size else 0.0, float(e_yard.max()) if e_yard.size else 0.0
+
+
+def select_mode(mode=-1):
+    """Query (-1) or set (0 sequential, 1 time-parallel) the lazy state-selection kernel of the library; returns the previous mode."""
+    from huggingface_asr_b200 import _lib
+
+    return _lib.lib().ctcps_set_select_pscan(mode)
+
+
 class Backend:
     """What a replay needs from an implementation."""
     device = "cpu"

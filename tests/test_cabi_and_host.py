@@ -135,9 +135,9 @@ def test_product_never_imports_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in src.replace("the oracle", "").replace("(oracle", "").lower() or f == "beam_search.py" or \
-                    "import oracle" not in src and "from oracle" not in src, f"{f} references the oracle"
-                assert "from oracle" not in src and "import oracle" not in src
+                # no import, no dlopen / ctypes load, no path into oracle/: comments may mention the oracle, code may not reach it
+                for needle in ("from oracle", "import oracle", "oracle/", "oracle.", "libctcps_oracle", "oracle/_build"):
+                    assert needle not in src, f"{os.path.relpath(os.path.join(dirpath, f), ROOT)} reaches into the oracle ({needle!r})"
     code = "import sys; import huggingface_asr_b200.decoding.ctc_scorer, huggingface_asr_b200.beam_search, huggingface_asr_b200.sharding; " \
            "assert not any(m.startswith('oracle') for m in sys.modules), 'oracle imported by the product'"
     subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
@@ -150,17 +150,17 @@ def test_reference_frame_counts():
     assert [frames_for_seconds(s, 1) for s in (10, 15, 30)] == [250, 375, 750]
 
 
-def test_ab_switches_query_set_restore():
-    """ctcps_set_psi_split / ctcps_set_select_pscan: any argument other than 0 / 1 only queries; both default to the validated kernels."""
+def test_ab_switch_query_set_restore():
+    """ctcps_set_select_pscan: any argument other than 0 / 1 only queries; the default is the time-parallel kernel."""
     from huggingface_asr_b200 import _lib
 
     L = _lib.lib()
-    for fn in (L.ctcps_set_psi_split, L.ctcps_set_select_pscan):
-        prev = fn(-1)
-        assert prev in (0, 1)
-        assert fn(1) == prev and fn(7) == 1 and fn(0) == 1 and fn(-1) == 0
-        fn(prev)
+    fn = L.ctcps_set_select_pscan
+    prev = fn(-1)
+    assert prev in (0, 1)
+    assert fn(1) == prev and fn(7) == 1 and fn(0) == 1 and fn(-1) == 0
+    fn(prev)
     import os
 
-    if "CTCPS_PSI_SPLIT" not in os.environ and "CTCPS_SELECT_PSCAN" not in os.environ:
-        assert L.ctcps_set_psi_split(-1) == 0 and L.ctcps_set_select_pscan(-1) == 0
+    if "CTCPS_SELECT_PSCAN" not in os.environ:
+        assert L.ctcps_set_select_pscan(-1) == 1

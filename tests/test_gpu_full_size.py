@@ -44,6 +44,8 @@ def test_full_size_properties(cfg_name, B):
     lazy = CTCRescorerLogitsProcessor(logits.to(dev), lens.to(dev), BLANK, EOS, 0, 0.3, W, -1, False, 1.0, materialize_state=False)
     sample = [0, B // 3, B - 1]
     cpu = orc.OracleCTCRescorerLogitsProcessor(logits[sample].clone(), lens[sample].clone(), BLANK, EOS, 0, 0.3, W)
+    cpu64 = orc.OracleCTCRescorerLogitsProcessor(logits[sample].double(), lens[sample].clone(), BLANK, EOS, 0, 0.3, W)
+    prev_mode = parity.select_mode(-1)
     rows = torch.tensor([b * W + w for b in sample for w in range(W)])
 
     ids = torch.zeros((BW, 1), dtype=torch.long)
@@ -54,6 +56,7 @@ def test_full_size_properties(cfg_name, B):
         out_m = mat(ids.to(dev), att.to(dev))
         out_l = lazy(ids.to(dev), att.to(dev))
         out_c = cpu(ids[rows], att[rows].clone())
+        cpu64(ids[rows], att[rows].double())
         # (1) sample rows vs the oracle
         parity.assert_parity(out_m[rows.to(dev)], out_c, f"{cfg_name} step {n} joint (materialised) vs oracle")
         parity.assert_parity(out_l[rows.to(dev)], out_c, f"{cfg_name} step {n} joint (lazy) vs oracle")
@@ -87,8 +90,17 @@ def test_full_size_properties(cfg_name, B):
         # survivors: gathered vs recomputed (bit-exact), and the prefix score for the conservation check of the next step
         best = ids[:, -1].reshape(-1, W).to(dev)
         sel_m = mat.ctc_prefix_scorer.index_select_state(mat.ctc_states, best)
+        parity.select_mode(0)  # sequential recompute: the same operations in the same order as the materialising kernel
         sel_l = lazy.ctc_prefix_scorer.index_select_state(lazy.ctc_states, best)
         assert torch.equal(sel_m[0], sel_l[0]), "recomputed survivors differ from the gathered ones"
+        parity.select_mode(1)  # time-parallel recompute (library default): adjudicated by the fp64 oracle on the sample rows
+        sel_p = lazy.ctc_prefix_scorer.index_select_state(lazy.ctc_states, best)
+        sel64 = cpu64.ctc_prefix_scorer.index_select_state(cpu64.ctc_states, ids[rows][:, -1].reshape(-1, W))
+        worst = parity.assert_no_further_from_fp64(sel_p[0][:, :, rows.to(dev)], sel_m[0][:, :, rows.to(dev)], sel64[0],
+                                                   f"{cfg_name} step {n} time-parallel survivors")
+        print(f"{cfg_name} step {n}: survivors vs fp64: time-parallel {worst[0]:.2e}, gathered {worst[1]:.2e}")
+        assert (sel_p[1][:, 0] - sel_m[1][:, 0]).abs().max().item() <= 2e-5
+        parity.select_mode(prev_mode)
         # log_psi is summed in a different association by the two kernels: ulp-level differences only
         assert (sel_m[1][:, 0] - sel_l[1][:, 0]).abs().max().item() <= 2e-5
         s_prev_next = sel_m[1][:, 0].double()

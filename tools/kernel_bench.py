@@ -50,7 +50,6 @@ def main():
     ap.add_argument("--ol", type=int, default=20)
     ap.add_argument("--only", default="")
     ap.add_argument("--pre-beam", type=int, default=32)
-    ap.add_argument("--psi-split", type=int, default=-1, help="0: k_psi_full (whole tiles), 1: k_psi_split; default: library default")
     ap.add_argument("--select-pscan", type=int, default=-1, help="0: k_select_lazy_scan (sequential), 1: k_select_lazy_pscan; default: library default")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
@@ -58,7 +57,6 @@ def main():
     BW = B * W
     dev = torch.device("cuda")
     L = _lib.lib()
-    L.ctcps_set_psi_split(args.psi_split)
     L.ctcps_set_select_pscan(args.select_pscan)
     logits, lens, _ = make_encoder_logits(B, T, V, cfg.kind, cfg.ragged, seed=1)
     logits, lens = logits.to(dev), lens.to(dev)
