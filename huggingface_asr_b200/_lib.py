@@ -79,6 +79,8 @@ SIGNATURES = {
     "ctcps_error_string": [_i],
     "ctcps_padded_ld": [_i],
     "ctcps_set_select_pscan": [_i],
+    "ctcps_set_psi_prefetch": [_i],
+    "ctcps_set_psi_max_group": [_i],
     "ctcps_workspace_bytes": [_i, _i, _i, _i, _i, ctypes.POINTER(_sz)],
     "ctcps_init": [_p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p],
     "ctcps_log_softmax": [_p, _i, _p, _i, _i, _i, _p],

@@ -126,6 +126,10 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+// TMA prefetch of a box into L2 (no shared-memory destination, no barrier): SASS UTMAPF.L2
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst)),
@@ -1303,17 +1307,36 @@ __device__ __forceinline__ void beam_bookkeep(const Cand *top, BeamShared &bs, c
     __syncthreads();
 
     // ---- copies: finished prefixes into the pool, reordered + extended rows into ids_next ----------
-    const int nt = blockDim.x;
-    for (int q = 0; q < bs.n_pool_jobs; ++q) {
-        const int64_t *src = o.ids_cur + ((size_t)b * W + bs.job_src[q]) * o.ld_ids + 1;  // drop bos
-        int64_t *dst = o.pool_seqs + ((size_t)b * W + bs.job_dst[q]) * o.ld_pool;
-        for (int k = tid; k < L - 1; k += nt) dst[k] = src[k];
-    }
-    for (int w = 0; w < W; ++w) {
-        const int64_t *src = o.ids_cur + ((size_t)b * W + bs.next_src[w]) * o.ld_ids;
-        int64_t *dst = o.ids_next + ((size_t)b * W + w) * o.ld_ids;
-        for (int k = tid; k < L; k += nt) dst[k] = src[k];
-        if (tid == 0) dst[L] = bs.next_tok[w];
+    // One warp per row, the row's loads issued together before its stores (round 1 walked the W rows one after the other with
+    // the whole CTA: W dependent global round trips, 10-20 us of the step at W = 10-20).
+    const int nt = blockDim.x, nw = nt >> 5, wid = tid >> 5;
+    const int64_t *__restrict__ ids_cur = o.ids_cur;
+    auto copy_row = [&](const int64_t *__restrict__ src, int64_t *__restrict__ dst, int n) {
+        for (int k0 = 0; k0 < n; k0 += 128) {
+            int64_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + u * 32 + lane;
+                v[u] = k < n ? src[k] : 0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int k = k0 + u * 32 + lane;
+                if (k < n) dst[k] = v[u];
+            }
+        }
+    };
+    const int njobs = bs.n_pool_jobs;
+    for (int q = wid; q < njobs + W; q += nw) {
+        if (q < njobs) {
+            copy_row(ids_cur + ((size_t)b * W + bs.job_src[q]) * o.ld_ids + 1 /* drop bos */,
+                     o.pool_seqs + ((size_t)b * W + bs.job_dst[q]) * o.ld_pool, L - 1);
+        } else {
+            const int w = q - njobs;
+            int64_t *dst = o.ids_next + ((size_t)b * W + w) * o.ld_ids;
+            copy_row(ids_cur + ((size_t)b * W + bs.next_src[w]) * o.ld_ids, dst, L);
+            if (lane == 0) dst[L] = bs.next_tok[w];
+        }
     }
 
     // ---- the last utterance to finish its step publishes (step, #done utterances) to host-visible memory
@@ -1588,15 +1611,28 @@ Workspace plan_workspace(int B, int T, int W) {
 // lazy mode: hypotheses per thread of k_psi_full (even: packed FMAs pair two hypotheses) and the padded width of its lin
 // stream.  Up to 20 hypotheses in one group (W = 20 reads and exponentiates its x tile once); wider beams are split into
 // the group size with the fewest padded lanes.
+int g_psi_max_group = -1;  // widest hypothesis group k_psi_full may use (CTCPS_PSI_MAX_GROUP / ctcps_set_psi_max_group; default 20)
+int psi_max_group() {
+    if (g_psi_max_group < 0) {
+        const char *ev = getenv("CTCPS_PSI_MAX_GROUP");
+        g_psi_max_group = ev != nullptr ? atoi(ev) : 20;
+        if (g_psi_max_group < 2 || g_psi_max_group > 20) g_psi_max_group = 20;
+    }
+    return g_psi_max_group;
+}
 void pick_hw_psi(int W, int *HW, int *HWP, int *G) {
-    static const int cand[] = {20, 16, 12, 10, 8, 6, 4, 2};
+    static const int all[] = {20, 16, 12, 10, 8, 6, 4, 2};
+    int cand[8], nc = 0;
+    for (int hw : all)
+        if (hw <= psi_max_group() || hw == 2) cand[nc++] = hw;
     int best = 2;
-    if (W <= 20) {
-        for (int hw : cand)
-            if (hw >= W) best = hw;  // the smallest group that holds every hypothesis
+    if (W <= cand[0]) {
+        for (int i = 0; i < nc; ++i)
+            if (cand[i] >= W) best = cand[i];  // the smallest group that holds every hypothesis
     } else {
         int best_pad = 1 << 30;
-        for (int hw : cand) {
+        for (int i = 0; i < nc; ++i) {
+            const int hw = cand[i];
             const int pad = ((W + hw - 1) / hw) * hw - W;
             if (pad < best_pad) best = hw, best_pad = pad;  // ties: the widest group (listed first)
         }
@@ -1729,6 +1765,19 @@ int select_pscan_mode() {
         g_select_pscan = (ev != nullptr && ev[0] == '0') ? 0 : 1;
     }
     return g_select_pscan;
+}
+
+// chunks (8 frames x 512 tokens = 16 KB) that k_psi_full prefetches into L2 beyond its shared-memory ring;
+// CTCPS_PSI_PREFETCH / ctcps_set_psi_prefetch.  Default 0: measured on B200 (profiles/r2d_psi_ab.md) the look-ahead does not
+// help -- 0 / 2 / 4 / 8 chunks: 0.371 / 0.376 / 0.390 / 0.489 ms per C2 scoring call -- the queue depth is not what limits the stream.
+int g_psi_prefetch = -1;
+int psi_prefetch_chunks() {
+    if (g_psi_prefetch < 0) {
+        const char *ev = getenv("CTCPS_PSI_PREFETCH");
+        g_psi_prefetch = ev != nullptr ? atoi(ev) : 0;
+        if (g_psi_prefetch < 0 || g_psi_prefetch > 64) g_psi_prefetch = 0;
+    }
+    return g_psi_prefetch;
 }
 
 // The descriptor only depends on (pointer, ldx, B*T, V): a decode makes one scoring call per output token on the same
@@ -1951,6 +2000,18 @@ int ctcps_set_select_pscan(int mode) {
     return prev;
 }
 
+int ctcps_set_psi_max_group(int hyps) {
+    const int prev = psi_max_group();
+    if (hyps >= 2 && hyps <= 20) g_psi_max_group = hyps;
+    return prev;
+}
+
+int ctcps_set_psi_prefetch(int chunks) {
+    const int prev = psi_prefetch_chunks();
+    if (chunks >= 0 && chunks <= 64) g_psi_prefetch = chunks;
+    return prev;
+}
+
 int ctcps_workspace_bytes(int B, int T, int V, int W, int S, size_t *out_bytes) {
     (void)V;
     (void)S;
@@ -2132,6 +2193,7 @@ static int score_lazy_impl(const float *x_logp, int ldx, const float *r_prev, co
     // was splitting the frame range of the last wave's tiles across CTAs (k_psi_split, removed in round 2: not faster on
     // any BASELINE shape, profiles/r1x_kernels_ncu.md section 3).
     a.nvt = (V + PSI_NT * 4 - 1) / (PSI_NT * 4);
+    a.prefetch = psi_prefetch_chunks();
     a.tk.beam_scores = nullptr, a.tk.lists = nullptr, a.tk.log_psi0 = nullptr, a.tk.K = 0;
     if (tk != nullptr) {
         a.tk = *tk;

@@ -18,9 +18,11 @@
 //     instead of one register move per hypothesis (10 at W = 10, 20 at W = 20);
 //   * up to 20 hypotheses per thread: a W = 20 tile is no longer processed by two hypothesis groups that each re-read the
 //     x tile from L2 and recompute exp(x) (round 1: C4 was MUFU / issue-bound at 0.46 of the HBM peak);
-//   * the warp that releases a pipeline stage LAST (a shared-memory ticket) refills it with TMA at once; round 1 made
-//     thread 0 both compute and issue, so a refill waited until warp 0 had finished its own chunk, and it paid three
-//     integer divisions per chunk -- the tile decode now happens once per tile;
+//   * thread 0 still issues the TMA loads (a refill by whichever warp releases a stage last, through a shared-memory ticket,
+//     was measured: the ticket's return value stalls every warp once per chunk -- slower on the small shapes), but it now
+//     walks the chunk sequence with incremental cursors (round 1 paid three integer divisions per chunk) and keeps a second
+//     cursor further ahead that prefetches chunks into L2 (UTMAPF): ncu showed 24 % of the warp samples spinning on the
+//     `full` barrier -- the ring (197 KB per SM, two thirds of it in flight at best) is too short a queue for HBM;
 //   * TOPK mode (native decode loop): the epilogue ranks the tile's 512 x HW joint scores (+ running beam scores) and
 //     publishes the tile's best 2W candidates; (BW,V) joint / log_psi tensors are never written or re-read, and the
 //     separate per-row top-2W kernel of round 1 disappears.  The beam step merges nvt x G short sorted lists.
@@ -43,6 +45,7 @@ struct PsiArgs {
     float omw, w;
     float *log_psi, *token_scores, *joint;
     int B, W, T, V, blank, ol, G, Tpad, nvt;
+    int prefetch;        // chunks of L2 look-ahead beyond the shared-memory ring (0 = none)
     PsiTopk tk;
 };
 
@@ -56,7 +59,7 @@ struct PsiSmem {
     alignas(128) float xs[NSTAGE][NBOX][TT][BOXC];
     alignas(16) float lin[NSTAGE][TT][HWP];
     alignas(8) uint64_t full[NSTAGE];
-    unsigned int released[NSTAGE];  // warps that have finished reading the stage (monotone ticket)
+    alignas(8) uint64_t empty[NSTAGE];
 };
 
 // one warp per (padded) hypothesis: lin stream, Gmax and the last-label column sum
@@ -330,10 +333,9 @@ __device__ __forceinline__ void epilogue_topk(const EpiArgs &e, const PsiTopk &t
 
 // Persistent kernel: grid = #SMs x resident CTAs, CTA i walks tiles i, i+grid, ... (tile = (utterance, 512-token tile,
 // hypothesis group)).  The chunks of all its tiles form one flat sequence kept NSTAGE stages ahead of the consumers with
-// TMA: a stage is refilled by whichever warp is the last to finish reading it (ticket in shared memory), so a refill
-// never waits for a particular warp and the warps of a CTA never meet at a CTA-wide barrier inside the stream.  The lin
-// stream is zero outside the summed frame range, which makes the inner loop branch-free:
-//   8 frames x (1 LDS.128 of x, 4 FMUL + 4 ex2, 4 MOV, HWP/4 LDS.128 of lin, 2*HW FFMA2).
+// TMA; stages are handed back through `empty` mbarriers (one arrival per warp), so the warps of a CTA never meet at a
+// CTA-wide barrier inside the stream.  The lin stream is zero outside the summed frame range, which makes the inner loop
+// branch-free: 8 frames x (1 LDS.128 of x, 4 FMUL + 4 ex2, HWP/4 LDS.128 of lin, 2*HW FFMA2 with a scalar operand).
 template <int HW, int HWP, int NT, int MINB, int NSTAGE, bool TOPK>
 __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ CUtensorMap tmx, const PsiArgs a) {
     static_assert(HW % 2 == 0 && HW <= HWP && HWP % 4 == 0, "hypotheses are processed in pairs");
@@ -365,22 +367,57 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
         vt = tile % a.nvt;
         b = tile / a.nvt;
     };
-    auto issue = [&](int b, int vt, int g, int ci, int s) {  // chunk c0 + ci of tile (b, vt, g) into stage s
-        const int c = c0 + ci;
+    // Thread 0 walks the CTA's flat chunk sequence twice ahead of the consumers, with two cursors that advance
+    // incrementally (a tile is decoded once, when a cursor enters it -- no division per chunk):
+    //   `is`  the next item to load into the shared-memory ring (NSTAGE items ahead of the one being consumed);
+    //   `pf`  the next item to prefetch into L2 with TMA (a.prefetch further items ahead).  The ring bounds what can
+    //         be in flight towards shared memory (4 CTAs x 3 stages x 16 KB per SM, a third of it being read at any time);
+    //         the L2 prefetches carry the rest of the HBM queue depth, and the ring's own loads then mostly hit L2.
+    struct Cursor {
+        int k, ti, ci, b, vt, g;
+    };
+    auto cursor_enter = [&](Cursor &c) {
+        if (c.ti < my_tiles) decode_tile((int)blockIdx.x + c.ti * (int)gridDim.x, c.b, c.vt, c.g);
+    };
+    auto cursor_next = [&](Cursor &c) {
+        ++c.k;
+        if (++c.ci == nchunk) {
+            c.ci = 0;
+            ++c.ti;
+            cursor_enter(c);
+        }
+    };
+    auto issue = [&](const Cursor &c) {  // chunk c0 + c.ci of tile (c.b, c.vt, c.g) into stage c.k % NSTAGE
+        const int s = c.k % NSTAGE;
+        const int ch = c0 + c.ci;
         mbar_expect_tx(&sm.full[s], STAGE_BYTES);
 #pragma unroll
-        for (int bx = 0; bx < NBOX; ++bx) tma_load_2d(&sm.xs[s][bx][0][0], &tmx, vt * VTILE + bx * BOXC, b * T + c * TT, &sm.full[s]);
-        bulk_load_1d(&sm.lin[s][0][0], a.lin + ((size_t)(b * a.G + g) * a.Tpad + (size_t)c * TT) * HWP, TT * HWP * 4, &sm.full[s]);
+        for (int bx = 0; bx < NBOX; ++bx)
+            tma_load_2d(&sm.xs[s][bx][0][0], &tmx, c.vt * VTILE + bx * BOXC, c.b * T + ch * TT, &sm.full[s]);
+        bulk_load_1d(&sm.lin[s][0][0], a.lin + ((size_t)(c.b * a.G + c.g) * a.Tpad + (size_t)ch * TT) * HWP, TT * HWP * 4, &sm.full[s]);
     };
+    auto prefetch = [&](const Cursor &c) {
+        const int ch = c0 + c.ci;
+#pragma unroll
+        for (int bx = 0; bx < NBOX; ++bx) tma_prefetch_2d(&tmx, c.vt * VTILE + bx * BOXC, c.b * T + ch * TT);
+    };
+    Cursor is = {0, 0, 0, 0, 0, 0}, pf = {0, 0, 0, 0, 0, 0};
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(&sm.full[s], 1), sm.released[s] = 0;
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&sm.full[s], 1), mbar_init(&sm.empty[s], NWARP);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int k = 0; k < nitems && k < NSTAGE; ++k) {  // prologue: the first NSTAGE chunks of this CTA's sequence
-            int b, vt, g;
-            decode_tile((int)blockIdx.x + (k / nchunk) * (int)gridDim.x, b, vt, g);
-            issue(b, vt, g, k % nchunk, k);
+        if (nitems > 0) {
+            cursor_enter(is);
+            while (is.k < nitems && is.k < NSTAGE) {  // prologue: fill the ring
+                issue(is);
+                cursor_next(is);
+            }
+            pf = is;
+            while (pf.k < nitems && pf.k < NSTAGE + a.prefetch) {  // and start the L2 look-ahead
+                prefetch(pf);
+                cursor_next(pf);
+            }
         }
     }
     __syncthreads();
@@ -390,9 +427,6 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
     for (int ti = 0; ti < my_tiles; ++ti) {
         int b, vt, g;
         decode_tile((int)blockIdx.x + ti * (int)gridDim.x, b, vt, g);
-        // where chunk ci + NSTAGE of this tile lives: the same tile, or one of the next tiles of this CTA (decoded once per
-        // tile by the lane that issues, not once per chunk)
-        int nb = b, nvt_ = vt, ng = g, n_ti = ti;  // tile that the look-ahead currently points into
         unsigned long long acc2[HP][4];  // (hyp 2p, hyp 2p+1) of token j, packed for FFMA2
         float x0[4];
 #pragma unroll
@@ -429,21 +463,18 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
 #pragma unroll
                     for (int j = 0; j < 4; ++j) acc2[hp][j] = ffma2(lp2[hp], pp[j], acc2[hp][j]);
             }
-            // release the stage; the last warp to do so refills it with the chunk NSTAGE ahead in this CTA's sequence
+            // hand the stage back (one arrival per warp); thread 0 refills it once every warp has, and moves the L2 look-ahead on
             __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                const unsigned prev = atomicAdd(&sm.released[s], 1u);
-                if ((prev % NWARP) == NWARP - 1 && k + NSTAGE < nitems) {
-                    __threadfence_block();
-                    int nci = ci + NSTAGE;
-                    int t2 = ti;
-                    while (nci >= nchunk) nci -= nchunk, ++t2;
-                    if (t2 != n_ti) {
-                        n_ti = t2;
-                        decode_tile((int)blockIdx.x + t2 * (int)gridDim.x, nb, nvt_, ng);
-                    }
-                    issue(nb, nvt_, ng, nci, s);
+            if (lane == 0) mbar_arrive(&sm.empty[s]);
+            if (tid == 0) {
+                if (is.k < nitems) {  // is.k == k + NSTAGE: the item that reuses this stage
+                    mbar_wait(&sm.empty[s], (uint32_t)((k / NSTAGE) & 1));
+                    issue(is);
+                    cursor_next(is);
+                }
+                if (pf.k < nitems) {
+                    prefetch(pf);
+                    cursor_next(pf);
                 }
             }
         }

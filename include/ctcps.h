@@ -57,6 +57,17 @@ int ctcps_padded_ld(int n);
  * scores agree to ~1e-6.  Returns the previous mode; any other argument only queries.  Process-wide. */
 int ctcps_set_select_pscan(int mode);
 
+/* L2 look-ahead of the lazy scoring kernel (ctcps_score_lazy / _topk): how many 16 KB chunks (8 frames x 512 tokens) beyond
+ * its shared-memory ring every CTA prefetches into L2 with TMA.  Default 0 = none (env CTCPS_PSI_PREFETCH): measured, the
+ * look-ahead only costs (0 / 2 / 4 / 8 chunks: 0.371 / 0.376 / 0.390 / 0.489 ms at C2); kept as an A/B switch.  Returns the
+ * previous value; an argument outside [0, 64] only queries.  Process-wide; results do not depend on it. */
+int ctcps_set_psi_prefetch(int chunks);
+
+/* Widest hypothesis group one thread of the lazy scoring kernel accumulates (2..20, default 20, env CTCPS_PSI_MAX_GROUP):
+ * beams wider than the group are split into several groups that each stream the x tile.  Changes the layout of the scoring
+ * workspace: set it before the first call of a decode, not in between.  Returns the previous value; other arguments query. */
+int ctcps_set_psi_max_group(int hyps);
+
 /* Bytes of scratch ctcps_score needs for these sizes. */
 int ctcps_workspace_bytes(int B, int T, int V, int W, int S, size_t *out_bytes);
 
