@@ -28,19 +28,32 @@ from typing import Callable
 import torch
 
 
-def _finalize(input_ids, beam_scores, pool_scores, pool_seqs, pool_lens, done, B, W, max_length, pad, length_penalty, steps):
-    """BeamSearchScorer.finalize: utterances still running contribute their W open beams; best hypothesis wins."""
+def _finalize(input_ids, beam_scores, pool_scores, pool_seqs, pool_lens, done, B, W, max_length, pad, length_penalty, steps,
+              num_return_sequences=1):
+    """BeamSearchScorer.finalize: utterances still running contribute their W open beams; the best hypothesis wins.  With
+    num_return_sequences = R > 1 the R best of (finished pool, open beams) are returned as well, best first -- what
+    do_generate asks of generate() (general_utils.py:197: num_return_sequences, sequences_scores)."""
     dev = input_ids.device
     NEG = float("-inf")
     L = input_ids.shape[1]
+    R = int(num_return_sequences)
+    if R < 1 or R > W:
+        raise ValueError(f"num_return_sequences must be in [1, num_beams = {W}], got {R}")
     open_scores = torch.where(done.view(B, 1), torch.full_like(beam_scores, NEG), beam_scores / float(L - 1) ** length_penalty)
     open_seqs = torch.nn.functional.pad(input_ids.reshape(B, W, L)[:, :, 1:], (0, max_length - (L - 1)), value=pad)
     all_scores = torch.cat([pool_scores, open_scores], dim=1)
-    best = all_scores.argmax(dim=1)
     all_seqs = torch.cat([pool_seqs, open_seqs], dim=1)
     all_lens = torch.cat([pool_lens, torch.full((B, W), L - 1, dtype=torch.long, device=dev)], dim=1)
+    best = all_scores.argmax(dim=1)
     ar = torch.arange(B, device=dev)
-    return BeamSearchOutput(all_seqs[ar, best], all_lens[ar, best], all_scores[ar, best], steps)
+    out = BeamSearchOutput(all_seqs[ar, best], all_lens[ar, best], all_scores[ar, best], steps)
+    if R > 1:
+        # stable descending order: equal scores keep pool-before-open, lower slot first (argmax above picks the same first entry)
+        order = torch.sort(all_scores, dim=1, descending=True, stable=True).indices[:, :R]
+        out.nbest_scores = torch.gather(all_scores, 1, order)
+        out.nbest_lengths = torch.gather(all_lens, 1, order)
+        out.nbest_sequences = torch.gather(all_seqs, 1, order.unsqueeze(-1).expand(B, R, all_seqs.shape[-1]))
+    return out
 
 
 @dataclass
@@ -49,13 +62,16 @@ class BeamSearchOutput:
     lengths: torch.Tensor    # (B,) int64
     scores: torch.Tensor     # (B,) fp32, length-normalised
     steps: int               # processor calls made
+    nbest_sequences: torch.Tensor | None = None  # (B, R, max_len) when num_return_sequences = R > 1, best first
+    nbest_lengths: torch.Tensor | None = None    # (B, R)
+    nbest_scores: torch.Tensor | None = None     # (B, R); -inf where an utterance has fewer than R hypotheses
 
 
 @torch.no_grad()
 def joint_beam_search(processor: Callable, decoder_log_probs: Callable[[torch.Tensor, int], torch.Tensor], batch: int,
                       num_beams: int, vocab: int, bos: int, eos: int, pad: int, max_length: int = 512,
                       length_penalty: float = 1.0, device: torch.device | str = "cpu",
-                      sync_every: int = 1) -> BeamSearchOutput:
+                      sync_every: int = 1, num_return_sequences: int = 1) -> BeamSearchOutput:
     """Run the decode loop; `decoder_log_probs(input_ids, step)` -> (B*W, V) log-probs (a fresh tensor)."""
     B, W, V = batch, num_beams, vocab
     dev = torch.device(device)
@@ -122,7 +138,8 @@ def joint_beam_search(processor: Callable, decoder_log_probs: Callable[[torch.Te
         if steps % sync_every == 0 and bool(done.all()):
             break
 
-    return _finalize(input_ids, beam_scores, pool_scores, pool_seqs, pool_lens, done, B, W, max_length, pad, length_penalty, steps)
+    return _finalize(input_ids, beam_scores, pool_scores, pool_seqs, pool_lens, done, B, W, max_length, pad, length_penalty, steps,
+                     num_return_sequences)
 
 
 _RING = 8
@@ -183,7 +200,8 @@ def _wait_ring(ring_np, tag: int, stream, what: str, timeout_s: float = 120.0) -
 @torch.no_grad()
 def joint_beam_search_fused(processor: Callable, decoder_log_probs: Callable[[torch.Tensor, int], torch.Tensor], batch: int,
                             num_beams: int, vocab: int, bos: int, eos: int, pad: int, max_length: int = 512,
-                            length_penalty: float = 1.0, device: torch.device | str = "cuda", done_check_lag: int = 0) -> BeamSearchOutput:
+                            length_penalty: float = 1.0, device: torch.device | str = "cuda", done_check_lag: int = 0,
+                            num_return_sequences: int = 1) -> BeamSearchOutput:
     """Same loop as joint_beam_search with the whole beam update of a step in ONE kernel (ctcps_beam_step).
 
     The processor boundary is unchanged: `processor(input_ids (BW,L), log_probs (BW,V))` is still called once per step --
@@ -262,14 +280,14 @@ def joint_beam_search_fused(processor: Callable, decoder_log_probs: Callable[[to
             if _wait_ring(ring_np, tag_base + look, stream, "joint_beam_search_fused") == B:
                 break
     return _finalize(ids[cur][:, :L], beam_scores, pool_scores, pool_seqs, pool_lens, done.bool(), B, W, max_length, pad,
-                     length_penalty, steps)
+                     length_penalty, steps, num_return_sequences)
 
 
 @torch.no_grad()
 def joint_beam_search_native(processor, decoder_log_probs: Callable[[torch.Tensor, int], torch.Tensor], batch: int, num_beams: int,
                              vocab: int, bos: int, eos: int, pad: int, max_length: int = 512, length_penalty: float = 1.0,
                              device: torch.device | str = "cuda", done_check_lag: int = 1, score_timing: list | None = None,
-                             fuse_topk: bool = True) -> BeamSearchOutput:
+                             fuse_topk: bool = True, num_return_sequences: int = 1) -> BeamSearchOutput:
     """joint_beam_search_fused with ONE host call per decode step (ctcps_decode_step): [top-S candidates,] prefix scoring +
     joint combine, beam step and -- on a side stream, under the next decoder forward pass -- the lazy state selection.
     Same kernels and results as the fused loop; the 5-10 ctypes / torch calls it makes per step cost more host time
@@ -404,7 +422,7 @@ def joint_beam_search_native(processor, decoder_log_probs: Callable[[torch.Tenso
                     if _wait_ring(ring_np, tag_base + look, stream, "joint_beam_search_native") == B:
                         break
             out = _finalize(ids[cur][:, :L], beam_scores, pool_scores, pool_seqs, pool_lens, done.bool(), B, W, max_length, pad,
-                            length_penalty, steps)
+                            length_penalty, steps, num_return_sequences)
         finally:
             # the selection of the last step may still run on the side stream and uses buffers this frame owns: order
             # everything the caller enqueues next behind it (no host synchronisation)

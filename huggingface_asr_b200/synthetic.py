@@ -156,6 +156,19 @@ class SyntheticDecoder:
             tgt[b, :n] = torch.tensor(tr[:n], dtype=torch.long)
         self.targets = tgt.to(dev).repeat_interleave(num_beams, dim=0)  # (BW, max_length + 1)
         self.boost = boost
+        self.max_length = max_length
+
+    def retarget(self, transcripts) -> "SyntheticDecoder":
+        """Same noise pool, new transcripts (a job that decodes many batches of the same shape: the C5 sharded decode)."""
+        B = len(transcripts)
+        if B * self.W != self.pool[0].shape[0]:
+            raise ValueError(f"retarget: {B} transcripts for a pool of {self.pool[0].shape[0] // self.W} utterances")
+        tgt = torch.full((B, self.max_length + 1), EOS, dtype=torch.long)
+        for b, tr in enumerate(transcripts):
+            n = min(len(tr), self.max_length + 1)
+            tgt[b, :n] = torch.tensor(tr[:n], dtype=torch.long)
+        self.targets = tgt.to(self.pool[0].device).repeat_interleave(self.W, dim=0)
+        return self
 
     def __call__(self, input_ids: torch.Tensor, step: int) -> torch.Tensor:
         logits = self.pool[step % len(self.pool)].clone()
