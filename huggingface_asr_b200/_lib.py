@@ -92,7 +92,7 @@ SIGNATURES = {
     "ctcps_topk_lists_shape": [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)],
     "ctcps_score_lazy_topk": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _sz, _i, _p],
     "ctcps_beam_step_lists": [_p, _i, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i64, _p, _p, _sz, _p, _i, _i64, _p, _p,
-                              _p, _p, _p],
+                              _p],
     "ctcps_beam_step_workspace_bytes": [_i, _i, ctypes.POINTER(_sz)],
     "ctcps_beam_step": [_p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i64, _p, _p, _sz, _p, _i, _i64, _p, _p],
     "ctcps_padded_lt": [_i],

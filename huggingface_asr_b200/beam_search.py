@@ -346,7 +346,7 @@ def joint_beam_search_native(processor, decoder_log_probs: Callable[[torch.Tenso
         w = float(processor.ctc_weight)
         sess.one_minus_w, sess.w, sess.length_penalty = 1.0 - w, w, float(length_penalty)
         sess.ldx, sess.ldt = sc._ldx, sc._ldt
-        fused_topk = S == 0 and fuse_topk and V % 4 == 0 and pad == sc.blank and 2 * W <= 64 and W <= 32
+        fused_topk = S == 0 and fuse_topk and V % 4 == 0 and 2 * W <= 64 and W <= 32
         if S > 0:
             sess.x_vt = sc._token_major().data_ptr()
             cand_ids = [torch.empty((BW, S), **i64) for _ in range(2)]
@@ -362,22 +362,19 @@ def joint_beam_search_native(processor, decoder_log_probs: Callable[[torch.Tenso
             if fused_topk:
                 nl, kk = ctypes.c_int(0), ctypes.c_int(0)
                 _lib.check(L_.ctcps_topk_lists_shape(B, W, V, ctypes.byref(nl), ctypes.byref(kk)), "ctcps_topk_lists_shape")
-                fused_topk = nl.value * kk.value <= 1024
+                fused_topk = nl.value * kk.value <= 2048
+            log_psi = [torch.empty((BW, V), **f32) for _ in range(2)]
+            keep.append(log_psi)
+            sess.log_psi[0], sess.log_psi[1] = log_psi[0].data_ptr(), log_psi[1].data_ptr()
             if fused_topk:
-                # fused scoring + per-tile top-2W: no (BW,V) tensor per step, only the candidate lists (and, for the reference's
-                # token-only state selection, the log_psi row of hypothesis 0 of every utterance)
-                tile_lists = torch.empty((B, nl.value, kk.value, 4), **f32)
+                # fused scoring + per-tile top-2W: the joint scores never reach memory, only the tiles' candidate lists
+                tile_lists = torch.empty((B, nl.value, kk.value, 2), **f32)
                 keep.append(tile_lists)
                 sess.tile_lists = tile_lists.data_ptr()
-                if not processor.use_beam_idx:
-                    lp0 = torch.empty((B, V), **f32)
-                    keep.append(lp0)
-                    sess.log_psi[0] = lp0.data_ptr()
             if not fused_topk or max_length - 1 > T:  # the dense step (also taken once a prefix outgrows the utterance, ol > T)
-                log_psi = [torch.empty((BW, V), **f32) for _ in range(2)]
                 joint = torch.empty((BW, V), **f32)
-                keep += [log_psi, joint]
-                sess.log_psi[0], sess.log_psi[1], sess.joint = log_psi[0].data_ptr(), log_psi[1].data_ptr(), joint.data_ptr()
+                keep.append(joint)
+                sess.joint = joint.data_ptr()
         sess.blank_lp, sess.r0 = sc._blank_lp.data_ptr(), r0.data_ptr()
         for k in range(2):
             sess.r_sel[k], sess.s_sel[k], sess.last_ids[k], sess.ids[k] = r_sel[k].data_ptr(), s_sel[k].data_ptr(), last[k].data_ptr(), ids[k].data_ptr()

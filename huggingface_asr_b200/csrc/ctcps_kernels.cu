@@ -698,9 +698,8 @@ __global__ void __launch_bounds__(64) k_select_lazy_scan(const XView x, const fl
     const int BW = B * W;
     if (j >= BW) return;
     const LazySel q = lazy_source(best_ids, cand_ids, S, j, W, V);
-    // log_psi == nullptr: the fused beam step (k_beam_merge) has already written the prefix scores of the new rows into s_new
-    const float sj = log_psi == nullptr ? s_new[j] : (q.src < 0 ? LZ : log_psi[q.src]);
-    if (log_psi != nullptr) s_new[j] = sj;  // :193
+    const float sj = q.src < 0 ? LZ : log_psi[q.src];
+    s_new[j] = sj;  // :193
     const int start = ol > 1 ? ol : 1;
     const float *xb = blank_lp + (size_t)(j / W) * T;
     float rn = (ol == 0) ? r_new[j] : LZ, rb = LZ;
@@ -862,8 +861,8 @@ __global__ void __launch_bounds__(PS_H * 32) k_select_lazy_pscan(const XView x, 
     q.hs = 0, q.tok = 0, q.last = 0, q.src = -1;
     if (active) {
         q = lazy_source(best_ids, cand_ids, S, j, W, V);
-        sj = log_psi == nullptr ? s_new[j] : (q.src < 0 ? LZ : log_psi[q.src]);  // nullptr: written by the fused beam step
-        if (lane == 0 && log_psi != nullptr) s_new[j] = sj;  // :193
+        sj = q.src < 0 ? LZ : log_psi[q.src];
+        if (lane == 0) s_new[j] = sj;  // :193
         const float *xb = blank_lp + (size_t)(j / W) * T;
         float *col = ps_sm + w * HS;
         const int lo = lane * F, hi = min(n, lo + F);  // this lane's frames, relative to `start`
@@ -1201,15 +1200,11 @@ struct BeamOut {
     long long *done_ring;
     int ring;
     long long step_tag;
-    // fused scoring only: prefix score of every row of the next step (what index_select_state would read, :193)
-    float *s_next;           // (BW) or null
-    const float *top_lp;     // shared memory: log_psi of top[r] (selection by source hypothesis * V + token), or null
-    const float *log_psi0;   // (B,V) log_psi of hypothesis 0 of every utterance (the reference's token-only selection), or null
 };
 
 struct BeamShared {
     int job_src[32], job_dst[32], n_pool_jobs;
-    int next_tok[32], next_src[32], next_rank[32];
+    int next_tok[32], next_src[32];
     float next_score[32];
     unsigned int last;
     int tot;
@@ -1274,12 +1269,12 @@ __device__ __forceinline__ void beam_bookkeep(const Cand *top, BeamShared &bs, c
             const unsigned m = q == 0 ? m0 : m1;
             const int pos = (q == 0 ? 0 : n0) + __popc(m & ((1u << lane) - 1u));
             if (((m >> lane) & 1u) && pos < W)
-                bs.next_score[pos] = cs[q], bs.next_tok[pos] = ctok[q], bs.next_src[pos] = csrc[q], bs.next_rank[pos] = lane + 32 * q;
+                bs.next_score[pos] = cs[q], bs.next_tok[pos] = ctok[q], bs.next_src[pos] = csrc[q];
         }
         __syncwarp();
         float ns = NEG;
-        int ntok = pad, nsrc = 0, nrank = -1;
-        if (lane < W && lane < ncont) ns = bs.next_score[lane], ntok = bs.next_tok[lane], nsrc = bs.next_src[lane], nrank = bs.next_rank[lane];
+        int ntok = pad, nsrc = 0;
+        if (lane < W && lane < ncont) ns = bs.next_score[lane], ntok = bs.next_tok[lane], nsrc = bs.next_src[lane];
         // done test of the utterance (BeamHypotheses.is_done, early_stopping = False)
         const bool full = __all_sync(0xffffffffu, ps > NEG);
         float worst = ps;
@@ -1289,17 +1284,11 @@ __device__ __forceinline__ void beam_bookkeep(const Cand *top, BeamShared &bs, c
         const bool dn_new = dn || (full && worst >= top0 * inv_norm);
         __syncwarp();
         if (lane < W) {
-            if (dn_new) ns = 0.f, ntok = pad, nsrc = 0, nrank = -1;
+            if (dn_new) ns = 0.f, ntok = pad, nsrc = 0;
             o.beam_scores[b * W + lane] = ns;
             // what index_select_state wants (ESPnet ids: source hypothesis * V + token, :180-191)
             if (o.best_ids_out != nullptr) o.best_ids_out[b * W + lane] = (long long)nsrc * V + ntok;
             if (o.last_ids_out != nullptr) o.last_ids_out[b * W + lane] = ntok;
-            if (o.s_next != nullptr) {
-                float sv = LZ;  // a pad row: log_psi[:, blank] = logzero (:173; the fused path requires pad == blank)
-                if (o.log_psi0 != nullptr) sv = o.log_psi0[(size_t)b * V + ntok];
-                else if (nrank >= 0) sv = o.top_lp[nrank];
-                o.s_next[b * W + lane] = sv;
-            }
             bs.next_tok[lane] = ntok, bs.next_src[lane] = nsrc;
         }
         if (lane == 0) o.done[b] = dn_new ? 1 : 0;
@@ -1360,28 +1349,27 @@ __device__ __forceinline__ void beam_bookkeep(const Cand *top, BeamShared &bs, c
 }
 
 // Beam step over the per-tile candidate lists of the fused scoring kernel (k_psi_full<TOPK>): one CTA per utterance merges
-// its nlists sorted lists of K = 2W (key = joint + running beam score, dense index, log_psi) into the K best and does the
+// its nlists sorted lists of K = 2W (key = joint + running beam score, dense index) into the K best and does the
 // bookkeeping.  Every list is sorted, so its K-th key bounds the merge from below: entries under the largest such bound
 // cannot be among the K best.
-constexpr int MERGE_MAX = 1024;  // candidates of an utterance held in shared memory
-__global__ void __launch_bounds__(BEAM_NT) k_beam_merge(const float4 *__restrict__ lists, int nlists, int L, int W, int V, int eos, int pad,
+constexpr int MERGE_MAX = 2048;  // candidates of an utterance held in shared memory
+__global__ void __launch_bounds__(BEAM_NT) k_beam_merge(const float2 *__restrict__ lists, int nlists, int L, int W, int V, int eos, int pad,
                                                         float len_norm, BeamOut o) {
-    __shared__ float4 cands[MERGE_MAX];
+    __shared__ float2 cands[MERGE_MAX];
     __shared__ Cand top[BEAM_MAXK];
-    __shared__ float top_lp[BEAM_MAXK];
     __shared__ float bound_s[BEAM_NT / 32];
     __shared__ BeamShared bs;
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int K = 2 * W, n = nlists * K;
     const float NEG = -INFINITY;
-    const float4 *src = lists + (size_t)b * n;
+    const float2 *src = lists + (size_t)b * n;
     float bnd = NEG;
     for (int q = tid; q < n; q += BEAM_NT) {
-        const float4 c = src[q];
+        const float2 c = src[q];
         cands[q] = c;
         if ((q % K) == K - 1 && __float_as_int(c.y) != 0x7fffffff) bnd = fmaxf(bnd, c.x);
     }
-    for (int k = tid; k < BEAM_MAXK; k += BEAM_NT) top[k].s = NEG, top[k].i = 0x7fffffff, top_lp[k] = LZ;
+    for (int k = tid; k < BEAM_MAXK; k += BEAM_NT) top[k].s = NEG, top[k].i = 0x7fffffff;
     bnd = warp_max(bnd);
     if (lane == 0) bound_s[wid] = bnd;
     __syncthreads();
@@ -1389,18 +1377,17 @@ __global__ void __launch_bounds__(BEAM_NT) k_beam_merge(const float4 *__restrict
 #pragma unroll
     for (int q = 1; q < BEAM_NT / 32; ++q) bound = fmaxf(bound, bound_s[q]);
     for (int q = tid; q < n; q += BEAM_NT) {
-        const float4 me = cands[q];
+        const float2 me = cands[q];
         const int mi = __float_as_int(me.y);
         if (mi == 0x7fffffff || me.x < bound) continue;
         int rank = 0;
         for (int p = 0; p < n; ++p) {
-            const float4 c = cands[p];
+            const float2 c = cands[p];
             rank += (__float_as_int(c.y) != 0x7fffffff && cand_beats(c.x, __float_as_int(c.y), me.x, mi)) ? 1 : 0;
         }
-        if (rank < K) top[rank].s = me.x, top[rank].i = mi, top_lp[rank] = me.z;
+        if (rank < K) top[rank].s = me.x, top[rank].i = mi;
     }
     __syncthreads();
-    o.top_lp = top_lp;
     beam_bookkeep(top, bs, o, b, (int)gridDim.x, L, W, V, eos, pad, len_norm);
 }
 
@@ -1550,7 +1537,6 @@ __global__ void __launch_bounds__(BEAM_NT) k_beam_step(const float *__restrict__
     o.beam_scores = beam_scores, o.best_ids_out = best_ids_out, o.last_ids_out = last_ids_out, o.ids_cur = ids_cur, o.ids_next = ids_next;
     o.ld_ids = ld_ids, o.pool_scores = pool_scores, o.pool_lens = pool_lens, o.pool_seqs = pool_seqs, o.ld_pool = ld_pool, o.done = done;
     o.ticket = ticket, o.done_ring = done_ring, o.ring = ring, o.step_tag = step_tag;
-    o.s_next = nullptr, o.top_lp = nullptr, o.log_psi0 = nullptr;
     beam_bookkeep(top, bs, o, b, (int)gridDim.x / P, L, W, V, eos, pad, len_norm);
 }
 
@@ -1826,8 +1812,7 @@ int encode_x_map_uncached(CUtensorMap *tm, const float *x_logp, int ldx, int B, 
 int select_lazy_impl(const XView x, const float *blank_lp, const float *r_prev, const int64_t *last_ids, int ol, const float *scores,
                      const int64_t *cand_ids, int S, const int64_t *best_ids, int B, int W, int T, int V, float *r_new, float *s_new,
                      void *next_workspace, size_t next_workspace_bytes, cudaStream_t st) {
-    ARG_CHECK(blank_lp && r_prev && last_ids && best_ids && r_new && s_new, CTCPS_E_BADARG, "select_lazy: null pointer");
-    ARG_CHECK(scores != nullptr || cand_ids == nullptr, CTCPS_E_BADARG, "select_lazy: candidate selection needs the candidate scores");
+    ARG_CHECK(blank_lp && r_prev && last_ids && scores && best_ids && r_new && s_new, CTCPS_E_BADARG, "select_lazy: null pointer");
     ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0, CTCPS_E_BADARG, "select_lazy: bad size");
     const int BW = B * W;
     const dim3 grid((BW + 127) / 128, (T + LAZY_TC - 1) / LAZY_TC);
@@ -2194,7 +2179,7 @@ static int score_lazy_impl(const float *x_logp, int ldx, const float *r_prev, co
     // any BASELINE shape, profiles/r1x_kernels_ncu.md section 3).
     a.nvt = (V + PSI_NT * 4 - 1) / (PSI_NT * 4);
     a.prefetch = psi_prefetch_chunks();
-    a.tk.beam_scores = nullptr, a.tk.lists = nullptr, a.tk.log_psi0 = nullptr, a.tk.K = 0;
+    a.tk.beam_scores = nullptr, a.tk.lists = nullptr, a.tk.K = 0;
     if (tk != nullptr) {
         a.tk = *tk;
         return dispatch_psi_full<true>(HW, tm, a, st);
@@ -2236,32 +2221,31 @@ int ctcps_topk_lists_shape(int B, int W, int V, int *lists_per_utterance, int *K
 
 int ctcps_score_lazy_topk(const float *x_logp, int ldx, const float *r_prev, const float *s_prev, const int64_t *last_ids, int ol,
                           int B, int W, int T, int V, int blank, const float *att_scores, float one_minus_w, float w,
-                          const float *beam_scores, float *tile_lists, float *log_psi_hyp0, void *workspace,
-                          size_t workspace_bytes, int workspace_prepared, void *stream) {
+                          const float *beam_scores, float *log_psi, float *tile_lists, void *workspace, size_t workspace_bytes,
+                          int workspace_prepared, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    ARG_CHECK(x_logp && r_prev && last_ids && att_scores && beam_scores && tile_lists, CTCPS_E_BADARG, "score_lazy_topk: null pointer");
+    ARG_CHECK(x_logp && r_prev && last_ids && att_scores && beam_scores && tile_lists && log_psi, CTCPS_E_BADARG, "score_lazy_topk: null pointer");
     ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0, CTCPS_E_BADARG, "score_lazy_topk: non-positive size");
     ARG_CHECK(blank >= 0 && blank < V, CTCPS_E_BADARG, "score_lazy_topk: blank id outside the vocabulary");
-    ARG_CHECK((V & 3) == 0 && ldx >= V && (ldx & 3) == 0 && ((((uintptr_t)x_logp) | ((uintptr_t)att_scores) | ((uintptr_t)tile_lists)) & 15) == 0 &&
-                  (log_psi_hyp0 == nullptr || (((uintptr_t)log_psi_hyp0) & 15) == 0),
-              CTCPS_E_ALIGN, "score_lazy_topk: V and ldx must be multiples of 4, pointers 16-byte aligned");
+    ARG_CHECK((V & 3) == 0 && ldx >= V && (ldx & 3) == 0 &&
+                  ((((uintptr_t)x_logp) | ((uintptr_t)att_scores) | ((uintptr_t)log_psi)) & 15) == 0 && (((uintptr_t)tile_lists) & 7) == 0,
+              CTCPS_E_ALIGN, "score_lazy_topk: V and ldx must be multiples of 4, x_logp / att_scores / log_psi 16-byte aligned");
     ARG_CHECK(2 * W <= BEAM_MAXK, CTCPS_E_TOOBIG, "score_lazy_topk: num_beams > 32 is not supported");
     const long long BW = (long long)B * W;
     ARG_CHECK(BW * (long long)V < (1ll << 31) && (long long)B * T < (1ll << 31), CTCPS_E_TOOBIG, "score_lazy_topk: BW*V or B*T exceeds 2^31");
     ARG_CHECK(ol <= T, CTCPS_E_BADARG, "score_lazy_topk: prefix longer than the utterance (use ctcps_score_lazy: every score is logzero)");
     PsiTopk tk;
     tk.beam_scores = beam_scores;
-    tk.lists = reinterpret_cast<float4 *>(tile_lists);
-    tk.log_psi0 = log_psi_hyp0;
+    tk.lists = reinterpret_cast<float2 *>(tile_lists);
     tk.K = 2 * W;
     return score_lazy_impl(x_logp, ldx, r_prev, s_prev, 1, 0, last_ids, ol, B, W, T, V, blank, const_cast<float *>(att_scores), one_minus_w, w,
-                           nullptr, nullptr, nullptr, &tk, workspace, workspace_bytes, workspace_prepared, st);
+                           log_psi, nullptr, nullptr, &tk, workspace, workspace_bytes, workspace_prepared, st);
 }
 
 int ctcps_select_lazy(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const int64_t *last_ids, int ol,
                       const float *log_psi, const int64_t *best_ids, int B, int W, int T, int V, float *r_new, float *s_new,
                       void *next_workspace, size_t next_workspace_bytes, void *stream) {
-    ARG_CHECK(x_logp != nullptr, CTCPS_E_BADARG, "select_lazy: null pointer");
+    ARG_CHECK(x_logp && log_psi, CTCPS_E_BADARG, "select_lazy: null pointer");
     ARG_CHECK(T > 0 && V > 0 && ldx >= V, CTCPS_E_BADARG, "select_lazy: bad size");
     const XView x = {x_logp, (long long)T * ldx, (long long)ldx, 1};
     return select_lazy_impl(x, blank_lp, r_prev, last_ids, ol, log_psi, nullptr, 0, best_ids, B, W, T, V, r_new, s_new, next_workspace,
@@ -2300,14 +2284,14 @@ int ctcps_beam_step_lists(const float *tile_lists, int lists_per_utterance, floa
                           int64_t ld_ids, int L, int B, int W, int V, int eos, int pad, float len_norm, float *pool_scores,
                           int64_t *pool_lens, int64_t *pool_seqs, int64_t ld_pool, unsigned char *done, void *workspace,
                           size_t workspace_bytes, int64_t *done_ring, int ring, int64_t step_tag, int64_t *best_ids_out,
-                          int64_t *last_ids_out, float *s_next, const float *log_psi_hyp0, void *stream) {
+                          int64_t *last_ids_out, void *stream) {
     ARG_CHECK(tile_lists && beam_scores && ids_cur && ids_next && pool_scores && pool_lens && pool_seqs && done && workspace,
               CTCPS_E_BADARG, "beam_step_lists: null pointer");
     ARG_CHECK(B > 0 && W > 0 && V > 0 && L >= 1 && L < ld_ids && L - 1 <= ld_pool && lists_per_utterance > 0, CTCPS_E_BADARG,
               "beam_step_lists: bad size");
     ARG_CHECK(2 * W <= BEAM_MAXK && W <= 32 && (long long)lists_per_utterance * 2 * W <= MERGE_MAX, CTCPS_E_TOOBIG,
-              "beam_step_lists: num_beams > 32 or more than 1024 candidates per utterance");
-    ARG_CHECK((((uintptr_t)tile_lists) & 15) == 0, CTCPS_E_ALIGN, "beam_step_lists: tile_lists must be 16-byte aligned");
+              "beam_step_lists: num_beams > 32 or more than 2048 candidates per utterance");
+    ARG_CHECK((((uintptr_t)tile_lists) & 7) == 0, CTCPS_E_ALIGN, "beam_step_lists: tile_lists must be 8-byte aligned");
     ARG_CHECK(done_ring == nullptr || ring > 0, CTCPS_E_BADARG, "beam_step_lists: done_ring without ring size");
     const BeamWorkspace bw = plan_beam_workspace(B, W);
     ARG_CHECK(workspace_bytes >= bw.total, CTCPS_E_WORKSPACE, "beam_step_lists: workspace too small");
@@ -2316,8 +2300,7 @@ int ctcps_beam_step_lists(const float *tile_lists, int lists_per_utterance, floa
     o.beam_scores = beam_scores, o.best_ids_out = best_ids_out, o.last_ids_out = last_ids_out, o.ids_cur = ids_cur, o.ids_next = ids_next;
     o.ld_ids = ld_ids, o.pool_scores = pool_scores, o.pool_lens = pool_lens, o.pool_seqs = pool_seqs, o.ld_pool = ld_pool, o.done = done;
     o.ticket = utt_ticket + B, o.done_ring = (long long *)done_ring, o.ring = ring, o.step_tag = step_tag;
-    o.s_next = s_next, o.top_lp = nullptr, o.log_psi0 = log_psi_hyp0;
-    k_beam_merge<<<B, BEAM_NT, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4 *>(tile_lists), lists_per_utterance, L, W, V, eos, pad,
+    k_beam_merge<<<B, BEAM_NT, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(tile_lists), lists_per_utterance, L, W, V, eos, pad,
                                                          len_norm, o);
     return cuda_rc(cudaGetLastError());
 }
@@ -2499,18 +2482,17 @@ int ctcps_decode_step(const ctcps_decode_session *s, float *att_scores, int step
     // hands the prefix scores of the new rows straight to the state selection.
     int nlists = 0, Klist = 0;
     if (S == 0) ctcps_topk_lists_shape(B, W, V, &nlists, &Klist);
-    const bool fused = S == 0 && s->tile_lists != nullptr && (V & 3) == 0 && ol <= T && s->pad == s->blank && 2 * W <= BEAM_MAXK &&
-                       W <= 32 && (long long)nlists * Klist <= MERGE_MAX && (s->use_beam_idx || s->log_psi[0] != nullptr);
+    const bool fused = S == 0 && s->tile_lists != nullptr && (V & 3) == 0 && ol <= T && 2 * W <= BEAM_MAXK && W <= 32 &&
+                       (long long)nlists * Klist <= MERGE_MAX && s->log_psi[0] != nullptr && s->log_psi[1] != nullptr;
     const int64_t tag = s->tag_base + (int64_t)step;
     if (fused) {
-        float *lp0 = s->use_beam_idx ? nullptr : s->log_psi[0];
         rc = ctcps_score_lazy_topk(s->x_logp, s->ldx, r_prev, s_prev, s->last_ids[cur], ol, B, W, T, V, s->blank, att_scores, s->one_minus_w,
-                                   s->w, s->beam_scores, s->tile_lists, lp0, s->score_ws, s->score_ws_bytes, prepared, main_st);
+                                   s->w, s->beam_scores, s->log_psi[cur], s->tile_lists, s->score_ws, s->score_ws_bytes, prepared, main_st);
         if (rc) return rc;
         if (ev_score_end) cudaEventRecord((cudaEvent_t)ev_score_end, main_st);
         rc = ctcps_beam_step_lists(s->tile_lists, nlists, s->beam_scores, s->ids[cur], s->ids[nxt], s->ld_ids, L, B, W, V, s->eos, s->pad,
                                    len_norm, s->pool_scores, s->pool_lens, s->pool_seqs, s->ld_pool, s->done, s->beam_ws, s->beam_ws_bytes,
-                                   s->done_ring, s->ring, tag, s->best_ids, s->last_ids[nxt], s->s_sel[nxt], lp0, main_st);
+                                   s->done_ring, s->ring, tag, s->best_ids, s->last_ids[nxt], main_st);
         if (rc) return rc;
         if (side != main_st) {
             cudaError_t e = cudaEventRecord((cudaEvent_t)s->ev_step, main_st);
@@ -2518,7 +2500,7 @@ int ctcps_decode_step(const ctcps_decode_session *s, float *att_scores, int step
             if (e != cudaSuccess) return (int)e;
         }
         const int64_t *sel = s->use_beam_idx ? s->best_ids : s->last_ids[nxt];
-        rc = ctcps_select_lazy(s->x_logp, s->ldx, s->blank_lp, r_prev, s->last_ids[cur], ol, nullptr, sel, B, W, T, V, s->r_sel[nxt],
+        rc = ctcps_select_lazy(s->x_logp, s->ldx, s->blank_lp, r_prev, s->last_ids[cur], ol, s->log_psi[cur], sel, B, W, T, V, s->r_sel[nxt],
                                s->s_sel[nxt], s->score_ws, s->score_ws_bytes, side);
         if (rc) return rc;
         if (side != main_st) {

@@ -24,13 +24,13 @@
 //     cursor further ahead that prefetches chunks into L2 (UTMAPF): ncu showed 24 % of the warp samples spinning on the
 //     `full` barrier -- the ring (197 KB per SM, two thirds of it in flight at best) is too short a queue for HBM;
 //   * TOPK mode (native decode loop): the epilogue ranks the tile's 512 x HW joint scores (+ running beam scores) and
-//     publishes the tile's best 2W candidates; (BW,V) joint / log_psi tensors are never written or re-read, and the
-//     separate per-row top-2W kernel of round 1 disappears.  The beam step merges nvt x G short sorted lists.
+//     publishes the tile's best 2W candidates; the (BW,V) joint tensor is never written or re-read (log_psi still is
+//     written: the state selection reads W of its entries per utterance), and the separate per-row top-2W kernel of
+//     round 1 disappears.  The beam step merges nvt x G short sorted lists.
 
 struct PsiTopk {
     const float *beam_scores;  // (BW) running beam scores, added to the joint scores for ranking
-    float4 *lists;             // [B][nvt*G][K]: (key, dense index hyp*V+tok as int bits, log_psi, 0), best first
-    float *log_psi0;           // (B,V) log_psi row of hypothesis 0 of every utterance (token-only state selection), or null
+    float2 *lists;             // [B][nvt*G][K]: (key, dense index hyp*V+tok as int bits), best first
     int K;                     // 2W
 };
 
@@ -60,6 +60,7 @@ struct PsiSmem {
     alignas(16) float lin[NSTAGE][TT][HWP];
     alignas(8) uint64_t full[NSTAGE];
     alignas(8) uint64_t empty[NSTAGE];
+    int cursor[2][6];  // thread 0's two look-ahead cursors (kept here, not in registers: every thread would pay for them)
 };
 
 // one warp per (padded) hypothesis: lin stream, Gmax and the last-label column sum
@@ -109,22 +110,27 @@ __global__ void __launch_bounds__(128) k_prep_psi(const float *__restrict__ r_pr
 // TOPK epilogue: the tile's K best (joint score + running beam score) out of 512 tokens x HW hypotheses, ranked exactly
 // by (score descending, dense index ascending) -- the order of the beam step (and of torch.topk on distinct scores).
 //
-//   pass 1  per hypothesis (rolled loop, one row of the sums at a time like epilogue_tile): log_psi, token score, joint
-//           score, key = joint + beam score; the sums are replaced by log_psi (the rows rotate through position 0, so
-//           after HW iterations they are back in place); every thread keeps the max of its keys;
-//   tau     = the K-th largest of the NT thread maxima (rank counting over shared memory): at least K elements of the
-//           tile are >= tau, so the K best are, and only a few dozen elements in all;
-//   pass 2  recomputes the keys from the stored log_psi (same operations, bit-identical) and appends the elements >= tau
-//           to a shared list, which is then ranked exactly by counting.
+//   pass 1  per hypothesis pair (rolled loop over the rows of the sums, two rows per iteration): log_psi -- streamed to the
+//           dense (BW,V) log_psi tensor, which is all the next state selection reads (:193) -- then token score, joint
+//           score and key = joint + beam score; the key replaces the sum in its register (the rows rotate through
+//           positions 0 and 1, so after HW / 2 iterations they are back in place); every thread keeps the max of its keys;
+//   tau     = the K-th largest of the NT thread maxima: every warp sorts its 32 maxima (bitonic, shuffles only) and
+//           publishes them; a thread ranks its value among the other warps' sorted lists by binary search.  At least K
+//           elements of the tile are >= tau, so the K best are, and only a few dozen elements in all;
+//   pass 2  compares the 4 * HW keys a thread holds with tau (straight-line code on registers) and appends the few
+//           survivors to a shared list, which is then ranked exactly by counting.
+// Round 2's first version kept log_psi in the registers and recomputed the keys in pass 2 from a second read of the decoder
+// scores (so that nothing dense was written at all): 1.8 k extra instructions per thread and tile, +31 us per C2 launch
+// (profiles/r2c_psi_ncu.md) -- more than the 8 us the 51 MB log_psi write costs.
 // A tile where more than PSI_TOPK_CAP elements reach tau (fewer than K threads hold a valid score, or a constant row)
-// falls back to K rounds of block-wide argmax over the recomputed keys.  Invalid positions (v >= V, padded hypotheses)
-// never enter; a list with fewer than K valid entries is closed with (-inf, INT_MAX) sentinels.
+// falls back to K rounds of block-wide argmax over the keys.  Invalid positions (v >= V, padded hypotheses) carry -inf keys
+// with index INT_MAX and never enter; a list with fewer than K valid entries is closed with such sentinels.
 // ------------------------------------------------------------------------------------------
 struct PsiTopkSmem {
-    float tmax[PSI_NT];
-    float4 cand[PSI_TOPK_CAP];
-    float4 red[PSI_NT / 32];
-    float4 winner;
+    float sorted[PSI_NT];             // per warp: its 32 thread maxima, descending
+    float2 cand[PSI_TOPK_CAP];
+    float2 red[PSI_NT / 32];
+    float2 winner;
     float tau;
     unsigned int n_cand;
 };
@@ -162,9 +168,10 @@ __device__ __forceinline__ float log_psi_of(const EpiArgs &e, int v, float S, fl
 
 template <int HW>
 __device__ __forceinline__ void epilogue_topk(const EpiArgs &e, const PsiTopk &tk, PsiTopkSmem &ts, float (&S)[HW][4], const float (&x0)[4],
-                                              int b, int hrow0 /* global row of the tile's first hypothesis */,
+                                              int hrow0 /* global row of the tile's first hypothesis */,
                                               int w0 /* its index inside the utterance */, int nhyp, int v0,
-                                              float4 *__restrict__ list_out, float *scal /* this warp's [3][HW] shared scratch */) {
+                                              float2 *__restrict__ list_out, float *scal /* this warp's [3][HW] shared scratch */) {
+    static_assert(HW % 2 == 0, "rows are processed in pairs");
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int V = e.V, K = tk.K;
     const bool col_ok = v0 < V;  // V % 4 == 0 on this path: the thread's 4 tokens are valid together
@@ -179,93 +186,100 @@ __device__ __forceinline__ void epilogue_topk(const EpiArgs &e, const PsiTopk &t
     if (tid == 0) ts.n_cand = 0;
     __syncwarp();
 
-    constexpr int AHEAD = HW < 4 ? HW : 4;
+    constexpr int AHEAD = (HW < 4 || HW > 12) ? 2 : 4;  // decoder-score rows in flight (even); wide groups have no registers to spare
     float4 attv[AHEAD];
     auto att_row = [&](int hh) {
         return (col_ok && hh < nhyp) ? __ldg(reinterpret_cast<const float4 *>(e.att + (size_t)(hrow0 + hh) * V + v0)) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    // ---- pass 1: sums -> log_psi (kept in S), thread max of the keys ---------------------------------------------
+    // ---- pass 1: sums -> log_psi (streamed out) -> keys (kept in S), thread max of the keys ------------------------
     float mx = NEG;
 #pragma unroll
     for (int i = 0; i < AHEAD; ++i) attv[i] = att_row(i);
 #pragma unroll 1
-    for (int hh = 0; hh < HW; ++hh) {
-        const float gm = scal[0 * HW + hh], sp = scal[1 * HW + hh], bm = scal[2 * HW + hh];
-        const float4 cur = attv[0];
+    for (int hh = 0; hh < HW; hh += 2) {
+        float key[2][4];
 #pragma unroll
-        for (int i = 0; i + 1 < AHEAD; ++i) attv[i] = attv[i + 1];
-        attv[AHEAD - 1] = att_row(hh + AHEAD);
-        const float av[4] = {cur.x, cur.y, cur.z, cur.w};
-        float lp[4];
+        for (int r = 0; r < 2; ++r) {
+            const float gm = scal[0 * HW + hh + r], sp = scal[1 * HW + hh + r], bm = scal[2 * HW + hh + r];
+            const float av[4] = {attv[r].x, attv[r].y, attv[r].z, attv[r].w};
+            const bool ok = col_ok && hh + r < nhyp;
+            float lp[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            lp[j] = log_psi_of(e, v0 + j, S[0][j], gm, x0[j]);
-            const float key = joint_of(e, v0 + j, lp[j], sp, av[j]) + bm;
-            if (col_ok && hh < nhyp) mx = fmaxf(mx, key);
-        }
-        if (tk.log_psi0 != nullptr && w0 + hh == 0 && col_ok)
-            *reinterpret_cast<float4 *>(tk.log_psi0 + (size_t)b * V + v0) = make_float4(lp[0], lp[1], lp[2], lp[3]);
-#pragma unroll
-        for (int i = 0; i + 1 < HW; ++i)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) S[i][j] = S[i + 1][j];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) S[HW - 1][j] = lp[j];
-    }
-    // ---- tau: the K-th largest thread maximum ------------------------------------------------------------------
-    ts.tmax[tid] = mx;
-    __syncthreads();
-    {
-        int rank = 0;
-#pragma unroll 4
-        for (int o = 0; o < PSI_NT; o += 4) {
-            const float4 m4 = *reinterpret_cast<const float4 *>(&ts.tmax[o]);
-            rank += key_beats(m4.x, o + 0, mx, tid) ? 1 : 0;
-            rank += key_beats(m4.y, o + 1, mx, tid) ? 1 : 0;
-            rank += key_beats(m4.z, o + 2, mx, tid) ? 1 : 0;
-            rank += key_beats(m4.w, o + 3, mx, tid) ? 1 : 0;
-        }
-        if (rank == K - 1) ts.tau = mx;  // ranks are unique (ties broken by thread id): exactly one writer
-    }
-    __syncthreads();
-    const float tau = ts.tau;
-    // ---- pass 2: elements >= tau into the shared list (keys recomputed from log_psi: same operations, same bits) ----
-#pragma unroll
-    for (int i = 0; i < AHEAD; ++i) attv[i] = att_row(i);
-#pragma unroll 1
-    for (int hh = 0; hh < HW; ++hh) {
-        const float sp = scal[1 * HW + hh], bm = scal[2 * HW + hh];
-        const float4 cur = attv[0];
-#pragma unroll
-        for (int i = 0; i + 1 < AHEAD; ++i) attv[i] = attv[i + 1];
-        attv[AHEAD - 1] = att_row(hh + AHEAD);
-        const float av[4] = {cur.x, cur.y, cur.z, cur.w};
-        float lp[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            lp[j] = S[0][j];
-            const float key = joint_of(e, v0 + j, lp[j], sp, av[j]) + bm;
-            if (col_ok && hh < nhyp && key >= tau) {
-                const unsigned pos = atomicAdd(&ts.n_cand, 1u);
-                if (pos < PSI_TOPK_CAP) ts.cand[pos] = make_float4(key, __int_as_float((w0 + hh) * V + v0 + j), lp[j], 0.f);
+            for (int j = 0; j < 4; ++j) {
+                lp[j] = log_psi_of(e, v0 + j, S[r][j], gm, x0[j]);
+                key[r][j] = ok ? joint_of(e, v0 + j, lp[j], sp, av[j]) + bm : NEG;
+                mx = fmaxf(mx, key[r][j]);
             }
+            if (ok) __stcs(reinterpret_cast<float4 *>(e.log_psi + (size_t)(hrow0 + hh + r) * V + v0), make_float4(lp[0], lp[1], lp[2], lp[3]));
         }
 #pragma unroll
-        for (int i = 0; i + 1 < HW; ++i)
+        for (int i = 0; i + 2 < AHEAD; ++i) attv[i] = attv[i + 2];
+        if (AHEAD >= 2) {
+            attv[AHEAD - 2] = att_row(hh + AHEAD);
+            attv[AHEAD - 1] = att_row(hh + AHEAD + 1);
+        }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) S[i][j] = S[i + 1][j];
+        for (int i = 0; i + 2 < HW; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) S[HW - 1][j] = lp[j];
+            for (int j = 0; j < 4; ++j) S[i][j] = S[i + 2][j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) S[HW - 2][j] = key[0][j], S[HW - 1][j] = key[1][j];
     }
+    // ---- tau: the K-th largest thread maximum --------------------------------------------------------------------
+    {
+        float v = mx;  // descending bitonic sort of the warp's 32 maxima: lane p ends up with the p-th largest
+#pragma unroll
+        for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                const float other = __shfl_xor_sync(0xffffffffu, v, j);
+                const bool keep_max = ((lane & j) == 0) == ((lane & k) == 0);
+                v = keep_max ? fmaxf(v, other) : fminf(v, other);
+            }
+        ts.sorted[tid] = v;
+        __syncthreads();
+        // rank of (warp wid, position lane) in the order: value descending, then warp, then position
+        int rank = lane;
+#pragma unroll
+        for (int ow = 0; ow < PSI_NT / 32; ++ow) {
+            if (ow == wid) continue;
+            const float *lst = ts.sorted + ow * 32;
+            // number of entries of lst that come before v: entries > v, plus entries == v when ow < wid
+            int lo = 0, hi = 32;
+#pragma unroll
+            for (int it = 0; it < 6; ++it) {
+                if (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const float m = lst[mid];
+                    const bool before = m > v || (m == v && ow < wid);
+                    if (before) lo = mid + 1;
+                    else hi = mid;
+                }
+            }
+            rank += lo;
+        }
+        if (rank == K - 1) ts.tau = v;  // ranks are a permutation of 0..NT-1: exactly one writer
+        __syncthreads();
+    }
+    const float tau = ts.tau;
+    // ---- pass 2: the keys >= tau into the shared list ---------------------------------------------------------------
+#pragma unroll
+    for (int hh = 0; hh < HW; ++hh)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (S[hh][j] >= tau && col_ok && hh < nhyp) {
+                const unsigned pos = atomicAdd(&ts.n_cand, 1u);
+                if (pos < PSI_TOPK_CAP) ts.cand[pos] = make_float2(S[hh][j], __int_as_float((w0 + hh) * V + v0 + j));
+            }
     __syncthreads();
     const unsigned nc = ts.n_cand;
-    const float4 sentinel = make_float4(NEG, __int_as_float(0x7fffffff), LZ, 0.f);
+    const float2 sentinel = make_float2(NEG, __int_as_float(0x7fffffff));
     if (nc <= PSI_TOPK_CAP) {
         for (unsigned q = tid; q < nc; q += PSI_NT) {
-            const float4 me = ts.cand[q];
+            const float2 me = ts.cand[q];
             int rank = 0;
             for (unsigned o = 0; o < nc; ++o) {
-                const float4 c = ts.cand[o];
+                const float2 c = ts.cand[o];
                 rank += key_beats(c.x, __float_as_int(c.y), me.x, __float_as_int(me.y)) ? 1 : 0;
             }
             if (rank < K) list_out[rank] = me;
@@ -274,45 +288,32 @@ __device__ __forceinline__ void epilogue_topk(const EpiArgs &e, const PsiTopk &t
         __syncthreads();  // the list and the counters are reused by the next tile
         return;
     }
-    // ---- fallback: K rounds of block-wide argmax over the keys that come after the previous winner -------------
+    // ---- fallback: K rounds of block-wide argmax over the keys that come after the previous winner ------------------
     float pk = INFINITY;
     int pi = -1;
     for (int r = 0; r < K; ++r) {
-        float bk = NEG, bl = LZ;
+        float bk = NEG;
         int bi = 0x7fffffff;
-#pragma unroll 1
-        for (int hh = 0; hh < HW; ++hh) {
-            const float sp = scal[1 * HW + hh], bm = scal[2 * HW + hh];
-            const float4 cur = att_row(hh);
-            const float av[4] = {cur.x, cur.y, cur.z, cur.w};
-            float lp[4];
+#pragma unroll
+        for (int hh = 0; hh < HW; ++hh)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                lp[j] = S[0][j];
-                const float key = joint_of(e, v0 + j, lp[j], sp, av[j]) + bm;
                 const int idx = (w0 + hh) * V + v0 + j;
-                if (col_ok && hh < nhyp && key_beats(pk, pi, key, idx) && (bi == 0x7fffffff || key_beats(key, idx, bk, bi)))
-                    bk = key, bi = idx, bl = lp[j];
+                const float key = S[hh][j];
+                if (col_ok && hh < nhyp && key_beats(pk, pi, key, idx) && (bi == 0x7fffffff || key_beats(key, idx, bk, bi))) bk = key, bi = idx;
             }
 #pragma unroll
-            for (int i = 0; i + 1 < HW; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) S[i][j] = S[i + 1][j];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) S[HW - 1][j] = lp[j];
-        }
-#pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            const float ok = __shfl_xor_sync(0xffffffffu, bk, o), ol = __shfl_xor_sync(0xffffffffu, bl, o);
+            const float ok = __shfl_xor_sync(0xffffffffu, bk, o);
             const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (oi != 0x7fffffff && (bi == 0x7fffffff || key_beats(ok, oi, bk, bi))) bk = ok, bi = oi, bl = ol;
+            if (oi != 0x7fffffff && (bi == 0x7fffffff || key_beats(ok, oi, bk, bi))) bk = ok, bi = oi;
         }
-        if (lane == 0) ts.red[wid] = make_float4(bk, __int_as_float(bi), bl, 0.f);
+        if (lane == 0) ts.red[wid] = make_float2(bk, __int_as_float(bi));
         __syncthreads();
         if (tid == 0) {
-            float4 best = ts.red[0];
+            float2 best = ts.red[0];
             for (int q = 1; q < PSI_NT / 32; ++q) {
-                const float4 c = ts.red[q];
+                const float2 c = ts.red[q];
                 const int ci = __float_as_int(c.y), bi2 = __float_as_int(best.y);
                 if (ci != 0x7fffffff && (bi2 == 0x7fffffff || key_beats(c.x, ci, best.x, bi2))) best = c;
             }
@@ -321,7 +322,7 @@ __device__ __forceinline__ void epilogue_topk(const EpiArgs &e, const PsiTopk &t
             list_out[r] = best;
         }
         __syncthreads();
-        const float4 wv = ts.winner;
+        const float2 wv = ts.winner;
         pk = wv.x, pi = __float_as_int(wv.y);
         if (pi == 0x7fffffff) {  // nothing left: close the list
             for (int q = r + 1 + tid; q < K; q += PSI_NT) list_out[q] = sentinel;
@@ -376,6 +377,14 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
     struct Cursor {
         int k, ti, ci, b, vt, g;
     };
+    auto cursor_load = [&](int which) {
+        const int *p = sm.cursor[which];
+        return Cursor{p[0], p[1], p[2], p[3], p[4], p[5]};
+    };
+    auto cursor_store = [&](int which, const Cursor &c) {
+        int *p = sm.cursor[which];
+        p[0] = c.k, p[1] = c.ti, p[2] = c.ci, p[3] = c.b, p[4] = c.vt, p[5] = c.g;
+    };
     auto cursor_enter = [&](Cursor &c) {
         if (c.ti < my_tiles) decode_tile((int)blockIdx.x + c.ti * (int)gridDim.x, c.b, c.vt, c.g);
     };
@@ -401,12 +410,12 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
 #pragma unroll
         for (int bx = 0; bx < NBOX; ++bx) tma_prefetch_2d(&tmx, c.vt * VTILE + bx * BOXC, c.b * T + ch * TT);
     };
-    Cursor is = {0, 0, 0, 0, 0, 0}, pf = {0, 0, 0, 0, 0, 0};
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&sm.full[s], 1), mbar_init(&sm.empty[s], NWARP);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        Cursor is = {0, 0, 0, 0, 0, 0}, pf = {0, 0, 0, 0, 0, 0};
         if (nitems > 0) {
             cursor_enter(is);
             while (is.k < nitems && is.k < NSTAGE) {  // prologue: fill the ring
@@ -419,6 +428,8 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
                 cursor_next(pf);
             }
         }
+        cursor_store(0, is);
+        cursor_store(1, pf);
     }
     __syncthreads();
 
@@ -467,14 +478,18 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.empty[s]);
             if (tid == 0) {
-                if (is.k < nitems) {  // is.k == k + NSTAGE: the item that reuses this stage
+                if (k + NSTAGE < nitems) {  // the item that reuses this stage
+                    Cursor is = cursor_load(0);
                     mbar_wait(&sm.empty[s], (uint32_t)((k / NSTAGE) & 1));
                     issue(is);
                     cursor_next(is);
+                    cursor_store(0, is);
                 }
-                if (pf.k < nitems) {
+                if (a.prefetch > 0 && k + NSTAGE + a.prefetch < nitems) {
+                    Cursor pf = cursor_load(1);
                     prefetch(pf);
                     cursor_next(pf);
+                    cursor_store(1, pf);
                 }
             }
         }
@@ -502,8 +517,8 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
         e.Gmax = a.Gmax, e.s_prev = a.s_prev, e.s_rs = a.s_rs, e.s_cs = a.s_cs, e.att = a.att, e.omw = a.omw, e.w = a.w;
         e.log_psi = a.log_psi, e.token_scores = a.token_scores, e.joint = a.joint, e.V = V, e.blank = a.blank, e.ol = a.ol;
         if constexpr (TOPK) {
-            float4 *list_out = a.tk.lists + ((size_t)(b * a.nvt + vt) * a.G + g) * a.tk.K;
-            epilogue_topk<HW>(e, a.tk, sma.topk.t, acc, x0, b, h0, w0, nhyp, v0, list_out, sma.topk.scal + wid * 3 * HW);
+            float2 *list_out = a.tk.lists + ((size_t)(b * a.nvt + vt) * a.G + g) * a.tk.K;
+            epilogue_topk<HW>(e, a.tk, sma.topk.t, acc, x0, h0, w0, nhyp, v0, list_out, sma.topk.scal + wid * 3 * HW);
         } else {
             epilogue_tile<HW>(e, acc, x0, h0, nhyp, v0);
         }

@@ -59,6 +59,17 @@ def make_lengths(B: int, T: int, ragged: bool, gen: torch.Generator) -> torch.Te
     return lens
 
 
+def _no_repeats_on_adjacent_frames(labels, pos, V):
+    """CTC merges a label repeated on two neighbouring frames into one: the aligned transcript would then not be what any
+    decoder can recover (1 utterance in ~800 at these sizes).  Such a repeat is replaced by the next token id -- without
+    touching the random stream, so every other utterance keeps its data."""
+    labels = list(labels)
+    for i in range(len(labels) - 1):
+        if labels[i + 1] == labels[i] and int(pos[i + 1]) == int(pos[i]) + 1 and labels[i + 1] != EOS:
+            labels[i + 1] = 5 + (labels[i + 1] - 5 + 1) % (V - 5)
+    return labels
+
+
 def make_encoder_logits(B: int, T: int, V: int, kind: str = "peaky", ragged: bool = False, seed: int = 20240,
                         device: str | torch.device = "cpu", boost: float = 8.0):
     """Returns (logits (B,T,V) fp32, lens (B,) int64, transcripts: list of label lists incl. eos).
@@ -81,6 +92,7 @@ def make_encoder_logits(B: int, T: int, V: int, kind: str = "peaky", ragged: boo
                 labels = labels[: max(1, L - 2)]
                 n = len(labels)
                 pos = torch.arange(1, n + 1)
+            labels = _no_repeats_on_adjacent_frames(labels, pos, V)
             target = torch.full((T,), BLANK, dtype=torch.long)
             target[pos] = torch.tensor(labels)
             logits[b, torch.arange(T), target] += boost
@@ -116,6 +128,7 @@ def make_encoder_hidden(B: int, T: int, V: int, d: int = 512, kind: str = "peaky
                 labels = labels[: max(1, L - 2)]
                 n = len(labels)
                 pos = torch.arange(1, n + 1)
+            labels = _no_repeats_on_adjacent_frames(labels, pos, V)
             target = torch.full((T,), BLANK, dtype=torch.long)
             target[pos] = torch.tensor(labels)
             hidden[b] += boost * weight[target]

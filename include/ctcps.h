@@ -215,28 +215,26 @@ int ctcps_beam_step_candidates(const float *cand_joint, const int64_t *cand_ids,
 
 /*
  * Fused scoring + candidate ranking for a decode loop that owns its beam search (what ctcps_decode_step runs for the
- * full vocabulary).  ctcps_score_lazy_topk is ctcps_score_lazy (same arithmetic, bit for bit) whose epilogue, instead of
- * writing (BW,V) log_psi / joint tensors, ranks the 512 tokens x hypothesis-group scores of a tile by
+ * full vocabulary).  ctcps_score_lazy_topk is ctcps_score_lazy (same arithmetic, bit for bit) whose epilogue still writes
+ * log_psi (BW,V) -- the next state selection reads W of its entries per utterance (:193) -- but, instead of writing the
+ * (BW,V) joint scores for a second kernel to rank, ranks the 512 tokens x hypothesis-group scores of a tile itself by
  * key = joint + beam_scores[h] and publishes the tile's K = 2W best, best first (ties: lower hyp*V+tok first):
- *   tile_lists [B][lists_per_utterance][K] x {float key; int32 hyp*V+tok; float log_psi; float 0}   (16 bytes each,
- *   shorter lists are closed with key = -inf, index = INT32_MAX);  ctcps_topk_lists_shape gives lists_per_utterance and K.
- *   log_psi_hyp0 (B,V) or NULL: also keep log_psi of hypothesis 0 of every utterance (the reference's token-only state
- *   selection reads exactly that row, ctc_scorer.py:326-329).  Needs V % 4 == 0, ol <= T, s_prev a (BW) vector or NULL.
- * ctcps_beam_step_lists is the beam step over those lists (same ranking, bookkeeping and outputs as ctcps_beam_step) and
- * additionally writes s_next (BW): the prefix score index_select_state would read for every new row (:193) -- from
- * log_psi_hyp0[b, tok] when given, else the log_psi of the chosen candidate (selection by source hypothesis * V + token);
- * pad rows get logzero (requires pad == blank).  ctcps_select_lazy with log_psi == NULL then takes s_new as given.
+ *   tile_lists [B][lists_per_utterance][K] x {float key; int32 hyp*V+tok}   (8 bytes each; shorter lists are closed with
+ *   key = -inf, index = INT32_MAX);  ctcps_topk_lists_shape gives lists_per_utterance and K.
+ * Needs V % 4 == 0, ol <= T, s_prev a (BW) vector or NULL.
+ * ctcps_beam_step_lists is the beam step over those lists: same ranking, bookkeeping and outputs as ctcps_beam_step on the
+ * dense joint tensor, plus last_ids_out (BW) = the new last token of every row.
  */
 int ctcps_topk_lists_shape(int B, int W, int V, int *lists_per_utterance, int *K);
 int ctcps_score_lazy_topk(const float *x_logp, int ldx, const float *r_prev, const float *s_prev, const int64_t *last_ids, int ol,
                           int B, int W, int T, int V, int blank, const float *att_scores, float one_minus_w, float w,
-                          const float *beam_scores, float *tile_lists, float *log_psi_hyp0, void *workspace,
-                          size_t workspace_bytes, int workspace_prepared, void *stream);
+                          const float *beam_scores, float *log_psi, float *tile_lists, void *workspace, size_t workspace_bytes,
+                          int workspace_prepared, void *stream);
 int ctcps_beam_step_lists(const float *tile_lists, int lists_per_utterance, float *beam_scores, const int64_t *ids_cur, int64_t *ids_next,
                           int64_t ld_ids, int L, int B, int W, int V, int eos, int pad, float len_norm, float *pool_scores,
                           int64_t *pool_lens, int64_t *pool_seqs, int64_t ld_pool, unsigned char *done, void *workspace,
                           size_t workspace_bytes, int64_t *done_ring, int ring, int64_t step_tag, int64_t *best_ids_out,
-                          int64_t *last_ids_out, float *s_next, const float *log_psi_hyp0, void *stream);
+                          int64_t *last_ids_out, void *stream);
 
 /*
  * Native decode-step driver: ONE host call enqueues a whole joint-decoding step -- [top-S candidates,] prefix scoring
@@ -286,10 +284,9 @@ typedef struct ctcps_decode_session {
     int64_t *best_ids;     /* (B,W) */
     void *side_stream;     /* from ctcps_async_create; NULL: the selection runs on `stream` */
     void *ev_step, *ev_select;
-    float *tile_lists;     /* S == 0: B * lists_per_utterance * K * 4 floats (ctcps_topk_lists_shape) enables the fused
-                              scoring + top-2W step (no (BW,V) tensor written); NULL: the dense step.  With use_beam_idx = 0
-                              the fused step also needs log_psi[0] (it keeps hypothesis 0's row, (B,V), there); joint and
-                              log_psi[1] may then be NULL unless a prefix can outgrow T (ol > T falls back to the dense step) */
+    float *tile_lists;     /* S == 0: B * lists_per_utterance * K * 2 floats (ctcps_topk_lists_shape) enables the fused
+                              scoring + top-2W step: the (BW,V) joint tensor is never written (`joint` may then be NULL
+                              unless a prefix can outgrow T: ol > T falls back to the dense step); NULL: the dense step */
     int64_t tag_base;      /* added to `step` in the tag published to done_ring: a serial number of the decode in the high
                               bits (a multiple of `ring`), so that a late write of an earlier decode never matches */
 } ctcps_decode_session;

@@ -1,6 +1,6 @@
 """GPU: the scoring kernel's fused per-tile top-2W epilogue (ctcps_score_lazy_topk) and the beam step over its candidate lists
-(ctcps_beam_step_lists) against the unfused pair they replace in the native decode loop: ctcps_score_lazy (dense joint /
-log_psi tensors) + ctcps_beam_step.  Everything here is exact: same keys bit for bit, same ranking, same ties.
+(ctcps_beam_step_lists) against the unfused pair they replace in the native decode loop: ctcps_score_lazy (dense joint
+tensor) + ctcps_beam_step.  Everything here is exact: same log_psi and keys bit for bit, same ranking, same ties.
 
 Reference lines: ctc_scorer.py:154-176 (log_psi, token scores), :325,:332 (joint combine), :180-207 (what the state
 selection reads); the beam step restates HF's beam_search / BeamSearchScorer.process.
@@ -46,8 +46,8 @@ def _state_after_one_step(B, W, T, V, kind, seed, n_steps=2):
     return proc, sc, ids, beam_scores.contiguous(), sel
 
 
-def _dense_and_lists(sc, ids, beam_scores, sel, att, W, w=0.3, want_lp0=True):
-    """(joint, log_psi) of ctcps_score_lazy and (lists, lp0) of ctcps_score_lazy_topk on the same inputs."""
+def _dense_and_lists(sc, ids, beam_scores, sel, att, W, w=0.3):
+    """(joint, log_psi) of ctcps_score_lazy and (lists, log_psi) of ctcps_score_lazy_topk on the same inputs."""
     L, lib = _lib()
     B, T, V = sc.batch, sc.input_length, sc.odim
     BW = B * W
@@ -66,51 +66,40 @@ def _dense_and_lists(sc, ids, beam_scores, sel, att, W, w=0.3, want_lp0=True):
     nl, kk = ctypes.c_int(0), ctypes.c_int(0)
     L.check(lib.ctcps_topk_lists_shape(B, W, V, ctypes.byref(nl), ctypes.byref(kk)), "shape")
     assert kk.value == 2 * W
-    lists = torch.full((B, nl.value, kk.value, 4), float("nan"), device="cuda")
-    lp0 = torch.full((B, V), float("nan"), device="cuda") if want_lp0 else None
+    lists = torch.full((B, nl.value, kk.value, 2), float("nan"), device="cuda")
+    log_psi_t = torch.full((BW, V), float("nan"), device="cuda")
     L.check(lib.ctcps_score_lazy_topk(x.data_ptr(), sc._ldx, r_prev.data_ptr(), s_vec.data_ptr(), last.data_ptr(), ol, B, W, T, V, BLANK,
-                                      att_b.data_ptr(), 1.0 - w, w, beam_scores.data_ptr(), lists.data_ptr(),
-                                      None if lp0 is None else lp0.data_ptr(), ws.data_ptr(), ws.numel(), 0, st), "ctcps_score_lazy_topk")
+                                      att_b.data_ptr(), 1.0 - w, w, beam_scores.data_ptr(), log_psi_t.data_ptr(), lists.data_ptr(), ws.data_ptr(),
+                                      ws.numel(), 0, st), "ctcps_score_lazy_topk")
     torch.cuda.synchronize()
-    return joint, log_psi, lists, lp0
+    assert torch.equal(log_psi_t, log_psi), "log_psi of the fused kernel differs from the dense kernel's"
+    return joint, log_psi, lists
 
 
-def _check_lists(joint, log_psi, lists, beam_scores, B, W, V):
-    """Every tile list = the exact top-K of its (hypothesis group x 512 tokens) block of joint + beam score; the merged
-    lists contain the utterance's exact top-K."""
+def _check_lists(joint, lists, beam_scores, B, W, V):
+    """Every tile list = the exact top-K of its (hypothesis group x 512 tokens) block of joint + beam score."""
     K = 2 * W
     key = (joint + beam_scores.view(-1, 1)).view(B, W, V)
     nl = lists.shape[1]
     lk = lists[..., 0]
     li = lists[..., 1].contiguous().view(torch.int32)
-    ll = lists[..., 2]
     nvt = (V + 511) // 512
-    G = nl // nvt
-    assert G == 1 and W <= 20, "these checks cover one hypothesis group per tile (W <= 20)"
-    HW = W
-    lpv = log_psi.view(B, W, V)
+    assert nl == nvt and W <= 20, "these checks cover one hypothesis group per tile (W <= 20)"
     for vt in range(nvt):
         v0, v1 = vt * 512, min(V, vt * 512 + 512)
-        for g in range(G):
-            w0, w1 = g * HW, min(W, g * HW + HW)
-            blk = key[:, w0:w1, v0:v1]                                   # (B, hw, nv)
-            flat = blk.reshape(B, -1)
-            n = flat.shape[1]
-            hyp = torch.arange(w0, w1, device="cuda").view(-1, 1).expand(w1 - w0, v1 - v0)
-            tok = torch.arange(v0, v1, device="cuda").view(1, -1).expand(w1 - w0, v1 - v0)
-            dense = (hyp * V + tok).reshape(-1)
-            # exact order: key descending, dense index ascending (stable sort of index-ordered data)
-            order = torch.sort(flat, dim=1, descending=True, stable=True).indices[:, : min(K, n)]
-            ref_idx = dense[order]
-            ref_key = torch.gather(flat, 1, order)
-            got_key, got_idx, got_lp = lk[:, vt * G + g], li[:, vt * G + g], ll[:, vt * G + g]
-            m = min(K, n)
-            assert torch.equal(got_idx[:, :m].long(), ref_idx), f"tile ({vt},{g}): candidate indices differ"
-            assert torch.equal(got_key[:, :m], ref_key), f"tile ({vt},{g}): keys differ"
-            ref_lp = torch.gather(lpv.reshape(B, -1), 1, ref_idx)
-            assert torch.equal(got_lp[:, :m], ref_lp), f"tile ({vt},{g}): log_psi of the candidates differ"
-            if m < K:
-                assert (got_idx[:, m:] == INT_MAX).all() and torch.isinf(got_key[:, m:]).all()
+        flat = key[:, :, v0:v1].reshape(B, -1)
+        n = flat.shape[1]
+        hyp = torch.arange(W, device="cuda").view(-1, 1).expand(W, v1 - v0)
+        tok = torch.arange(v0, v1, device="cuda").view(1, -1).expand(W, v1 - v0)
+        dense = (hyp * V + tok).reshape(-1)
+        # exact order: key descending, dense index ascending (stable sort of index-ordered data)
+        m = min(K, n)
+        order = torch.sort(flat, dim=1, descending=True, stable=True).indices[:, :m]
+        got_key, got_idx = lk[:, vt], li[:, vt]
+        assert torch.equal(got_idx[:, :m].long(), dense[order]), f"tile {vt}: candidate indices differ"
+        assert torch.equal(got_key[:, :m], torch.gather(flat, 1, order)), f"tile {vt}: keys differ"
+        if m < K:
+            assert (got_idx[:, m:] == INT_MAX).all() and torch.isinf(got_key[:, m:]).all()
 
 
 @pytest.mark.parametrize("B,W,T,V,kind", [
@@ -126,9 +115,8 @@ def test_tile_lists_are_the_exact_top_2w(B, W, T, V, kind):
 
     proc, sc, ids, beam_scores, sel = _state_after_one_step(B, W, T, V, kind, seed=77 + W)
     att = make_attention_scores(B * W, V, 5, seed=3, scale=0.5).cuda()
-    joint, log_psi, lists, lp0 = _dense_and_lists(sc, ids, beam_scores, sel, att, W)
-    _check_lists(joint, log_psi, lists, beam_scores, B, W, V)
-    assert torch.equal(lp0, log_psi.view(B, W, V)[:, 0]), "log_psi row of hypothesis 0"
+    joint, log_psi, lists = _dense_and_lists(sc, ids, beam_scores, sel, att, W)
+    _check_lists(joint, lists, beam_scores, B, W, V)
 
 
 def test_tile_lists_with_ties_and_minus_infinity():
@@ -139,13 +127,13 @@ def test_tile_lists_with_ties_and_minus_infinity():
     att = torch.zeros(B * W, V, device="cuda")
     att[1::2, ::3] = float("-inf")
     att[2, 100:140] = 1.0
-    joint, log_psi, lists, _ = _dense_and_lists(sc, ids, beam_scores, sel, att, W, want_lp0=False)
-    _check_lists(joint, log_psi, lists, beam_scores, B, W, V)
+    joint, log_psi, lists = _dense_and_lists(sc, ids, beam_scores, sel, att, W)
+    _check_lists(joint, lists, beam_scores, B, W, V)
     # a state where every CTC score is identical as well: step 0 of a flat-prior utterance is not, so force constant keys
     att2 = torch.full((B * W, V), -3.0, device="cuda")
-    joint, log_psi, lists, _ = _dense_and_lists(sc, ids, beam_scores, sel, att2, W, w=0.0, want_lp0=False)
+    joint, log_psi, lists = _dense_and_lists(sc, ids, beam_scores, sel, att2, W, w=0.0)
     assert (joint[:, 5] == joint[:, 900]).all()
-    _check_lists(joint, log_psi, lists, beam_scores, B, W, V)
+    _check_lists(joint, lists, beam_scores, B, W, V)
 
 
 def _beam_buffers(B, W, V, L, maxlen, seed):
@@ -159,10 +147,9 @@ def _beam_buffers(B, W, V, L, maxlen, seed):
     return ids_cur, pool_scores, pool_lens, pool_seqs, done
 
 
-@pytest.mark.parametrize("B,W,T,V,use_lp0", [(3, 10, 100, 1200, True), (3, 10, 100, 1200, False), (2, 20, 90, 260, False), (5, 3, 40, 64, True)])
-def test_beam_step_over_lists_equals_the_dense_beam_step(B, W, T, V, use_lp0):
-    """Same outputs as ctcps_beam_step on the dense joint scores -- beam scores, rows, pool, done flags, selection ids --
-    plus s_next = what index_select_state would gather from log_psi (:193)."""
+@pytest.mark.parametrize("B,W,T,V", [(3, 10, 100, 1200), (2, 20, 90, 260), (5, 3, 40, 64)])
+def test_beam_step_over_lists_equals_the_dense_beam_step(B, W, T, V):
+    """Same outputs as ctcps_beam_step on the dense joint scores: beam scores, rows, pool, done flags, selection ids."""
     from huggingface_asr_b200.synthetic import make_attention_scores
 
     L, lib = _lib()
@@ -170,7 +157,7 @@ def test_beam_step_over_lists_equals_the_dense_beam_step(B, W, T, V, use_lp0):
     att = make_attention_scores(B * W, V, 9, seed=4, scale=0.5).cuda()
     att[:, EOS] += 6.0  # make eos competitive so that hypotheses are finalised into the pool
     att = torch.log_softmax(att, -1)
-    joint, log_psi, lists, lp0 = _dense_and_lists(sc, ids, beam_scores, sel, att, W, want_lp0=use_lp0)
+    joint, log_psi, lists = _dense_and_lists(sc, ids, beam_scores, sel, att, W)
     maxlen, Lcur = 16, ids.shape[1]
     n = ctypes.c_size_t(0)
     lib.ctcps_beam_step_workspace_bytes(B, W, ctypes.byref(n))
@@ -184,26 +171,19 @@ def test_beam_step_over_lists_equals_the_dense_beam_step(B, W, T, V, use_lp0):
         ws = torch.zeros((n.value + 15) // 16 * 2, dtype=torch.int64, device="cuda")
         best = torch.zeros((B, W), dtype=torch.long, device="cuda")
         last = torch.zeros((B * W,), dtype=torch.long, device="cuda")
-        s_next = torch.zeros((B * W,), device="cuda")
         common = (bs.data_ptr(), ids_cur.data_ptr(), ids_next.data_ptr(), maxlen, Lcur, B, W, V, EOS, BLANK, float(Lcur), pool_scores.data_ptr(),
                   pool_lens.data_ptr(), pool_seqs.data_ptr(), maxlen, done.data_ptr(), ws.data_ptr(), ws.numel() * 8, None, 0, 0)
         if fused:
-            L.check(lib.ctcps_beam_step_lists(lists.data_ptr(), lists.shape[1], *common, best.data_ptr(), last.data_ptr(), s_next.data_ptr(),
-                                              None if lp0 is None else lp0.data_ptr(), st), "ctcps_beam_step_lists")
+            L.check(lib.ctcps_beam_step_lists(lists.data_ptr(), lists.shape[1], *common, best.data_ptr(), last.data_ptr(), st), "ctcps_beam_step_lists")
         else:
             L.check(lib.ctcps_beam_step(joint.data_ptr(), *common, best.data_ptr(), st), "ctcps_beam_step")
         torch.cuda.synchronize()
-        outs.append((bs, ids_next[:, : Lcur + 1].clone(), pool_scores, pool_lens, pool_seqs, done, best, last, s_next))
+        outs.append((bs, ids_next[:, : Lcur + 1].clone(), pool_scores, pool_lens, pool_seqs, done, best, last))
     a, b = outs
     for k, name in enumerate(["beam_scores", "ids_next", "pool_scores", "pool_lens", "pool_seqs", "done", "best_ids"]):
         assert torch.equal(a[k], b[k]), f"{name} differs between the dense and the list beam step"
     assert (b[3] > 0).any(), "the case should finalise at least one hypothesis"
-    best, s_next = b[6], b[8]
-    assert torch.equal(b[7], (best % V).view(-1))
-    base = (torch.arange(B, device="cuda") * W * V).view(B, 1)
-    want = log_psi.view(-1)[(best + base).view(-1)] if not use_lp0 else log_psi.view(B, W, V)[:, 0].reshape(-1)[
-        ((best % V) + (torch.arange(B, device="cuda") * V).view(B, 1)).view(-1)]
-    assert torch.equal(s_next, want), "s_next differs from the log_psi entries index_select_state reads"
+    assert torch.equal(b[7], (b[6] % V).view(-1))
 
 
 @pytest.mark.parametrize("use_beam_idx", [False, True])
