@@ -14,6 +14,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SRC = os.path.join(_PKG, "csrc", "ctcps_kernels.cu")
+SOURCES = [SRC, os.path.join(_PKG, "csrc", "ctcps_head.cu")]  # translation units of the one library
 INCLUDE = os.path.join(_ROOT, "include")
 LIB_PATH = os.path.join(_PKG, "libctcps_b200.so")
 
@@ -52,7 +53,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if not force and fresh():
                 return LIB_PATH
             tmp = f"{LIB_PATH}.{os.getpid()}.tmp"
-            cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, SRC, "-o", tmp]
+            cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, *SOURCES, "-o", tmp]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
             env = dict(os.environ)
@@ -110,6 +111,9 @@ SIGNATURES = {
     "ctcps_decode_finish": [_p, _p],
     "ctcps_decode_session_size": [],
     "ctcps_split_tf32": [_p, _i64, _i, _i, _p, _p],
+    "ctcps_head_workspace_bytes": [_i64, _i, ctypes.POINTER(_sz)],
+    "ctcps_split_hi_lo": [_p, _i64, _p, _p, _p],
+    "ctcps_ctc_head": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _sz, _p],
     "ctcps_beam_step_candidates": [_p, _p, _i, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i64, _p, _p, _sz, _p, _i,
                                    _i64, _p, _p],
     "ctcps_select": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p],

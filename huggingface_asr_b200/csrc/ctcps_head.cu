@@ -1,0 +1,463 @@
+// ctcps_head.cu -- N4: the CTC head in front of the scorer as a hand-written tcgen05 kernel.
+//
+// Replaces, for BUTSpeechFIT/huggingface_asr, the step before the path:
+//   logits = Wav2Vec2ForCTC.lm_head(hidden)                 src/reguler/e_branchformer.py:245-252   (fp32 Linear: hidden W^T + b)
+//   x      = F.log_softmax(logits, dim=-1) + length padding src/decoding/ctc_scorer.py:279, :39-46
+//
+// k_head_gemm: logits tile by tile on the 5th-generation tensor cores at fp32 accuracy (3xTF32), bias and the row-wise
+// softmax statistics (running max, sum of exponentials) fused into the TMEM -> register epilogue; the raw logits go
+// straight into the scorer's padded (B,T,ldx) buffer, the per-row statistics into a small side array.
+// k_head_finish: one streaming pass turns the buffer into log-posteriors in place -- (z - max) - log(sum), the order
+// torch.log_softmax uses -- applies the length padding and extracts the blank column (what k_init does after a library GEMM,
+// without its two block-wide reductions).
+//
+// 3xTF32.  h and W are split into TF32-exact high parts (round to nearest) and fp32 remainders, h = h_hi + h_lo, and
+//   h W^T ~= h_lo W_hi^T + h_hi W_lo^T + h_hi W_hi^T          (the dropped h_lo W_lo^T is 2^-22 relative)
+// The tensor core accumulates in fp32 but rounds toward zero at every k-step, a bias proportional to the running sum
+// (round 1 measured it through cuBLAS: 7.6e-5 when the large term shares an accumulator with 192 k-steps, 1.8e-5 with 64).
+// So the two small cross terms accumulate in their OWN TMEM accumulator and the large term in another (64 k-steps at
+// d = 512); the epilogue adds the two in fp32 registers.
+//
+// Structure (one CTA per SM, persistent, 192 threads):
+//   warp 0      TMA producer: per k-block of 32 floats (128-byte rows, SWIZZLE_128B) the tiles h_hi, h_lo (128 x 32) and
+//               W_hi, W_lo (256 x 32) -- 96 KB per stage, 2 stages -- behind full / empty mbarriers
+//   warp 1      TMEM allocation (512 columns: two 128 x 256 fp32 accumulators) and, one elected lane, the MMA issue:
+//               per k-block 4 x (UMMA 128x256x8, kind::tf32) x 3 products; tcgen05.commit frees the stage / publishes the tile
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns at a time (a thread owns one row of the tile), big + small + bias,
+//               online max / sum-exp, 128-byte row segments stored with st.global.v4
+// Work item = (128-row tile, quarter of the vocabulary tiles): 4 x 746 items at C2 keep the last wave short; the partial
+// statistics of a row's quarters are combined by k_head_finish.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "ctcps.h"
+
+namespace {
+
+constexpr float LZ = CTCPS_LOGZERO;
+constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 32;  // BLOCK_K floats = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;                                  // kind::tf32: 32 bytes of K per instruction
+constexpr int NSTAGE = 2;
+constexpr int NCHUNK = 4;                                  // vocabulary quarters per row tile
+constexpr int HEAD_NT = 192;
+constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
+constexpr uint32_t B_TILE_BYTES = BLOCK_N * BLOCK_K * 4;   // 32 KB
+constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+constexpr uint32_t TMEM_COLS = 512;
+
+struct HeadSmem {
+    alignas(1024) unsigned char a_hi[NSTAGE][A_TILE_BYTES];
+    alignas(1024) unsigned char a_lo[NSTAGE][A_TILE_BYTES];
+    alignas(1024) unsigned char b_hi[NSTAGE][B_TILE_BYTES];
+    alignas(1024) unsigned char b_lo[NSTAGE][B_TILE_BYTES];
+    alignas(8) uint64_t full[NSTAGE];
+    alignas(8) uint64_t empty[NSTAGE];
+    alignas(8) uint64_t tmem_full;
+    alignas(8) uint64_t tmem_empty;
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .b32 rx;\n"
+        ".reg .pred px;\n"
+        "elect.sync rx|px, 0xffffffff;\n"
+        "selp.b32 %0, 1, 0, px;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// tcgen05.commit: the mbarrier gets one arrival when every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major, kind::tf32, issued by one thread for the CTA
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// shared-memory matrix descriptor of a K-major tile whose rows are 128 bytes, SWIZZLE_128B (what TMA wrote): 8-row groups
+// are 1024 bytes apart (stride byte offset), the leading byte offset is unused for swizzled K-major layouts, descriptor
+// version 1 (sm_100), layout type 2 = SWIZZLE_128B.  A K-step of 32 bytes inside the swizzle row advances the start address.
+__device__ __forceinline__ uint64_t smem_desc_sw128(const void *tile, uint32_t byte_offset) {
+    const uint32_t addr = smem_u32(tile) + byte_offset;
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);          // start address, bits [0,14)
+    d |= (uint64_t)1 << 16;                         // leading byte offset (ignored), bits [16,30)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset, bits [32,46)
+    d |= (uint64_t)1 << 46;                         // version, bits [46,48)
+    d |= (uint64_t)2 << 61;                         // layout type SWIZZLE_128B, bits [61,64)
+    return d;
+}
+// instruction descriptor of kind::tf32 (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, dense, N x M
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// 32 TMEM lanes (this warp's quarter) x 32 consecutive columns -> 32 registers per thread (thread = lane = tile row)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+struct HeadArgs {
+    const float *bias;   // (V) or null
+    float *z;            // (n, ldz) raw logits out (the scorer's padded posterior buffer)
+    float2 *stats;       // (n, NCHUNK): running max and sum of exp(z - max) over the chunk's columns
+    int n, d, V, ldz;
+    int n_mtiles, n_ntiles, tiles_per_chunk;
+};
+
+__global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                                                          const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                                                          const HeadArgs a) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    HeadSmem &sm = *reinterpret_cast<HeadSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_kblocks = a.d / BLOCK_K;
+    const int n_items = a.n_mtiles * NCHUNK;
+
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < NSTAGE; ++s) mbar_init(&sm.full[s], 1), mbar_init(&sm.empty[s], 1);
+            mbar_init(&sm.tmem_full, 1);
+            mbar_init(&sm.tmem_empty, 4);  // one arrival per epilogue warp
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        // the whole warp allocates all 512 TMEM columns (one CTA per SM) and lets go of the permit
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (elect_one()) {
+            uint32_t it = 0;  // k-blocks issued so far (stage = it % NSTAGE)
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                const int mt = item / NCHUNK, ch = item % NCHUNK;
+                const int nt0 = ch * a.tiles_per_chunk, nt1 = min(a.n_ntiles, nt0 + a.tiles_per_chunk);
+                for (int nt = nt0; nt < nt1; ++nt)
+                    for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
+                        const int s = it % NSTAGE;
+                        mbar_wait(&sm.empty[s], ((it / NSTAGE) & 1) ^ 1);  // first pass over the ring: passes at once
+                        mbar_expect_tx(&sm.full[s], STAGE_BYTES);
+                        tma_load_2d(sm.a_hi[s], &tm_a_hi, kb * BLOCK_K, mt * BLOCK_M, &sm.full[s]);
+                        tma_load_2d(sm.a_lo[s], &tm_a_lo, kb * BLOCK_K, mt * BLOCK_M, &sm.full[s]);
+                        tma_load_2d(sm.b_hi[s], &tm_b_hi, kb * BLOCK_K, nt * BLOCK_N, &sm.full[s]);
+                        tma_load_2d(sm.b_lo[s], &tm_b_lo, kb * BLOCK_K, nt * BLOCK_N, &sm.full[s]);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+        const uint32_t d_big = tmem_base, d_small = tmem_base + BLOCK_N;
+        uint32_t it = 0, tile = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int ch = item % NCHUNK;
+            const int nt0 = ch * a.tiles_per_chunk, nt1 = min(a.n_ntiles, nt0 + a.tiles_per_chunk);
+            for (int nt = nt0; nt < nt1; ++nt, ++tile) {
+                mbar_wait(&sm.tmem_empty, (tile & 1) ^ 1);  // the epilogue has drained the accumulators of the previous tile
+                tc_fence_after();
+                for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
+                    const int s = it % NSTAGE;
+                    mbar_wait(&sm.full[s], (it / NSTAGE) & 1);
+                    tc_fence_after();
+                    if (elect_one()) {
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint32_t off = k * UMMA_K * 4;
+                            const uint64_t ah = smem_desc_sw128(sm.a_hi[s], off), al = smem_desc_sw128(sm.a_lo[s], off);
+                            const uint64_t bh = smem_desc_sw128(sm.b_hi[s], off), bl = smem_desc_sw128(sm.b_lo[s], off);
+                            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                            umma_tf32(d_small, al, bh, idesc, acc);  // h_lo W_hi^T
+                            umma_tf32(d_small, ah, bl, idesc, 1u);   // h_hi W_lo^T
+                            umma_tf32(d_big, ah, bh, idesc, acc);    // h_hi W_hi^T
+                        }
+                    }
+                    __syncwarp();
+                    if (elect_one()) {
+                        umma_commit(&sm.empty[s]);                          // the stage is free once these MMAs have read it
+                        if (kb == n_kblocks - 1) umma_commit(&sm.tmem_full);  // and the tile is complete
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else {
+        // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4, thread = one row of the tile =====
+        const int quarter = warp & 3;
+        const int row_in_tile = quarter * 32 + lane;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        uint32_t tile = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+            const int mt = item / NCHUNK, ch = item % NCHUNK;
+            const int nt0 = ch * a.tiles_per_chunk, nt1 = min(a.n_ntiles, nt0 + a.tiles_per_chunk);
+            const long long row = (long long)mt * BLOCK_M + row_in_tile;
+            const bool row_ok = row < a.n;
+            float *zrow = a.z + (size_t)(row_ok ? row : 0) * a.ldz;
+            float m_run = -INFINITY, s_run = 0.f;
+            for (int nt = nt0; nt < nt1; ++nt, ++tile) {
+                mbar_wait(&sm.tmem_full, tile & 1);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N / 32; ++c) {
+                    float big[32], small[32];
+                    tmem_ld_32x32(lane_base + (uint32_t)(c * 32), big);
+                    tmem_ld_32x32(lane_base + (uint32_t)(BLOCK_N + c * 32), small);
+                    const int v0 = nt * BLOCK_N + c * 32;
+                    if (v0 >= a.V) continue;  // warp-uniform: a column group beyond the vocabulary
+                    float zv[32];
+                    float gmax = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float b = 0.f;
+                        if (a.bias != nullptr && v0 + j < a.V) b = __ldg(a.bias + v0 + j);
+                        zv[j] = (big[j] + small[j]) + b;
+                        if (v0 + j < a.V) gmax = fmaxf(gmax, zv[j]);
+                    }
+                    const float m_new = fmaxf(m_run, gmax);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (v0 + j < a.V) acc += expf(zv[j] - m_new);
+                    s_run = s_run * expf(m_run - m_new) + acc;  // exp(-inf) = 0 on the first group
+                    m_run = m_new;
+                    if (row_ok) {
+                        if (v0 + 32 <= a.V) {
+#pragma unroll
+                            for (int q = 0; q < 8; ++q)
+                                *reinterpret_cast<float4 *>(zrow + v0 + q * 4) = make_float4(zv[q * 4], zv[q * 4 + 1], zv[q * 4 + 2], zv[q * 4 + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (v0 + j < a.V) zrow[v0 + j] = zv[j];
+                        }
+                    }
+                }
+                // every value of this tile is in registers or stored: hand the accumulators back to the MMA warp
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.tmem_empty);
+            }
+            if (row_ok) a.stats[(size_t)row * NCHUNK + ch] = make_float2(m_run, s_run);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+// x -> (TF32-exact high part, fp32 remainder): hi = round-to-nearest TF32, lo = x - hi (exact in fp32)
+__global__ void __launch_bounds__(256) k_split_hi_lo(const float *__restrict__ x, long long n4, float *__restrict__ hi, float *__restrict__ lo) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = reinterpret_cast<const float4 *>(x)[i];
+        const float in[4] = {v.x, v.y, v.z, v.w};
+        float h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            unsigned t;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(in[j]));
+            h[j] = __uint_as_float(t);
+            l[j] = in[j] - h[j];
+        }
+        reinterpret_cast<float4 *>(hi)[i] = make_float4(h[0], h[1], h[2], h[3]);
+        reinterpret_cast<float4 *>(lo)[i] = make_float4(l[0], l[1], l[2], l[3]);
+    }
+}
+
+// One CTA per (b, t) row: combine the row's partial statistics, then stream the row once: x = (z - max) - log(sum),
+// length padding (:39-42) and the blank column (:44-46).  No reduction, no barrier: what k_init does in three phases.
+__global__ void __launch_bounds__(256) k_head_finish(float *x, int ldx, const float2 *__restrict__ stats, const int64_t *__restrict__ lens,
+                                                     int T, int V, int blank, float *__restrict__ blank_lp) {
+    const int row = blockIdx.x;
+    const int b = row / T, t = row - b * T;
+    float *dst = x + (size_t)row * ldx;
+    if (lens != nullptr) {
+        const long long lraw = lens[b];
+        long long l = lraw < 0 ? lraw + T : lraw;
+        if (l < 0) l = 0;
+        if (lraw < T && t >= l) {  // ctc_scorer.py:39-42
+            for (int v = threadIdx.x; v < V; v += blockDim.x) dst[v] = (v == blank) ? 0.f : LZ;
+            if (blank_lp != nullptr && threadIdx.x == 0) blank_lp[row] = 0.f;
+            return;
+        }
+    }
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) m = fmaxf(m, stats[(size_t)row * NCHUNK + c].x);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+        const float2 p = stats[(size_t)row * NCHUNK + c];
+        if (p.y > 0.f) s += p.y * expf(p.x - m);
+    }
+    const float ls = logf(s);
+    if ((V & 3) == 0 && (ldx & 3) == 0) {
+        const int n4 = V >> 2;
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+            const float4 z = reinterpret_cast<const float4 *>(dst)[i];
+            const float4 o = make_float4((z.x - m) - ls, (z.y - m) - ls, (z.z - m) - ls, (z.w - m) - ls);
+            reinterpret_cast<float4 *>(dst)[i] = o;
+            if (blank_lp != nullptr && (blank >> 2) == i) blank_lp[row] = (&o.x)[blank & 3];
+        }
+    } else {
+        for (int v = threadIdx.x; v < V; v += blockDim.x) {
+            const float o = (dst[v] - m) - ls;
+            dst[v] = o;
+            if (v == blank && blank_lp != nullptr) blank_lp[row] = o;
+        }
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+// (rows, d) fp32 row-major operand: boxes of box_rows x 32 floats, 128-byte swizzle
+int encode_operand(CUtensorMap *tm, const float *p, long long rows, int d, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) return CTCPS_E_NODRIVER;
+    cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)d * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return cr == CUDA_SUCCESS ? 0 : CTCPS_E_NODRIVER;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ctcps_head_workspace_bytes(int64_t n, int d, size_t *out_bytes) {
+    if (out_bytes == nullptr || n <= 0 || d <= 0) return CTCPS_E_BADARG;
+    // h_hi, h_lo (n, d) + the partial softmax statistics (n, NCHUNK) float2
+    *out_bytes = 2 * (size_t)n * d * sizeof(float) + (size_t)n * NCHUNK * sizeof(float2) + 512;
+    return 0;
+}
+
+int ctcps_split_hi_lo(const float *x, int64_t count, float *hi, float *lo, void *stream) {
+    if (!x || !hi || !lo || count <= 0 || (count & 3)) return CTCPS_E_BADARG;
+    if ((((uintptr_t)x) | ((uintptr_t)hi) | ((uintptr_t)lo)) & 15) return CTCPS_E_ALIGN;
+    const long long n4 = count >> 2;
+    long long g = (n4 + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    k_split_hi_lo<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(x, n4, hi, lo);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+int ctcps_ctc_head(const float *hidden, const float *w_hi, const float *w_lo, const float *bias, const int64_t *lens, int B, int T, int d,
+                   int V, int blank, int apply_log_softmax, float *x_logp, int ldx, float *blank_lp, void *workspace,
+                   size_t workspace_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!hidden || !w_hi || !w_lo || !x_logp || !workspace || B <= 0 || T <= 0 || d <= 0 || V <= 0) return CTCPS_E_BADARG;
+    if (blank < 0 || blank >= V || ldx < V) return CTCPS_E_BADARG;
+    if ((d % BLOCK_K) != 0 || (ldx & 3) != 0) return CTCPS_E_ALIGN;
+    if ((((uintptr_t)hidden) | ((uintptr_t)w_hi) | ((uintptr_t)w_lo) | ((uintptr_t)x_logp) | ((uintptr_t)workspace)) & 15) return CTCPS_E_ALIGN;
+    const long long n = (long long)B * T;
+    if (n >= (1ll << 31)) return CTCPS_E_TOOBIG;
+    size_t need = 0;
+    ctcps_head_workspace_bytes(n, d, &need);
+    if (workspace_bytes < need) return CTCPS_E_WORKSPACE;
+    float *h_hi = reinterpret_cast<float *>(workspace);
+    float *h_lo = h_hi + (size_t)n * d;
+    float2 *stats = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(h_lo + (size_t)n * d) + 255) & ~(uintptr_t)255);
+    int rc = ctcps_split_hi_lo(hidden, n * d, h_hi, h_lo, stream);
+    if (rc) return rc;
+
+    CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
+    if ((rc = encode_operand(&tm_a_hi, h_hi, n, d, BLOCK_M)) || (rc = encode_operand(&tm_a_lo, h_lo, n, d, BLOCK_M)) ||
+        (rc = encode_operand(&tm_b_hi, w_hi, V, d, BLOCK_N)) || (rc = encode_operand(&tm_b_lo, w_lo, V, d, BLOCK_N)))
+        return rc;
+    HeadArgs a;
+    a.bias = bias, a.z = x_logp, a.stats = stats, a.n = (int)n, a.d = d, a.V = V, a.ldz = ldx;
+    a.n_mtiles = (int)((n + BLOCK_M - 1) / BLOCK_M);
+    a.n_ntiles = (V + BLOCK_N - 1) / BLOCK_N;
+    a.tiles_per_chunk = (a.n_ntiles + NCHUNK - 1) / NCHUNK;
+    const size_t smem = sizeof(HeadSmem) + 1024;
+    cudaError_t e = cudaFuncSetAttribute(k_head_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int items = a.n_mtiles * NCHUNK;
+    k_head_gemm<<<items < sms ? items : sms, HEAD_NT, smem, st>>>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, a);
+    if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+    if (!apply_log_softmax) return 0;  // raw logits (tests, callers that want the head alone)
+    k_head_finish<<<(unsigned)n, 256, 0, st>>>(x_logp, ldx, stats, lens, T, V, blank, blank_lp);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+}  // extern "C"

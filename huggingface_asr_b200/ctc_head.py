@@ -1,19 +1,24 @@
-"""The CTC head in front of the scorer: logits = hidden @ W^T + b at fp32 accuracy on tensor cores.
+"""The CTC head in front of the scorer: hidden states -> log-posteriors on the tensor cores at fp32 accuracy.
 
 In the reference the head is the stock `Wav2Vec2ForCTC.lm_head` Linear (src/reguler/e_branchformer.py:245-252), an fp32
 SGEMM of (B*T, d) x (d, V) on the CUDA cores (C2: 0.49 TFLOP, ~7 ms on a B200) whose (B,T,V) output the processor then
-log-softmaxes.  A single-pass TF32 GEMM would be 10x faster but misses the 1e-4 log-space tolerance of the path
-(10-bit mantissas).  Here both operands are split into TF32-exact high and low parts by `ctcps_split_tf32` and stacked
-along K, so ONE TF32 GEMM with fp32 accumulation computes hi*lo + lo*hi + hi*hi -- the dropped lo*lo term is 2^-22
-relative -- at a third of the TF32 rate.  The GEMM itself is a plain library call (cuBLAS through
-torch.addmm, bias in its epilogue); the log-softmax + padding that follows is K-a (`ctcps_init`).
+log-softmaxes (src/decoding/ctc_scorer.py:279).  A single-pass TF32 GEMM would be 10x faster but misses the 1e-4 log-space
+tolerance of the path (10-bit mantissas).  Both operands are therefore split into TF32-exact high parts and fp32 remainders,
+and three TF32 products -- hi*lo + lo*hi + hi*hi, the dropped lo*lo term is 2^-22 relative -- give fp32-grade logits.
 
-Status: N4 is only started -- fusing the bias / row-max / sum-exp epilogue into a hand-written tcgen05 GEMM (so that the
-logits are never written to HBM) is the remaining work.
+Two implementations behind one class (`implementation`, env CTCPS_HEAD):
+  "tcgen05" (default)  csrc/ctcps_head.cu: a hand-written sm_100a kernel -- TMA-fed `tcgen05.mma.kind::tf32`, the large
+                       product and the two small cross terms in separate TMEM accumulators, bias and the row-wise softmax
+                       statistics in the TMEM -> register epilogue, logits written straight into the scorer's padded posterior
+                       buffer -- followed by one streaming normalisation pass (log-softmax, length padding, blank column).
+  "cublas"             round 1's form, kept for A/B: `ctcps_split_tf32` stacks the split operands along K and ONE library TF32
+                       GEMM (cuBLAS through torch.addmm) accumulates the three products; K-a (`ctcps_init`) follows.
 """
 from __future__ import annotations
 
 import contextlib
+import ctypes
+import os
 
 import torch
 
@@ -46,23 +51,99 @@ def split_tf32(x: torch.Tensor, weight_order: bool) -> torch.Tensor:
     return out
 
 
-class CTCHead:
-    """`lm_head` of the encoder: weight (V,d), bias (V) or None.  The weight is split once; __call__ maps encoder hidden
-    states (B,T,d) to the (B,T,V) logits the processor takes."""
+def split_hi_lo(x: torch.Tensor) -> tuple[torch.Tensor, torch.Tensor]:
+    """fp32 tensor -> (TF32-exact high part, fp32 remainder), same shape (ctcps_split_hi_lo)."""
+    if not x.is_cuda or x.dtype != torch.float32 or not x.is_contiguous() or x.numel() % 4:
+        raise ValueError("split_hi_lo needs a contiguous float32 CUDA tensor whose size is a multiple of 4")
+    with torch.cuda.device(x.device):
+        hi, lo = torch.empty_like(x), torch.empty_like(x)
+        _lib.check(_lib.lib().ctcps_split_hi_lo(x.data_ptr(), x.numel(), hi.data_ptr(), lo.data_ptr(), _stream(x.device)), "ctcps_split_hi_lo")
+    return hi, lo
 
-    def __init__(self, weight: torch.Tensor, bias: torch.Tensor | None = None):
+
+class CTCHead:
+    """`lm_head` of the encoder: weight (V,d), bias (V) or None.  The weight is split once; `log_posteriors` maps encoder
+    hidden states (B,T,d) to what the scorer keeps -- padded log-posteriors (B,T,ldx) and the blank column -- and `__call__` to
+    the (B,T,V) logits (the head alone)."""
+
+    def __init__(self, weight: torch.Tensor, bias: torch.Tensor | None = None, implementation: str | None = None):
         if weight.dim() != 2 or weight.shape[1] % 4 != 0:
             raise ValueError("lm_head weight must be (V, d) with d a multiple of 4")
+        if not weight.is_cuda:
+            raise RuntimeError("the CTC head runs on the GPU only (there is no CPU path)")
         self.vocab, self.dim = (int(v) for v in weight.shape)
-        self.weight3 = split_tf32(weight.detach().contiguous(), weight_order=True)
+        impl = implementation or os.environ.get("CTCPS_HEAD", "tcgen05")
+        if impl not in ("tcgen05", "cublas"):
+            raise ValueError(f"unknown CTC head implementation {impl!r}")
+        if impl == "tcgen05" and self.dim % 32 != 0:
+            raise ValueError("the tcgen05 CTC head needs a hidden size that is a multiple of 32 (one 128-byte swizzle row of fp32)")
+        self.implementation = impl
+        w = weight.detach().to(torch.float32).contiguous()
         self.bias = None if bias is None else bias.detach().to(torch.float32).contiguous()
+        if impl == "tcgen05":
+            self.w_hi, self.w_lo = split_hi_lo(w)
+            self._ws = None
+        else:
+            self.weight3 = split_tf32(w, weight_order=True)
+
+    def _workspace(self, n: int, device):
+        need = ctypes.c_size_t(0)
+        _lib.check(_lib.lib().ctcps_head_workspace_bytes(n, self.dim, ctypes.byref(need)), "ctcps_head_workspace_bytes")
+        if self._ws is None or self._ws.numel() < need.value or self._ws.device != device:
+            self._ws = torch.empty((need.value,), dtype=torch.uint8, device=device)
+        return self._ws
+
+    def _check_hidden(self, hidden):
+        if hidden.dim() != 3 or hidden.shape[-1] != self.dim:
+            raise ValueError(f"hidden states must be (B, T, {self.dim}), got {tuple(hidden.shape)}")
+        if not hidden.is_cuda:
+            raise RuntimeError("hidden states must be a CUDA tensor (there is no CPU path)")
+        if hidden.is_floating_point() and hidden.dtype != torch.float32:
+            hidden = hidden.float()
+        return hidden.contiguous()
+
+    def _run_tcgen05(self, hidden, lens, blank, out, ldx, blank_lp, apply_log_softmax):
+        B, T, _ = hidden.shape
+        L = _lib.lib()
+        with torch.cuda.device(hidden.device):
+            ws = self._workspace(B * T, hidden.device)
+            _lib.check(L.ctcps_ctc_head(hidden.data_ptr(), self.w_hi.data_ptr(), self.w_lo.data_ptr(),
+                                        None if self.bias is None else self.bias.data_ptr(), None if lens is None else lens.data_ptr(),
+                                        B, T, self.dim, self.vocab, int(blank), int(apply_log_softmax), out.data_ptr(), ldx,
+                                        None if blank_lp is None else blank_lp.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        _stream(hidden.device)), "ctcps_ctc_head")
+
+    @torch.no_grad()
+    def log_posteriors(self, hidden: torch.Tensor, lens: torch.Tensor, blank: int):
+        """(x (B,T,ldx) padded log-posteriors, blank_lp (B,T)): what CTCPrefixScoreTH.from_logits builds from the logits."""
+        hidden = self._check_hidden(hidden)
+        B, T, _ = hidden.shape
+        L = _lib.lib()
+        ldx = L.ctcps_padded_ld(self.vocab)
+        lens = lens.to(device=hidden.device, dtype=torch.long).contiguous()
+        with torch.cuda.device(hidden.device):
+            x = torch.empty((B, T, ldx), dtype=torch.float32, device=hidden.device)
+            blank_lp = torch.empty((B, T), dtype=torch.float32, device=hidden.device)
+            if self.implementation == "tcgen05":
+                self._run_tcgen05(hidden, lens, blank, x, ldx, blank_lp, True)
+            else:
+                logits = self(hidden)
+                _lib.check(L.ctcps_init(logits.data_ptr(), self.vocab, lens.data_ptr(), B, T, self.vocab, int(blank), 1, x.data_ptr(), ldx,
+                                        blank_lp.data_ptr(), _stream(hidden.device)), "ctcps_init")
+        return x, blank_lp
 
     @torch.no_grad()
     def __call__(self, hidden: torch.Tensor) -> torch.Tensor:
-        if hidden.dim() != 3 or hidden.shape[-1] != self.dim:
-            raise ValueError(f"hidden states must be (B, T, {self.dim}), got {tuple(hidden.shape)}")
+        """The head alone: (B,T,V) logits."""
+        hidden = self._check_hidden(hidden)
         B, T, d = hidden.shape
-        h3 = split_tf32(hidden.reshape(B * T, d).contiguous(), weight_order=False)
+        if self.implementation == "tcgen05":
+            ldz = (self.vocab + 3) & ~3
+            with torch.cuda.device(hidden.device):
+                z = torch.empty((B, T, ldz), dtype=torch.float32, device=hidden.device)
+            self._run_tcgen05(hidden, None, 0, z, ldz, None, False)
+            return z[..., : self.vocab]
+        h3 = split_tf32(hidden.reshape(B * T, d), weight_order=False)
         with _tf32_matmul():
             if self.bias is not None:
                 logits = torch.addmm(self.bias, h3, self.weight3.t())

@@ -151,6 +151,31 @@ class CTCPrefixScoreTH(object):
         self._setup(logits.contiguous(), xlens, blank, eos, margin, apply_log_softmax=True, token_major=token_major)
         return self
 
+    @classmethod
+    def from_hidden_states(cls, hidden, head, xlens, blank, eos, margin=0, token_major=False):
+        """the scorer built from the encoder's last hidden states (B,T,d) and its CTC head (ctc_head.CTCHead):
+        the head kernel writes the padded log-posteriors and the blank column itself, K-a is not run."""
+        self = cls.__new__(cls)
+        L = _lib.lib()
+        self.logzero = LOGZERO
+        self.blank, self.eos, self.margin = int(blank), eos, margin
+        self.batch, self.input_length, self.odim = int(hidden.shape[0]), int(hidden.shape[1]), int(head.vocab)
+        self.dtype, self.device = torch.float32, hidden.device
+        if not 0 <= self.blank < self.odim:
+            raise ValueError(f"blank id {blank} is outside the CTC vocabulary of size {self.odim}")
+        lens = torch.as_tensor(xlens)
+        if lens.numel() != self.batch:
+            raise ValueError(f"xlens has {lens.numel()} entries for a batch of {self.batch}")
+        self.end_frames = lens - 1
+        self._lens = lens.to(device=self.device, dtype=torch.long).contiguous()
+        self._ldx = L.ctcps_padded_ld(self.odim)
+        self._xt, self._ldt = None, L.ctcps_padded_lt(self.input_length)
+        self._x, self._blank_lp = head.log_posteriors(hidden, self._lens, self.blank)
+        if token_major:
+            self._token_major()
+        self._finish_setup(margin)
+        return self
+
     def _setup(self, x, xlens, blank, eos, margin, apply_log_softmax, token_major=False):
         L = _lib.lib()
         self.logzero = LOGZERO
@@ -578,15 +603,26 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
             every beam inherits from hypothesis 0 of its utterance).  True = use the ids handed over by `set_beam_idx` /
             `prefetch_state(best_ids=...)` (source hypothesis * V + token, ESPnet's semantics, reference :180-191).
             None = True when pre_beam_size > 0 (a token is only scored for the hypothesis that proposed it), else False."""
-        super().__init__()
+        self._init_common(encoder_logits, encoder_output_lens, pad_token_id, eos_token_id, ctc_margin, ctc_weight, num_beams, space_token_id,
+                          apply_eos_space_trick, eos_space_trick_weight, debug, materialize_state=materialize_state,
+                          pre_beam_size=pre_beam_size, use_beam_idx=use_beam_idx)
+
+    def _init_common(self, encoder_logits, encoder_output_lens, pad_token_id, eos_token_id, ctc_margin, ctc_weight, num_beams,
+                     space_token_id, apply_eos_space_trick, eos_space_trick_weight, debug=False, *, materialize_state=None,
+                     pre_beam_size=0, use_beam_idx=None, hidden_states=None, ctc_head=None):
+        LogitsProcessor.__init__(self)
         self.pad_token_id = pad_token_id
         self.pre_beam_size = int(pre_beam_size)
         if self.pre_beam_size < 0 or self.pre_beam_size > 64 or self.pre_beam_size == 1:
             # beam search draws 2W candidates out of the W * S scored ones: S = 1 leaves fewer than 2W, and the unscored
             # tokens it would then pick select lane 0 with a logzero prefix score -- every later state would be garbage
             raise ValueError("pre_beam_size must be 0 (full vocabulary) or in [2, 64] (W * S >= 2W candidates are needed)")
-        self.ctc_prefix_scorer = CTCPrefixScoreTH.from_logits(encoder_logits, encoder_output_lens, pad_token_id, eos_token_id,
-                                                              ctc_margin, token_major=self.pre_beam_size > 0)
+        if hidden_states is not None:
+            self.ctc_prefix_scorer = CTCPrefixScoreTH.from_hidden_states(hidden_states, ctc_head, encoder_output_lens, pad_token_id,
+                                                                        eos_token_id, ctc_margin, token_major=self.pre_beam_size > 0)
+        else:
+            self.ctc_prefix_scorer = CTCPrefixScoreTH.from_logits(encoder_logits, encoder_output_lens, pad_token_id, eos_token_id,
+                                                                  ctc_margin, token_major=self.pre_beam_size > 0)
         if materialize_state is None:
             materialize_state = os.environ.get("CTCPS_MATERIALIZE_STATE", "0") not in ("0", "false", "False", "no")
         self.materialize_state = bool(materialize_state)
@@ -612,7 +648,9 @@ class CTCRescorerLogitsProcessor(LogitsProcessor):
         """take the encoder's last hidden states (B,T,d) and its CTC head (ctc_head.CTCHead) instead of the
         (B,T,V) logits -- a tenth of the bytes -- and compute the logits here (TF32x3 tensor-core GEMM, fp32 accuracy).
         The remaining arguments are those of the constructor after `encoder_output_lens`."""
-        return cls(ctc_head(hidden_states), encoder_output_lens, *args, **kwargs)
+        self = cls.__new__(cls)
+        self._init_common(None, encoder_output_lens, *args, hidden_states=hidden_states, ctc_head=ctc_head, **kwargs)
+        return self
 
     # -- state selection ----------------------------------------------------------------------------------
     def set_beam_idx(self, beam_idx: torch.LongTensor) -> None:

@@ -315,7 +315,23 @@ int ctcps_eos_space_trick(const float *att_scores, const float *ctc_scores, floa
                           int space, float k, void *stream);
 
 /*
- * N4 (the step before the path): operand split for the CTC head's GEMM (Wav2Vec2ForCTC.lm_head, src/reguler/
+ * N4 (the step before the path): the CTC head itself.  Replaces Wav2Vec2ForCTC.lm_head (src/reguler/e_branchformer.py:245-252:
+ * logits = hidden W^T + b, an fp32 Linear) followed by F.log_softmax (src/decoding/ctc_scorer.py:279) and the length padding
+ * (:39-46), i.e. it produces what ctcps_init produces, from the encoder's hidden states instead of its logits.
+ *   hidden (B*T, d) fp32;  w_hi / w_lo (V, d): the head's weight split once with ctcps_split_hi_lo;  bias (V) or NULL
+ *   x_logp (B,T,ldx), blank_lp (B,T): as ctcps_init;  apply_log_softmax = 0: x_logp receives the raw logits (no padding)
+ * A hand-written tcgen05 kernel (TMA-fed 3xTF32 UMMA, two TMEM accumulators -- large term / small cross terms -- bias and the
+ * softmax statistics in the TMEM -> register epilogue) + one streaming normalisation pass; fp32-grade accuracy (max logit
+ * error ~2e-5 at d = 512).  d must be a multiple of 32.  workspace: ctcps_head_workspace_bytes(B*T, d), 16-byte aligned.
+ */
+int ctcps_head_workspace_bytes(int64_t n, int d, size_t *out_bytes);
+int ctcps_split_hi_lo(const float *x, int64_t count, float *hi, float *lo, void *stream);
+int ctcps_ctc_head(const float *hidden, const float *w_hi, const float *w_lo, const float *bias, const int64_t *lens, int B, int T, int d,
+                   int V, int blank, int apply_log_softmax, float *x_logp, int ldx, float *blank_lp, void *workspace,
+                   size_t workspace_bytes, void *stream);
+
+/*
+ * Round-1 form of the same head, kept for A/B (CTCPS_HEAD=cublas): operand split for a library GEMM (Wav2Vec2ForCTC.lm_head, src/reguler/
  * e_branchformer.py:245-252) at fp32 accuracy on the TF32 tensor cores.  x (n,d) -> out (n,3d):
  * weight_order = 0: [hi | lo | hi] (activations), 1: [lo | hi | hi] (weights); hi = tf32(x) rounded to nearest,
  * lo = x - hi.  out_h out_W^T = hi lo + lo hi + hi hi in one TF32 GEMM with fp32 accumulation (small terms first).
