@@ -113,6 +113,8 @@ SIGNATURES = {
     "ctcps_split_tf32": [_p, _i64, _i, _i, _p, _p],
     "ctcps_head_workspace_bytes": [_i64, _i, ctypes.POINTER(_sz)],
     "ctcps_split_hi_lo": [_p, _i64, _p, _p, _p],
+    "ctcps_head_weight_bytes": [_i, _i, ctypes.POINTER(_sz)],
+    "ctcps_head_prepare_weight": [_p, _i, _i, _p, _p, _p],
     "ctcps_ctc_head": [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _sz, _p],
     "ctcps_beam_step_candidates": [_p, _p, _i, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i64, _p, _p, _sz, _p, _i,
                                    _i64, _p, _p],

@@ -18,13 +18,14 @@
 // So the two small cross terms accumulate in their OWN TMEM accumulator and the large term in another (64 k-steps at
 // d = 512); the epilogue adds the two in fp32 registers.
 //
-// Structure (one CTA per SM, persistent, 192 threads):
-//   warp 0      TMA producer: per k-block of 32 floats (128-byte rows, SWIZZLE_128B) the tiles h_hi, h_lo (128 x 32) and
-//               W_hi, W_lo (256 x 32) -- 96 KB per stage, 2 stages -- behind full / empty mbarriers
+// Structure (one CTA per SM, persistent, 320 threads):
+//   warp 0      TMA producer: per k-block of 16 floats the tiles h_hi, h_lo (128 x 16) and W_hi, W_lo (256 x 16), each ONE
+//               contiguous bulk copy of a pre-swizzled image (k_split_blocked) -- 48 KB per stage, 4 stages -- behind
+//               full / empty mbarriers
 //   warp 1      TMEM allocation (512 columns: two 128 x 256 fp32 accumulators) and, one elected lane, the MMA issue:
-//               per k-block 4 x (UMMA 128x256x8, kind::tf32) x 3 products; tcgen05.commit frees the stage / publishes the tile
-//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns at a time (a thread owns one row of the tile), big + small + bias,
-//               online max / sum-exp, 128-byte row segments stored with st.global.v4
+//               per k-block 2 x (UMMA 128x256x8, kind::tf32) x 3 products; tcgen05.commit frees the stage / publishes the tile
+//   warps 2-9   epilogue: tcgen05.ld 32 lanes x 32 columns at a time, software-pipelined (a thread owns one row of the tile and
+//               half of its columns), big + small + bias, online max / sum-exp, 128-byte row segments stored with st.global.v4
 // Work item = (128-row tile, quarter of the vocabulary tiles): 4 x 746 items at C2 keep the last wave short; the partial
 // statistics of a row's quarters are combined by k_head_finish.
 #include <cuda.h>
@@ -37,13 +38,15 @@
 namespace {
 
 constexpr float LZ = CTCPS_LOGZERO;
-constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 32;  // BLOCK_K floats = 128 bytes = one swizzle row
+constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 16;  // BLOCK_K floats = 64 bytes = one SWIZZLE_64B row
 constexpr int UMMA_K = 8;                                  // kind::tf32: 32 bytes of K per instruction
-constexpr int NSTAGE = 2;
+constexpr int NSTAGE = 4;                                  // 4 x 48 KB: the first version (2 x 96 KB, 128-byte rows) starved the MMAs
+constexpr float LOG2E_F = 1.4426950408889634f;
 constexpr int NCHUNK = 4;                                  // vocabulary quarters per row tile
-constexpr int HEAD_NT = 192;
-constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;   // 16 KB
-constexpr uint32_t B_TILE_BYTES = BLOCK_N * BLOCK_K * 4;   // 32 KB
+constexpr int HEAD_NT = 320;                               // TMA warp, MMA warp, 8 epilogue warps
+constexpr int NPART = NCHUNK * 2;                          // partial softmax statistics per row: (vocabulary quarter, column half)
+constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;   // 8 KB
+constexpr uint32_t B_TILE_BYTES = BLOCK_N * BLOCK_K * 4;   // 16 KB
 constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
 
@@ -82,11 +85,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(smem_u32(dst)),
-        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-        : "memory");
+// TMA bulk copy of one contiguous, pre-swizzled operand tile (SASS UBLKCP)
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
@@ -117,26 +120,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// shared-memory matrix descriptor of a K-major tile whose rows are 128 bytes, SWIZZLE_128B (what TMA wrote): 8-row groups
-// are 1024 bytes apart (stride byte offset), the leading byte offset is unused for swizzled K-major layouts, descriptor
-// version 1 (sm_100), layout type 2 = SWIZZLE_128B.  A K-step of 32 bytes inside the swizzle row advances the start address.
-__device__ __forceinline__ uint64_t smem_desc_sw128(const void *tile, uint32_t byte_offset) {
+// shared-memory matrix descriptor of a K-major tile whose rows are 64 bytes, SWIZZLE_64B (what TMA wrote): 8-row groups are
+// 512 bytes apart (stride byte offset), the leading byte offset is unused for swizzled K-major layouts, descriptor version 1
+// (sm_100), layout type 4 = SWIZZLE_64B.  A K-step of 32 bytes inside the swizzle row advances the start address.
+__device__ __forceinline__ uint64_t smem_desc_sw64(const void *tile, uint32_t byte_offset) {
     const uint32_t addr = smem_u32(tile) + byte_offset;
     uint64_t d = 0;
     d |= (uint64_t)((addr >> 4) & 0x3fff);          // start address, bits [0,14)
     d |= (uint64_t)1 << 16;                         // leading byte offset (ignored), bits [16,30)
-    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset, bits [32,46)
+    d |= (uint64_t)(512 >> 4) << 32;                // stride byte offset, bits [32,46)
     d |= (uint64_t)1 << 46;                         // version, bits [46,48)
-    d |= (uint64_t)2 << 61;                         // layout type SWIZZLE_128B, bits [61,64)
+    d |= (uint64_t)4 << 61;                         // layout type SWIZZLE_64B, bits [61,64)
     return d;
 }
 // instruction descriptor of kind::tf32 (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, dense, N x M
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-// 32 TMEM lanes (this warp's quarter) x 32 consecutive columns -> 32 registers per thread (thread = lane = tile row)
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// 32 TMEM lanes (this warp's quarter) x 32 consecutive columns -> 32 registers per thread (thread = lane = tile row);
+// the loads of both accumulators are issued before the one wait
+__device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -146,22 +149,25 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float (&v)[32]) {
           "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
 
 struct HeadArgs {
+    const unsigned char *a_hi, *a_lo;  // blocked, pre-swizzled operand tiles: [row tile][k-block][128 rows][64 bytes]
+    const unsigned char *b_hi, *b_lo;  //                                      [vocabulary tile][k-block][256 rows][64 bytes]
     const float *bias;   // (V) or null
     float *z;            // (n, ldz) raw logits out (the scorer's padded posterior buffer)
-    float2 *stats;       // (n, NCHUNK): running max and sum of exp(z - max) over the chunk's columns
+    float2 *stats;       // (n, NPART): running max and sum of exp(z - max) over the columns of a (vocabulary quarter, column half)
     int n, d, V, ldz;
     int n_mtiles, n_ntiles, tiles_per_chunk;
 };
 
-__global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
-                                                          const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
-                                                          const HeadArgs a) {
+__global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const HeadArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     HeadSmem &sm = *reinterpret_cast<HeadSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -172,7 +178,7 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const __grid_constant_
         if (lane == 0) {
             for (int s = 0; s < NSTAGE; ++s) mbar_init(&sm.full[s], 1), mbar_init(&sm.empty[s], 1);
             mbar_init(&sm.tmem_full, 1);
-            mbar_init(&sm.tmem_empty, 4);  // one arrival per epilogue warp
+            mbar_init(&sm.tmem_empty, 8);  // one arrival per epilogue warp
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -197,10 +203,11 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const __grid_constant_
                         const int s = it % NSTAGE;
                         mbar_wait(&sm.empty[s], ((it / NSTAGE) & 1) ^ 1);  // first pass over the ring: passes at once
                         mbar_expect_tx(&sm.full[s], STAGE_BYTES);
-                        tma_load_2d(sm.a_hi[s], &tm_a_hi, kb * BLOCK_K, mt * BLOCK_M, &sm.full[s]);
-                        tma_load_2d(sm.a_lo[s], &tm_a_lo, kb * BLOCK_K, mt * BLOCK_M, &sm.full[s]);
-                        tma_load_2d(sm.b_hi[s], &tm_b_hi, kb * BLOCK_K, nt * BLOCK_N, &sm.full[s]);
-                        tma_load_2d(sm.b_lo[s], &tm_b_lo, kb * BLOCK_K, nt * BLOCK_N, &sm.full[s]);
+                        const size_t ao = ((size_t)mt * n_kblocks + kb) * A_TILE_BYTES, bo = ((size_t)nt * n_kblocks + kb) * B_TILE_BYTES;
+                        bulk_load_1d(sm.a_hi[s], a.a_hi + ao, A_TILE_BYTES, &sm.full[s]);
+                        bulk_load_1d(sm.a_lo[s], a.a_lo + ao, A_TILE_BYTES, &sm.full[s]);
+                        bulk_load_1d(sm.b_hi[s], a.b_hi + bo, B_TILE_BYTES, &sm.full[s]);
+                        bulk_load_1d(sm.b_lo[s], a.b_lo + bo, B_TILE_BYTES, &sm.full[s]);
                     }
             }
         }
@@ -223,8 +230,8 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const __grid_constant_
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                             const uint32_t off = k * UMMA_K * 4;
-                            const uint64_t ah = smem_desc_sw128(sm.a_hi[s], off), al = smem_desc_sw128(sm.a_lo[s], off);
-                            const uint64_t bh = smem_desc_sw128(sm.b_hi[s], off), bl = smem_desc_sw128(sm.b_lo[s], off);
+                            const uint64_t ah = smem_desc_sw64(sm.a_hi[s], off), al = smem_desc_sw64(sm.a_lo[s], off);
+                            const uint64_t bh = smem_desc_sw64(sm.b_hi[s], off), bl = smem_desc_sw64(sm.b_lo[s], off);
                             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
                             umma_tf32(d_small, al, bh, idesc, acc);  // h_lo W_hi^T
                             umma_tf32(d_small, ah, bl, idesc, 1u);   // h_hi W_lo^T
@@ -241,10 +248,14 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const __grid_constant_
             }
         }
     } else {
-        // ===== epilogue (warps 2..5): TMEM lane quarter = warp % 4, thread = one row of the tile =====
-        const int quarter = warp & 3;
+        // ===== epilogue (warps 2..9): TMEM lane quarter = warp % 4 (a hardware rule), column half = (warp - 2) / 4; a thread
+        // owns one row of the tile and 128 of its 256 columns.  The TMEM loads of the next 32-column group are in flight
+        // while the current one is processed (the first version waited for every load: ncu showed the MMA warp idle 43 % of the
+        // time behind a serialised epilogue).
+        const int quarter = warp & 3, half = (warp - 2) >> 2;
         const int row_in_tile = quarter * 32 + lane;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * (BLOCK_N / 2));
+        constexpr int NGROUP = BLOCK_N / 2 / 32;  // 4 groups of 32 columns per thread and tile
         uint32_t tile = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int mt = item / NCHUNK, ch = item % NCHUNK;
@@ -253,56 +264,117 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const __grid_constant_
             const bool row_ok = row < a.n;
             float *zrow = a.z + (size_t)(row_ok ? row : 0) * a.ldz;
             float m_run = -INFINITY, s_run = 0.f;
+            auto process = [&](const uint32_t (&big)[32], const uint32_t (&small)[32], int v0) {
+                if (v0 >= a.V) return;  // warp-uniform: a column group beyond the vocabulary
+                const bool whole = v0 + 32 <= a.V;
+                float zv[32];
+                float gmax = -INFINITY;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (a.bias != nullptr) {
+                        if (whole) b4 = __ldg(reinterpret_cast<const float4 *>(a.bias + v0) + q);
+                        else {
+                            b4.x = v0 + q * 4 + 0 < a.V ? __ldg(a.bias + v0 + q * 4 + 0) : 0.f;
+                            b4.y = v0 + q * 4 + 1 < a.V ? __ldg(a.bias + v0 + q * 4 + 1) : 0.f;
+                            b4.z = v0 + q * 4 + 2 < a.V ? __ldg(a.bias + v0 + q * 4 + 2) : 0.f;
+                            b4.w = v0 + q * 4 + 3 < a.V ? __ldg(a.bias + v0 + q * 4 + 3) : 0.f;
+                        }
+                    }
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i = q * 4 + j;
+                        zv[i] = (__uint_as_float(big[i]) + __uint_as_float(small[i])) + bb[j];
+                        if (whole || v0 + i < a.V) gmax = fmaxf(gmax, zv[i]);
+                    }
+                }
+                const float m_new = fmaxf(m_run, gmax);
+                const float ml2 = m_new * LOG2E_F;
+                float acc = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (whole || v0 + j < a.V) acc += ex2_fast(fmaf(zv[j], LOG2E_F, -ml2));
+                s_run = s_run * ex2_fast((m_run - m_new) * LOG2E_F) + acc;  // 2^-inf = 0 on the first group
+                m_run = m_new;
+                if (row_ok) {
+                    if (whole) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4 *>(zrow + v0 + q * 4) = make_float4(zv[q * 4], zv[q * 4 + 1], zv[q * 4 + 2], zv[q * 4 + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (v0 + j < a.V) zrow[v0 + j] = zv[j];
+                    }
+                }
+            };
             for (int nt = nt0; nt < nt1; ++nt, ++tile) {
                 mbar_wait(&sm.tmem_full, tile & 1);
                 tc_fence_after();
-#pragma unroll 1
-                for (int c = 0; c < BLOCK_N / 32; ++c) {
-                    float big[32], small[32];
-                    tmem_ld_32x32(lane_base + (uint32_t)(c * 32), big);
-                    tmem_ld_32x32(lane_base + (uint32_t)(BLOCK_N + c * 32), small);
-                    const int v0 = nt * BLOCK_N + c * 32;
-                    if (v0 >= a.V) continue;  // warp-uniform: a column group beyond the vocabulary
-                    float zv[32];
-                    float gmax = -INFINITY;
+                const int vbase = nt * BLOCK_N + half * (BLOCK_N / 2);
+                uint32_t big0[32], small0[32], big1[32], small1[32];
+                tmem_ld_32x32_issue(lane_base, big0);
+                tmem_ld_32x32_issue(lane_base + BLOCK_N, small0);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float b = 0.f;
-                        if (a.bias != nullptr && v0 + j < a.V) b = __ldg(a.bias + v0 + j);
-                        zv[j] = (big[j] + small[j]) + b;
-                        if (v0 + j < a.V) gmax = fmaxf(gmax, zv[j]);
+                for (int c = 0; c < NGROUP; c += 2) {
+                    tmem_ld_wait();  // group c has landed
+                    tmem_ld_32x32_issue(lane_base + (uint32_t)((c + 1) * 32), big1);
+                    tmem_ld_32x32_issue(lane_base + (uint32_t)(BLOCK_N + (c + 1) * 32), small1);
+                    process(big0, small0, vbase + c * 32);
+                    tmem_ld_wait();  // group c + 1 has landed
+                    if (c + 2 < NGROUP) {
+                        tmem_ld_32x32_issue(lane_base + (uint32_t)((c + 2) * 32), big0);
+                        tmem_ld_32x32_issue(lane_base + (uint32_t)(BLOCK_N + (c + 2) * 32), small0);
+                    } else {
+                        // the last values of this tile are in registers: hand the accumulators back to the MMA warp before computing
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sm.tmem_empty);
                     }
-                    const float m_new = fmaxf(m_run, gmax);
-                    float acc = 0.f;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (v0 + j < a.V) acc += expf(zv[j] - m_new);
-                    s_run = s_run * expf(m_run - m_new) + acc;  // exp(-inf) = 0 on the first group
-                    m_run = m_new;
-                    if (row_ok) {
-                        if (v0 + 32 <= a.V) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                *reinterpret_cast<float4 *>(zrow + v0 + q * 4) = make_float4(zv[q * 4], zv[q * 4 + 1], zv[q * 4 + 2], zv[q * 4 + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (v0 + j < a.V) zrow[v0 + j] = zv[j];
-                        }
-                    }
+                    process(big1, small1, vbase + (c + 1) * 32);
                 }
-                // every value of this tile is in registers or stored: hand the accumulators back to the MMA warp
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.tmem_empty);
             }
-            if (row_ok) a.stats[(size_t)row * NCHUNK + ch] = make_float2(m_run, s_run);
+            if (row_ok) a.stats[((size_t)row * NCHUNK + ch) * 2 + half] = make_float2(m_run, s_run);
         }
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+}
+
+// (rows, d) fp32 row-major -> two operand images in the layout the GEMM streams: [tile of RPT rows][k-block of 16 floats]
+// [RPT rows][64 bytes], the four 16-byte chunks of a row XOR-ed with (row >> 1) & 3 -- exactly what TMA's SWIZZLE_64B (CuTe
+// Swizzle<2,4,3>) would leave in shared memory, so that a tile is ONE contiguous bulk copy.  (The first versions loaded
+// 64 / 128-byte row segments 2 KB apart through a tensor map: ncu showed the MMA warp waiting for operands 80 % of the time
+// at a third of the L2 bandwidth.)  Rows beyond `rows` (the padding of the last tile) are zero.
+__global__ void __launch_bounds__(256) k_split_blocked(const float *__restrict__ x, long long rows, int d, int rpt, long long rows_padded,
+                                                       unsigned char *__restrict__ hi, unsigned char *__restrict__ lo) {
+    const int c4n = d >> 2;  // 16-byte chunks per row
+    const long long total = rows_padded * c4n;
+    const int nkb = d / BLOCK_K;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / c4n;
+        const int c4 = (int)(i - row * c4n);
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < rows) v = reinterpret_cast<const float4 *>(x + row * d)[c4];
+        const float in[4] = {v.x, v.y, v.z, v.w};
+        float h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            unsigned t;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(in[j]));
+            h[j] = __uint_as_float(t);
+            l[j] = in[j] - h[j];
+        }
+        const long long tile = row / rpt;
+        const int r = (int)(row - tile * rpt);
+        const int kb = c4 >> 2, ch = c4 & 3;
+        const size_t off = (((size_t)tile * nkb + kb) * rpt + r) * 64 + (size_t)((ch ^ ((r >> 1) & 3)) * 16);
+        *reinterpret_cast<float4 *>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4 *>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+    }
 }
 
 // x -> (TF32-exact high part, fp32 remainder): hi = round-to-nearest TF32, lo = x - hi (exact in fp32)
@@ -342,11 +414,11 @@ __global__ void __launch_bounds__(256) k_head_finish(float *x, int ldx, const fl
     }
     float m = -INFINITY;
 #pragma unroll
-    for (int c = 0; c < NCHUNK; ++c) m = fmaxf(m, stats[(size_t)row * NCHUNK + c].x);
+    for (int c = 0; c < NPART; ++c) m = fmaxf(m, stats[(size_t)row * NPART + c].x);
     float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < NCHUNK; ++c) {
-        const float2 p = stats[(size_t)row * NCHUNK + c];
+    for (int c = 0; c < NPART; ++c) {
+        const float2 p = stats[(size_t)row * NPART + c];
         if (p.y > 0.f) s += p.y * expf(p.x - m);
     }
     const float ls = logf(s);
@@ -367,32 +439,16 @@ __global__ void __launch_bounds__(256) k_head_finish(float *x, int ldx, const fl
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-// (rows, d) fp32 row-major operand: boxes of box_rows x 32 floats, 128-byte swizzle
-int encode_operand(CUtensorMap *tm, const float *p, long long rows, int d, int box_rows) {
-    EncodeTiledFn enc = get_encode();
-    if (enc == nullptr) return CTCPS_E_NODRIVER;
-    cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)d * sizeof(float)};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    const CUresult cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(p), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    return cr == CUDA_SUCCESS ? 0 : CTCPS_E_NODRIVER;
+long long padded_rows(long long rows, int rpt) { return (rows + rpt - 1) / rpt * rpt; }
+
+int launch_split_blocked(const float *x, long long rows, int d, int rpt, unsigned char *hi, unsigned char *lo, cudaStream_t st) {
+    const long long rp = padded_rows(rows, rpt);
+    const long long total = rp * (d >> 2);
+    long long g = (total + 255) / 256;
+    if (g > 148 * 32) g = 148 * 32;
+    k_split_blocked<<<(unsigned)g, 256, 0, st>>>(x, rows, d, rpt, rp, hi, lo);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : (int)e;
 }
 
 }  // namespace
@@ -401,9 +457,22 @@ extern "C" {
 
 int ctcps_head_workspace_bytes(int64_t n, int d, size_t *out_bytes) {
     if (out_bytes == nullptr || n <= 0 || d <= 0) return CTCPS_E_BADARG;
-    // h_hi, h_lo (n, d) + the partial softmax statistics (n, NCHUNK) float2
-    *out_bytes = 2 * (size_t)n * d * sizeof(float) + (size_t)n * NCHUNK * sizeof(float2) + 512;
+    // blocked h_hi, h_lo (rows padded to whole 128-row tiles) + the partial softmax statistics (n, NPART) float2
+    *out_bytes = 2 * (size_t)padded_rows(n, BLOCK_M) * d * sizeof(float) + (size_t)n * NPART * sizeof(float2) + 512;
     return 0;
+}
+
+int ctcps_head_weight_bytes(int V, int d, size_t *out_bytes) {
+    if (out_bytes == nullptr || V <= 0 || d <= 0) return CTCPS_E_BADARG;
+    *out_bytes = (size_t)padded_rows(V, BLOCK_N) * d * sizeof(float);  // each of w_hi, w_lo
+    return 0;
+}
+
+int ctcps_head_prepare_weight(const float *weight, int V, int d, float *w_hi, float *w_lo, void *stream) {
+    if (!weight || !w_hi || !w_lo || V <= 0 || d <= 0) return CTCPS_E_BADARG;
+    if ((d % BLOCK_K) != 0 || ((((uintptr_t)weight) | ((uintptr_t)w_hi) | ((uintptr_t)w_lo)) & 15)) return CTCPS_E_ALIGN;
+    return launch_split_blocked(weight, V, d, BLOCK_N, reinterpret_cast<unsigned char *>(w_hi), reinterpret_cast<unsigned char *>(w_lo),
+                                (cudaStream_t)stream);
 }
 
 int ctcps_split_hi_lo(const float *x, int64_t count, float *hi, float *lo, void *stream) {
@@ -423,24 +492,21 @@ int ctcps_ctc_head(const float *hidden, const float *w_hi, const float *w_lo, co
     cudaStream_t st = (cudaStream_t)stream;
     if (!hidden || !w_hi || !w_lo || !x_logp || !workspace || B <= 0 || T <= 0 || d <= 0 || V <= 0) return CTCPS_E_BADARG;
     if (blank < 0 || blank >= V || ldx < V) return CTCPS_E_BADARG;
-    if ((d % BLOCK_K) != 0 || (ldx & 3) != 0) return CTCPS_E_ALIGN;
+    if ((d % BLOCK_K) != 0 || (ldx & 3) != 0 || (bias != nullptr && (((uintptr_t)bias) & 15))) return CTCPS_E_ALIGN;
     if ((((uintptr_t)hidden) | ((uintptr_t)w_hi) | ((uintptr_t)w_lo) | ((uintptr_t)x_logp) | ((uintptr_t)workspace)) & 15) return CTCPS_E_ALIGN;
     const long long n = (long long)B * T;
     if (n >= (1ll << 31)) return CTCPS_E_TOOBIG;
     size_t need = 0;
     ctcps_head_workspace_bytes(n, d, &need);
     if (workspace_bytes < need) return CTCPS_E_WORKSPACE;
-    float *h_hi = reinterpret_cast<float *>(workspace);
-    float *h_lo = h_hi + (size_t)n * d;
-    float2 *stats = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(h_lo + (size_t)n * d) + 255) & ~(uintptr_t)255);
-    int rc = ctcps_split_hi_lo(hidden, n * d, h_hi, h_lo, stream);
+    unsigned char *h_hi = reinterpret_cast<unsigned char *>(workspace);
+    unsigned char *h_lo = h_hi + (size_t)padded_rows(n, BLOCK_M) * d * sizeof(float);
+    float2 *stats = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(h_lo + (size_t)padded_rows(n, BLOCK_M) * d * sizeof(float)) + 255) & ~(uintptr_t)255);
+    int rc = launch_split_blocked(hidden, n, d, BLOCK_M, h_hi, h_lo, st);
     if (rc) return rc;
-
-    CUtensorMap tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo;
-    if ((rc = encode_operand(&tm_a_hi, h_hi, n, d, BLOCK_M)) || (rc = encode_operand(&tm_a_lo, h_lo, n, d, BLOCK_M)) ||
-        (rc = encode_operand(&tm_b_hi, w_hi, V, d, BLOCK_N)) || (rc = encode_operand(&tm_b_lo, w_lo, V, d, BLOCK_N)))
-        return rc;
     HeadArgs a;
+    a.a_hi = h_hi, a.a_lo = h_lo;
+    a.b_hi = reinterpret_cast<const unsigned char *>(w_hi), a.b_lo = reinterpret_cast<const unsigned char *>(w_lo);
     a.bias = bias, a.z = x_logp, a.stats = stats, a.n = (int)n, a.d = d, a.V = V, a.ldz = ldx;
     a.n_mtiles = (int)((n + BLOCK_M - 1) / BLOCK_M);
     a.n_ntiles = (V + BLOCK_N - 1) / BLOCK_N;
@@ -452,7 +518,7 @@ int ctcps_ctc_head(const float *hidden, const float *w_hi, const float *w_lo, co
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int items = a.n_mtiles * NCHUNK;
-    k_head_gemm<<<items < sms ? items : sms, HEAD_NT, smem, st>>>(tm_a_hi, tm_a_lo, tm_b_hi, tm_b_lo, a);
+    k_head_gemm<<<items < sms ? items : sms, HEAD_NT, smem, st>>>(a);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
     if (!apply_log_softmax) return 0;  // raw logits (tests, callers that want the head alone)
     k_head_finish<<<(unsigned)n, 256, 0, st>>>(x_logp, ldx, stats, lens, T, V, blank, blank_lp);

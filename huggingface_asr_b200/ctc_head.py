@@ -75,13 +75,20 @@ class CTCHead:
         impl = implementation or os.environ.get("CTCPS_HEAD", "tcgen05")
         if impl not in ("tcgen05", "cublas"):
             raise ValueError(f"unknown CTC head implementation {impl!r}")
-        if impl == "tcgen05" and self.dim % 32 != 0:
-            raise ValueError("the tcgen05 CTC head needs a hidden size that is a multiple of 32 (one 128-byte swizzle row of fp32)")
+        if impl == "tcgen05" and self.dim % 16 != 0:
+            raise ValueError("the tcgen05 CTC head needs a hidden size that is a multiple of 16 (one 64-byte swizzle row of fp32)")
         self.implementation = impl
         w = weight.detach().to(torch.float32).contiguous()
         self.bias = None if bias is None else bias.detach().to(torch.float32).contiguous()
         if impl == "tcgen05":
-            self.w_hi, self.w_lo = split_hi_lo(w)
+            # the weight, split and laid out tile by tile in the swizzled image the kernel's bulk copies expect: once per model
+            nb = ctypes.c_size_t(0)
+            _lib.check(_lib.lib().ctcps_head_weight_bytes(self.vocab, self.dim, ctypes.byref(nb)), "ctcps_head_weight_bytes")
+            with torch.cuda.device(w.device):
+                self.w_hi = torch.empty((nb.value // 4,), dtype=torch.float32, device=w.device)
+                self.w_lo = torch.empty((nb.value // 4,), dtype=torch.float32, device=w.device)
+                _lib.check(_lib.lib().ctcps_head_prepare_weight(w.data_ptr(), self.vocab, self.dim, self.w_hi.data_ptr(), self.w_lo.data_ptr(),
+                                                                _stream(w.device)), "ctcps_head_prepare_weight")
             self._ws = None
         else:
             self.weight3 = split_tf32(w, weight_order=True)

@@ -318,13 +318,18 @@ int ctcps_eos_space_trick(const float *att_scores, const float *ctc_scores, floa
  * N4 (the step before the path): the CTC head itself.  Replaces Wav2Vec2ForCTC.lm_head (src/reguler/e_branchformer.py:245-252:
  * logits = hidden W^T + b, an fp32 Linear) followed by F.log_softmax (src/decoding/ctc_scorer.py:279) and the length padding
  * (:39-46), i.e. it produces what ctcps_init produces, from the encoder's hidden states instead of its logits.
- *   hidden (B*T, d) fp32;  w_hi / w_lo (V, d): the head's weight split once with ctcps_split_hi_lo;  bias (V) or NULL
+ *   hidden (B*T, d) fp32;  bias (V) or NULL;  w_hi / w_lo: the head's weight (V, d) prepared ONCE by
+ *   ctcps_head_prepare_weight (each ctcps_head_weight_bytes(V, d) bytes): split into a TF32-exact high part and the fp32
+ *   remainder and stored tile by tile in the swizzled image the kernel's TMA bulk copies drop into shared memory
  *   x_logp (B,T,ldx), blank_lp (B,T): as ctcps_init;  apply_log_softmax = 0: x_logp receives the raw logits (no padding)
  * A hand-written tcgen05 kernel (TMA-fed 3xTF32 UMMA, two TMEM accumulators -- large term / small cross terms -- bias and the
  * softmax statistics in the TMEM -> register epilogue) + one streaming normalisation pass; fp32-grade accuracy (max logit
- * error ~2e-5 at d = 512).  d must be a multiple of 32.  workspace: ctcps_head_workspace_bytes(B*T, d), 16-byte aligned.
+ * error ~2e-5 at d = 512).  d must be a multiple of 16.  workspace: ctcps_head_workspace_bytes(B*T, d), 16-byte aligned.
+ * ctcps_split_hi_lo is the plain elementwise split (hi = round-to-nearest TF32, lo = x - hi), same shapes.
  */
 int ctcps_head_workspace_bytes(int64_t n, int d, size_t *out_bytes);
+int ctcps_head_weight_bytes(int V, int d, size_t *out_bytes);
+int ctcps_head_prepare_weight(const float *weight, int V, int d, float *w_hi, float *w_lo, void *stream);
 int ctcps_split_hi_lo(const float *x, int64_t count, float *hi, float *lo, void *stream);
 int ctcps_ctc_head(const float *hidden, const float *w_hi, const float *w_lo, const float *bias, const int64_t *lens, int B, int T, int d,
                    int V, int blank, int apply_log_softmax, float *x_logp, int ldx, float *blank_lp, void *workspace,
