@@ -1563,9 +1563,22 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
+// Widest hypothesis group of the materialising kernel (CTCPS_SCORE_MAX_GROUP, 2..5).  Default 2: the kernel is bound by the
+// store stream of r, so what counts is how many CTAs keep stores in flight, not how often the x tile is re-read from L2:
+// measured (profiles/r2p_score_group_ab.md) C1 0.584 -> 0.734 of the HBM peak (320 -> 800 tiles on 592 slots), C2 0.860 -> 0.868.
+constexpr int SCORE_DEFAULT_GROUP = 2;
+int g_score_max_group = -1;
+int score_max_group() {
+    if (g_score_max_group < 0) {
+        const char *ev = getenv("CTCPS_SCORE_MAX_GROUP");
+        g_score_max_group = ev != nullptr ? atoi(ev) : SCORE_DEFAULT_GROUP;
+        if (g_score_max_group < 2 || g_score_max_group > MAX_HW) g_score_max_group = SCORE_DEFAULT_GROUP;
+    }
+    return g_score_max_group;
+}
 void pick_hw(int W, int *HW, int *G) {
     int best = 1, best_pad = 1 << 30;
-    for (int hw = MAX_HW; hw >= 1; --hw) {
+    for (int hw = score_max_group(); hw >= 1; --hw) {
         const int g = (W + hw - 1) / hw;
         const int pad = g * hw - W;
         // prefer no padded lanes, then the widest group (more reuse of x per shared-memory read)

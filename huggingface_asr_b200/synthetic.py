@@ -157,12 +157,18 @@ class SyntheticDecoder:
     """
 
     def __init__(self, transcripts, num_beams: int, vocab: int, max_length: int, seed: int = 7, device="cpu", pool: int = 8,
-                 boost: float = 10.0, noise: float = 0.5):
+                 boost: float = 10.0, noise: float = 0.5, per_row_noise: bool = True):
+        """per_row_noise=False: every utterance sees the same (num_beams, vocab) noise, so an utterance's decode does not
+        depend on which batch, or which row of it, the utterance lands in (the sharded job compares hypotheses across
+        different shardings)."""
         B = len(transcripts)
         self.W, self.V = num_beams, vocab
         dev = torch.device(device)
         gen = torch.Generator(device=dev).manual_seed(seed)
-        self.pool = [noise * torch.randn(B * num_beams, vocab, generator=gen, device=dev, dtype=torch.float32) for _ in range(pool)]
+        if per_row_noise:
+            self.pool = [noise * torch.randn(B * num_beams, vocab, generator=gen, device=dev, dtype=torch.float32) for _ in range(pool)]
+        else:
+            self.pool = [(noise * torch.randn(num_beams, vocab, generator=gen, device=dev, dtype=torch.float32)).repeat(B, 1) for _ in range(pool)]
         tgt = torch.full((B, max_length + 1), EOS, dtype=torch.long)
         for b, tr in enumerate(transcripts):
             n = min(len(tr), max_length + 1)
