@@ -91,7 +91,21 @@ def test_cuda_library_is_sm_100a_with_tma():
     assert "sm_100a" in sass
     assert "UTMALDG" in sass, "the recursion kernel must stage x tiles with TMA (cp.async.bulk.tensor)"
     assert "UBLKCP" in sass
-    assert "HMMA" not in sass and "UTCHMMA" not in sass  # no tensor cores on this path, by design
+    # tensor cores: only the CTC head contracts -- tcgen05.mma with TMEM accumulators (UTCHMMA / LDTM), never
+    # the legacy mma.sync (a bare HMMA); the prefix-scoring kernels are HBM-bound FP32 streams and must stay off them
+    per_fn = {}
+    name = None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            name = m.group(1)
+            per_fn[name] = []
+        elif name is not None:
+            per_fn[name].append(line)
+    tc = {fn for fn, body in per_fn.items() if any("UTCHMMA" in ln for ln in body)}
+    assert tc and all("k_head_gemm" in fn for fn in tc), tc
+    assert any("LDTM" in ln for fn in tc for ln in per_fn[fn]), "the head's epilogue reads its accumulators from TMEM"
+    assert not any(re.search(r"(?<!UTC)HMMA", ln) for body in per_fn.values() for ln in body), "no mma.sync kernels"
 
 
 def test_scorer_refuses_cpu_tensors_and_bad_dtypes():
