@@ -4,31 +4,38 @@
 //   logits = Wav2Vec2ForCTC.lm_head(hidden)                 src/reguler/e_branchformer.py:245-252   (fp32 Linear: hidden W^T + b)
 //   x      = F.log_softmax(logits, dim=-1) + length padding src/decoding/ctc_scorer.py:279, :39-46
 //
-// k_head_gemm: logits tile by tile on the 5th-generation tensor cores at fp32 accuracy (3xTF32), bias and the row-wise
-// softmax statistics (running max, sum of exponentials) fused into the TMEM -> register epilogue; the raw logits go
-// straight into the scorer's padded (B,T,ldx) buffer, the per-row statistics into a small side array.
+// k_head_gemm: logits tile by tile on the 5th-generation tensor cores at fp32 accuracy (three half-precision products, below),
+// bias and the row-wise softmax statistics (running max, sum of exponentials) fused into the TMEM -> register epilogue; the raw
+// logits go straight into the scorer's padded (B,T,ldx) buffer, the per-row statistics into a small side array.
 // k_head_finish: one streaming pass turns the buffer into log-posteriors in place -- (z - max) - log(sum), the order
 // torch.log_softmax uses -- applies the length padding and extracts the blank column (what k_init does after a library GEMM,
 // without its two block-wide reductions).
 //
-// 3xTF32.  h and W are split into TF32-exact high parts (round to nearest) and fp32 remainders, h = h_hi + h_lo, and
-//   h W^T ~= h_lo W_hi^T + h_hi W_lo^T + h_hi W_hi^T          (the dropped h_lo W_lo^T is 2^-22 relative)
+// 3xFP16.  An fp16 significand has 11 bits -- exactly TF32's -- in 2 bytes instead of 4, and kind::f16 runs at twice the rate
+// of kind::tf32.  What fp16 lacks is range, so every row of h (and W as a whole) is first scaled by a power of two that puts
+// its largest magnitude into [2^13, 2^14) (exact; undone in the epilogue), then split
+//   h s = H1 + 2^-11 H2,   H1 = fp16(h s),  H2 = fp16((h s - H1) 2^11)        (22 significand bits; the remainder is exact in fp32)
+//   h W^T ~= [ H1 W1^T + 2^-11 (H2 W1^T + H1 W2^T) ] / (s_h s_W)               (the dropped H2 W2^T is 2^-22 relative)
+// The first version of this kernel did the same with TF32 operands (3xTF32, 8 bytes per element and half the MMA rate): ncu
+// showed it bound by the L2 -> SM operand stream (1.5 MB per 128 x 256 tile, 8.3 TB/s against a ~12 TB/s fabric limit).
 // The tensor core accumulates in fp32 but rounds toward zero at every k-step, a bias proportional to the running sum
 // (round 1 measured it through cuBLAS: 7.6e-5 when the large term shares an accumulator with 192 k-steps, 1.8e-5 with 64).
-// So the two small cross terms accumulate in their OWN TMEM accumulator and the large term in another (64 k-steps at
+// So the two small cross terms accumulate in their OWN TMEM accumulator and the large term in another (32 k-steps at
 // d = 512); the epilogue adds the two in fp32 registers.
 //
 // Structure (one CTA per SM, persistent, 320 threads):
-//   warp 0      TMA producer: per k-block of 16 floats the tiles h_hi, h_lo (128 x 16) and W_hi, W_lo (256 x 16), each ONE
+//   warp 0      TMA producer: per k-block of 32 halves the tiles H1, H2 (128 x 32) and W1, W2 (256 x 32), each ONE
 //               contiguous bulk copy of a pre-swizzled image (k_split_blocked) -- 48 KB per stage, 4 stages -- behind
 //               full / empty mbarriers
 //   warp 1      TMEM allocation (512 columns: two 128 x 256 fp32 accumulators) and, one elected lane, the MMA issue:
-//               per k-block 2 x (UMMA 128x256x8, kind::tf32) x 3 products; tcgen05.commit frees the stage / publishes the tile
+//               per k-block 2 x (UMMA 128x256x16, kind::f16) x 3 products; tcgen05.commit frees the stage / publishes the tile
 //   warps 2-9   epilogue: tcgen05.ld 32 lanes x 32 columns at a time, software-pipelined (a thread owns one row of the tile and
-//               half of its columns), big + small + bias, online max / sum-exp, 128-byte row segments stored with st.global.v4
+//               half of its columns), (big + 2^-11 small) / scale + bias, online max / sum-exp, 128-byte row segments stored with
+//               st.global.v4
 // Work item = (128-row tile, quarter of the vocabulary tiles): 4 x 746 items at C2 keep the last wave short; the partial
 // statistics of a row's quarters are combined by k_head_finish.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -38,23 +45,27 @@
 namespace {
 
 constexpr float LZ = CTCPS_LOGZERO;
-constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 16;  // BLOCK_K floats = 64 bytes = one SWIZZLE_64B row
-constexpr int UMMA_K = 8;                                  // kind::tf32: 32 bytes of K per instruction
+constexpr int BLOCK_M = 128, BLOCK_N = 256, BLOCK_K = 32;  // BLOCK_K halves = 64 bytes = one SWIZZLE_64B row
+constexpr int UMMA_K = 16;                                 // kind::f16: 32 bytes of K per instruction
+constexpr float LO_SCALE = 2048.f, LO_UNSCALE = 1.f / 2048.f;  // the low parts are stored times 2^11 (fp16 range)
 constexpr int NSTAGE = 4;                                  // 4 x 48 KB: the first version (2 x 96 KB, 128-byte rows) starved the MMAs
 constexpr float LOG2E_F = 1.4426950408889634f;
 constexpr int NCHUNK = 4;                                  // vocabulary quarters per row tile
 constexpr int HEAD_NT = 320;                               // TMA warp, MMA warp, 8 epilogue warps
 constexpr int NPART = NCHUNK * 2;                          // partial softmax statistics per row: (vocabulary quarter, column half)
-constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 4;   // 8 KB
-constexpr uint32_t B_TILE_BYTES = BLOCK_N * BLOCK_K * 4;   // 16 KB
+constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;   // 8 KB
+constexpr uint32_t B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;   // 16 KB
 constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
+constexpr int STORE_COLS = 16;                             // columns per pass of the epilogue's shared-memory transposition
 
 struct HeadSmem {
     alignas(1024) unsigned char a_hi[NSTAGE][A_TILE_BYTES];
     alignas(1024) unsigned char a_lo[NSTAGE][A_TILE_BYTES];
     alignas(1024) unsigned char b_hi[NSTAGE][B_TILE_BYTES];
     alignas(1024) unsigned char b_lo[NSTAGE][B_TILE_BYTES];
+    alignas(16) float stage_out[HEAD_NT / 32 - 2][32][STORE_COLS];  // per epilogue warp: 32 rows x 16 columns on their way to global memory
+    alignas(16) float bias[2][BLOCK_N];                             // bias of the current / next vocabulary tile
     alignas(8) uint64_t full[NSTAGE];
     alignas(8) uint64_t empty[NSTAGE];
     alignas(8) uint64_t tmem_full;
@@ -109,13 +120,13 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major, kind::tf32, issued by one thread for the CTA
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem] * B[smem]^T, both operands K-major, kind::f16 (fp16 x fp16 -> fp32), issued by one thread for the CTA
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
         "}\n" ::"r"(d_tmem),
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
@@ -133,9 +144,19 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(const void *tile, uint32_t by
     d |= (uint64_t)4 << 61;                         // layout type SWIZZLE_64B, bits [61,64)
     return d;
 }
-// instruction descriptor of kind::tf32 (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, dense, N x M
+// instruction descriptor of kind::f16 (cute::UMMA::InstrDescriptor): D = F32 (bits 4-5 = 1), A = B = F16 (bits 7-9, 10-12 = 0),
+// both K-major, dense, N >> 3 at bit 17, M >> 4 at bit 24
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// power-of-two scale that puts a largest magnitude m into [2^13, 2^14) (fp16 overflows at 2^16), and its inverse; both normal
+// fp32 numbers for every m (0, subnormal, huge, inf / nan included)
+__device__ __forceinline__ void scale_from_absmax(float m, float &s, float &inv) {
+    const int e = (int)((__float_as_uint(m) >> 23) & 0xffu);
+    int k = 13 - (e - 127);
+    k = k > 100 ? 100 : (k < -120 ? -120 : k);
+    s = __uint_as_float((uint32_t)(127 + k) << 23);
+    inv = __uint_as_float((uint32_t)(127 - k) << 23);
 }
 // 32 TMEM lanes (this warp's quarter) x 32 consecutive columns -> 32 registers per thread (thread = lane = tile row);
 // the loads of both accumulators are issued before the one wait
@@ -160,10 +181,12 @@ __device__ __forceinline__ float ex2_fast(float x) {
 struct HeadArgs {
     const unsigned char *a_hi, *a_lo;  // blocked, pre-swizzled operand tiles: [row tile][k-block][128 rows][64 bytes]
     const unsigned char *b_hi, *b_lo;  //                                      [vocabulary tile][k-block][256 rows][64 bytes]
+    const float *a_inv;                // (padded n) 1 / scale of every row of h
+    const uint32_t *w_absmax;          // bits of max |W| (the weight's scale is derived from it)
     const float *bias;   // (V) or null
     float *z;            // (n, ldz) raw logits out (the scorer's padded posterior buffer)
     float2 *stats;       // (n, NPART): running max and sum of exp(z - max) over the columns of a (vocabulary quarter, column half)
-    int n, d, V, ldz;
+    int n, d_pad, V, ldz;
     int n_mtiles, n_ntiles, tiles_per_chunk;
 };
 
@@ -171,7 +194,7 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const HeadArgs a) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     HeadSmem &sm = *reinterpret_cast<HeadSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_kblocks = a.d / BLOCK_K;
+    const int n_kblocks = a.d_pad / BLOCK_K;
     const int n_items = a.n_mtiles * NCHUNK;
 
     if (warp == 1) {
@@ -229,13 +252,13 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const HeadArgs a) {
                     if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            const uint32_t off = k * UMMA_K * 4;
+                            const uint32_t off = k * UMMA_K * 2;
                             const uint64_t ah = smem_desc_sw64(sm.a_hi[s], off), al = smem_desc_sw64(sm.a_lo[s], off);
                             const uint64_t bh = smem_desc_sw64(sm.b_hi[s], off), bl = smem_desc_sw64(sm.b_lo[s], off);
                             const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                            umma_tf32(d_small, al, bh, idesc, acc);  // h_lo W_hi^T
-                            umma_tf32(d_small, ah, bl, idesc, 1u);   // h_hi W_lo^T
-                            umma_tf32(d_big, ah, bh, idesc, acc);    // h_hi W_hi^T
+                            umma_f16(d_small, al, bh, idesc, acc);  // H2 W1^T
+                            umma_f16(d_small, ah, bl, idesc, 1u);   // H1 W2^T
+                            umma_f16(d_big, ah, bh, idesc, acc);    // H1 W1^T
                         }
                     }
                     __syncwarp();
@@ -251,41 +274,43 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const HeadArgs a) {
         // ===== epilogue (warps 2..9): TMEM lane quarter = warp % 4 (a hardware rule), column half = (warp - 2) / 4; a thread
         // owns one row of the tile and 128 of its 256 columns.  The TMEM loads of the next 32-column group are in flight
         // while the current one is processed (the first version waited for every load: ncu showed the MMA warp idle 43 % of the
-        // time behind a serialised epilogue).
+        // time behind a serialised epilogue).  The second version still spent 14 us per tile here against 13 us of MMAs (ncu
+        // r2r): every float4 of the bias was a global load in front of its first use -- 32 dependent L2 round trips per
+        // tile -- and a warp's float4 stores went to 32 different rows (32 half-written sectors per instruction, twice the
+        // bytes on the way to L2).  Now the tile's bias is staged in shared memory while the MMAs of the tile still run, and the
+        // logits leave through a per-warp shared-memory transposition: 8 rows x 64 contiguous bytes per store instruction.
         const int quarter = warp & 3, half = (warp - 2) >> 2;
         const int row_in_tile = quarter * 32 + lane;
         const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * (BLOCK_N / 2));
         constexpr int NGROUP = BLOCK_N / 2 / 32;  // 4 groups of 32 columns per thread and tile
+        float(*st)[STORE_COLS] = sm.stage_out[warp - 2];
+        const int st_r = lane >> 2, st_c = lane & 3;  // store pass: this lane moves chunk st_c of rows st_r, st_r + 8, ...
+        float w_s, w_inv;
+        scale_from_absmax(__uint_as_float(__ldg(a.w_absmax)), w_s, w_inv);
         uint32_t tile = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
             const int mt = item / NCHUNK, ch = item % NCHUNK;
             const int nt0 = ch * a.tiles_per_chunk, nt1 = min(a.n_ntiles, nt0 + a.tiles_per_chunk);
             const long long row = (long long)mt * BLOCK_M + row_in_tile;
             const bool row_ok = row < a.n;
-            float *zrow = a.z + (size_t)(row_ok ? row : 0) * a.ldz;
+            const long long st_row0 = (long long)mt * BLOCK_M + quarter * 32 + st_r;
+            float *zst = a.z + (size_t)st_row0 * a.ldz + st_c * 4;
             float m_run = -INFINITY, s_run = 0.f;
-            auto process = [&](const uint32_t (&big)[32], const uint32_t (&small)[32], int v0) {
+            const float unscale = __ldg(a.a_inv + row) * w_inv;  // a_inv covers the padded rows
+            const float *bias_s = nullptr;
+            auto process = [&](const uint32_t (&big)[32], const uint32_t (&small)[32], int g, int v0) {
                 if (v0 >= a.V) return;  // warp-uniform: a column group beyond the vocabulary
                 const bool whole = v0 + 32 <= a.V;
                 float zv[32];
                 float gmax = -INFINITY;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (a.bias != nullptr) {
-                        if (whole) b4 = __ldg(reinterpret_cast<const float4 *>(a.bias + v0) + q);
-                        else {
-                            b4.x = v0 + q * 4 + 0 < a.V ? __ldg(a.bias + v0 + q * 4 + 0) : 0.f;
-                            b4.y = v0 + q * 4 + 1 < a.V ? __ldg(a.bias + v0 + q * 4 + 1) : 0.f;
-                            b4.z = v0 + q * 4 + 2 < a.V ? __ldg(a.bias + v0 + q * 4 + 2) : 0.f;
-                            b4.w = v0 + q * 4 + 3 < a.V ? __ldg(a.bias + v0 + q * 4 + 3) : 0.f;
-                        }
-                    }
+                    const float4 b4 = *reinterpret_cast<const float4 *>(bias_s + g * 32 + q * 4);
                     const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const int i = q * 4 + j;
-                        zv[i] = (__uint_as_float(big[i]) + __uint_as_float(small[i])) + bb[j];
+                        zv[i] = fmaf(fmaf(__uint_as_float(small[i]), LO_UNSCALE, __uint_as_float(big[i])), unscale, bb[j]);
                         if (whole || v0 + i < a.V) gmax = fmaxf(gmax, zv[i]);
                     }
                 }
@@ -297,19 +322,40 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const HeadArgs a) {
                     if (whole || v0 + j < a.V) acc += ex2_fast(fmaf(zv[j], LOG2E_F, -ml2));
                 s_run = s_run * ex2_fast((m_run - m_new) * LOG2E_F) + acc;  // 2^-inf = 0 on the first group
                 m_run = m_new;
-                if (row_ok) {
-                    if (whole) {
+                // rows -> shared memory (16-byte chunks XOR-ed with (row >> 1) & 3: conflict-free both ways), then out by rows
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            *reinterpret_cast<float4 *>(zrow + v0 + q * 4) = make_float4(zv[q * 4], zv[q * 4 + 1], zv[q * 4 + 2], zv[q * 4 + 3]);
-                    } else {
+                for (int h = 0; h < 32 / STORE_COLS; ++h) {
+                    __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (v0 + j < a.V) zrow[v0 + j] = zv[j];
+                    for (int q = 0; q < STORE_COLS / 4; ++q)
+                        *reinterpret_cast<float4 *>(&st[lane][(q ^ ((lane >> 1) & 3)) * 4]) =
+                            make_float4(zv[h * STORE_COLS + q * 4], zv[h * STORE_COLS + q * 4 + 1], zv[h * STORE_COLS + q * 4 + 2],
+                                        zv[h * STORE_COLS + q * 4 + 3]);
+                    __syncwarp();
+                    const int v = v0 + h * STORE_COLS + st_c * 4;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int r = i * 8 + st_r;
+                        const float4 o = *reinterpret_cast<const float4 *>(&st[r][(st_c ^ ((r >> 1) & 3)) * 4]);
+                        if (st_row0 + i * 8 < a.n) {
+                            float *dst = zst + (size_t)(i * 8) * a.ldz + (v0 + h * STORE_COLS);
+                            if (v + 4 <= a.V) *reinterpret_cast<float4 *>(dst) = o;
+                            else {
+                                if (v + 0 < a.V) dst[0] = o.x;
+                                if (v + 1 < a.V) dst[1] = o.y;
+                                if (v + 2 < a.V) dst[2] = o.z;
+                            }
+                        }
                     }
                 }
             };
             for (int nt = nt0; nt < nt1; ++nt, ++tile) {
+                {   // this tile's bias (zero beyond the vocabulary / without a bias) while its MMAs are still running
+                    const int et = (int)threadIdx.x - 64, v = nt * BLOCK_N + et;
+                    sm.bias[tile & 1][et] = (a.bias != nullptr && v < a.V) ? __ldg(a.bias + v) : 0.f;
+                    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps; two buffers, so one barrier per tile is enough
+                }
+                bias_s = &sm.bias[tile & 1][half * (BLOCK_N / 2)];
                 mbar_wait(&sm.tmem_full, tile & 1);
                 tc_fence_after();
                 const int vbase = nt * BLOCK_N + half * (BLOCK_N / 2);
@@ -321,7 +367,7 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const HeadArgs a) {
                     tmem_ld_wait();  // group c has landed
                     tmem_ld_32x32_issue(lane_base + (uint32_t)((c + 1) * 32), big1);
                     tmem_ld_32x32_issue(lane_base + (uint32_t)(BLOCK_N + (c + 1) * 32), small1);
-                    process(big0, small0, vbase + c * 32);
+                    process(big0, small0, c, vbase + c * 32);
                     tmem_ld_wait();  // group c + 1 has landed
                     if (c + 2 < NGROUP) {
                         tmem_ld_32x32_issue(lane_base + (uint32_t)((c + 2) * 32), big0);
@@ -332,7 +378,7 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const HeadArgs a) {
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&sm.tmem_empty);
                     }
-                    process(big1, small1, vbase + (c + 1) * 32);
+                    process(big1, small1, c + 1, vbase + (c + 1) * 32);
                 }
             }
             if (row_ok) a.stats[((size_t)row * NCHUNK + ch) * 2 + half] = make_float2(m_run, s_run);
@@ -344,37 +390,73 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const HeadArgs a) {
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
 }
 
-// (rows, d) fp32 row-major -> two operand images in the layout the GEMM streams: [tile of RPT rows][k-block of 16 floats]
+// (rows, d) fp32 row-major -> two fp16 operand images in the layout the GEMM streams: [tile of RPT rows][k-block of 32 halves]
 // [RPT rows][64 bytes], the four 16-byte chunks of a row XOR-ed with (row >> 1) & 3 -- exactly what TMA's SWIZZLE_64B (CuTe
 // Swizzle<2,4,3>) would leave in shared memory, so that a tile is ONE contiguous bulk copy.  (The first versions loaded
 // 64 / 128-byte row segments 2 KB apart through a tensor map: ncu showed the MMA warp waiting for operands 80 % of the time
-// at a third of the L2 bandwidth.)  Rows beyond `rows` (the padding of the last tile) are zero.
-__global__ void __launch_bounds__(256) k_split_blocked(const float *__restrict__ x, long long rows, int d, int rpt, long long rows_padded,
-                                                       unsigned char *__restrict__ hi, unsigned char *__restrict__ lo) {
-    const int c4n = d >> 2;  // 16-byte chunks per row
-    const long long total = rows_padded * c4n;
-    const int nkb = d / BLOCK_K;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long row = i / c4n;
-        const int c4 = (int)(i - row * c4n);
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row < rows) v = reinterpret_cast<const float4 *>(x + row * d)[c4];
-        const float in[4] = {v.x, v.y, v.z, v.w};
-        float h[4], l[4];
+// at a third of the L2 bandwidth.)  One warp per row: the row's largest magnitude gives its power-of-two scale (absmax == null;
+// 1 / scale goes to inv_scale) or the whole tensor shares one (absmax = bits of max |x|, the weight); hi = fp16(x s),
+// lo = fp16((x s - hi) 2^11).  Rows beyond `rows` (the padding of the last tile) and columns beyond d (the padding of the
+// last k-block) are zero.
+__global__ void __launch_bounds__(256) k_split_blocked(const float *__restrict__ x, long long rows, int d, int d_pad, int rpt, long long rows_padded,
+                                                       const uint32_t *__restrict__ absmax, unsigned char *__restrict__ hi,
+                                                       unsigned char *__restrict__ lo, float *__restrict__ inv_scale) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int c4n = d >> 2;        // float4 per row
+    const int nchunk = d_pad >> 3;  // 16-byte chunks of 8 halves per row
+    const int nkb = d_pad / BLOCK_K;
+    for (long long row = warp0; row < rows_padded; row += nwarps) {
+        const float4 *xr = reinterpret_cast<const float4 *>(x + row * d);
+        const bool live = row < rows;
+        float s, inv;
+        if (absmax != nullptr) {
+            scale_from_absmax(__uint_as_float(__ldg(absmax)), s, inv);
+        } else {
+            float m = 0.f;
+            if (live)
+                for (int c = lane; c < c4n; c += 32) {
+                    const float4 v = __ldg(xr + c);
+                    m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            unsigned t;
-            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(in[j]));
-            h[j] = __uint_as_float(t);
-            l[j] = in[j] - h[j];
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            scale_from_absmax(m, s, inv);
+            if (lane == 0 && inv_scale != nullptr) inv_scale[row] = inv;
         }
         const long long tile = row / rpt;
         const int r = (int)(row - tile * rpt);
-        const int kb = c4 >> 2, ch = c4 & 3;
-        const size_t off = (((size_t)tile * nkb + kb) * rpt + r) * 64 + (size_t)((ch ^ ((r >> 1) & 3)) * 16);
-        *reinterpret_cast<float4 *>(hi + off) = make_float4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<float4 *>(lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+        for (int c = lane; c < nchunk; c += 32) {
+            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+            if (live && 2 * c < c4n) v0 = __ldg(xr + 2 * c);
+            if (live && 2 * c + 1 < c4n) v1 = __ldg(xr + 2 * c + 1);
+            const float in[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            __align__(16) __half h[8], l[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xs = in[j] * s;
+                h[j] = __float2half_rn(xs);
+                l[j] = __float2half_rn((xs - __half2float(h[j])) * LO_SCALE);
+            }
+            const int kb = c >> 2, ch = c & 3;
+            const size_t off = (((size_t)tile * nkb + kb) * rpt + r) * 64 + (size_t)((ch ^ ((r >> 1) & 3)) * 16);
+            *reinterpret_cast<uint4 *>(hi + off) = *reinterpret_cast<const uint4 *>(h);
+            *reinterpret_cast<uint4 *>(lo + off) = *reinterpret_cast<const uint4 *>(l);
+        }
     }
+}
+
+// bits of max |x| over a tensor (non-negative floats order like their bit patterns); *out zeroed by the caller
+__global__ void __launch_bounds__(256) k_absmax(const float *__restrict__ x, long long n4, uint32_t *out) {
+    float m = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
+        m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, __float_as_uint(m));
 }
 
 // x -> (TF32-exact high part, fp32 remainder): hi = round-to-nearest TF32, lo = x - hi (exact in fp32)
@@ -440,13 +522,17 @@ __global__ void __launch_bounds__(256) k_head_finish(float *x, int ldx, const fl
 }
 
 long long padded_rows(long long rows, int rpt) { return (rows + rpt - 1) / rpt * rpt; }
+int padded_k(int d) { return (d + BLOCK_K - 1) / BLOCK_K * BLOCK_K; }
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+// one fp16 operand image of a (rows, d) matrix: rows padded to whole tiles, K to whole k-blocks
+size_t image_bytes(long long rows, int rpt, int d) { return (size_t)padded_rows(rows, rpt) * padded_k(d) * sizeof(__half); }
 
-int launch_split_blocked(const float *x, long long rows, int d, int rpt, unsigned char *hi, unsigned char *lo, cudaStream_t st) {
+int launch_split_blocked(const float *x, long long rows, int d, int rpt, const uint32_t *absmax, unsigned char *hi, unsigned char *lo,
+                         float *inv_scale, cudaStream_t st) {
     const long long rp = padded_rows(rows, rpt);
-    const long long total = rp * (d >> 2);
-    long long g = (total + 255) / 256;
+    long long g = (rp + 7) / 8;  // a warp per row, 8 warps per CTA
     if (g > 148 * 32) g = 148 * 32;
-    k_split_blocked<<<(unsigned)g, 256, 0, st>>>(x, rows, d, rpt, rp, hi, lo);
+    k_split_blocked<<<(unsigned)g, 256, 0, st>>>(x, rows, d, padded_k(d), rpt, rp, absmax, hi, lo, inv_scale);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? 0 : (int)e;
 }
@@ -457,22 +543,33 @@ extern "C" {
 
 int ctcps_head_workspace_bytes(int64_t n, int d, size_t *out_bytes) {
     if (out_bytes == nullptr || n <= 0 || d <= 0) return CTCPS_E_BADARG;
-    // blocked h_hi, h_lo (rows padded to whole 128-row tiles) + the partial softmax statistics (n, NPART) float2
-    *out_bytes = 2 * (size_t)padded_rows(n, BLOCK_M) * d * sizeof(float) + (size_t)n * NPART * sizeof(float2) + 512;
+    // blocked H1, H2 (rows padded to whole 128-row tiles) + 1 / scale of every padded row + the partial softmax statistics
+    // (n, NPART) float2
+    *out_bytes = 2 * align256(image_bytes(n, BLOCK_M, d)) + align256((size_t)padded_rows(n, BLOCK_M) * sizeof(float)) +
+                 (size_t)n * NPART * sizeof(float2) + 512;
     return 0;
 }
 
 int ctcps_head_weight_bytes(int V, int d, size_t *out_bytes) {
     if (out_bytes == nullptr || V <= 0 || d <= 0) return CTCPS_E_BADARG;
-    *out_bytes = (size_t)padded_rows(V, BLOCK_N) * d * sizeof(float);  // each of w_hi, w_lo
+    *out_bytes = align256(image_bytes(V, BLOCK_N, d)) + 256;  // each of w_hi, w_lo; w_hi ends with the bits of max |W|
     return 0;
 }
 
 int ctcps_head_prepare_weight(const float *weight, int V, int d, float *w_hi, float *w_lo, void *stream) {
     if (!weight || !w_hi || !w_lo || V <= 0 || d <= 0) return CTCPS_E_BADARG;
-    if ((d % BLOCK_K) != 0 || ((((uintptr_t)weight) | ((uintptr_t)w_hi) | ((uintptr_t)w_lo)) & 15)) return CTCPS_E_ALIGN;
-    return launch_split_blocked(weight, V, d, BLOCK_N, reinterpret_cast<unsigned char *>(w_hi), reinterpret_cast<unsigned char *>(w_lo),
-                                (cudaStream_t)stream);
+    if ((d % 16) != 0 || ((((uintptr_t)weight) | ((uintptr_t)w_hi) | ((uintptr_t)w_lo)) & 15)) return CTCPS_E_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t *absmax = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(w_hi) + align256(image_bytes(V, BLOCK_N, d)));
+    cudaError_t e = cudaMemsetAsync(absmax, 0, 256, st);
+    if (e != cudaSuccess) return (int)e;
+    const long long n4 = (long long)V * d / 4;
+    long long g = (n4 + 255) / 256;
+    if (g > 148 * 8) g = 148 * 8;
+    k_absmax<<<(unsigned)g, 256, 0, st>>>(weight, n4, absmax);
+    if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
+    return launch_split_blocked(weight, V, d, BLOCK_N, absmax, reinterpret_cast<unsigned char *>(w_hi), reinterpret_cast<unsigned char *>(w_lo),
+                                nullptr, st);
 }
 
 int ctcps_split_hi_lo(const float *x, int64_t count, float *hi, float *lo, void *stream) {
@@ -492,7 +589,7 @@ int ctcps_ctc_head(const float *hidden, const float *w_hi, const float *w_lo, co
     cudaStream_t st = (cudaStream_t)stream;
     if (!hidden || !w_hi || !w_lo || !x_logp || !workspace || B <= 0 || T <= 0 || d <= 0 || V <= 0) return CTCPS_E_BADARG;
     if (blank < 0 || blank >= V || ldx < V) return CTCPS_E_BADARG;
-    if ((d % BLOCK_K) != 0 || (ldx & 3) != 0 || (bias != nullptr && (((uintptr_t)bias) & 15))) return CTCPS_E_ALIGN;
+    if ((d % 16) != 0 || (ldx & 3) != 0 || (bias != nullptr && (((uintptr_t)bias) & 15))) return CTCPS_E_ALIGN;
     if ((((uintptr_t)hidden) | ((uintptr_t)w_hi) | ((uintptr_t)w_lo) | ((uintptr_t)x_logp) | ((uintptr_t)workspace)) & 15) return CTCPS_E_ALIGN;
     const long long n = (long long)B * T;
     if (n >= (1ll << 31)) return CTCPS_E_TOOBIG;
@@ -500,14 +597,17 @@ int ctcps_ctc_head(const float *hidden, const float *w_hi, const float *w_lo, co
     ctcps_head_workspace_bytes(n, d, &need);
     if (workspace_bytes < need) return CTCPS_E_WORKSPACE;
     unsigned char *h_hi = reinterpret_cast<unsigned char *>(workspace);
-    unsigned char *h_lo = h_hi + (size_t)padded_rows(n, BLOCK_M) * d * sizeof(float);
-    float2 *stats = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(h_lo + (size_t)padded_rows(n, BLOCK_M) * d * sizeof(float)) + 255) & ~(uintptr_t)255);
-    int rc = launch_split_blocked(hidden, n, d, BLOCK_M, h_hi, h_lo, st);
+    unsigned char *h_lo = h_hi + align256(image_bytes(n, BLOCK_M, d));
+    float *a_inv = reinterpret_cast<float *>(h_lo + align256(image_bytes(n, BLOCK_M, d)));
+    float2 *stats = reinterpret_cast<float2 *>(reinterpret_cast<unsigned char *>(a_inv) + align256((size_t)padded_rows(n, BLOCK_M) * sizeof(float)));
+    int rc = launch_split_blocked(hidden, n, d, BLOCK_M, nullptr, h_hi, h_lo, a_inv, st);
     if (rc) return rc;
     HeadArgs a;
     a.a_hi = h_hi, a.a_lo = h_lo;
     a.b_hi = reinterpret_cast<const unsigned char *>(w_hi), a.b_lo = reinterpret_cast<const unsigned char *>(w_lo);
-    a.bias = bias, a.z = x_logp, a.stats = stats, a.n = (int)n, a.d = d, a.V = V, a.ldz = ldx;
+    a.a_inv = a_inv;
+    a.w_absmax = reinterpret_cast<const uint32_t *>(a.b_hi + align256(image_bytes(V, BLOCK_N, d)));
+    a.bias = bias, a.z = x_logp, a.stats = stats, a.n = (int)n, a.d_pad = padded_k(d), a.V = V, a.ldz = ldx;
     a.n_mtiles = (int)((n + BLOCK_M - 1) / BLOCK_M);
     a.n_ntiles = (V + BLOCK_N - 1) / BLOCK_N;
     a.tiles_per_chunk = (a.n_ntiles + NCHUNK - 1) / NCHUNK;
