@@ -88,6 +88,8 @@ SIGNATURES = {
     "ctcps_initial_state": [_p, _i, _i, _i, _i, _p, _p],
     "ctcps_score": [_p, _i, _p, _p, _p, _i64, _i64, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _f, _f, _p, _i, _p, _p, _p,
                     _p, _sz, _p],
+    "ctcps_score_window": [_p, _i, _p, _p, _p, _i64, _i64, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _f, _f, _p, _i, _p, _p,
+                           _p, _p, _sz, _p],
     "ctcps_score_lazy": [_p, _i, _p, _p, _p, _i64, _i64, _p, _i, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _sz, _i, _p],
     "ctcps_select_lazy": [_p, _i, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p],
     "ctcps_topk_lists_shape": [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)],

@@ -268,10 +268,10 @@ __global__ void k_initial_state(const float *__restrict__ blank_lp, int B, int T
 // K-b prep: one warp per (padded) hypothesis builds the stream the recursion consumes.
 //   aux[((b*G+g)*Tpad + t)*(HW+1) + hh] = {r_sum[t-1], r_prev[t-1,1], exp(r_sum[t-1]-Gm), exp(r_prev[t-1,1]-Gm)}
 //   aux[...                      + HW] = {blank_lp[b,t], 0, 0, 0}
-//   Gm[h] = max over the frames log_psi sums over, t-1 in [start-1, T-2]
+//   Gm[h] = max over the frames log_psi sums over, t-1 in [start-1, end-2]   (end = T unless an attention window is given)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_prep(const float *__restrict__ r_prev, const float *__restrict__ blank_lp, int B,
-                                              int W, int T, int HW, int G, int start, int Tpad,
+                                              int W, int T, int HW, int G, int start, int end, int Tpad,
                                               float4 *__restrict__ aux, float *__restrict__ Gmax) {
     const int lane = threadIdx.x & 31;
     const int hp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(128) k_prep(const float *__restrict__ r_prev, 
     float gm = -INFINITY;
     if (valid) {
         for (int t = lane; t < T; t += 32) {
-            if (t >= start - 1 && t <= T - 2) {
+            if (t >= start - 1 && t <= end - 2) {
                 const float a = r_prev[((size_t)t * 2 + 0) * BW + h], c = r_prev[((size_t)t * 2 + 1) * BW + h];
                 gm = fmaxf(gm, lse2_precise(a, c));
             }
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(128) k_prep(const float *__restrict__ r_prev, 
             const float rs = lse2_precise(a, c);
             e.x = rs;
             e.y = c;
-            if (f >= start - 1 && f <= T - 2) {
+            if (f >= start - 1 && f <= end - 2) {
                 e.z = expf(rs - gm);
                 e.w = expf(c - gm);
             }
@@ -444,6 +444,7 @@ struct ScoreArgs {
     int ldr;
     float *log_psi, *token_scores, *joint;
     int B, W, T, V, blank, ol, G, Tpad, nvt;
+    int start, end;  // frames the recursion runs over (:127-136): max(ol, 1) .. T unless an attention window is given
 };
 
 template <int HW, int NT>
@@ -487,10 +488,10 @@ __global__ void __launch_bounds__(NT, MINB) k_score_full(const __grid_constant__
 
     const int tid = threadIdx.x;
     const int T = a.T, V = a.V, W = a.W, BW = a.B * a.W;
-    const int start = a.ol > 1 ? a.ol : 1;
+    const int start = a.start, end = a.end;
     const int c0 = (a.ol == 0 ? 0 : start) / TT;
-    const int cN = (T - 1) / TT;
-    const int nchunk = cN - c0 + 1;
+    const int cN = (end - 1) / TT;
+    const int nchunk = cN >= c0 ? cN - c0 + 1 : 0;  // an empty window (start == end) streams nothing
     const int ntiles = a.B * a.nvt * a.G;
     const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int nitems = my_tiles * nchunk;
@@ -563,7 +564,7 @@ __global__ void __launch_bounds__(NT, MINB) k_score_full(const __grid_constant__
             const int c = c0 + ci;
             const int s = k % NS;
             mbar_wait(&sm.full[s], (uint32_t)((k / NS) & 1));
-            const int tmax = min(TT, T - c * TT);
+            const int tmax = min(TT, end - c * TT);
             for (int tt = 0; tt < tmax; ++tt) {
                 const int t = c * TT + tt;
                 const float4 xv4 = *reinterpret_cast<const float4 *>(&sm.xs[s][bx][tt][col]);
@@ -605,6 +606,18 @@ __global__ void __launch_bounds__(NT, MINB) k_score_full(const __grid_constant__
             if (tid == 0 && k + NS < nitems) {  // refill the stage just released, once every warp is done with it
                 mbar_wait(&sm.empty[s], (uint32_t)((k / NS) & 1));
                 issue(k + NS);
+            }
+        }
+
+        // frames past an attention window stay logzero as well (r = full(logzero), :106-111)
+        if (lane_ok && end < T) {
+            const float4 lz4 = make_float4(LZ, LZ, LZ, LZ);
+            for (int t = end; t < T; ++t) {
+                float *rp = rbase + (size_t)t * frame;
+                for (int hh = 0; hh < nhyp; ++hh) {
+                    __stcs(reinterpret_cast<float4 *>(rp + (size_t)hh * a.ldr), lz4);
+                    __stcs(reinterpret_cast<float4 *>(rp + (size_t)hh * a.ldr + plane), lz4);
+                }
             }
         }
 
@@ -973,7 +986,8 @@ __global__ void k_build_idmap(const int64_t *__restrict__ ids, int BW, int S, in
 __global__ void __launch_bounds__(128) k_score_partial(const float *__restrict__ x, int ldx, const float *__restrict__ blank_lp,
                                                        const float *__restrict__ r_prev, const int64_t *__restrict__ last_ids,
                                                        const int64_t *__restrict__ ids, const int64_t *__restrict__ idmap, int ol,
-                                                       int B, int W, int T, int V, int S, float *r, int ldr, float *log_psi) {
+                                                       int start, int end, int B, int W, int T, int V, int S, float *r, int ldr,
+                                                       float *log_psi) {
     const int lane = blockIdx.x * blockDim.x + threadIdx.x;
     const int BW = B * W;
     if (lane >= BW * S) return;
@@ -982,7 +996,6 @@ __global__ void __launch_bounds__(128) k_score_partial(const float *__restrict__
     const int64_t v = ids[lane];
     const int64_t c = last_ids[h];
     const bool last = (c >= 0 && c < V) ? (idmap[(size_t)h * V + c] == s) : false;  // :117-121
-    const int start = ol > 1 ? ol : 1;
     const size_t plane = (size_t)BW * ldr, frame = 2 * plane;
     float *rp = r + (size_t)h * ldr + s;
     if (v < 0 || v >= V) {  // the reference raises an IndexError here; never read outside the posteriors: the lane is logzero
@@ -1002,8 +1015,12 @@ __global__ void __launch_bounds__(128) k_score_partial(const float *__restrict__
         rn = xr[0];
         rp[0] = rn;
     }
+    for (int t = end; t < T; ++t) {  // frames past an attention window (:127-136)
+        rp[(size_t)t * frame] = LZ;
+        rp[(size_t)t * frame + plane] = LZ;
+    }
     float m = rn, acc = 1.f;  // running-max logsumexp seeded with r[start-1,0]       (:158,165)
-    for (int t = start; t < T; ++t) {
+    for (int t = start; t < end; ++t) {
         const float p0 = r_prev[((size_t)(t - 1) * 2 + 0) * BW + h], p1 = r_prev[((size_t)(t - 1) * 2 + 1) * BW + h];
         const float phi = last ? p1 : lse2_precise(p0, p1);
         const float xv = xr[(size_t)t * ldx];
@@ -2043,12 +2060,13 @@ int ctcps_initial_state(const float *blank_lp, int B, int T, int W, int t_begin,
     return cuda_rc(cudaGetLastError());
 }
 
-int ctcps_score(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const float *s_prev,
-                int64_t s_row_stride, int64_t s_col_stride, const int64_t *last_ids, int ol, int B, int W, int T, int V,
-                int blank, const int64_t *scoring_ids, int S, int64_t *scoring_idmap, float *att_scores, float one_minus_w,
-                float w, float *r, int ldr, float *log_psi, float *token_scores, float *joint, void *workspace,
-                size_t workspace_bytes, void *stream) {
+int ctcps_score_window(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const float *s_prev,
+                       int64_t s_row_stride, int64_t s_col_stride, const int64_t *last_ids, int ol, int start, int end, int B, int W,
+                       int T, int V, int blank, const int64_t *scoring_ids, int S, int64_t *scoring_idmap, float *att_scores,
+                       float one_minus_w, float w, float *r, int ldr, float *log_psi, float *token_scores, float *joint,
+                       void *workspace, size_t workspace_bytes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    ARG_CHECK(start >= 1 && end >= 1 && end <= T && (ol > 0 || start == 1), CTCPS_E_BADARG, "score: frame window outside [1, T]");
     ARG_CHECK(x_logp && blank_lp && r_prev && last_ids && r && log_psi, CTCPS_E_BADARG, "score: null pointer");
     ARG_CHECK(token_scores != nullptr || (S == 0 && ol <= T), CTCPS_E_BADARG, "score: token_scores may only be omitted on the full-vocabulary path");
     ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0 && S >= 0, CTCPS_E_BADARG, "score: non-positive size");
@@ -2062,9 +2080,8 @@ int ctcps_score(const float *x_logp, int ldx, const float *blank_lp, const float
     const long long BW = (long long)B * W;
     ARG_CHECK(BW * (long long)(V > snum ? V : snum) < (1ll << 31) && (long long)B * T < (1ll << 31), CTCPS_E_TOOBIG,
               "score: BW*V or B*T exceeds 2^31");
-    const int start = ol > 1 ? ol : 1;
 
-    if (start > T) {  // ctc_scorer.py:138-145
+    if (start > end) {  // ctc_scorer.py:138-145
         k_fill_f32<<<grid_for((size_t)T * 2 * BW * ldr, 256), 256, 0, st>>>(r, (size_t)T * 2 * BW * ldr, LZ);
         if (S > 0) {
             k_fill_i64<<<grid_for((size_t)BW * V, 256), 256, 0, st>>>(scoring_idmap, (size_t)BW * V, -1);
@@ -2081,7 +2098,7 @@ int ctcps_score(const float *x_logp, int ldx, const float *blank_lp, const float
         k_fill_f32<<<grid_for((size_t)BW * V, 256), 256, 0, st>>>(log_psi, (size_t)BW * V, LZ);  // :156
         const long long lanes = BW * S;
         k_score_partial<<<(unsigned)((lanes + 127) / 128), 128, 0, st>>>(x_logp, ldx, blank_lp, r_prev, last_ids, scoring_ids,
-                                                                        scoring_idmap, ol, B, W, T, V, S, r, ldr, log_psi);
+                                                                        scoring_idmap, ol, start, end, B, W, T, V, S, r, ldr, log_psi);
         k_finalize<<<grid_for((size_t)BW * V, 256), 256, 0, st>>>(log_psi, s_prev, s_row_stride, s_col_stride, att_scores,
                                                                  one_minus_w, w, (int)BW, V, blank, token_scores, joint, 0);
         return cuda_rc(cudaGetLastError());
@@ -2098,7 +2115,7 @@ int ctcps_score(const float *x_logp, int ldx, const float *blank_lp, const float
     const int Tpad = tpad_of(T);
     {
         const int warps = B * G * HW;
-        k_prep<<<(warps + 3) / 4, 128, 0, st>>>(r_prev, blank_lp, B, W, T, HW, G, start, Tpad, aux, Gmax);
+        k_prep<<<(warps + 3) / 4, 128, 0, st>>>(r_prev, blank_lp, B, W, T, HW, G, start, end, Tpad, aux, Gmax);
     }
 
     CUtensorMap tm;
@@ -2127,6 +2144,8 @@ int ctcps_score(const float *x_logp, int ldx, const float *blank_lp, const float
     a.V = V;
     a.blank = blank;
     a.ol = ol;
+    a.start = start;
+    a.end = end;
     a.G = G;
     a.Tpad = Tpad;
     constexpr int NT = 128;
@@ -2140,6 +2159,17 @@ int ctcps_score(const float *x_logp, int ldx, const float *blank_lp, const float
         default: rc = launch_score_full<5, NT, 4>(tm, a, st); break;
     }
     return rc;
+}
+
+// the call without attention weights (:133-136): frames max(ol, 1) .. T; ol > T takes the early return of :138-145
+int ctcps_score(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const float *s_prev,
+                int64_t s_row_stride, int64_t s_col_stride, const int64_t *last_ids, int ol, int B, int W, int T, int V,
+                int blank, const int64_t *scoring_ids, int S, int64_t *scoring_idmap, float *att_scores, float one_minus_w,
+                float w, float *r, int ldr, float *log_psi, float *token_scores, float *joint, void *workspace,
+                size_t workspace_bytes, void *stream) {
+    return ctcps_score_window(x_logp, ldx, blank_lp, r_prev, s_prev, s_row_stride, s_col_stride, last_ids, ol, ol > 1 ? ol : 1, T, B, W,
+                              T, V, blank, scoring_ids, S, scoring_idmap, att_scores, one_minus_w, w, r, ldr, log_psi, token_scores,
+                              joint, workspace, workspace_bytes, stream);
 }
 
 // shared body of ctcps_score_lazy (dense outputs) and ctcps_score_lazy_topk (per-tile candidate lists)

@@ -288,9 +288,6 @@ class CTCPrefixScoreTH(object):
 
     def _parse_step(self, y, state, scoring_ids, att_w):
         """Shared argument handling of a scoring call: (n_bh, ol, last_ids, W, S, scoring_ids, r_prev, s_prev)."""
-        if att_w is not None and self.margin > 0:
-            raise NotImplementedError("CTC windowing (att_w with margin > 0, reference :127-132) is dead code in the "
-                                      "reference's processor and is not implemented")
         dev = self.device
         B, T = self.batch, self.input_length
         if isinstance(y, torch.Tensor):
@@ -323,8 +320,30 @@ class CTCPrefixScoreTH(object):
             r_prev = r_prev.contiguous()
         return n_bh, ol, last_ids, W, S, scoring_ids, r_prev, s_prev
 
+    def _window(self, att_w, state, ol, n_bh):
+        """The frame window of reference :127-132: (start, end, f_min, f_max), host scalars there too (two .cpu() reads)."""
+        T = self.input_length
+        if not isinstance(att_w, torch.Tensor) or not att_w.is_cuda:
+            raise RuntimeError("att_w must be a CUDA tensor")
+        if tuple(att_w.shape) != (n_bh, T):
+            raise ValueError(f"att_w must be {(n_bh, T)}, got {tuple(att_w.shape)}")
+        f_min_prev, f_max_prev = (0, 1) if state is None else (int(state[2]), int(state[3]))   # :84-85
+        f_arg = torch.matmul(att_w.to(self.dtype), self.frame_ids)
+        lo_hi = torch.stack([f_arg.min(), f_arg.max()]).cpu()
+        f_min = max(int(lo_hi[0]), f_min_prev)
+        f_max = max(int(lo_hi[1]), f_max_prev)
+        start = min(f_max_prev, max(f_min - self.margin, ol, 1))
+        end = min(f_max + self.margin, T)
+        return start, end, f_min, f_max
+
     def _score(self, y, state, scoring_ids, att_w, att_scores, ctc_weight, need_token_scores=True):
         n_bh, ol, last_ids, W, S, scoring_ids, r_prev, s_prev = self._parse_step(y, state, scoring_ids, att_w)
+        if att_w is not None and self.margin > 0:
+            # windowed call (dead code in the reference's processor, part of the scorer's interface): the materialising kernels
+            # take the window; the state they return is the reference's tensor
+            window = self._window(att_w, state, ol, n_bh)
+            return self._launch_score(r_prev, s_prev, last_ids, ol, W, scoring_ids, att_scores, ctc_weight, False,
+                                      need_token_scores, False, window)
         prepared = (state is not None and getattr(state, "prepared_gen", None) == self._ws_gen
                     and self._ws_key == (self.batch, self.input_length, W, S))
         return self._launch_score(r_prev, s_prev, last_ids, ol, W, scoring_ids, att_scores, ctc_weight,
@@ -377,7 +396,7 @@ class CTCPrefixScoreTH(object):
         return cand_log_psi, cand_ts, cand_joint, CandidateState(self, r_prev, last_ids, ol, W, scoring_ids, cand_log_psi), s_vec
 
     def _launch_score(self, r_prev, s_prev, last_ids, ol, W, scoring_ids, att_scores, ctc_weight, lazy, need_token_scores=True,
-                      prepared=False):
+                      prepared=False, window=None):
         L = _lib.lib()
         dev = self.device
         B, T, V = self.batch, self.input_length, self.odim
@@ -426,16 +445,19 @@ class CTCPrefixScoreTH(object):
                                               int(bool(prepared)), _stream(dev)), "ctcps_score_lazy")
             else:
                 r = torch.empty((T, 2, n_bh, ldr), dtype=torch.float32, device=dev)
-                _lib.check(L.ctcps_score(_ptr(x_fm), self._ldx, _ptr(self._blank_lp), _ptr(r_prev), s_ptr, s_rs, s_cs,
-                                         _ptr(last_ids), ol, B, W, T, V, self.blank, _ptr(scoring_ids), S, _ptr(idmap),
-                                         _ptr(att_scores), 1.0 - w, w, _ptr(r), ldr, _ptr(log_psi), _ptr(token_scores),
-                                         _ptr(joint), _ptr(ws), ws.numel(), _stream(dev)), "ctcps_score")
+                start, end = (max(ol, 1), T) if window is None else window[:2]
+                _lib.check(L.ctcps_score_window(_ptr(x_fm), self._ldx, _ptr(self._blank_lp), _ptr(r_prev), s_ptr, s_rs, s_cs,
+                                                _ptr(last_ids), ol, start, end, B, W, T, V, self.blank, _ptr(scoring_ids), S,
+                                                _ptr(idmap), _ptr(att_scores), 1.0 - w, w, _ptr(r), ldr, _ptr(log_psi),
+                                                _ptr(token_scores), _ptr(joint), _ptr(ws), ws.numel(), _stream(dev)),
+                           "ctcps_score_window")
                 if ldr != snum:
                     r = r[..., :snum]
             if timing is not None:
                 ev1.record()
                 timing.append((ev0, ev1))
-        return token_scores, (r, log_psi, 0, 0, idmap), joint
+        f_min, f_max = (0, 0) if window is None else window[2:]
+        return token_scores, (r, log_psi, f_min, f_max, idmap), joint
 
     def index_select_state(self, state, best_ids, _out=None):
         """Select CTC states according to best ids (reference :180-207).

@@ -95,8 +95,11 @@ int ctcps_log_softmax(const float *in, int ld_in, float *out, int ld_out, int ro
 int ctcps_initial_state(const float *blank_lp, int B, int T, int W, int t_begin, float *r0, void *stream);
 
 /*
- * K-b.  Replaces CTCPrefixScoreTH.__call__ (ctc_scorer.py:58-178) for margin == 0, fused with the
- * processor arithmetic around it (ctc_scorer.py:325,332).
+ * K-b.  Replaces CTCPrefixScoreTH.__call__ (ctc_scorer.py:58-178), fused with the processor arithmetic
+ * around it (ctc_scorer.py:325,332).  ctcps_score is the call without attention weights (frames
+ * max(ol, 1) .. T, :133-136); ctcps_score_window takes the frame window [start, end) the reference
+ * derives from att_w and margin on the host (:127-132): the recursion and the log_psi sum run over
+ * start <= t < end, r stays logzero outside (1 <= start, 1 <= end <= T; start == 1 when ol == 0).
  *   in  x_logp (B,T,ldx), blank_lp (B,T)
  *       r_prev (T,2,BW)            selected state (or ctcps_initial_state output)
  *       s_prev                     NULL = scalar 0.0 (:83); else element (h,v) at
@@ -118,6 +121,11 @@ int ctcps_score(const float *x_logp, int ldx, const float *blank_lp, const float
                 int V, int blank, const int64_t *scoring_ids, int S, int64_t *scoring_idmap, float *att_scores,
                 float one_minus_w, float w, float *r, int ldr, float *log_psi, float *token_scores, float *joint,
                 void *workspace, size_t workspace_bytes, void *stream);
+int ctcps_score_window(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const float *s_prev,
+                       int64_t s_row_stride, int64_t s_col_stride, const int64_t *last_ids, int ol, int start, int end,
+                       int B, int W, int T, int V, int blank, const int64_t *scoring_ids, int S, int64_t *scoring_idmap,
+                       float *att_scores, float one_minus_w, float w, float *r, int ldr, float *log_psi,
+                       float *token_scores, float *joint, void *workspace, size_t workspace_bytes, void *stream);
 
 /*
  * K-c.  Replaces CTCPrefixScoreTH.index_select_state (ctc_scorer.py:180-207).

@@ -128,14 +128,13 @@ void FN(build_idmap)(const int64_t *scoring_ids, int64_t BW, int64_t S, int64_t 
  * Returns 1 when the reference would take the "start > end" early return (:138-145; all
  * outputs logzero, r left as initialised), else 0.
  */
-int FN(score)(const REAL *x, int64_t B, int64_t T, int64_t V, int64_t blank, const REAL *r_prev,
-              const REAL *s_prev, const int64_t *last_ids, int64_t ol, int64_t W,
-              const int64_t *scoring_ids, int64_t S, REAL *r, REAL *log_psi, REAL *token_scores,
-              int64_t *idmap) {
+int FN(score_window)(const REAL *x, int64_t B, int64_t T, int64_t V, int64_t blank, const REAL *r_prev,
+                     const REAL *s_prev, const int64_t *last_ids, int64_t ol, int64_t W,
+                     const int64_t *scoring_ids, int64_t S, int64_t start, int64_t end, REAL *r, REAL *log_psi,
+                     REAL *token_scores, int64_t *idmap) {
+    /* start / end: the frame window of :127-136 (host scalars there too); without att_w, (max(ol,1), T) */
     const int64_t BW = B * W;
     const int64_t snum = S > 0 ? S : V;
-    const int64_t start = ol > 1 ? ol : 1; /* :135 */
-    const int64_t end = T;                 /* :136 */
     if (S > 0) FN(build_idmap)(scoring_ids, BW, S, V, idmap);
 
     if (start > end) { /* :138-145 */
@@ -171,6 +170,7 @@ int FN(score)(const REAL *x, int64_t B, int64_t T, int64_t V, int64_t blank, con
 #define R(t, k) r[(((t)*2 + (k)) * BW + h) * snum + s]
             /* r = full(logzero); if ol == 0: r[0,0] = x_[0,0]           :106-113 */
             for (int64_t t = 0; t < start; ++t) { R(t, 0) = LOGZERO; R(t, 1) = LOGZERO; }
+            for (int64_t t = end; t < T; ++t) { R(t, 0) = LOGZERO; R(t, 1) = LOGZERO; } /* frames past the window */
             if (ol == 0) R(0, 0) = xb_[0 * V + v];
             /* forward recursion                                          :148-151 */
             REAL rn = R(start - 1, 0), rb = R(start - 1, 1);
@@ -204,6 +204,15 @@ int FN(score)(const REAL *x, int64_t B, int64_t T, int64_t V, int64_t blank, con
         }
     }
     return 0;
+}
+
+/* The call without attention weights (:133-136): start = max(output_length, 1), end = T. */
+int FN(score)(const REAL *x, int64_t B, int64_t T, int64_t V, int64_t blank, const REAL *r_prev,
+              const REAL *s_prev, const int64_t *last_ids, int64_t ol, int64_t W,
+              const int64_t *scoring_ids, int64_t S, REAL *r, REAL *log_psi, REAL *token_scores,
+              int64_t *idmap) {
+    return FN(score_window)(x, B, T, V, blank, r_prev, s_prev, last_ids, ol, W, scoring_ids, S, ol > 1 ? ol : 1, T, r,
+                            log_psi, token_scores, idmap);
 }
 
 /*

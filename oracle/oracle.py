@@ -90,8 +90,9 @@ def init_state(x: np.ndarray, blank: int, W: int, prec: int = 32) -> np.ndarray:
     return r0
 
 
-def score(x, blank, r_prev, s_prev, last_ids, ol, W, scoring_ids=None, prec: int = 32):
-    """Returns (token_scores, r, log_psi, idmap_or_None, early_return_flag)."""
+def score(x, blank, r_prev, s_prev, last_ids, ol, W, scoring_ids=None, prec: int = 32, window=None):
+    """Returns (token_scores, r, log_psi, idmap_or_None, early_return_flag).  window = (start, end) of ctc_scorer.py:127-136
+    (None: max(ol, 1), T)."""
     B, T, V = x.shape
     BW = B * W
     dt = _dt(prec)
@@ -110,9 +111,10 @@ def score(x, blank, r_prev, s_prev, last_ids, ol, W, scoring_ids=None, prec: int
     r = np.empty((T, 2, BW, snum), dtype=dt)
     log_psi = np.empty((BW, V), dtype=dt)
     ts = np.empty((BW, V), dtype=dt)
-    early = _fn("score", prec)(
+    start, end = (max(ol, 1), T) if window is None else window
+    early = _fn("score_window", prec)(
         _p(x), _i64(B), _i64(T), _i64(V), _i64(blank), _p(r_prev), _p(s_prev), _p(last_ids), _i64(ol), _i64(W),
-        _p(scoring_ids), _i64(S), _p(r), _p(log_psi), _p(ts), _p(idmap))
+        _p(scoring_ids), _i64(S), _i64(start), _i64(end), _p(r), _p(log_psi), _p(ts), _p(idmap))
     return ts, r, log_psi, idmap, bool(early)
 
 
@@ -147,13 +149,11 @@ def combine(scores, ctc, pad_id, w, apply_trick=False, eos=1, space=-1, trick_w=
 # Reference-shaped objects over torch CPU tensors (for the shared beam-search harness).
 # --------------------------------------------------------------------------------------------
 class OracleCTCPrefixScore:
-    """Same surface as CTCPrefixScoreTH (ctc_scorer.py:7-207), margin == 0 only."""
+    """Same surface as CTCPrefixScoreTH (ctc_scorer.py:7-207), the attention window of :127-136 included."""
 
     def __init__(self, x, xlens, blank, eos, margin=0, prec: int | None = None):
         import torch
 
-        if margin != 0:
-            raise NotImplementedError("the oracle restates the margin == 0 path only")
         self._torch = torch
         self.prec = prec or (64 if x.dtype == torch.float64 else 32)
         self.logzero = LOGZERO
@@ -174,12 +174,21 @@ class OracleCTCPrefixScore:
         if state is None:
             r_prev = init_state(self._x, self.blank, W, self.prec)
             s_prev = None
+            f_min_prev, f_max_prev = 0, 1                                   # :84-85
         else:
             r_prev, s_prev = state[0].numpy(), state[1].numpy()
+            f_min_prev, f_max_prev = int(state[2]), int(state[3])
         sid = None if scoring_ids is None else scoring_ids.numpy()
         self.scoring_num = 0 if sid is None else sid.shape[-1]
-        ts, r, log_psi, idmap, _ = score(self._x, self.blank, r_prev, s_prev, last_ids, ol, W, sid, self.prec)
-        return torch.from_numpy(ts), (torch.from_numpy(r), torch.from_numpy(log_psi), 0, 0,
+        window, f_min, f_max = None, 0, 0
+        if att_w is not None and self.margin > 0:                           # :127-132
+            T = self.input_length
+            f_arg = att_w.to(self.dtype) @ torch.arange(T, dtype=self.dtype)
+            f_min = max(int(f_arg.min()), f_min_prev)
+            f_max = max(int(f_arg.max()), f_max_prev)
+            window = (min(f_max_prev, max(f_min - self.margin, ol, 1)), min(f_max + self.margin, T))
+        ts, r, log_psi, idmap, _ = score(self._x, self.blank, r_prev, s_prev, last_ids, ol, W, sid, self.prec, window)
+        return torch.from_numpy(ts), (torch.from_numpy(r), torch.from_numpy(log_psi), f_min, f_max,
                                       None if idmap is None else torch.from_numpy(idmap))
 
     def index_select_state(self, state, best_ids):

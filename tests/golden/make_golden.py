@@ -22,6 +22,9 @@ Case kinds
   decode_*  : 1-best sequences of the shared beam-search harness with the reference processor.
   lm_fusion_*: the reference's LMRescorerLogitsProcessor (shallow_fussion.py, full-prefix LM forward per step) with a small
               random GPT-2 (weights stored in the fixture), over a beam search that reorders hypotheses and a greedy decode.
+  window_*  : the reference SCORER with margin > 0 and attention weights (the frame window of ctc_scorer.py:127-136, dead code
+              in the reference's processor but part of the scorer's interface): per-step replay, full vocabulary and
+              scoring_ids, states selected with general ids.
   prebeam_* : the reference SCORER driven with ESPnet's pre-beam policy (scoring_ids = top-S decoder tokens per
               hypothesis, states selected with source hypothesis * V + token): per-step replay and 1-best decodes.
 """
@@ -285,6 +288,79 @@ class ReferencePreBeamProcessor:
         return out
 
 
+def monotonic_attention(n_bh, T, step, n_steps, seed, dtype):
+    """(n_bh, T) attention weights: a soft peak that walks through the utterance with the decode step, a little different
+    for every hypothesis."""
+    g = torch.Generator().manual_seed(seed * 131 + step)
+    centre = (step + 0.5) / n_steps * (T - 1) + torch.randn(n_bh, generator=g) * 1.5
+    t = torch.arange(T, dtype=torch.float64)
+    w = torch.softmax(-0.5 * ((t.view(1, -1) - centre.view(-1, 1).double()) / 2.0) ** 2, dim=-1)
+    return w.to(dtype)
+
+
+def replay_window(logits, lens, W, margin, n_steps, S, seed, dtype):
+    """Drive the reference scorer (margin > 0) with attention weights for n_steps; beam update = top-W of the token scores
+    plus noise over the (W, V) candidates of every utterance, general hyp*V+tok ids into index_select_state."""
+    B, T, V = logits.shape
+    x = torch.log_softmax(logits.to(dtype), -1)
+    scorer = CTCPrefixScoreTH(x.clone(), lens.clone(), BLANK, EOS, margin)
+    g = torch.Generator().manual_seed(seed)
+    y = torch.full((B * W, 1), BOS, dtype=torch.long)
+    state = None
+    rec = {"n_steps": n_steps}
+    for n in range(n_steps):
+        att_w = monotonic_attention(B * W, T, n, n_steps, seed, dtype)
+        sids = None
+        if S > 0:
+            sids = torch.stack([torch.randperm(V, generator=g)[:S] for _ in range(B * W)])
+            if n > 0:
+                sids[:, 0] = y[:, -1]  # the last label is a candidate of every hypothesis but the first
+                sids[0, 0] = (sids[0, 1] + 1) % V if (sids[0, 1] + 1) % V not in sids[0].tolist() else sids[0, 0]
+        rec[f"y_{n}"] = y.numpy().copy()
+        rec[f"att_w_{n}"] = att_w.numpy().copy()
+        if sids is not None:
+            rec[f"sids_{n}"] = sids.numpy().copy()
+        ts, st = scorer([row.tolist() for row in y], state, scoring_ids=sids, att_w=att_w)
+        rec[f"ts_{n}"] = ts.numpy().copy()
+        rec[f"r_{n}"] = st[0].numpy().copy()
+        rec[f"log_psi_{n}"] = st[1].numpy().copy()
+        rec[f"f_{n}"] = np.asarray([st[2], st[3]], dtype=np.int64)
+        noise = torch.randn(B * W, V, generator=g).to(dtype) * 2.0
+        cand = torch.where(ts > -1e9, ts + noise, torch.full_like(ts, -1e9))
+        if n == 0:
+            cand.view(B, W, V)[:, 1:] = -1e9  # all hypotheses of the first step are the same prefix
+        best = cand.view(B, W * V).topk(W, dim=1).indices  # hyp*V + tok
+        rec[f"best_{n}"] = best.numpy().copy()
+        state = scorer.index_select_state(st, best)
+        rec[f"sel_r_{n}"] = state[0].numpy().copy()
+        rec[f"sel_s_{n}"] = state[1][:, 0].numpy().copy()
+        src = best // V + (torch.arange(B) * W).view(B, 1)
+        y = torch.cat([y[src.view(-1)], (best % V).view(-1, 1)], dim=1)
+    return rec
+
+
+def case_window():
+    specs = [
+        # name, B, W, T, V, kind, ragged, margin, steps, S, seed
+        ("window_full_m3", 2, 3, 40, 48, "peaky", True, 3, 6, 0, 41),
+        ("window_full_m8_w5", 1, 5, 70, 37, "flat", False, 8, 7, 0, 42),      # V % 4 != 0, windows of several 8-frame chunks
+        ("window_partial_m4", 2, 4, 36, 40, "peaky", True, 4, 5, 7, 43),
+    ]
+    for name, B, W, T, V, kind, ragged, margin, steps, S, seed in specs:
+        logits, lens, _ = make_encoder_logits(B, T, V, kind, ragged, seed=seed)
+        r32 = replay_window(logits, lens, W, margin, steps, S, seed, torch.float32)
+        r64 = replay_window(logits, lens, W, margin, steps, S, seed, torch.float64)
+        for key, v in r64.items():
+            if isinstance(v, np.ndarray) and v.dtype == np.float64 and key.startswith(("ts_", "log_psi_", "sel_", "r_")):
+                r32[key + "_f64"] = v
+        # the fp64 run must take the same beam path for its tensors to adjudicate the fp32 ones
+        same = all((r32[f"best_{n}"] == r64[f"best_{n}"]).all() and (r32[f"f_{n}"] == r64[f"f_{n}"]).all() for n in range(steps))
+        r32.update(logits=logits.numpy(), lens=lens.numpy(), W=W, margin=margin, S=S, f64_same_path=same)
+        windows = [tuple(int(v) for v in r32[f"f_{n}"]) for n in range(steps)]
+        print(name, "f_min/f_max per step:", windows, "fp64 same path:", same)
+        save(name, r32)
+
+
 def case_prebeam():
     # (1) per-step replay under the shared harness (records what the processor saw and returned at every step)
     specs = [
@@ -372,10 +448,14 @@ if __name__ == "__main__":
     if "--lm-only" in sys.argv:
         case_lm_fusion()
         sys.exit(0)
+    if "--window-only" in sys.argv:
+        case_window()
+        sys.exit(0)
     case_steps()
     case_partial_and_select()
     case_edges()
     case_decode()
     case_extend()
+    case_window()
     case_prebeam()
     case_lm_fusion()

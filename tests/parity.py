@@ -18,6 +18,7 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 ATOL = 1e-4
 RTOL = 2e-6
 LZ_CLASS = -1e9
+WINDOW_CASES = ["window_full_m3", "window_full_m8_w5", "window_partial_m4"]
 
 
 def load(name):
@@ -139,6 +140,33 @@ def replay_steps(be: Backend, name: str, blank=3, eos=1):
                                                              ref64=g.get(f"out_{n}_f64")))
         # the in-place scores[:, pad] = logzero must reach the caller's tensor (ctc_scorer.py:325)
         assert_parity(att, g[f"att_after_{n}"], f"{name} step {n} att in-place", atol=0, rtol=0)
+    return worst
+
+
+def replay_window(be: Backend, name: str, blank=3, eos=1):
+    """Replay a window_* golden file: the scorer with margin > 0 and attention weights (ctc_scorer.py:127-136), full
+    vocabulary or scoring_ids, states selected with general ids.  Every tensor of every step, and the (f_min, f_max) the state
+    carries."""
+    g = load(name)
+    W, margin, S = int(g["W"]), int(g["margin"]), int(g["S"])
+    logits, lens = be.t(g["logits"]), be.t(g["lens"])
+    scorer = be.make_scorer(torch.log_softmax(logits, -1), lens.clone(), blank, eos, margin)
+    state = None
+    worst = {}
+    for n in range(int(g["n_steps"])):
+        y = be.t(g[f"y_{n}"])
+        sids = be.t(g[f"sids_{n}"]) if S > 0 else None
+        ts, st = scorer(y, state, scoring_ids=sids, att_w=be.t(g[f"att_w_{n}"]))
+        assert (int(st[2]), int(st[3])) == tuple(int(v) for v in g[f"f_{n}"]), f"{name} step {n}: f_min / f_max"
+        worst["ts"] = max(worst.get("ts", 0), assert_parity(ts, g[f"ts_{n}"], f"{name} step {n} token_scores", rtol=0,
+                                                           ref64=g.get(f"ts_{n}_f64")))
+        worst["r"] = max(worst.get("r", 0), assert_parity(st[0], g[f"r_{n}"], f"{name} step {n} r", ref64=g.get(f"r_{n}_f64")))
+        assert_parity(st[1], g[f"log_psi_{n}"], f"{name} step {n} log_psi", ref64=g.get(f"log_psi_{n}_f64"))
+        state = scorer.index_select_state(st, be.t(g[f"best_{n}"]))
+        worst["sel_r"] = max(worst.get("sel_r", 0), assert_parity(state[0], g[f"sel_r_{n}"], f"{name} step {n} sel_r",
+                                                                 ref64=g.get(f"sel_r_{n}_f64")))
+        assert_parity(state[1][:, 0], g[f"sel_s_{n}"], f"{name} step {n} sel_s", ref64=g.get(f"sel_s_{n}_f64"))
+        assert (int(state[2]), int(state[3])) == tuple(int(v) for v in g[f"f_{n}"])
     return worst
 
 

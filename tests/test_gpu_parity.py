@@ -130,6 +130,14 @@ def test_edges_vs_reference_golden():
     parity.replay_edges(BE)
 
 
+@pytest.mark.parametrize("lazy", [False, True])
+@pytest.mark.parametrize("name", parity.WINDOW_CASES)
+def test_attention_window_vs_reference_golden(name, lazy):
+    """margin > 0 with attention weights (ctc_scorer.py:127-136): full vocabulary and scoring_ids, on a materialising scorer
+    and on a lazy one (windowed calls go through the materialising kernels either way)."""
+    print(name, parity.replay_window(BE_LAZY if lazy else BE, name))
+
+
 def test_extend_prob_and_state_vs_reference_golden():
     parity.replay_extend(BE)
     parity.replay_extend(BE_LAZY)

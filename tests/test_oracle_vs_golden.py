@@ -41,6 +41,12 @@ def test_oracle_edges():
     parity.replay_edges(BE)
 
 
+@pytest.mark.parametrize("name", parity.WINDOW_CASES)
+def test_oracle_attention_window(name):
+    """margin > 0 with attention weights: the frame window of ctc_scorer.py:127-136."""
+    print(name, parity.replay_window(BE, name))
+
+
 def test_oracle_extend_prob_and_state():
     parity.replay_extend(BE)
 
