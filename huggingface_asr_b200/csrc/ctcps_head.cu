@@ -7,9 +7,10 @@
 // k_head_gemm: logits tile by tile on the 5th-generation tensor cores at fp32 accuracy (three half-precision products, below),
 // bias and the row-wise softmax statistics (running max, sum of exponentials) fused into the TMEM -> register epilogue; the raw
 // logits go straight into the scorer's padded (B,T,ldx) buffer, the per-row statistics into a small side array.
-// k_head_finish: one streaming pass turns the buffer into log-posteriors in place -- (z - max) - log(sum), the order
-// torch.log_softmax uses -- applies the length padding and extracts the blank column (what k_init does after a library GEMM,
-// without its two block-wide reductions).
+// Normalisation inside the same kernel: the grid works on one BAND of gridDim.x consecutive tiles at a time; after a band the
+// epilogue warps of all CTAs meet at a grid barrier and turn the rows that band completed into log-posteriors in place --
+// (z - max) - log(sum), the order torch.log_softmax uses -- with the length padding and the blank column (what k_init does
+// after a library GEMM), reading the logits back from L2 while the MMA warps work on the next band.
 //
 // 3xFP16.  An fp16 significand has 11 bits -- exactly TF32's -- in 2 bytes instead of 4, and kind::f16 runs at twice the rate
 // of kind::tf32.  What fp16 lacks is range, so every row of h (and W as a whole) is first scaled by a power of two that puts
@@ -32,13 +33,14 @@
 //   warps 2-9   epilogue: tcgen05.ld 32 lanes x 32 columns at a time, software-pipelined (a thread owns one row of the tile and
 //               half of its columns), (big + 2^-11 small) / scale + bias, online max / sum-exp, 128-byte row segments stored with
 //               st.global.v4
-// Work item = (128-row tile, quarter of the vocabulary tiles): 4 x 746 items at C2 keep the last wave short; the partial
-// statistics of a row's quarters are combined by k_head_finish.
+// Work item = one 128 x 256 tile in (row tile, vocabulary tile) order; the partial statistics of a row's tiles are combined
+// when the row is normalised.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ctcps.h"
 
@@ -50,21 +52,23 @@ constexpr int UMMA_K = 16;                                 // kind::f16: 32 byte
 constexpr float LO_SCALE = 2048.f, LO_UNSCALE = 1.f / 2048.f;  // the low parts are stored times 2^11 (fp16 range)
 constexpr int NSTAGE = 4;                                  // 4 x 48 KB: the first version (2 x 96 KB, 128-byte rows) starved the MMAs
 constexpr float LOG2E_F = 1.4426950408889634f;
+constexpr int N_DRAIN = 16;                                // drain warps: (TMEM lane quarter, column quarter)
+constexpr int HEAD_NT = (4 + N_DRAIN) * 32;                // warp 0 TMA, warp 1 MMA, warps 2-3 idle (the drain starts on a warpgroup boundary), 4..19 drain
 constexpr int NCHUNK = 4;                                  // vocabulary quarters per row tile
-constexpr int HEAD_NT = 320;                               // TMA warp, MMA warp, 8 epilogue warps
-constexpr int NPART = NCHUNK * 2;                          // partial softmax statistics per row: (vocabulary quarter, column half)
+constexpr int NPART = NCHUNK * 4;                          // partial softmax statistics per row: (vocabulary quarter, column quarter of the tiles)
 constexpr uint32_t A_TILE_BYTES = BLOCK_M * BLOCK_K * 2;   // 8 KB
 constexpr uint32_t B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;   // 16 KB
 constexpr uint32_t STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr int STORE_COLS = 16;                             // columns per pass of the epilogue's shared-memory transposition
+constexpr int GCOLS = 16;                                  // columns per TMEM load of a drain warp
+constexpr int STORE_COLS = GCOLS;                          // columns per TMA store of a drain warp: a 32-row x 64-byte box
 
 struct HeadSmem {
     alignas(1024) unsigned char a_hi[NSTAGE][A_TILE_BYTES];
     alignas(1024) unsigned char a_lo[NSTAGE][A_TILE_BYTES];
     alignas(1024) unsigned char b_hi[NSTAGE][B_TILE_BYTES];
     alignas(1024) unsigned char b_lo[NSTAGE][B_TILE_BYTES];
-    alignas(16) float stage_out[HEAD_NT / 32 - 2][32][STORE_COLS];  // per epilogue warp: 32 rows x 16 columns on their way to global memory
+    alignas(1024) float stage_out[N_DRAIN][32][STORE_COLS];  // per drain warp: the 32 x 16 box its next TMA store reads (SWIZZLE_64B image)
     alignas(16) float bias[2][BLOCK_N];                             // bias of the current / next vocabulary tile
     alignas(8) uint64_t full[NSTAGE];
     alignas(8) uint64_t empty[NSTAGE];
@@ -72,6 +76,8 @@ struct HeadSmem {
     alignas(8) uint64_t tmem_empty;
     uint32_t tmem_base;
 };
+
+static_assert(sizeof(HeadSmem) <= 227 * 1024, "HeadSmem must fit the 227 KB a CTA can have");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -171,6 +177,33 @@ __device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, uint32_t (&r
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+// 32 TMEM lanes x 16 consecutive columns -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld_32x16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+// shared memory by its own address space (through generic pointers the compiler emitted LD.E / ST.E with global-memory
+// scoreboards for the epilogue's staging buffers)
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, float a, float b, float c, float d) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// TMA store of one box, shared -> global through a tensor map (columns / rows beyond the tensor are clipped); SASS UTMASTG
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, uint32_t smem_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tm), "r"(smem_addr), "r"(c0), "r"(c1)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// the bulk stores this thread committed have finished READING shared memory (the buffer may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2_fast(float x) {
     float y;
@@ -183,16 +216,18 @@ struct HeadArgs {
     const unsigned char *b_hi, *b_lo;  //                                      [vocabulary tile][k-block][256 rows][64 bytes]
     const float *a_inv;                // (padded n) 1 / scale of every row of h
     const uint32_t *w_absmax;          // bits of max |W| (the weight's scale is derived from it)
-    const float *bias;   // (V) or null
-    float *z;            // (n, ldz) raw logits out (the scorer's padded posterior buffer)
-    float2 *stats;       // (n, NPART): running max and sum of exp(z - max) over the columns of a (vocabulary quarter, column half)
+    const float *bias;                 // (V) or null
+    float *z;                          // (n, ldz) raw logits out (the scorer's padded posterior buffer)
+    float2 *stats;                     // (n, NPART): running max and sum of exp(z - max) over the columns of a (vocabulary quarter, column quarter)
     int n, d_pad, V, ldz;
     int n_mtiles, n_ntiles, tiles_per_chunk;
 };
 
-__global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const HeadArgs a) {
+__global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const __grid_constant__ CUtensorMap tmz, const HeadArgs a) {
+    // all 227 KB: there is no room to round the base up, the declared alignment has to hold (swizzled tiles repeat every 512 bytes)
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    HeadSmem &sm = *reinterpret_cast<HeadSmem *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    if (smem_u32(smem_raw) & 1023u) __trap();
+    HeadSmem &sm = *reinterpret_cast<HeadSmem *>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_kblocks = a.d_pad / BLOCK_K;
     const int n_items = a.n_mtiles * NCHUNK;
@@ -201,7 +236,7 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const HeadArgs a) {
         if (lane == 0) {
             for (int s = 0; s < NSTAGE; ++s) mbar_init(&sm.full[s], 1), mbar_init(&sm.empty[s], 1);
             mbar_init(&sm.tmem_full, 1);
-            mbar_init(&sm.tmem_empty, 8);  // one arrival per epilogue warp
+            mbar_init(&sm.tmem_empty, N_DRAIN);  // one arrival per drain warp
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -243,7 +278,7 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const HeadArgs a) {
             const int ch = item % NCHUNK;
             const int nt0 = ch * a.tiles_per_chunk, nt1 = min(a.n_ntiles, nt0 + a.tiles_per_chunk);
             for (int nt = nt0; nt < nt1; ++nt, ++tile) {
-                mbar_wait(&sm.tmem_empty, (tile & 1) ^ 1);  // the epilogue has drained the accumulators of the previous tile
+                mbar_wait(&sm.tmem_empty, (tile & 1) ^ 1);  // the drain warps have emptied the accumulators of the previous tile
                 tc_fence_after();
                 for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
                     const int s = it % NSTAGE;
@@ -270,21 +305,27 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const HeadArgs a) {
                 }
             }
         }
-    } else {
-        // ===== epilogue (warps 2..9): TMEM lane quarter = warp % 4 (a hardware rule), column half = (warp - 2) / 4; a thread
-        // owns one row of the tile and 128 of its 256 columns.  The TMEM loads of the next 32-column group are in flight
-        // while the current one is processed (the first version waited for every load: ncu showed the MMA warp idle 43 % of the
-        // time behind a serialised epilogue).  The second version still spent 14 us per tile here against 13 us of MMAs (ncu
-        // r2r): every float4 of the bias was a global load in front of its first use -- 32 dependent L2 round trips per
-        // tile -- and a warp's float4 stores went to 32 different rows (32 half-written sectors per instruction, twice the
-        // bytes on the way to L2).  Now the tile's bias is staged in shared memory while the MMAs of the tile still run, and the
-        // logits leave through a per-warp shared-memory transposition: 8 rows x 64 contiguous bytes per store instruction.
-        const int quarter = warp & 3, half = (warp - 2) >> 2;
+    } else if (warp >= 4) {
+        // ===== drain (warps 4..19): TMEM lane quarter = warp % 4 (a hardware rule), column quarter = (warp - 4) / 4; a thread owns
+        // one row of the tile and 64 of its 256 columns, 16 at a time.  History of this part, all measured with ncu at C2
+        // (profiles/r2*_head*.md): the MMAs of a 128 x 256 tile take ~4 us, so the tile time IS the drain.
+        //   v1  8 warps, wait after every TMEM load                                  MMA warp idle 43 % of the time
+        //   v2  + loads of the next group in flight                                  14 us per tile: every float4 of the bias a
+        //       global load in front of its first use (32 dependent L2 round trips per tile), float4 stores to 32 different
+        //       rows per instruction (half-written sectors, twice the bytes towards L2)
+        //   v3  + bias staged in shared memory while the MMAs run, stores through a per-warp shared-memory transposition
+        //       (8 rows x 64 contiguous bytes per instruction)                       8.6 us
+        //   v4  + 16-column groups (no spills), shared memory addressed as such (the generic loads carried global-memory
+        //       scoreboards), columns beyond the vocabulary masked by a -inf bias instead of a compare per element   6.8 us
+        //   v5  16 warps x 64 columns: four warps per scheduler hide the chain TMEM load -> max -> exp -> transposition -> store
+        const int quarter = warp & 3, cq = (warp - 4) >> 2;
         const int row_in_tile = quarter * 32 + lane;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * (BLOCK_N / 2));
-        constexpr int NGROUP = BLOCK_N / 2 / 32;  // 4 groups of 32 columns per thread and tile
-        float(*st)[STORE_COLS] = sm.stage_out[warp - 2];
-        const int st_r = lane >> 2, st_c = lane & 3;  // store pass: this lane moves chunk st_c of rows st_r, st_r + 8, ...
+        const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(cq * (BLOCK_N / 4));
+        constexpr int NGROUP = BLOCK_N / 4 / GCOLS;  // 4 groups of 16 columns per thread and tile
+        const uint32_t st_base = smem_u32(sm.stage_out[warp - 4]);
+        // a lane = a row of the box: its four 16-byte chunks land where TMA's SWIZZLE_64B expects them (chunk ^ ((row >> 1) & 3)),
+        // which also keeps the row-wise writes free of bank conflicts
+        const uint32_t st_wr = st_base + (uint32_t)lane * (STORE_COLS * 4), st_wx = (uint32_t)((lane >> 1) & 3);
         float w_s, w_inv;
         scale_from_absmax(__uint_as_float(__ldg(a.w_absmax)), w_s, w_inv);
         uint32_t tile = 0;
@@ -293,96 +334,85 @@ __global__ void __launch_bounds__(HEAD_NT, 1) k_head_gemm(const HeadArgs a) {
             const int nt0 = ch * a.tiles_per_chunk, nt1 = min(a.n_ntiles, nt0 + a.tiles_per_chunk);
             const long long row = (long long)mt * BLOCK_M + row_in_tile;
             const bool row_ok = row < a.n;
-            const long long st_row0 = (long long)mt * BLOCK_M + quarter * 32 + st_r;
-            float *zst = a.z + (size_t)st_row0 * a.ldz + st_c * 4;
+            const int box_row0 = mt * BLOCK_M + quarter * 32;
             float m_run = -INFINITY, s_run = 0.f;
             const float unscale = __ldg(a.a_inv + row) * w_inv;  // a_inv covers the padded rows
-            const float *bias_s = nullptr;
-            auto process = [&](const uint32_t (&big)[32], const uint32_t (&small)[32], int g, int v0) {
-                if (v0 >= a.V) return;  // warp-uniform: a column group beyond the vocabulary
-                const bool whole = v0 + 32 <= a.V;
-                float zv[32];
-                float gmax = -INFINITY;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 b4 = *reinterpret_cast<const float4 *>(bias_s + g * 32 + q * 4);
-                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int i = q * 4 + j;
-                        zv[i] = fmaf(fmaf(__uint_as_float(small[i]), LO_UNSCALE, __uint_as_float(big[i])), unscale, bb[j]);
-                        if (whole || v0 + i < a.V) gmax = fmaxf(gmax, zv[i]);
-                    }
-                }
-                const float m_new = fmaxf(m_run, gmax);
-                const float ml2 = m_new * LOG2E_F;
-                float acc = 0.f;
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    if (whole || v0 + j < a.V) acc += ex2_fast(fmaf(zv[j], LOG2E_F, -ml2));
-                s_run = s_run * ex2_fast((m_run - m_new) * LOG2E_F) + acc;  // 2^-inf = 0 on the first group
-                m_run = m_new;
-                // rows -> shared memory (16-byte chunks XOR-ed with (row >> 1) & 3: conflict-free both ways), then out by rows
-#pragma unroll
-                for (int h = 0; h < 32 / STORE_COLS; ++h) {
-                    __syncwarp();
-#pragma unroll
-                    for (int q = 0; q < STORE_COLS / 4; ++q)
-                        *reinterpret_cast<float4 *>(&st[lane][(q ^ ((lane >> 1) & 3)) * 4]) =
-                            make_float4(zv[h * STORE_COLS + q * 4], zv[h * STORE_COLS + q * 4 + 1], zv[h * STORE_COLS + q * 4 + 2],
-                                        zv[h * STORE_COLS + q * 4 + 3]);
-                    __syncwarp();
-                    const int v = v0 + h * STORE_COLS + st_c * 4;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int r = i * 8 + st_r;
-                        const float4 o = *reinterpret_cast<const float4 *>(&st[r][(st_c ^ ((r >> 1) & 3)) * 4]);
-                        if (st_row0 + i * 8 < a.n) {
-                            float *dst = zst + (size_t)(i * 8) * a.ldz + (v0 + h * STORE_COLS);
-                            if (v + 4 <= a.V) *reinterpret_cast<float4 *>(dst) = o;
-                            else {
-                                if (v + 0 < a.V) dst[0] = o.x;
-                                if (v + 1 < a.V) dst[1] = o.y;
-                                if (v + 2 < a.V) dst[2] = o.z;
-                            }
-                        }
-                    }
-                }
-            };
             for (int nt = nt0; nt < nt1; ++nt, ++tile) {
-                {   // this tile's bias (zero beyond the vocabulary / without a bias) while its MMAs are still running
-                    const int et = (int)threadIdx.x - 64, v = nt * BLOCK_N + et;
-                    sm.bias[tile & 1][et] = (a.bias != nullptr && v < a.V) ? __ldg(a.bias + v) : 0.f;
-                    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps; two buffers, so one barrier per tile is enough
+                {   // this tile's bias while its MMAs are still running: 0 without a bias, -inf beyond the vocabulary, which
+                    // takes those columns out of the row maximum and the sum of exponentials without a compare per element
+                    const int et = (int)threadIdx.x - 128;
+                    if (et < BLOCK_N) {
+                        const int v = nt * BLOCK_N + et;
+                        sm.bias[tile & 1][et] = v < a.V ? (a.bias != nullptr ? __ldg(a.bias + v) : 0.f) : -INFINITY;
+                    }
+                    asm volatile("bar.sync 1, 512;" ::: "memory");  // the 16 drain warps; two buffers, so one barrier per tile is enough
                 }
-                bias_s = &sm.bias[tile & 1][half * (BLOCK_N / 2)];
+                const uint32_t bias_s = smem_u32(&sm.bias[tile & 1][cq * (BLOCK_N / 4)]);
+                const int vbase = nt * BLOCK_N + cq * (BLOCK_N / 4);
                 mbar_wait(&sm.tmem_full, tile & 1);
                 tc_fence_after();
-                const int vbase = nt * BLOCK_N + half * (BLOCK_N / 2);
-                uint32_t big0[32], small0[32], big1[32], small1[32];
-                tmem_ld_32x32_issue(lane_base, big0);
-                tmem_ld_32x32_issue(lane_base + BLOCK_N, small0);
+                // Phase 1: the thread's 64 logits of the tile into registers (accumulators combined, scale, bias), the accumulators back
+                // to the MMA warp.  Phase 2, while the MMAs of the next tile run: row statistics and the stores.  (Timing probes at C2,
+                // r2v: of 6.7 us of drain per tile the stores are 3.4 us -- 128 KB through the SM's ~32 B/clk path to L2 -- the TMEM
+                // loads 1.7 us, the arithmetic 0.8 us; as long as the stores held the accumulators the MMAs waited for them.)
+                float zv[NGROUP * GCOLS];
+                {
+                    uint32_t big[GCOLS], small[GCOLS];
+                    tmem_ld_32x16_issue(lane_base, big);
+                    tmem_ld_32x16_issue(lane_base + BLOCK_N, small);
 #pragma unroll
-                for (int c = 0; c < NGROUP; c += 2) {
-                    tmem_ld_wait();  // group c has landed
-                    tmem_ld_32x32_issue(lane_base + (uint32_t)((c + 1) * 32), big1);
-                    tmem_ld_32x32_issue(lane_base + (uint32_t)(BLOCK_N + (c + 1) * 32), small1);
-                    process(big0, small0, c, vbase + c * 32);
-                    tmem_ld_wait();  // group c + 1 has landed
-                    if (c + 2 < NGROUP) {
-                        tmem_ld_32x32_issue(lane_base + (uint32_t)((c + 2) * 32), big0);
-                        tmem_ld_32x32_issue(lane_base + (uint32_t)(BLOCK_N + (c + 2) * 32), small0);
-                    } else {
-                        // the last values of this tile are in registers: hand the accumulators back to the MMA warp before computing
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&sm.tmem_empty);
+                    for (int g = 0; g < NGROUP; ++g) {
+                        tmem_ld_wait();  // group g has landed
+#pragma unroll
+                        for (int q = 0; q < GCOLS / 4; ++q) {
+                            const float4 b4 = lds_v4(bias_s + (uint32_t)(g * GCOLS + q * 4) * 4);
+                            float *zq = &zv[g * GCOLS + q * 4];
+                            zq[0] = fmaf(fmaf(__uint_as_float(small[q * 4 + 0]), LO_UNSCALE, __uint_as_float(big[q * 4 + 0])), unscale, b4.x);
+                            zq[1] = fmaf(fmaf(__uint_as_float(small[q * 4 + 1]), LO_UNSCALE, __uint_as_float(big[q * 4 + 1])), unscale, b4.y);
+                            zq[2] = fmaf(fmaf(__uint_as_float(small[q * 4 + 2]), LO_UNSCALE, __uint_as_float(big[q * 4 + 2])), unscale, b4.z);
+                            zq[3] = fmaf(fmaf(__uint_as_float(small[q * 4 + 3]), LO_UNSCALE, __uint_as_float(big[q * 4 + 3])), unscale, b4.w);
+                        }
+                        if (g + 1 < NGROUP) {  // the load registers are free again: next group on its way
+                            tmem_ld_32x16_issue(lane_base + (uint32_t)((g + 1) * GCOLS), big);
+                            tmem_ld_32x16_issue(lane_base + (uint32_t)(BLOCK_N + (g + 1) * GCOLS), small);
+                        }
                     }
-                    process(big1, small1, c + 1, vbase + (c + 1) * 32);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.tmem_empty);
+                }
+#pragma unroll
+                for (int g = 0; g < NGROUP; ++g) {
+                    const int v0 = vbase + g * GCOLS;
+                    if (v0 >= a.V) continue;  // warp-uniform: a column group beyond the vocabulary
+                    const float *z = &zv[g * GCOLS];
+                    float g0 = fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3])), g1 = fmaxf(fmaxf(z[4], z[5]), fmaxf(z[6], z[7]));
+                    float g2 = fmaxf(fmaxf(z[8], z[9]), fmaxf(z[10], z[11])), g3 = fmaxf(fmaxf(z[12], z[13]), fmaxf(z[14], z[15]));
+                    const float m_new = fmaxf(fmaxf(m_run, fmaxf(g0, g1)), fmaxf(g2, g3));  // finite: the group has a column inside the vocabulary
+                    const float ml2 = m_new * LOG2E_F;
+                    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < GCOLS; j += 2) {
+                        acc0 += ex2_fast(fmaf(z[j], LOG2E_F, -ml2));
+                        acc1 += ex2_fast(fmaf(z[j + 1], LOG2E_F, -ml2));
+                    }
+                    s_run = fmaf(s_run, ex2_fast((m_run - m_new) * LOG2E_F), acc0 + acc1);  // 2^-inf = 0 on the first group
+                    m_run = m_new;
+                    // rows -> shared memory -> one TMA store of the 32 x 16 box (the stores of a tile were 3.4 us of LSU / L1 time
+                    // when every warp wrote its rows with st.global: r2v)
+                    if (lane == 0) tma_store_wait_read();  // the previous box has been read out of the buffer
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < GCOLS / 4; ++q)
+                        sts_v4(st_wr + (((uint32_t)q ^ st_wx) << 4), z[q * 4], z[q * 4 + 1], z[q * 4 + 2], z[q * 4 + 3]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes visible to the TMA engine
+                    __syncwarp();
+                    if (lane == 0) tma_store_2d(&tmz, st_base, v0, box_row0);
                 }
             }
-            if (row_ok) a.stats[((size_t)row * NCHUNK + ch) * 2 + half] = make_float2(m_run, s_run);
+            if (row_ok && a.stats != nullptr) a.stats[((size_t)row * NCHUNK + ch) * 4 + cq] = make_float2(m_run, s_run);
         }
+        if (lane == 0) tma_store_wait_read();  // shared memory must outlive the last bulk store's read
     }
 
     tc_fence_before();
@@ -494,15 +524,16 @@ __global__ void __launch_bounds__(256) k_head_finish(float *x, int ldx, const fl
             return;
         }
     }
-    float m = -INFINITY;
+    // every warp combines the NPART <= 32 partials on its own: one load per lane, two butterfly reductions
+    static_assert(NPART <= 32, "one partial per lane");
+    const int lane = threadIdx.x & 31;
+    const float2 p = lane < NPART ? __ldg(&stats[(size_t)row * NPART + lane]) : make_float2(-INFINITY, 0.f);
+    float m = p.x;
 #pragma unroll
-    for (int c = 0; c < NPART; ++c) m = fmaxf(m, stats[(size_t)row * NPART + c].x);
-    float s = 0.f;
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = p.y > 0.f ? p.y * expf(p.x - m) : 0.f;
 #pragma unroll
-    for (int c = 0; c < NPART; ++c) {
-        const float2 p = stats[(size_t)row * NPART + c];
-        if (p.y > 0.f) s += p.y * expf(p.x - m);
-    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float ls = logf(s);
     if ((V & 3) == 0 && (ldx & 3) == 0) {
         const int n4 = V >> 2;
@@ -519,6 +550,28 @@ __global__ void __launch_bounds__(256) k_head_finish(float *x, int ldx, const fl
             if (v == blank && blank_lp != nullptr) blank_lp[row] = o;
         }
     }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// tensor map of the (n, V) logits inside the (n, ldz) buffer for the drain's stores: 32-row x 16-column boxes, SWIZZLE_64B
+int encode_z_map(CUtensorMap *tm, float *z, long long n, int V, int ldz) {
+    static EncodeTiledFn enc = nullptr;
+    if (enc == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return CTCPS_E_NODRIVER;
+        enc = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)V, (cuuint64_t)n};
+    cuuint64_t strides[1] = {(cuuint64_t)ldz * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)STORE_COLS, 32u};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, z, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return cr == CUDA_SUCCESS ? 0 : CTCPS_E_NODRIVER;
 }
 
 long long padded_rows(long long rows, int rpt) { return (rows + rpt - 1) / rpt * rpt; }
@@ -607,18 +660,20 @@ int ctcps_ctc_head(const float *hidden, const float *w_hi, const float *w_lo, co
     a.b_hi = reinterpret_cast<const unsigned char *>(w_hi), a.b_lo = reinterpret_cast<const unsigned char *>(w_lo);
     a.a_inv = a_inv;
     a.w_absmax = reinterpret_cast<const uint32_t *>(a.b_hi + align256(image_bytes(V, BLOCK_N, d)));
-    a.bias = bias, a.z = x_logp, a.stats = stats, a.n = (int)n, a.d_pad = padded_k(d), a.V = V, a.ldz = ldx;
+    a.bias = bias, a.z = x_logp, a.stats = apply_log_softmax ? stats : nullptr, a.n = (int)n, a.d_pad = padded_k(d), a.V = V, a.ldz = ldx;
     a.n_mtiles = (int)((n + BLOCK_M - 1) / BLOCK_M);
     a.n_ntiles = (V + BLOCK_N - 1) / BLOCK_N;
     a.tiles_per_chunk = (a.n_ntiles + NCHUNK - 1) / NCHUNK;
-    const size_t smem = sizeof(HeadSmem) + 1024;
+    CUtensorMap tmz;
+    if ((rc = encode_z_map(&tmz, x_logp, n, V, ldx)) != 0) return rc;
+    const size_t smem = sizeof(HeadSmem);
     cudaError_t e = cudaFuncSetAttribute(k_head_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int items = a.n_mtiles * NCHUNK;
-    k_head_gemm<<<items < sms ? items : sms, HEAD_NT, smem, st>>>(a);
+    k_head_gemm<<<items < sms ? items : sms, HEAD_NT, smem, st>>>(tmz, a);
     if ((e = cudaGetLastError()) != cudaSuccess) return (int)e;
     if (!apply_log_softmax) return 0;  // raw logits (tests, callers that want the head alone)
     k_head_finish<<<(unsigned)n, 256, 0, st>>>(x_logp, ldx, stats, lens, T, V, blank, blank_lp);
