@@ -7,10 +7,14 @@
 // k_head_gemm: logits tile by tile on the 5th-generation tensor cores at fp32 accuracy (three half-precision products, below),
 // bias and the row-wise softmax statistics (running max, sum of exponentials) fused into the TMEM -> register epilogue; the raw
 // logits go straight into the scorer's padded (B,T,ldx) buffer, the per-row statistics into a small side array.
-// Normalisation inside the same kernel: the grid works on one BAND of gridDim.x consecutive tiles at a time; after a band the
-// epilogue warps of all CTAs meet at a grid barrier and turn the rows that band completed into log-posteriors in place --
-// (z - max) - log(sum), the order torch.log_softmax uses -- with the length padding and the blank column (what k_init does
-// after a library GEMM), reading the logits back from L2 while the MMA warps work on the next band.
+// k_head_finish: one streaming pass turns the buffer into log-posteriors in place -- (z - max) - log(sum), the order
+// torch.log_softmax uses -- applies the length padding and extracts the blank column (what k_init does after a library GEMM,
+// without its two block-wide reductions).  Fusing this pass into the GEMM kernel was tried three ways and measured (C2, r2u):
+// the grid works through the tiles in bands of 148 (~19 MB of logits, L2-resident), reports finished tiles to per-band counters
+// in global memory (cooperative launch) and normalises the rows a band completed out of L2 -- by the drain warps after a grid
+// barrier (2.6 ms: lock step), by the drain warps one band behind (2.26 ms) or by six warps of their own (2.33 ms, and the
+// rows fall out of L2 before their turn).  HBM traffic did drop to one write of the posteriors, but the SM's load / store path
+// is what the drain is short of, so the two-kernel form (1.90 ms) stayed.
 //
 // 3xFP16.  An fp16 significand has 11 bits -- exactly TF32's -- in 2 bytes instead of 4, and kind::f16 runs at twice the rate
 // of kind::tf32.  What fp16 lacks is range, so every row of h (and W as a whole) is first scaled by a power of two that puts
@@ -24,17 +28,22 @@
 // So the two small cross terms accumulate in their OWN TMEM accumulator and the large term in another (32 k-steps at
 // d = 512); the epilogue adds the two in fp32 registers.
 //
-// Structure (one CTA per SM, persistent, 320 threads):
+// Structure (one CTA per SM, persistent, 640 threads, 96 registers each, all 227 KB of shared memory):
 //   warp 0      TMA producer: per k-block of 32 halves the tiles H1, H2 (128 x 32) and W1, W2 (256 x 32), each ONE
 //               contiguous bulk copy of a pre-swizzled image (k_split_blocked) -- 48 KB per stage, 4 stages -- behind
 //               full / empty mbarriers
 //   warp 1      TMEM allocation (512 columns: two 128 x 256 fp32 accumulators) and, one elected lane, the MMA issue:
 //               per k-block 2 x (UMMA 128x256x16, kind::f16) x 3 products; tcgen05.commit frees the stage / publishes the tile
-//   warps 2-9   epilogue: tcgen05.ld 32 lanes x 32 columns at a time, software-pipelined (a thread owns one row of the tile and
-//               half of its columns), (big + 2^-11 small) / scale + bias, online max / sum-exp, 128-byte row segments stored with
-//               st.global.v4
-// Work item = one 128 x 256 tile in (row tile, vocabulary tile) order; the partial statistics of a row's tiles are combined
-// when the row is normalised.
+//   warps 4-19  drain: (TMEM lane quarter, column quarter) per warp; phase 1 moves the thread's 64 logits into registers
+//               (tcgen05.ld 32 lanes x 16 columns, (big + 2^-11 small) / scale + bias) and hands the accumulators back; phase 2,
+//               under the MMAs of the next tile: online max / sum-exp, rows through a swizzled shared-memory box, one TMA
+//               store (cp.async.bulk.tensor, SASS UTMASTG) per 32 x 16 box
+//   (warps 2-3 idle: the drain starts on a warpgroup boundary so that warp % 4 is the TMEM lane quarter)
+// Work item = (128-row tile, quarter of the vocabulary tiles): 4 x 746 items at C2 keep the last wave short; the partial
+// statistics of a row's quarters are combined by k_head_finish.
+// Measured at C2 (B*T = 95 488 rows, d = 512, V = 5000; profiles/r2_head_ncu.md): split 0.06 ms + GEMM 1.19 ms (1.47 PFLOP of
+// fp16 tensor work: 1.23 PFLOP/s = 0.78 of the measured bf16 burst peak, tensor pipe active 67 % of the time, the rest is
+// phase 1) + finish 0.63 ms (3.78 GB at 6.0 TB/s) = 1.90 ms; 3xTF32 version 3.44 ms; split + cuBLAS + K-a 2.42 ms.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>

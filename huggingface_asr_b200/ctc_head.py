@@ -3,14 +3,16 @@
 In the reference the head is the stock `Wav2Vec2ForCTC.lm_head` Linear (src/reguler/e_branchformer.py:245-252), an fp32
 SGEMM of (B*T, d) x (d, V) on the CUDA cores (C2: 0.49 TFLOP, ~7 ms on a B200) whose (B,T,V) output the processor then
 log-softmaxes (src/decoding/ctc_scorer.py:279).  A single-pass TF32 GEMM would be 10x faster but misses the 1e-4 log-space
-tolerance of the path (10-bit mantissas).  Both operands are therefore split into TF32-exact high parts and fp32 remainders,
-and three TF32 products -- hi*lo + lo*hi + hi*hi, the dropped lo*lo term is 2^-22 relative -- give fp32-grade logits.
+tolerance of the path (10-bit mantissas).  Both operands are therefore split into two 11-bit parts and three tensor-core
+products -- hi*lo + lo*hi + hi*hi, the dropped lo*lo term is 2^-22 relative -- give fp32-grade logits.
 
 Two implementations behind one class (`implementation`, env CTCPS_HEAD):
-  "tcgen05" (default)  csrc/ctcps_head.cu: a hand-written sm_100a kernel -- TMA-fed `tcgen05.mma.kind::tf32`, the large
-                       product and the two small cross terms in separate TMEM accumulators, bias and the row-wise softmax
-                       statistics in the TMEM -> register epilogue, logits written straight into the scorer's padded posterior
-                       buffer -- followed by one streaming normalisation pass (log-softmax, length padding, blank column).
+  "tcgen05" (default)  csrc/ctcps_head.cu: a hand-written sm_100a kernel.  The parts are fp16 (an fp16 significand has TF32's 11
+                       bits in half the bytes at twice the MMA rate; rows of the hidden states and the weight are scaled by powers
+                       of two into fp16's range first), fed by TMA bulk copies to `tcgen05.mma.kind::f16`, the large product and
+                       the two small cross terms in separate TMEM accumulators, bias and the row-wise softmax statistics in the
+                       TMEM -> register drain, logits written by TMA stores straight into the scorer's padded posterior buffer --
+                       followed by one streaming normalisation pass (log-softmax, length padding, blank column).
   "cublas"             round 1's form, kept for A/B: `ctcps_split_tf32` stacks the split operands along K and ONE library TF32
                        GEMM (cuBLAS through torch.addmm) accumulates the three products; K-a (`ctcps_init`) follows.
 """
@@ -76,7 +78,7 @@ class CTCHead:
         if impl not in ("tcgen05", "cublas"):
             raise ValueError(f"unknown CTC head implementation {impl!r}")
         if impl == "tcgen05" and self.dim % 16 != 0:
-            raise ValueError("the tcgen05 CTC head needs a hidden size that is a multiple of 16 (one 64-byte swizzle row of fp32)")
+            raise ValueError("the tcgen05 CTC head needs a hidden size that is a multiple of 16")
         self.implementation = impl
         w = weight.detach().to(torch.float32).contiguous()
         self.bias = None if bias is None else bias.detach().to(torch.float32).contiguous()

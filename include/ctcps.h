@@ -327,12 +327,14 @@ int ctcps_eos_space_trick(const float *att_scores, const float *ctc_scores, floa
  * logits = hidden W^T + b, an fp32 Linear) followed by F.log_softmax (src/decoding/ctc_scorer.py:279) and the length padding
  * (:39-46), i.e. it produces what ctcps_init produces, from the encoder's hidden states instead of its logits.
  *   hidden (B*T, d) fp32;  bias (V) or NULL;  w_hi / w_lo: the head's weight (V, d) prepared ONCE by
- *   ctcps_head_prepare_weight (each ctcps_head_weight_bytes(V, d) bytes): split into a TF32-exact high part and the fp32
- *   remainder and stored tile by tile in the swizzled image the kernel's TMA bulk copies drop into shared memory
+ *   ctcps_head_prepare_weight (each ctcps_head_weight_bytes(V, d) bytes): scaled by a power of two into fp16's range, split
+ *   into two fp16 parts (11 + 11 significand bits) and stored tile by tile in the swizzled image the kernel's TMA bulk copies
+ *   drop into shared memory (opaque to the caller; w_hi ends with the scale)
  *   x_logp (B,T,ldx), blank_lp (B,T): as ctcps_init;  apply_log_softmax = 0: x_logp receives the raw logits (no padding)
- * A hand-written tcgen05 kernel (TMA-fed 3xTF32 UMMA, two TMEM accumulators -- large term / small cross terms -- bias and the
- * softmax statistics in the TMEM -> register epilogue) + one streaming normalisation pass; fp32-grade accuracy (max logit
- * error ~2e-5 at d = 512).  d must be a multiple of 16.  workspace: ctcps_head_workspace_bytes(B*T, d), 16-byte aligned.
+ * A hand-written tcgen05 kernel (TMA-fed 3xFP16 UMMA, two TMEM accumulators -- large term / small cross terms -- bias and the
+ * softmax statistics in the TMEM -> register drain, TMA stores) + one streaming normalisation pass; fp32-grade accuracy (max
+ * logit error ~1.4e-5 at d = 512, |logit| ~ 10).  d must be a multiple of 16.  workspace: ctcps_head_workspace_bytes(B*T, d),
+ * 16-byte aligned.
  * ctcps_split_hi_lo is the plain elementwise split (hi = round-to-nearest TF32, lo = x - hi), same shapes.
  */
 int ctcps_head_workspace_bytes(int64_t n, int d, size_t *out_bytes);

@@ -1,6 +1,6 @@
-"""GPU: N4 -- the CTC head at fp32 accuracy on the TF32 tensor cores: the hand-written tcgen05 kernel (csrc/ctcps_head.cu: 3xTF32
-UMMA, bias + softmax statistics in the epilogue, streaming normalisation) and round 1's library form (operand split + one
-stacked-K cuBLAS GEMM + K-a), and the processor built from encoder hidden states.  Reference: Wav2Vec2ForCTC.lm_head
+"""GPU: N4 -- the CTC head at fp32 accuracy on the tensor cores: the hand-written tcgen05 kernel (csrc/ctcps_head.cu: 3xFP16
+UMMA on power-of-two-scaled operands, bias + softmax statistics in the drain, TMA stores, streaming normalisation) and round 1's
+library form (TF32 operand split + one stacked-K cuBLAS GEMM + K-a), and the processor built from encoder hidden states.  Reference: Wav2Vec2ForCTC.lm_head
 (src/reguler/e_branchformer.py:245-252) -> F.log_softmax (src/decoding/ctc_scorer.py:279) -> padding (:39-46).
 Run on the B200 box with -m gpu."""
 import pytest
