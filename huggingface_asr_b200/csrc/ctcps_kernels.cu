@@ -1772,7 +1772,7 @@ int dispatch_psi_full(int HW, const CUtensorMap &tm, const PsiArgs &a, cudaStrea
 }
 
 // 1 = time-parallel warp per hypothesis (k_select_lazy_pscan, the default since it passed its fp64-adjudicated hardware
-// gate and measured faster on every BASELINE shape: profiles/r2a_pscan_gate.md), 0 = one thread per hypothesis walks the
+// gate and measured faster on every BASELINE shape: DESIGN.md section 4), 0 = one thread per hypothesis walks the
 // T frames (k_select_lazy_scan); ctcps_set_select_pscan / CTCPS_SELECT_PSCAN
 int g_select_pscan = -1;
 int select_pscan_mode() {

@@ -12,7 +12,7 @@
 // is a skinny (W x T) x (T x V) product per utterance with exp() applied on the fly to the streamed operand; it is bound
 // by reading x once from HBM, so it stays on the FP32 pipes (the 1e-4 log-space tolerance needs the fp32 mantissa).
 //
-// Round-2 structure (what changed against round 1 and why, profiles/r2*_psi_ncu.md):
+// Round-2 structure (what changed against round 1 and why, profiles/r2d_psi_ab.md):
 //   * packed FMAs pair two HYPOTHESES of one token (acc = (h0, h1) += (lin_h0, lin_h1) * (p, p)): the lin pairs come out
 //     of shared memory already packed (LDS.128 = two pairs) and only the 4 token probabilities are duplicated per frame,
 //     instead of one register move per hypothesis (10 at W = 10, 20 at W = 20);

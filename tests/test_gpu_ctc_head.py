@@ -103,6 +103,29 @@ def test_log_posteriors_of_the_tcgen05_head_vs_fp64(B, T, V, d, use_bias):
     assert float((logits - z).abs().max()) <= tol
 
 
+def test_head_scaling_covers_the_fp32_range_fp16_lacks():
+    """The tcgen05 head multiplies in fp16: rows of the hidden states whose magnitudes span 1e-5 .. 1e4 (and a weight far from 1)
+    must come out as accurately as a row of ordinary size -- the error scale of a dot product is sum_k |h_k| |w_k|."""
+    from huggingface_asr_b200.ctc_head import CTCHead
+
+    g = torch.Generator().manual_seed(77)
+    n, d, V = 300, 256, 520
+    hidden = torch.randn(1, n, d, generator=g) * torch.logspace(-5, 4, n).view(1, n, 1)
+    hidden[0, 7] = 0.0                                   # an all-zero row
+    hidden[0, 9, :] = 0.0
+    hidden[0, 9, 3] = 6.0e4                              # one huge element among zeros
+    weight = torch.randn(V, d, generator=g) * 3.0e-3
+    weight[5] *= 1.0e-4                                   # a vocabulary entry far below the tensor's scale
+    bias = torch.randn(V, generator=g)
+    ref = hidden.double().view(n, d) @ weight.double().t() + bias.double()
+    scale = hidden.double().abs().view(n, d) @ weight.double().abs().t() + bias.double().abs()
+    out = CTCHead(weight.cuda(), bias.cuda(), implementation="tcgen05")(hidden.cuda()).cpu().double().view(n, V)
+    assert torch.isfinite(out).all()
+    rel = ((out - ref).abs() / scale.clamp_min(1e-30)).max()
+    print(f"max |error| / sum |h||w|: {float(rel):.2e}")
+    assert float(rel) <= 1e-6
+
+
 def test_both_head_implementations_feed_the_scorer_the_same_posteriors():
     from huggingface_asr_b200.ctc_head import CTCHead
     from huggingface_asr_b200.synthetic import make_encoder_hidden

@@ -5,7 +5,7 @@ orders -- the fp64 oracle.
 History: written at the end of round 1, first hardware run failed the then-criterion at T = 748 (1.95e-3 at r = -872
 between the two kernels).  Round 2 adjudicated with fp64 (this file): the sequential kernel itself is 1.7e-3 .. 2.2e-3
 from fp64 on those entries (747 fp32 roundings at |r| ~ 900, one ulp = 6e-5), the time-parallel kernel is no further,
-and joint scores / log_psi of both stay ~1e-6 from fp64 (profiles/r2a_pscan_gate.md).  22/22 passed on B200, the kernel
+and joint scores / log_psi of both stay ~1e-6 from fp64.  22/22 passed on B200, the kernel
 is faster on every BASELINE shape, and the default was flipped (CTCPS_SELECT_PSCAN=0 selects the sequential kernel).
 """
 import pytest

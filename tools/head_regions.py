@@ -1,5 +1,7 @@
-"""Warp-state samples of k_head_gemm by code region (TMA / MMA / drain / band barrier / row normalisation) from the
-source page of an ncu capture:  ncu -i X.ncu-rep --page source --csv > X.src.csv;  python tools/head_regions.py X.src.csv"""
+"""Warp-state samples of k_head_gemm by warp role from the source page of an ncu capture (SASS order follows the roles):
+    ncu -i X.ncu-rep --page source --csv > X.src.csv;  python tools/head_regions.py X.src.csv
+Regions are found by their landmark instructions: UBLKCP (TMA producer), BAR.SYNC 0x1 + the tmem_full wait + LDTM (drain),
+UTCHMMA (MMA issuer)."""
 import csv
 import sys
 
@@ -19,27 +21,24 @@ def first(pat, start=0):
     return len(src)
 
 
-k_tma = first("UBLKCP")
-k_ldtm = first("LDTM")
-k_bar2 = first("BAR.SYNC.DEFER_BLOCKING 0x2")
-k_call = first("CALL.REL", k_bar2)
-k_exit = first("EXIT", k_call)
-k_ret = first("RET.REL", k_exit)
-k_bar1 = first("BAR.SYNC.DEFER_BLOCKING 0x1")
-k_mma = first("UTCHMMA")
-regions = [("prologue", 0, k_tma - 30), ("TMA producer", k_tma - 30, min(k_mma, k_bar1) - 60)]
-if k_mma < k_bar1:
-    regions += [("MMA issuer", k_mma - 60, k_bar1 - 30), ("epilogue: bias + wait for the tile", k_bar1 - 30, k_ldtm), ("epilogue: drain", k_ldtm, k_bar2 - 10)]
-else:
-    regions += [("epilogue: bias + wait for the tile", k_bar1 - 30, k_ldtm), ("epilogue: drain", k_ldtm, k_bar2 - 10)]
-regions += [("band report + wait", k_bar2 - 10, k_call), ("tail", k_call, k_exit + 1)]
-if k_mma > k_exit:
-    regions += [("MMA issuer", k_exit + 1, k_ret - 200 if k_ret - 200 > k_exit else k_exit + 1)]
-regions += [("rest (incl. row normalisation)", regions[-1][2], len(S))]
+def last(pat):
+    for k in range(len(src) - 1, -1, -1):
+        if pat in src[k]:
+            return k
+    return 0
+
+
+marks = sorted([(first("UBLKCP"), "TMA producer"), (first("BAR.SYNC.DEFER_BLOCKING 0x1") - 40, "drain: bias + wait for the tile"),
+                (first("LDTM"), "drain: TMEM loads, statistics, stores"), (first("UTCHMMA") - 80, "MMA issuer")])
+marks = [(max(k, 0), n) for k, n in marks]
+bounds = [(0, "prologue")] + marks
 tot = sum(S)
 print(f"total samples {tot}")
-for name, a, b in regions:
-    print(f"{name:36s} [{a:5d},{b:5d})  {sum(S[a:b]):7d}  {sum(S[a:b]) / tot:6.1%}")
-top = sorted(range(len(S)), key=lambda k: -S[k])[:14]
-for k in sorted(top):
-    print(k, S[k], ex[k], src[k][:90])
+for i, (k, name) in enumerate(bounds):
+    end = bounds[i + 1][0] if i + 1 < len(bounds) else len(S)
+    if name == "drain: TMEM loads, statistics, stores":
+        end = min(end, last("UTMASTG") + 40) if "UTMASTG" in " ".join(src) else end
+    print(f"{name:40s} [{k:5d},{end:5d})  {sum(S[k:end]):7d}  {sum(S[k:end]) / max(tot, 1):6.1%}")
+print("hottest instructions:")
+for k in sorted(sorted(range(len(S)), key=lambda k: -S[k])[:12]):
+    print(f"  {k:5d} {S[k]:6d} {ex[k]:9d}  {src[k][:90]}")
