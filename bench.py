@@ -83,6 +83,15 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def peak_tensor():
+    """Dense bf16 tensor peak of this pool's B200s (burst figure: the kernel is timed alone), else the profiling recipe's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["bf16_tflops"]), "measured (MEASURED_PEAKS.json, cuBLAS bf16 burst)"
+    except Exception:
+        return 1590.0, "fallback (B200_PROFILING.md)"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -402,6 +411,38 @@ class Runner:
         head_ms = sum(a.elapsed_time(b) for a, b in head_ev) / max(len(head_ev), 1)
         return ms, head_ms, hid_h.numel() * 4 + hl_h.numel() * 8, ok, getattr(head, "implementation", "cublas")
 
+    def head_roofline(self, wl):
+        """Tensor-bound roofline of the CTC head's GEMM (N4): CUDA events around `head(hidden)` -- operand split + k_head_gemm
+        writing raw logits, no normalisation pass -- on resident hidden states; flops = the three fp16 products the kernel issues."""
+        from huggingface_asr_b200.ctc_head import CTCHead
+
+        args, dev = self.args, self.dev
+        B, T, V, d = wl.B, wl.T, wl.V, args.hidden_dim
+        hid_h, w_h, b_h, _, _ = make_encoder_hidden(B, T, V, d, wl.cfg.kind, wl.ragged, seed=20240 + 1000 * 2 + 500 + self.rank)
+        head = CTCHead(w_h.to(dev), b_h.to(dev))
+        if getattr(head, "implementation", "cublas") != "tcgen05":
+            return None
+        hid = hid_h.to(dev)
+        for _ in range(3):
+            z = head(hid)
+        del z
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 10
+        e0.record()
+        for _ in range(n):
+            z = head(hid)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        del z, hid
+        ms = e0.elapsed_time(e1) / n
+        peak, src = peak_tensor()
+        flops = 3 * 2.0 * B * T * V * d
+        return {"bound": "tensor", "kernel": "k_split_blocked + k_head_gemm (3xFP16 tcgen05 UMMA, raw logits out)", "achieved": flops / (ms * 1e-3) / 1e12,
+                "peak": peak, "unit": "TFLOP/s", "peak_source": src, "frac": flops / (ms * 1e-3) / 1e12 / peak, "avg_launch_ms": ms,
+                "flops_per_launch": flops, "traffic": None,
+                "note": "flops = 3 products x 2 B T V d of fp16 tensor work for fp32-grade logits (an fp32 GEMM of the same shape is a third of it)"}
+
     # ------------------------------------------------------------------------------------------------
     def roofline(self, wl, r, materialized):
         abytes = algorithmic_bytes_per_score(wl.B, wl.W, wl.T, wl.V)
@@ -621,6 +662,7 @@ def run_ours(args):
         hidden = {"lazy": R.measure_from_hidden(wl, 0)}
         if pre is not None:
             hidden["pre_beam"] = R.measure_from_hidden(wl, args.pre_beam)
+    head_roof = R.head_roofline(wl) if hidden is not None else None
 
     drop_in = None if (args.single_mode or args.no_drop_in) else R.drop_in(wl)
 
@@ -686,6 +728,8 @@ def run_ours(args):
                     "ctc_head_ms": head_ms, "ctc_head_tflops_fp32_equivalent": flops / (head_ms * 1e-3) / 1e12,
                     "ctc_head_implementation": impl, "transcripts_recovered": ok}
                 for k, (ms, head_ms, h2d, ok, impl) in hidden.items()}
+            if head_roof is not None:
+                line["e2e_from_hidden"]["head_roofline"] = head_roof
             line["e2e_from_hidden"]["note"] = (
                 f"SURVEY 8(f) N4 boundary, not the reference-facing call: host buffers hold the encoder hidden states (B,T,{d}) "
                 "instead of the (B,T,V) logits; the CTC head (GEMM + log-softmax + padding) runs on the GPU inside the timed region; "
