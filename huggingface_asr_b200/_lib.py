@@ -81,6 +81,7 @@ SIGNATURES = {
     "ctcps_padded_ld": [_i],
     "ctcps_set_select_pscan": [_i],
     "ctcps_set_psi_prefetch": [_i],
+    "ctcps_set_skip_done": [_i],
     "ctcps_set_psi_max_group": [_i],
     "ctcps_workspace_bytes": [_i, _i, _i, _i, _i, ctypes.POINTER(_sz)],
     "ctcps_init": [_p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p],
@@ -94,6 +95,7 @@ SIGNATURES = {
     "ctcps_select_lazy": [_p, _i, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p],
     "ctcps_topk_lists_shape": [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)],
     "ctcps_score_lazy_topk": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _sz, _i, _p],
+    "ctcps_score_lazy_topk_active": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _sz, _i, _p],
     "ctcps_beam_step_lists": [_p, _i, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i64, _p, _p, _sz, _p, _i, _i64, _p, _p,
                               _p],
     "ctcps_beam_step_workspace_bytes": [_i, _i, ctypes.POINTER(_sz)],

@@ -1796,6 +1796,17 @@ int psi_prefetch_chunks() {
     return g_psi_prefetch;
 }
 
+// Native decode loop: do not score the utterances whose beam search has finished (CTCPS_SKIP_DONE, default 1).  Their rows
+// never reach a hypothesis (the beam step ignores a finished utterance), so the returned n-best lists are bit-identical.
+int g_skip_done = -1;
+bool skip_done() {
+    if (g_skip_done < 0) {
+        const char *ev = getenv("CTCPS_SKIP_DONE");
+        g_skip_done = (ev != nullptr && atoi(ev) == 0) ? 0 : 1;
+    }
+    return g_skip_done != 0;
+}
+
 // The descriptor only depends on (pointer, ldx, B*T, V): a decode makes one scoring call per output token on the same
 // posteriors, so the last few descriptors are kept per host thread instead of calling the driver every step.
 struct MapCacheEntry {
@@ -2027,6 +2038,12 @@ int ctcps_set_psi_prefetch(int chunks) {
     return prev;
 }
 
+int ctcps_set_skip_done(int on) {
+    const int prev = skip_done() ? 1 : 0;
+    if (on == 0 || on == 1) g_skip_done = on;
+    return prev;
+}
+
 int ctcps_workspace_bytes(int B, int T, int V, int W, int S, size_t *out_bytes) {
     (void)V;
     (void)S;
@@ -2222,7 +2239,7 @@ static int score_lazy_impl(const float *x_logp, int ldx, const float *r_prev, co
     // any BASELINE shape, profiles/r1x_kernels_ncu.md section 3).
     a.nvt = (V + PSI_NT * 4 - 1) / (PSI_NT * 4);
     a.prefetch = psi_prefetch_chunks();
-    a.tk.beam_scores = nullptr, a.tk.lists = nullptr, a.tk.K = 0;
+    a.tk.beam_scores = nullptr, a.tk.lists = nullptr, a.tk.K = 0, a.tk.done = nullptr;
     if (tk != nullptr) {
         a.tk = *tk;
         return dispatch_psi_full<true>(HW, tm, a, st);
@@ -2266,6 +2283,14 @@ int ctcps_score_lazy_topk(const float *x_logp, int ldx, const float *r_prev, con
                           int B, int W, int T, int V, int blank, const float *att_scores, float one_minus_w, float w,
                           const float *beam_scores, float *log_psi, float *tile_lists, void *workspace, size_t workspace_bytes,
                           int workspace_prepared, void *stream) {
+    return ctcps_score_lazy_topk_active(x_logp, ldx, r_prev, s_prev, last_ids, ol, B, W, T, V, blank, att_scores, one_minus_w, w, beam_scores,
+                                        nullptr, log_psi, tile_lists, workspace, workspace_bytes, workspace_prepared, stream);
+}
+
+int ctcps_score_lazy_topk_active(const float *x_logp, int ldx, const float *r_prev, const float *s_prev, const int64_t *last_ids, int ol,
+                                 int B, int W, int T, int V, int blank, const float *att_scores, float one_minus_w, float w,
+                                 const float *beam_scores, const unsigned char *done, float *log_psi, float *tile_lists, void *workspace,
+                                 size_t workspace_bytes, int workspace_prepared, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     ARG_CHECK(x_logp && r_prev && last_ids && att_scores && beam_scores && tile_lists && log_psi, CTCPS_E_BADARG, "score_lazy_topk: null pointer");
     ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0, CTCPS_E_BADARG, "score_lazy_topk: non-positive size");
@@ -2281,6 +2306,7 @@ int ctcps_score_lazy_topk(const float *x_logp, int ldx, const float *r_prev, con
     tk.beam_scores = beam_scores;
     tk.lists = reinterpret_cast<float2 *>(tile_lists);
     tk.K = 2 * W;
+    tk.done = done;
     return score_lazy_impl(x_logp, ldx, r_prev, s_prev, 1, 0, last_ids, ol, B, W, T, V, blank, const_cast<float *>(att_scores), one_minus_w, w,
                            log_psi, nullptr, nullptr, &tk, workspace, workspace_bytes, workspace_prepared, st);
 }
@@ -2529,8 +2555,9 @@ int ctcps_decode_step(const ctcps_decode_session *s, float *att_scores, int step
                        (long long)nlists * Klist <= MERGE_MAX && s->log_psi[0] != nullptr && s->log_psi[1] != nullptr;
     const int64_t tag = s->tag_base + (int64_t)step;
     if (fused) {
-        rc = ctcps_score_lazy_topk(s->x_logp, s->ldx, r_prev, s_prev, s->last_ids[cur], ol, B, W, T, V, s->blank, att_scores, s->one_minus_w,
-                                   s->w, s->beam_scores, s->log_psi[cur], s->tile_lists, s->score_ws, s->score_ws_bytes, prepared, main_st);
+        rc = ctcps_score_lazy_topk_active(s->x_logp, s->ldx, r_prev, s_prev, s->last_ids[cur], ol, B, W, T, V, s->blank, att_scores,
+                                          s->one_minus_w, s->w, s->beam_scores, skip_done() ? s->done : nullptr, s->log_psi[cur],
+                                          s->tile_lists, s->score_ws, s->score_ws_bytes, prepared, main_st);
         if (rc) return rc;
         if (ev_score_end) cudaEventRecord((cudaEvent_t)ev_score_end, main_st);
         rc = ctcps_beam_step_lists(s->tile_lists, nlists, s->beam_scores, s->ids[cur], s->ids[nxt], s->ld_ids, L, B, W, V, s->eos, s->pad,

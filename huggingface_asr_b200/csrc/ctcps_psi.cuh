@@ -32,6 +32,7 @@ struct PsiTopk {
     const float *beam_scores;  // (BW) running beam scores, added to the joint scores for ranking
     float2 *lists;             // [B][nvt*G][K]: (key, dense index hyp*V+tok as int bits), best first
     int K;                     // 2W
+    const unsigned char *done; // (B) or null: utterances whose beam search has finished -- their tiles are not streamed at all
 };
 
 struct PsiArgs {
@@ -359,7 +360,6 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
     const int nchunk = cN - c0 + 1;
     const int ntiles = a.B * a.nvt * a.G;
     const int my_tiles = ((int)blockIdx.x < ntiles) ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    const int nitems = my_tiles * nchunk;
     constexpr uint32_t STAGE_BYTES = TT * VTILE * 4 + TT * HWP * 4;
 
     auto decode_tile = [&](int tile, int &b, int &vt, int &g) {
@@ -368,6 +368,26 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
         vt = tile % a.nvt;
         b = tile / a.nvt;
     };
+    // TOPK mode (a decode loop that owns its beam search): the tiles of an utterance whose search has finished are skipped --
+    // producer and consumers agree on that from the same `done` flags, which do not change while the kernel runs.  HF's
+    // loop scores such rows until the whole batch is done and throws the result away; under the synthetic decoder the last
+    // two steps of a decode (every utterance finished, all-tie scores: the epilogue's slow path) cost 1.7x a normal step.
+    auto tile_skipped = [&](int b) -> bool {
+        if constexpr (TOPK) return a.tk.done != nullptr && a.tk.done[b] != 0;
+        return false;
+    };
+    int n_active = my_tiles;
+    if constexpr (TOPK) {
+        if (a.tk.done != nullptr) {
+            n_active = 0;
+            for (int ti = 0; ti < my_tiles; ++ti) {
+                int b, vt, g;
+                decode_tile((int)blockIdx.x + ti * (int)gridDim.x, b, vt, g);
+                n_active += tile_skipped(b) ? 0 : 1;
+            }
+        }
+    }
+    const int nitems = n_active * nchunk;
     // Thread 0 walks the CTA's flat chunk sequence twice ahead of the consumers, with two cursors that advance
     // incrementally (a tile is decoded once, when a cursor enters it -- no division per chunk):
     //   `is`  the next item to load into the shared-memory ring (NSTAGE items ahead of the one being consumed);
@@ -385,8 +405,12 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
         int *p = sm.cursor[which];
         p[0] = c.k, p[1] = c.ti, p[2] = c.ci, p[3] = c.b, p[4] = c.vt, p[5] = c.g;
     };
-    auto cursor_enter = [&](Cursor &c) {
-        if (c.ti < my_tiles) decode_tile((int)blockIdx.x + c.ti * (int)gridDim.x, c.b, c.vt, c.g);
+    auto cursor_enter = [&](Cursor &c) {  // decode the cursor's tile, stepping over skipped ones
+        while (c.ti < my_tiles) {
+            decode_tile((int)blockIdx.x + c.ti * (int)gridDim.x, c.b, c.vt, c.g);
+            if (!tile_skipped(c.b)) break;
+            ++c.ti;
+        }
     };
     auto cursor_next = [&](Cursor &c) {
         ++c.k;
@@ -438,6 +462,7 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
     for (int ti = 0; ti < my_tiles; ++ti) {
         int b, vt, g;
         decode_tile((int)blockIdx.x + ti * (int)gridDim.x, b, vt, g);
+        if (tile_skipped(b)) continue;  // its candidate list keeps the last step's contents: the beam step ignores a finished utterance
         unsigned long long acc2[HP][4];  // (hyp 2p, hyp 2p+1) of token j, packed for FFMA2
         float x0[4];
 #pragma unroll

@@ -62,6 +62,11 @@ int ctcps_set_select_pscan(int mode);
  * look-ahead only costs (0 / 2 / 4 / 8 chunks: 0.371 / 0.376 / 0.390 / 0.489 ms at C2); kept as an A/B switch.  Returns the
  * previous value; an argument outside [0, 64] only queries.  Process-wide; results do not depend on it. */
 int ctcps_set_psi_prefetch(int chunks);
+/* Native decode loop (ctcps_decode_step, full vocabulary): 1 (default; env CTCPS_SKIP_DONE) = the scoring kernel does not stream
+ * the tiles of utterances whose beam search has finished (HF's loop scores them until the whole batch is done and discards the
+ * result); the hypotheses returned are bit-identical.  0 = score every row every step.  Returns the previous setting; any
+ * other argument only queries. */
+int ctcps_set_skip_done(int on);
 
 /* Widest hypothesis group one thread of the lazy scoring kernel accumulates (2..20, default 20, env CTCPS_PSI_MAX_GROUP):
  * beams wider than the group are split into several groups that each stream the x tile.  Changes the layout of the scoring
@@ -238,6 +243,12 @@ int ctcps_score_lazy_topk(const float *x_logp, int ldx, const float *r_prev, con
                           int B, int W, int T, int V, int blank, const float *att_scores, float one_minus_w, float w,
                           const float *beam_scores, float *log_psi, float *tile_lists, void *workspace, size_t workspace_bytes,
                           int workspace_prepared, void *stream);
+/* the same with `done` (B) flags of the beam search (NULL = none): tiles of finished utterances are neither streamed nor ranked,
+ * their lists and log_psi rows keep their previous contents */
+int ctcps_score_lazy_topk_active(const float *x_logp, int ldx, const float *r_prev, const float *s_prev, const int64_t *last_ids, int ol,
+                                 int B, int W, int T, int V, int blank, const float *att_scores, float one_minus_w, float w,
+                                 const float *beam_scores, const unsigned char *done, float *log_psi, float *tile_lists, void *workspace,
+                                 size_t workspace_bytes, int workspace_prepared, void *stream);
 int ctcps_beam_step_lists(const float *tile_lists, int lists_per_utterance, float *beam_scores, const int64_t *ids_cur, int64_t *ids_next,
                           int64_t ld_ids, int L, int B, int W, int V, int eos, int pad, float len_norm, float *pool_scores,
                           int64_t *pool_lens, int64_t *pool_seqs, int64_t ld_pool, unsigned char *done, void *workspace,

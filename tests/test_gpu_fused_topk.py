@@ -211,3 +211,36 @@ def test_native_loop_with_fused_topk_equals_the_unfused_loop(B, W, T, V, use_bea
     assert a.steps == b.steps
     assert torch.equal(a.sequences, b.sequences) and torch.equal(a.lengths, b.lengths)
     assert torch.equal(a.scores, b.scores), f"scores differ by {(a.scores - b.scores).abs().max().item()}"
+
+
+@pytest.mark.parametrize("B,W,T,V,lag", [(12, 10, 96, 1000, 1), (6, 20, 120, 516, 0), (9, 4, 60, 2048, 2)])
+def test_skipping_finished_utterances_changes_nothing_that_is_returned(B, W, T, V, lag):
+    """The native loop does not score utterances whose beam search has finished (ctcps_set_skip_done, default on).  Ragged
+    lengths make the utterances finish at different steps; n-best sequences, lengths, scores and the number of steps must be
+    identical bit for bit with the switch off, for every done-check lag."""
+    from huggingface_asr_b200 import _lib
+    from huggingface_asr_b200.beam_search import joint_beam_search_native
+    from huggingface_asr_b200.decoding.ctc_scorer import CTCRescorerLogitsProcessor
+    from huggingface_asr_b200.synthetic import SyntheticDecoder, make_encoder_logits
+
+    logits, lens, tr = make_encoder_logits(B, T, V, "peaky", True, seed=31)
+    assert len({len(t) for t in tr}) > 1, "the transcripts must differ in length"
+    L = _lib.lib()
+    prev = L.ctcps_set_skip_done(-1)
+    outs = []
+    try:
+        for on in (0, 1):
+            L.ctcps_set_skip_done(on)
+            dec = SyntheticDecoder(tr, W, V, 64, seed=2, device="cuda")
+            proc = CTCRescorerLogitsProcessor(logits.cuda(), lens.cuda(), BLANK, EOS, 0, 0.3, W, -1, False, 1.0, materialize_state=False)
+            outs.append(joint_beam_search_native(proc, dec, B, W, V, BOS, EOS, BLANK, max_length=64, device=torch.device("cuda"),
+                                                 done_check_lag=lag, fuse_topk=True, num_return_sequences=min(W, 3)))
+    finally:
+        L.ctcps_set_skip_done(prev)
+    a, b = outs
+    assert a.steps == b.steps
+    assert torch.equal(a.sequences, b.sequences) and torch.equal(a.lengths, b.lengths)
+    assert torch.equal(a.scores, b.scores), f"scores differ by {(a.scores - b.scores).abs().max().item()}"
+    assert torch.equal(a.nbest_sequences, b.nbest_sequences) and torch.equal(a.nbest_lengths, b.nbest_lengths)
+    assert torch.equal(a.nbest_scores, b.nbest_scores)
+    assert (a.lengths.cpu() == torch.tensor([len(t) - 1 for t in tr])).all()
