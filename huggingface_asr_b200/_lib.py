@@ -92,10 +92,11 @@ SIGNATURES = {
     "ctcps_score_window": [_p, _i, _p, _p, _p, _i64, _i64, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _i, _p, _p, _f, _f, _p, _i, _p, _p,
                            _p, _p, _sz, _p],
     "ctcps_score_lazy": [_p, _i, _p, _p, _p, _i64, _i64, _p, _i, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _sz, _i, _p],
+    "ctcps_score_lazy_lens": [_p, _i, _p, _p, _p, _p, _i64, _i64, _p, _i, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _sz, _i, _p],
     "ctcps_select_lazy": [_p, _i, _p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _sz, _p],
     "ctcps_topk_lists_shape": [_i, _i, _i, ctypes.POINTER(_i), ctypes.POINTER(_i)],
     "ctcps_score_lazy_topk": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _sz, _i, _p],
-    "ctcps_score_lazy_topk_active": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _sz, _i, _p],
+    "ctcps_score_lazy_topk_active": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p, _sz, _i, _p],
     "ctcps_beam_step_lists": [_p, _i, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _i64, _p, _p, _sz, _p, _i, _i64, _p, _p,
                               _p],
     "ctcps_beam_step_workspace_bytes": [_i, _i, ctypes.POINTER(_sz)],
@@ -141,7 +142,7 @@ class DecodeSession(ctypes.Structure):
         ("beam_scores", _p), ("ids", _p * 2), ("ld_ids", _i64), ("pool_scores", _p), ("pool_lens", _p), ("pool_seqs", _p),
         ("ld_pool", _i64), ("done", _p), ("beam_ws", _p), ("beam_ws_bytes", _sz), ("done_ring", _p), ("best_ids", _p),
         ("side_stream", _p), ("ev_step", _p), ("ev_select", _p),
-        ("tile_lists", _p), ("tag_base", _i64),
+        ("tile_lists", _p), ("tag_base", _i64), ("xlens", _p),
     ]
 
 

@@ -388,6 +388,8 @@ def joint_beam_search_native(processor, decoder_log_probs: Callable[[torch.Tenso
         ring_np = ring.numpy()
         tag_base = _next_tag_base()
         sess.done_ring, sess.ring, sess.best_ids, sess.tag_base = ring.data_ptr(), RING, best_ids.data_ptr(), tag_base
+        score_lens = sc._score_lens()  # padded frames of short utterances are not streamed
+        sess.xlens = None if score_lens is None else score_lens.data_ptr()
         side, ev_a, ev_b = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
         _lib.check(L_.ctcps_async_create(ctypes.byref(side), ctypes.byref(ev_a), ctypes.byref(ev_b)), "ctcps_async_create")
         sess.side_stream, sess.ev_step, sess.ev_select = side, ev_a, ev_b

@@ -2193,7 +2193,8 @@ int ctcps_score(const float *x_logp, int ldx, const float *blank_lp, const float
 static int score_lazy_impl(const float *x_logp, int ldx, const float *r_prev, const float *s_prev, int64_t s_row_stride,
                            int64_t s_col_stride, const int64_t *last_ids, int ol, int B, int W, int T, int V, int blank,
                            float *att_scores, float one_minus_w, float w, float *log_psi, float *token_scores, float *joint,
-                           const PsiTopk *tk, void *workspace, size_t workspace_bytes, int workspace_prepared, cudaStream_t st) {
+                           const PsiTopk *tk, const int64_t *xlens, void *workspace, size_t workspace_bytes, int workspace_prepared,
+                           cudaStream_t st) {
     int HW, HWP, G;
     pick_hw_psi(W, &HW, &HWP, &G);
     const WorkspaceLazy ws = plan_workspace_lazy(B, T, W, V);
@@ -2239,6 +2240,7 @@ static int score_lazy_impl(const float *x_logp, int ldx, const float *r_prev, co
     // any BASELINE shape, profiles/r1x_kernels_ncu.md section 3).
     a.nvt = (V + PSI_NT * 4 - 1) / (PSI_NT * 4);
     a.prefetch = psi_prefetch_chunks();
+    a.xlens = xlens;
     a.tk.beam_scores = nullptr, a.tk.lists = nullptr, a.tk.K = 0, a.tk.done = nullptr;
     if (tk != nullptr) {
         a.tk = *tk;
@@ -2251,6 +2253,14 @@ int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const 
                      int64_t s_row_stride, int64_t s_col_stride, const int64_t *last_ids, int ol, int B, int W, int T, int V,
                      int blank, float *att_scores, float one_minus_w, float w, float *log_psi, float *token_scores,
                      float *joint, void *workspace, size_t workspace_bytes, int workspace_prepared, void *stream) {
+    return ctcps_score_lazy_lens(x_logp, ldx, blank_lp, nullptr, r_prev, s_prev, s_row_stride, s_col_stride, last_ids, ol, B, W, T, V, blank,
+                                 att_scores, one_minus_w, w, log_psi, token_scores, joint, workspace, workspace_bytes, workspace_prepared, stream);
+}
+
+int ctcps_score_lazy_lens(const float *x_logp, int ldx, const float *blank_lp, const int64_t *xlens, const float *r_prev, const float *s_prev,
+                          int64_t s_row_stride, int64_t s_col_stride, const int64_t *last_ids, int ol, int B, int W, int T, int V,
+                          int blank, float *att_scores, float one_minus_w, float w, float *log_psi, float *token_scores,
+                          float *joint, void *workspace, size_t workspace_bytes, int workspace_prepared, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     (void)blank_lp;
     ARG_CHECK(x_logp && r_prev && last_ids && log_psi, CTCPS_E_BADARG, "score_lazy: null pointer");
@@ -2267,7 +2277,7 @@ int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const 
         return cuda_rc(cudaGetLastError());
     }
     return score_lazy_impl(x_logp, ldx, r_prev, s_prev, s_row_stride, s_col_stride, last_ids, ol, B, W, T, V, blank, att_scores,
-                           one_minus_w, w, log_psi, token_scores, joint, nullptr, workspace, workspace_bytes, workspace_prepared, st);
+                           one_minus_w, w, log_psi, token_scores, joint, nullptr, xlens, workspace, workspace_bytes, workspace_prepared, st);
 }
 
 int ctcps_topk_lists_shape(int B, int W, int V, int *lists_per_utterance, int *K) {
@@ -2284,13 +2294,13 @@ int ctcps_score_lazy_topk(const float *x_logp, int ldx, const float *r_prev, con
                           const float *beam_scores, float *log_psi, float *tile_lists, void *workspace, size_t workspace_bytes,
                           int workspace_prepared, void *stream) {
     return ctcps_score_lazy_topk_active(x_logp, ldx, r_prev, s_prev, last_ids, ol, B, W, T, V, blank, att_scores, one_minus_w, w, beam_scores,
-                                        nullptr, log_psi, tile_lists, workspace, workspace_bytes, workspace_prepared, stream);
+                                        nullptr, nullptr, log_psi, tile_lists, workspace, workspace_bytes, workspace_prepared, stream);
 }
 
 int ctcps_score_lazy_topk_active(const float *x_logp, int ldx, const float *r_prev, const float *s_prev, const int64_t *last_ids, int ol,
                                  int B, int W, int T, int V, int blank, const float *att_scores, float one_minus_w, float w,
-                                 const float *beam_scores, const unsigned char *done, float *log_psi, float *tile_lists, void *workspace,
-                                 size_t workspace_bytes, int workspace_prepared, void *stream) {
+                                 const float *beam_scores, const unsigned char *done, const int64_t *xlens, float *log_psi, float *tile_lists,
+                                 void *workspace, size_t workspace_bytes, int workspace_prepared, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     ARG_CHECK(x_logp && r_prev && last_ids && att_scores && beam_scores && tile_lists && log_psi, CTCPS_E_BADARG, "score_lazy_topk: null pointer");
     ARG_CHECK(B > 0 && W > 0 && T > 0 && V > 0 && ol >= 0, CTCPS_E_BADARG, "score_lazy_topk: non-positive size");
@@ -2308,7 +2318,7 @@ int ctcps_score_lazy_topk_active(const float *x_logp, int ldx, const float *r_pr
     tk.K = 2 * W;
     tk.done = done;
     return score_lazy_impl(x_logp, ldx, r_prev, s_prev, 1, 0, last_ids, ol, B, W, T, V, blank, const_cast<float *>(att_scores), one_minus_w, w,
-                           log_psi, nullptr, nullptr, &tk, workspace, workspace_bytes, workspace_prepared, st);
+                           log_psi, nullptr, nullptr, &tk, xlens, workspace, workspace_bytes, workspace_prepared, st);
 }
 
 int ctcps_select_lazy(const float *x_logp, int ldx, const float *blank_lp, const float *r_prev, const int64_t *last_ids, int ol,
@@ -2556,7 +2566,7 @@ int ctcps_decode_step(const ctcps_decode_session *s, float *att_scores, int step
     const int64_t tag = s->tag_base + (int64_t)step;
     if (fused) {
         rc = ctcps_score_lazy_topk_active(s->x_logp, s->ldx, r_prev, s_prev, s->last_ids[cur], ol, B, W, T, V, s->blank, att_scores,
-                                          s->one_minus_w, s->w, s->beam_scores, skip_done() ? s->done : nullptr, s->log_psi[cur],
+                                          s->one_minus_w, s->w, s->beam_scores, skip_done() ? s->done : nullptr, s->xlens, s->log_psi[cur],
                                           s->tile_lists, s->score_ws, s->score_ws_bytes, prepared, main_st);
         if (rc) return rc;
         if (ev_score_end) cudaEventRecord((cudaEvent_t)ev_score_end, main_st);
@@ -2586,8 +2596,9 @@ int ctcps_decode_step(const ctcps_decode_session *s, float *att_scores, int step
     } else {
         ARG_CHECK(s->joint != nullptr && s->log_psi[0] != nullptr && s->log_psi[1] != nullptr, CTCPS_E_BADARG,
                   "decode_step: this step needs the dense (BW,V) buffers (joint, log_psi[2]) of the session");
-        rc = ctcps_score_lazy(s->x_logp, s->ldx, s->blank_lp, r_prev, s_prev, 1, 0, s->last_ids[cur], ol, B, W, T, V, s->blank, att_scores,
-                              s->one_minus_w, s->w, s->log_psi[cur], nullptr, s->joint, s->score_ws, s->score_ws_bytes, prepared, main_st);
+        rc = ctcps_score_lazy_lens(s->x_logp, s->ldx, s->blank_lp, s->xlens, r_prev, s_prev, 1, 0, s->last_ids[cur], ol, B, W, T, V, s->blank,
+                                   att_scores, s->one_minus_w, s->w, s->log_psi[cur], nullptr, s->joint, s->score_ws, s->score_ws_bytes, prepared,
+                                   main_st);
     }
     if (rc) return rc;
     if (ev_score_end) cudaEventRecord((cudaEvent_t)ev_score_end, main_st);

@@ -47,6 +47,7 @@ struct PsiArgs {
     float *log_psi, *token_scores, *joint;
     int B, W, T, V, blank, ol, G, Tpad, nvt;
     int prefetch;        // chunks of L2 look-ahead beyond the shared-memory ring (0 = none)
+    const int64_t *xlens; // (B) utterance lengths or null: frames past the length hold exp(x) == 0 and are not streamed
     PsiTopk tk;
 };
 
@@ -61,7 +62,7 @@ struct PsiSmem {
     alignas(16) float lin[NSTAGE][TT][HWP];
     alignas(8) uint64_t full[NSTAGE];
     alignas(8) uint64_t empty[NSTAGE];
-    int cursor[2][6];  // thread 0's two look-ahead cursors (kept here, not in registers: every thread would pay for them)
+    int cursor[2][7];  // thread 0's two look-ahead cursors (kept here, not in registers: every thread would pay for them)
 };
 
 // one warp per (padded) hypothesis: lin stream, Gmax and the last-label column sum
@@ -376,18 +377,30 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
         if constexpr (TOPK) return a.tk.done != nullptr && a.tk.done[b] != 0;
         return false;
     };
-    int n_active = my_tiles;
-    if constexpr (TOPK) {
-        if (a.tk.done != nullptr) {
-            n_active = 0;
-            for (int ti = 0; ti < my_tiles; ++ti) {
-                int b, vt, g;
-                decode_tile((int)blockIdx.x + ti * (int)gridDim.x, b, vt, g);
-                n_active += tile_skipped(b) ? 0 : 1;
-            }
+    // Chunks of a tile that are streamed: -1 = the tile is skipped altogether (no epilogue either), else the chunks from c0 up to
+    // the one that holds the utterance's last frame.  Past the length x is logzero for every token but blank (:39-42), exp(x)
+    // is exactly 0 and lin * 0 + acc == acc bit for bit; the blank column's score is overwritten with logzero anyway (:173).
+    auto tile_chunks = [&](int b) -> int {
+        if (tile_skipped(b)) return -1;
+        if (a.xlens == nullptr) return nchunk;
+        const long long lraw = a.xlens[b];
+        long long l = lraw < 0 ? lraw + T : lraw;  // the length as K-a applied it
+        if (l < 0) l = 0;
+        if (lraw >= T) l = T;
+        const int last = l > 0 ? (int)((l - 1) / TT) : -1;
+        const int n = (last < cN ? last : cN) - c0 + 1;
+        return n > 0 ? n : 0;
+    };
+    int nitems = my_tiles * nchunk;
+    if ((TOPK && a.tk.done != nullptr) || a.xlens != nullptr) {
+        nitems = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            int b, vt, g;
+            decode_tile((int)blockIdx.x + ti * (int)gridDim.x, b, vt, g);
+            const int n = tile_chunks(b);
+            nitems += n > 0 ? n : 0;
         }
     }
-    const int nitems = n_active * nchunk;
     // Thread 0 walks the CTA's flat chunk sequence twice ahead of the consumers, with two cursors that advance
     // incrementally (a tile is decoded once, when a cursor enters it -- no division per chunk):
     //   `is`  the next item to load into the shared-memory ring (NSTAGE items ahead of the one being consumed);
@@ -395,26 +408,27 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
     //         be in flight towards shared memory (4 CTAs x 3 stages x 16 KB per SM, a third of it being read at any time);
     //         the L2 prefetches carry the rest of the HBM queue depth, and the ring's own loads then mostly hit L2.
     struct Cursor {
-        int k, ti, ci, b, vt, g;
+        int k, ti, ci, b, vt, g, nch;
     };
     auto cursor_load = [&](int which) {
         const int *p = sm.cursor[which];
-        return Cursor{p[0], p[1], p[2], p[3], p[4], p[5]};
+        return Cursor{p[0], p[1], p[2], p[3], p[4], p[5], p[6]};
     };
     auto cursor_store = [&](int which, const Cursor &c) {
         int *p = sm.cursor[which];
-        p[0] = c.k, p[1] = c.ti, p[2] = c.ci, p[3] = c.b, p[4] = c.vt, p[5] = c.g;
+        p[0] = c.k, p[1] = c.ti, p[2] = c.ci, p[3] = c.b, p[4] = c.vt, p[5] = c.g, p[6] = c.nch;
     };
-    auto cursor_enter = [&](Cursor &c) {  // decode the cursor's tile, stepping over skipped ones
+    auto cursor_enter = [&](Cursor &c) {  // decode the cursor's tile, stepping over tiles that stream nothing
         while (c.ti < my_tiles) {
             decode_tile((int)blockIdx.x + c.ti * (int)gridDim.x, c.b, c.vt, c.g);
-            if (!tile_skipped(c.b)) break;
+            c.nch = tile_chunks(c.b);
+            if (c.nch > 0) break;
             ++c.ti;
         }
     };
     auto cursor_next = [&](Cursor &c) {
         ++c.k;
-        if (++c.ci == nchunk) {
+        if (++c.ci == c.nch) {
             c.ci = 0;
             ++c.ti;
             cursor_enter(c);
@@ -439,7 +453,7 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&sm.full[s], 1), mbar_init(&sm.empty[s], NWARP);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        Cursor is = {0, 0, 0, 0, 0, 0}, pf = {0, 0, 0, 0, 0, 0};
+        Cursor is = {0, 0, 0, 0, 0, 0, 0}, pf = {0, 0, 0, 0, 0, 0, 0};
         if (nitems > 0) {
             cursor_enter(is);
             while (is.k < nitems && is.k < NSTAGE) {  // prologue: fill the ring
@@ -462,7 +476,8 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
     for (int ti = 0; ti < my_tiles; ++ti) {
         int b, vt, g;
         decode_tile((int)blockIdx.x + ti * (int)gridDim.x, b, vt, g);
-        if (tile_skipped(b)) continue;  // its candidate list keeps the last step's contents: the beam step ignores a finished utterance
+        const int nch = tile_chunks(b);
+        if (nch < 0) continue;  // its candidate list keeps the last step's contents: the beam step ignores a finished utterance
         unsigned long long acc2[HP][4];  // (hyp 2p, hyp 2p+1) of token j, packed for FFMA2
         float x0[4];
 #pragma unroll
@@ -472,7 +487,7 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
 #pragma unroll
         for (int j = 0; j < 4; ++j) x0[j] = LZ;
 
-        for (int ci = 0; ci < nchunk; ++ci, ++k) {
+        for (int ci = 0; ci < nch; ++ci, ++k) {
             const int s = k % NSTAGE;
             mbar_wait(&sm.full[s], (uint32_t)((k / NSTAGE) & 1));
             if (a.ol == 0 && ci == 0) {  // r[0,0] = x_[0,0] enters log_psi as its own term (:158,165)

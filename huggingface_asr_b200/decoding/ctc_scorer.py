@@ -256,6 +256,13 @@ class CTCPrefixScoreTH(object):
                                                          _stream(self.device)), "ctcps_transpose_vt")
         return self._xt
 
+    def _score_lens(self):
+        """(B) int64 lengths for the scoring kernels, or None when they do not describe the current posteriors (extend_prob)."""
+        lens = getattr(self, "_lens", None)
+        if lens is None or lens.numel() != self.batch or not lens.is_cuda:
+            return None
+        return lens
+
     def _workspace(self, W, S):
         key = (self.batch, self.input_length, W, S)
         if self._ws_key != key:
@@ -439,10 +446,11 @@ class CTCPrefixScoreTH(object):
             x_fm = self._frame_major()
             if lazy:
                 r = LazyForwardVariables(self, r_prev, last_ids, ol, W)
-                _lib.check(L.ctcps_score_lazy(_ptr(x_fm), self._ldx, _ptr(self._blank_lp), _ptr(r_prev), s_ptr, s_rs, s_cs,
-                                              _ptr(last_ids), ol, B, W, T, V, self.blank, _ptr(att_scores), 1.0 - w, w,
-                                              _ptr(log_psi), _ptr(token_scores), _ptr(joint), _ptr(ws), ws.numel(),
-                                              int(bool(prepared)), _stream(dev)), "ctcps_score_lazy")
+                # the lengths let the kernel leave out the padded frames of short utterances (they add exactly 0)
+                _lib.check(L.ctcps_score_lazy_lens(_ptr(x_fm), self._ldx, _ptr(self._blank_lp), _ptr(self._score_lens()), _ptr(r_prev),
+                                                   s_ptr, s_rs, s_cs, _ptr(last_ids), ol, B, W, T, V, self.blank, _ptr(att_scores),
+                                                   1.0 - w, w, _ptr(log_psi), _ptr(token_scores), _ptr(joint), _ptr(ws), ws.numel(),
+                                                   int(bool(prepared)), _stream(dev)), "ctcps_score_lazy_lens")
             else:
                 r = torch.empty((T, 2, n_bh, ldr), dtype=torch.float32, device=dev)
                 start, end = (max(ol, 1), T) if window is None else window[:2]
@@ -564,6 +572,7 @@ class CTCPrefixScoreTH(object):
             self.input_length = T_new
             self._ldt = L.ctcps_padded_lt(T_new)
             self.end_frames = torch.as_tensor([T_new]) - 1
+            self._lens = None  # the new frames are not padding: the scoring kernels must stream all of them
             self._ws_key = None
 
     def extend_state(self, state):

@@ -154,6 +154,14 @@ int ctcps_score_lazy(const float *x_logp, int ldx, const float *blank_lp, const 
                      int V, int blank, float *att_scores, float one_minus_w, float w, float *log_psi,
                      float *token_scores, float *joint, void *workspace, size_t workspace_bytes, int workspace_prepared,
                      void *stream);
+/* ctcps_score_lazy with the utterance lengths `xlens` (B) that ctcps_init padded with (NULL = none): frames past an utterance's
+ * length hold logzero for every token but blank (:39-42), exp(x) is exactly 0 there, so their chunks are not streamed --
+ * results are bit-identical, a ragged batch costs its real frames instead of B x T. */
+int ctcps_score_lazy_lens(const float *x_logp, int ldx, const float *blank_lp, const int64_t *xlens, const float *r_prev,
+                          const float *s_prev, int64_t s_row_stride, int64_t s_col_stride, const int64_t *last_ids, int ol, int B,
+                          int W, int T, int V, int blank, float *att_scores, float one_minus_w, float w, float *log_psi,
+                          float *token_scores, float *joint, void *workspace, size_t workspace_bytes, int workspace_prepared,
+                          void *stream);
 
 /* next_workspace (nullable): the workspace of the NEXT ctcps_score_lazy call.  When given, the scan also writes the
  * per-hypothesis stream that call needs (for r_prev = r_new, s_prev = s_new, last ids = the selected tokens,
@@ -244,11 +252,11 @@ int ctcps_score_lazy_topk(const float *x_logp, int ldx, const float *r_prev, con
                           const float *beam_scores, float *log_psi, float *tile_lists, void *workspace, size_t workspace_bytes,
                           int workspace_prepared, void *stream);
 /* the same with `done` (B) flags of the beam search (NULL = none): tiles of finished utterances are neither streamed nor ranked,
- * their lists and log_psi rows keep their previous contents */
+ * their lists and log_psi rows keep their previous contents; and with the utterance lengths (NULL = none), see ctcps_score_lazy_lens */
 int ctcps_score_lazy_topk_active(const float *x_logp, int ldx, const float *r_prev, const float *s_prev, const int64_t *last_ids, int ol,
                                  int B, int W, int T, int V, int blank, const float *att_scores, float one_minus_w, float w,
-                                 const float *beam_scores, const unsigned char *done, float *log_psi, float *tile_lists, void *workspace,
-                                 size_t workspace_bytes, int workspace_prepared, void *stream);
+                                 const float *beam_scores, const unsigned char *done, const int64_t *xlens, float *log_psi, float *tile_lists,
+                                 void *workspace, size_t workspace_bytes, int workspace_prepared, void *stream);
 int ctcps_beam_step_lists(const float *tile_lists, int lists_per_utterance, float *beam_scores, const int64_t *ids_cur, int64_t *ids_next,
                           int64_t ld_ids, int L, int B, int W, int V, int eos, int pad, float len_norm, float *pool_scores,
                           int64_t *pool_lens, int64_t *pool_seqs, int64_t ld_pool, unsigned char *done, void *workspace,
@@ -308,6 +316,8 @@ typedef struct ctcps_decode_session {
                               unless a prefix can outgrow T: ol > T falls back to the dense step); NULL: the dense step */
     int64_t tag_base;      /* added to `step` in the tag published to done_ring: a serial number of the decode in the high
                               bits (a multiple of `ring`), so that a late write of an earlier decode never matches */
+    const int64_t *xlens;  /* (B) utterance lengths as given to ctcps_init, or NULL: the full-vocabulary scoring kernel does not
+                              stream the frames past an utterance's length (they contribute exactly 0) */
 } ctcps_decode_session;
 
 /* sizeof(ctcps_decode_session) as this library was compiled: lets a binding check its mirror of the struct. */

@@ -244,3 +244,73 @@ def test_skipping_finished_utterances_changes_nothing_that_is_returned(B, W, T, 
     assert torch.equal(a.nbest_sequences, b.nbest_sequences) and torch.equal(a.nbest_lengths, b.nbest_lengths)
     assert torch.equal(a.nbest_scores, b.nbest_scores)
     assert (a.lengths.cpu() == torch.tensor([len(t) - 1 for t in tr])).all()
+
+
+@pytest.mark.parametrize("B,W,T,V,kind,n_steps", [
+    (6, 10, 100, 1200, "peaky", 2),   # ragged lengths 60 .. 100 frames: up to 5 of 13 chunks are padding
+    (5, 4, 61, 516, "flat", 1),
+    (4, 20, 90, 260, "peaky", 3),
+    (3, 3, 40, 64, "peaky", 0),       # first step (ol = 0: the x[0] term comes from chunk 0)
+])
+def test_leaving_out_padded_frames_is_bit_identical(B, W, T, V, kind, n_steps):
+    """ctcps_score_lazy_lens / _topk_active with the utterance lengths do not stream the chunks past an utterance's last frame:
+    exp(logzero) is exactly 0, so log_psi, joint scores and the tile lists must equal those of the calls without lengths bit for
+    bit -- including an utterance of length 0 and one that ends exactly on a chunk boundary."""
+    L, lib = _lib()
+    from huggingface_asr_b200.decoding.ctc_scorer import CTCRescorerLogitsProcessor
+    from huggingface_asr_b200.synthetic import make_attention_scores, make_encoder_logits
+
+    logits, lens, _ = make_encoder_logits(B, T, V, kind, True, seed=71)
+    lens[0] = 0
+    lens[1] = 48 if T > 48 else 8     # a multiple of the 8-frame chunk
+    proc = CTCRescorerLogitsProcessor(logits.cuda(), lens.cuda(), BLANK, EOS, 0, 0.3, W, -1, False, 1.0, materialize_state=False)
+    sc = proc.ctc_prefix_scorer
+    ids = torch.zeros((B * W, 1), dtype=torch.long, device="cuda")
+    beam_scores = torch.zeros(B, W, device="cuda")
+    beam_scores[:, 1:] = -1e9
+    for n in range(n_steps):
+        att = make_attention_scores(B * W, V, n, seed=5, scale=0.5).cuda()
+        out = proc(ids, att)
+        cand = (out + beam_scores.view(-1, 1)).view(B, W * V)
+        top, idx = cand.topk(W, dim=1)
+        base = (torch.arange(B, device="cuda") * W).view(B, 1)
+        ids = torch.cat([ids[(idx // V + base).view(-1)], (idx % V).view(-1, 1)], dim=1)
+        beam_scores = top
+    beam_scores = beam_scores.contiguous()
+    if n_steps > 0:
+        sel = sc.index_select_state(proc.ctc_states, ids[:, -1].reshape(-1, W))
+        r_prev, s_ptr = sel[0].contiguous(), sel[1][:, 0].contiguous()
+    else:
+        r_prev, s_ptr = sc.initial_state(W), None
+    att = make_attention_scores(B * W, V, n_steps, seed=5, scale=0.5).cuda()
+    BW, ol = B * W, ids.shape[1] - 1
+    last = ids[:, -1].contiguous()
+    st = torch.cuda.current_stream().cuda_stream
+    ws = sc._workspace(W, 0)
+    x = sc._frame_major()
+    xl = sc._score_lens()
+    assert xl is not None
+    nl, kk = ctypes.c_int(0), ctypes.c_int(0)
+    L.check(lib.ctcps_topk_lists_shape(B, W, V, ctypes.byref(nl), ctypes.byref(kk)), "shape")
+    outs = []
+    for lens_ptr in (None, xl.data_ptr()):
+        a1, a2 = att.clone(), att.clone()
+        log_psi, ts, joint = (torch.full((BW, V), float("nan"), device="cuda") for _ in range(3))
+        L.check(lib.ctcps_score_lazy_lens(x.data_ptr(), sc._ldx, sc._blank_lp.data_ptr(), lens_ptr, r_prev.data_ptr(),
+                                          None if s_ptr is None else s_ptr.data_ptr(), 1, 0, last.data_ptr(), ol, B, W, T, V, BLANK,
+                                          a1.data_ptr(), 0.7, 0.3, log_psi.data_ptr(), ts.data_ptr(), joint.data_ptr(), ws.data_ptr(),
+                                          ws.numel(), 0, st), "ctcps_score_lazy_lens")
+        res = [log_psi, ts, joint]
+        if V % 4 == 0:
+            lists = torch.full((B, nl.value, kk.value, 2), float("nan"), device="cuda")
+            lp2 = torch.full((BW, V), float("nan"), device="cuda")
+            L.check(lib.ctcps_score_lazy_topk_active(x.data_ptr(), sc._ldx, r_prev.data_ptr(), None if s_ptr is None else s_ptr.data_ptr(),
+                                                     last.data_ptr(), ol, B, W, T, V, BLANK, a2.data_ptr(), 0.7, 0.3, beam_scores.data_ptr(),
+                                                     None, lens_ptr, lp2.data_ptr(), lists.data_ptr(), ws.data_ptr(), ws.numel(), 0, st),
+                    "ctcps_score_lazy_topk_active")
+            res += [lists, lp2]
+        torch.cuda.synchronize()
+        outs.append(res)
+    for a, b in zip(*outs):
+        assert not torch.isnan(a).any()
+        assert torch.equal(a, b)
