@@ -66,6 +66,7 @@ def test_head_has_fp32_accuracy_where_single_pass_tf32_does_not(impl):
     (2, 40, 300, 64, True),       # 2 vocabulary tiles: two of the four quarters are empty; 2 k-blocks
     (5, 33, 260, 32, True),       # one k-block, V = 260: 4 valid columns in the second tile
     (2, 17, 6, 96, True),         # tiny vocabulary (blank inside): a single partial column group
+    (3, 21, 40, 16, False),       # hidden size 16: half of the only k-block is zero padding
 ])
 def test_log_posteriors_of_the_tcgen05_head_vs_fp64(B, T, V, d, use_bias):
     """What the scorer keeps -- padded log-posteriors and the blank column -- against an fp64 restatement of the reference's
