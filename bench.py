@@ -178,7 +178,8 @@ def count_launches(steps, harness, materialize, pre_beam, V, fused_topk):
     profiles/ are the evidence).  K-a (1) + initial state (1); per step: scoring kernel (1) + beam step (native / fused
     harness: the list merge alone with the fused top-2W, else per-row top-2W + candidate kernel); the preparation kernel every
     step when materialised, on the first step only in lazy mode (the select of the previous step prepares the next call);
-    all steps but the first: select (1 gather, or 2 for the lazy stage + scan); the native loop also selects after the last step."""
+    all steps but the first: select (1 gather, or 3 for the lazy stage + scan + lin range; the range kernel also follows the
+    first step's preparation); the native loop also selects after the last step."""
     two_kernel = not pre_beam and V % 4 == 0 and V <= 8192
     native = 1 if (harness == "native" and not materialize) else 0
     beam = 0 if harness in ("torch", "hf") else (1 if fused_topk else (2 if two_kernel else 1))
@@ -186,8 +187,8 @@ def count_launches(steps, harness, materialize, pre_beam, V, fused_topk):
         # K-a + transpose + initial state; per step: top-S, candidate scores, [dense scatter when the harness is not sparse],
         # [beam step]; first step: k_prep_psi; all steps but the first: select stage + scan
         dense = 0 if (harness not in ("torch", "hf") and pre_beam >= 2) else 1
-        return 3 + steps * (2 + dense + beam) + 1 + (steps - 1 + native) * 2
-    return 2 + steps * (1 + beam) + (steps if materialize else 1) + (steps - 1 + native) * (1 if materialize else 2)
+        return 3 + steps * (2 + dense + beam) + 2 + (steps - 1 + native) * 3
+    return 2 + steps * (1 + beam) + (steps if materialize else 2) + (steps - 1 + native) * (1 if materialize else 3)
 
 
 class Runner:
@@ -214,6 +215,7 @@ class Runner:
             self.dist = dist
         _lib.lib()  # build / load outside the timed region
         self.skip_done = bool(_lib.lib().ctcps_set_skip_done(-1))
+        self.frame_window = bool(_lib.lib().ctcps_set_frame_window(-1))
         self.peak, self.peak_src = peak_hbm()
         self.last_sequences = {}
 
@@ -260,6 +262,9 @@ class Runner:
         launches = [0]
         score_events, native_events = [], []
         fused_tk = self.fused_topk(wl, harness, materialize, pre_beam)
+        from huggingface_asr_b200 import _lib as _libmod
+
+        L_ = _libmod.lib()
 
         def run(lg, ln, timing=None):
             if decode_fn is not None:
@@ -280,6 +285,10 @@ class Runner:
         self.sync_all()
         launches[0] = 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # the lazy scoring kernel reports how many chunks it actually streamed (finished utterances, padded frames and frames
+        # whose weights underflowed to zero are left out): the roofline divides THOSE bytes by the time of the calls
+        stream_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)
+        L_.ctcps_set_stream_counter(stream_counter.data_ptr())
         self.sync_all()
         e0.record()
         steps_total = 0
@@ -289,9 +298,12 @@ class Runner:
             steps_total += out.steps
         e1.record()
         self.sync_all()
+        L_.ctcps_set_stream_counter(None)
+        streamed_chunks = int(stream_counter.item())
         clk = sampler.stop() if (self.rank == 0 and clocks) else None
         ms = e0.elapsed_time(e1)
         score_ms = [a.elapsed_time(b) for a, b in score_events] + resolve_score_timing(native_events)
+        score_ms_all = list(score_ms)
         # The native loop does not score finished utterances: a call on a batch that is (partly) finished streams less than the
         # algorithmic bytes the roofline divides by.  All utterances of a bench batch finish on the same step, so such calls are
         # the last one or two of a decode: the roofline averages the FULL calls only (>= half the median) and counts the others.
@@ -300,7 +312,8 @@ class Runner:
             med = sorted(score_ms)[n_all // 2]
             score_ms = [t for t in score_ms if t >= 0.5 * med]
         res = {"ms": ms, "launches": launches[0], "score_ms": sum(score_ms) / max(len(score_ms), 1), "n_score": len(score_ms),
-               "n_score_skipped": n_all - len(score_ms),
+               "n_score_skipped": n_all - len(score_ms), "score_ms_total": sum(score_ms_all), "n_score_all": n_all,
+               "streamed_chunks": streamed_chunks, "chunk_bytes": int(L_.ctcps_stream_chunk_bytes(wl.W)),
                "decode_steps": steps_total / steps, "clocks": clk, "ms_e2e": float("nan"), "steps": steps, "warm": warm,
                "fused_topk": fused_tk, "harness": harness, "transcripts_recovered": wl.transcripts_recovered(out)}
         if args.profile or not e2e:
@@ -465,6 +478,21 @@ class Runner:
              "traffic": load_traffic(("k_score_full" if materialized else "k_psi_full") + ("" if wl.name == "C2" else "_" + wl.name)),
              "algorithmic_bytes_per_launch": true_bytes, "avg_launch_ms": r["score_ms"], "launches_timed": r["n_score"],
              "launches_on_finished_batches_not_counted": r.get("n_score_skipped", 0)}
+        if not materialized and r.get("streamed_chunks", 0) > 0 and r.get("n_score_all", 0) > 0:
+            # bytes the launches of the timed region really moved: the chunks the kernel counted (8 frames x 512 tokens of
+            # posteriors + the group's weights each) + per launch the decoder scores it reads and the small per-hypothesis vectors
+            BW = wl.B * wl.W
+            fixed = 12 * BW + 4 * BW * wl.V + (0 if r["fused_topk"] else 8 * BW * wl.V)
+            moved = r["streamed_chunks"] * r["chunk_bytes"] + r["n_score_all"] * fixed
+            d["achieved"] = moved / (r["score_ms_total"] * 1e-3) / 1e9
+            d["avg_launch_ms"] = r["score_ms_total"] / r["n_score_all"]
+            d["launches_timed"] = r["n_score_all"]
+            d["launches_on_finished_batches_not_counted"] = 0
+            d["streamed_bytes_per_launch"] = moved / r["n_score_all"]
+            d["streamed_fraction_of_all_frames"] = moved / (r["n_score_all"] * true_bytes)
+            d["algorithmic_bytes_per_launch_note"] = ("all frames from the prefix length to T; the kernel leaves out the chunks whose weights "
+                                                      "exp(r_sum - offset) are exactly zero, the padded frames and finished utterances "
+                                                      "(bit-identical scores): achieved = streamed bytes (counted by the kernel) / time of all calls")
         d["frac"] = d["achieved"] / self.peak
         d["frac_of_read_stream"] = d["achieved"] / READ_STREAM_GBS
         d["read_stream_gbs"] = READ_STREAM_GBS
@@ -472,7 +500,7 @@ class Runner:
             d["note"] = ("lazy state: r (T,2,BW,V) is not written; true bytes = posteriors read once + scores; effective_* is the "
                          "interface-faithful figure of SURVEY 8(d) divided by the same time; read_stream_gbs = best read-only stream "
                          "measured on this pool (the copy peak counts read + write)")
-            d["effective_achieved"] = abytes / (r["score_ms"] * 1e-3) / 1e9
+            d["effective_achieved"] = abytes / (d["avg_launch_ms"] * 1e-3) / 1e9
             d["effective_frac"] = d["effective_achieved"] / self.peak
         return d
 
@@ -495,6 +523,9 @@ class Runner:
                 "finished_utterances": ("not scored (native loop, ctcps_set_skip_done; the returned hypotheses are bit-identical)"
                                         if r["harness"] == "native" and r["fused_topk"] and self.skip_done else
                                         "scored until the whole batch is finished, like HF's loop"),
+                "frames_streamed": ("only the 8-frame chunks in which some hypothesis' weight exp(r_sum - offset) is nonzero in fp32 "
+                                    "(ctcps_set_frame_window; exact: the others add 0 to every score)" if self.frame_window and state == "lazy"
+                                    else "every frame from the prefix length to T"),
                 "decode_steps_per_utterance_batch": r["decode_steps"]}
 
     # ------------------------------------------------------------------------------------------------
@@ -667,16 +698,20 @@ def run_ours(args):
             emit({"profile_run": True, "state": args.state, "ms_per_step": res["ms"] / res["steps"], "avg_score_ms": res["score_ms"]})
         return
     other = None if args.single_mode else R.measure(wl, not main_mode, clocks=False)
-    # the same decode with every row scored at every step until the whole batch is finished (what HF's loop does)
+    # the same decode with every row scored at every step until the whole batch is finished and every frame from the prefix
+    # length to T streamed (what the reference's dense scorer under HF's loop computes): the two exact shortcuts of the native
+    # loop switched off -- same hypotheses bit for bit, and the scoring kernel's roofline on the full algorithmic bytes
     all_rows = None
-    if not args.single_mode and main_mode is False and args.harness == "native" and R.skip_done:
+    if not args.single_mode and main_mode is False and args.harness == "native":
         from huggingface_asr_b200 import _lib as _l
 
-        _l.lib().ctcps_set_skip_done(0)
+        prev_skip, prev_win = _l.lib().ctcps_set_skip_done(0), _l.lib().ctcps_set_frame_window(0)
         try:
-            all_rows = R.measure(wl, False, steps=3, warm=2, e2e=False, clocks=False)
+            all_rows = R.measure(wl, False, steps=4, warm=2, e2e=False, clocks=False)
+            all_rows_roof = R.roofline(wl, all_rows, False)
         finally:
-            _l.lib().ctcps_set_skip_done(1)
+            _l.lib().ctcps_set_skip_done(prev_skip)
+            _l.lib().ctcps_set_frame_window(prev_win)
     pre = R.measure(wl, False, args.pre_beam, clocks=False) if (args.pre_beam > 0 and not args.single_mode) else None
     agreement = None
     key_full, key_pre = (wl.name, False, 0, args.harness), (wl.name, False, args.pre_beam, args.harness)
@@ -703,7 +738,7 @@ def run_ours(args):
     if not args.single_mode and args.extra_configs:
         for name in [c for c in args.extra_configs.split(",") if c and c != args.config]:
             w2 = Workload(name, rank, R.dev)
-            r_l = R.measure(w2, False, steps=3, warm=3, clocks=False)
+            r_l = R.measure(w2, False, steps=6, warm=3, clocks=False)  # short decodes: a few more of them against host jitter
             entry = R.summary(w2, r_l, False)
             entry["config"] = R.workload_config(w2, r_l, "lazy")
             r_m = R.measure(w2, True, steps=2, warm=1, e2e=False, clocks=False)
@@ -746,11 +781,12 @@ def run_ours(args):
                          "loop (no (BW,V) tensor); score_candidates_ms = CUDA-event time of ctcps_score_candidates"),
             }
         if all_rows is not None:
-            line["finished_utterances_scored"] = {
+            line["every_row_every_frame"] = {
                 "value": world * B_main * all_rows["steps"] / (all_rows["ms"] * 1e-3), "unit": UNIT, "ms_per_step": all_rows["ms"] / all_rows["steps"],
-                "avg_score_ms": all_rows["score_ms"],
-                "note": "ctcps_set_skip_done(0): the native loop scores the rows of finished utterances until the whole batch is done, "
-                        "like HF's beam search; same hypotheses, bit for bit (tests/test_gpu_fused_topk.py)"}
+                "roofline": all_rows_roof,
+                "note": "ctcps_set_skip_done(0) + ctcps_set_frame_window(0): the native loop scores the rows of finished utterances until the "
+                        "whole batch is done and streams every frame from the prefix length to T, like the reference's dense scorer under HF's "
+                        "beam search; same hypotheses, bit for bit (tests/test_gpu_fused_topk.py)"}
         if hidden is not None:
             d = args.hidden_dim
             cfg = CONFIGS[args.config]

@@ -82,6 +82,9 @@ SIGNATURES = {
     "ctcps_set_select_pscan": [_i],
     "ctcps_set_psi_prefetch": [_i],
     "ctcps_set_skip_done": [_i],
+    "ctcps_set_frame_window": [_i],
+    "ctcps_set_stream_counter": [_p],
+    "ctcps_stream_chunk_bytes": [_i],
     "ctcps_set_psi_max_group": [_i],
     "ctcps_workspace_bytes": [_i, _i, _i, _i, _i, ctypes.POINTER(_sz)],
     "ctcps_init": [_p, _i, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p],

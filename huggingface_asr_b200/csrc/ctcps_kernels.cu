@@ -1675,7 +1675,7 @@ void pick_hw_psi(int W, int *HW, int *HWP, int *G) {
     *G = (W + best - 1) / best;
 }
 struct WorkspaceLazy {
-    size_t lin_off, lin_bytes, g_off, c_off, total;
+    size_t lin_off, lin_bytes, g_off, c_off, r_off, total;
 };
 WorkspaceLazy plan_workspace_lazy(int B, int T, int W, int V) {
     (void)V;
@@ -1687,7 +1687,8 @@ WorkspaceLazy plan_workspace_lazy(int B, int T, int W, int V) {
     ws.g_off = (ws.lin_bytes + 255) & ~(size_t)255;
     const size_t gb = ((size_t)B * W * sizeof(float) + 255) & ~(size_t)255;
     ws.c_off = ws.g_off + gb;
-    ws.total = ws.c_off + gb;
+    ws.r_off = ws.c_off + gb;  // (B*G) int2: chunk range of the nonzero part of the lin stream (k_lin_range)
+    ws.total = ws.r_off + (((size_t)B * G * sizeof(int2) + 255) & ~(size_t)255);
     return ws;
 }
 
@@ -1815,6 +1816,18 @@ int psi_prefetch_chunks() {
 
 // Native decode loop: do not score the utterances whose beam search has finished (CTCPS_SKIP_DONE, default 1).  Their rows
 // never reach a hypothesis (the beam step ignores a finished utterance), so the returned n-best lists are bit-identical.
+// Lazy scoring kernel: stream only the chunks in which the lin stream of a hypothesis group is nonzero (CTCPS_FRAME_WINDOW,
+// default 1; see k_lin_range).  Bit-identical either way.
+int g_frame_window = -1;
+bool frame_window() {
+    if (g_frame_window < 0) {
+        const char *ev = getenv("CTCPS_FRAME_WINDOW");
+        g_frame_window = (ev != nullptr && atoi(ev) == 0) ? 0 : 1;
+    }
+    return g_frame_window != 0;
+}
+unsigned long long *g_stream_counter = nullptr;  // device word the lazy scoring kernel adds its streamed chunks to (bench.py)
+
 int g_skip_done = -1;
 bool skip_done() {
     if (g_skip_done < 0) {
@@ -1901,6 +1914,7 @@ int select_lazy_impl(const XView x, const float *blank_lp, const float *r_prev, 
         k_select_lazy_pscan<true><<<(BW + PS_H - 1) / PS_H, PS_H * 32, ps_smem, st>>>(x, blank_lp, ol, scores, best_ids, cand_ids, S, B, W, T, V,
                                                                                   r_new, s_new, lin, Gmax, psic, HW, HWP, G, tpad_of(T),
                                                                                   ps_F, ps_Fo, ps_HS);
+        k_lin_range<<<B * G, 128, 0, st>>>(lin, tpad_of(T), HWP, reinterpret_cast<int2 *>((char *)next_workspace + ws.r_off));
     } else if (pscan) {
         k_select_lazy_pscan<false><<<(BW + PS_H - 1) / PS_H, PS_H * 32, ps_smem, st>>>(x, blank_lp, ol, scores, best_ids, cand_ids, S, B, W, T, V,
                                                                                    r_new, s_new, nullptr, nullptr, nullptr, 1, 4, 1, 0, ps_F,
@@ -1916,6 +1930,7 @@ int select_lazy_impl(const XView x, const float *blank_lp, const float *r_prev, 
         float *psic = reinterpret_cast<float *>((char *)next_workspace + ws.c_off);
         k_select_lazy_scan<true><<<(BW + 63) / 64, 64, 0, st>>>(x, blank_lp, ol, scores, best_ids, cand_ids, S, B, W, T, V, r_new, s_new, lin,
                                                                Gmax, psic, HW, HWP, G, tpad_of(T));
+        k_lin_range<<<B * G, 128, 0, st>>>(lin, tpad_of(T), HWP, reinterpret_cast<int2 *>((char *)next_workspace + ws.r_off));
     } else {
         k_select_lazy_scan<false><<<(BW + 63) / 64, 64, 0, st>>>(x, blank_lp, ol, scores, best_ids, cand_ids, S, B, W, T, V, r_new, s_new,
                                                                 nullptr, nullptr, nullptr, 1, 4, 1, 0);
@@ -2053,6 +2068,23 @@ int ctcps_set_psi_prefetch(int chunks) {
     const int prev = psi_prefetch_chunks();
     if (chunks >= 0 && chunks <= 64) g_psi_prefetch = chunks;
     return prev;
+}
+
+int ctcps_set_frame_window(int on) {
+    const int prev = frame_window() ? 1 : 0;
+    if (on == 0 || on == 1) g_frame_window = on;
+    return prev;
+}
+
+int ctcps_set_stream_counter(void *device_u64) {
+    g_stream_counter = reinterpret_cast<unsigned long long *>(device_u64);
+    return 0;
+}
+
+int ctcps_stream_chunk_bytes(int W) {
+    int HW, HWP, G;
+    pick_hw_psi(W, &HW, &HWP, &G);
+    return TT * PSI_NT * 4 * 4 + TT * HWP * 4;  // one chunk of a tile: 8 frames x 512 tokens of x + 8 frames of the group's lin
 }
 
 int ctcps_set_skip_done(int on) {
@@ -2220,11 +2252,13 @@ static int score_lazy_impl(const float *x_logp, int ldx, const float *r_prev, co
     float *lin = reinterpret_cast<float *>((char *)workspace + ws.lin_off);
     float *Gmax = reinterpret_cast<float *>((char *)workspace + ws.g_off);
     float *psic = reinterpret_cast<float *>((char *)workspace + ws.c_off);
+    int2 *frange = reinterpret_cast<int2 *>((char *)workspace + ws.r_off);
     const int Tpad = tpad_of(T);
     const int start = ol > 1 ? ol : 1;
     if (!workspace_prepared) {  // else ctcps_select_lazy already wrote lin / Gmax / psic for this very call
         const int warps = B * G * HWP;
         k_prep_psi<<<(warps + 3) / 4, 128, 0, st>>>(r_prev, XView{x_logp, (long long)T * ldx, (long long)ldx, 1}, last_ids, B, W, T, V, HW, HWP, G, start, Tpad, lin, Gmax, psic);
+        k_lin_range<<<B * G, 128, 0, st>>>(lin, Tpad, HWP, frange);
     }
     CUtensorMap tm;
     int rc = encode_x_map(&tm, x_logp, ldx, B, T, V);
@@ -2258,6 +2292,8 @@ static int score_lazy_impl(const float *x_logp, int ldx, const float *r_prev, co
     a.nvt = (V + PSI_NT * 4 - 1) / (PSI_NT * 4);
     a.prefetch = psi_prefetch_chunks();
     a.xlens = xlens;
+    a.frange = frame_window() ? frange : nullptr;
+    a.counter = g_stream_counter;
     a.tk.beam_scores = nullptr, a.tk.lists = nullptr, a.tk.K = 0, a.tk.done = nullptr;
     if (tk != nullptr) {
         a.tk = *tk;

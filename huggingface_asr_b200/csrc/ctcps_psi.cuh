@@ -48,6 +48,8 @@ struct PsiArgs {
     int B, W, T, V, blank, ol, G, Tpad, nvt;
     int prefetch;        // chunks of L2 look-ahead beyond the shared-memory ring (0 = none)
     const int64_t *xlens; // (B) utterance lengths or null: frames past the length hold exp(x) == 0 and are not streamed
+    const int2 *frange;   // (B*G) or null: first / last 8-frame chunk in which any hypothesis of the group has lin != 0 (k_lin_range)
+    unsigned long long *counter;  // or null: every launch adds the number of chunks it streams (instrumentation of bench.py)
     PsiTopk tk;
 };
 
@@ -62,7 +64,7 @@ struct PsiSmem {
     alignas(16) float lin[NSTAGE][TT][HWP];
     alignas(8) uint64_t full[NSTAGE];
     alignas(8) uint64_t empty[NSTAGE];
-    int cursor[2][7];  // thread 0's two look-ahead cursors (kept here, not in registers: every thread would pay for them)
+    int cursor[2][8];  // thread 0's two look-ahead cursors (kept here, not in registers: every thread would pay for them)
 };
 
 // one warp per (padded) hypothesis: lin stream, Gmax and the last-label column sum
@@ -105,6 +107,39 @@ __global__ void __launch_bounds__(128) k_prep_psi(const float *__restrict__ r_pr
     if (valid && lane == 0) {
         Gmax[h] = gm;
         psic[h] = sc;
+    }
+}
+
+// The lin stream is sparse in time: lin[t, h] = exp(r_sum[t-1, h] - offset) underflows to exactly 0 wherever the prefix is more
+// than e^-87 (e^-103 with subnormals) less probable than at its best frame -- far behind and far ahead of where the prefix
+// ends in the audio.  A chunk in which lin is 0 for every hypothesis of the group adds lin * p = 0 to every sum, bit for bit
+// (p = exp(x) <= 1 is finite), so the scoring kernel need not stream it.  One CTA per (utterance, hypothesis group) finds
+// the first and last chunk with a nonzero entry; {1, 0} = none.
+__global__ void __launch_bounds__(128) k_lin_range(const float *__restrict__ lin, int Tpad, int HWP, int2 *__restrict__ frange) {
+    __shared__ int s_lo[4], s_hi[4];
+    const float *base = lin + (size_t)blockIdx.x * Tpad * HWP;
+    int lo = 0x7fffffff, hi = -1;
+    const int n4 = HWP >> 2;  // HWP % 4 == 0: a frame's row is n4 float4
+    for (int te = threadIdx.x; te < Tpad; te += 128) {
+        const float4 *row = reinterpret_cast<const float4 *>(base + (size_t)te * HWP);
+        bool nz = false;
+        for (int q = 0; q < n4; ++q) {
+            const float4 v = row[q];
+            nz = nz || v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f;
+        }
+        if (nz) lo = min(lo, te), hi = max(hi, te);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) s_lo[threadIdx.x >> 5] = lo, s_hi[threadIdx.x >> 5] = hi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        lo = min(min(s_lo[0], s_lo[1]), min(s_lo[2], s_lo[3]));
+        hi = max(max(s_hi[0], s_hi[1]), max(s_hi[2], s_hi[3]));
+        frange[blockIdx.x] = hi >= 0 ? make_int2(lo / TT, hi / TT) : make_int2(1, 0);
     }
 }
 
@@ -377,30 +412,42 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
         if constexpr (TOPK) return a.tk.done != nullptr && a.tk.done[b] != 0;
         return false;
     };
-    // Chunks of a tile that are streamed: -1 = the tile is skipped altogether (no epilogue either), else the chunks from c0 up to
-    // the one that holds the utterance's last frame.  Past the length x is logzero for every token but blank (:39-42), exp(x)
-    // is exactly 0 and lin * 0 + acc == acc bit for bit; the blank column's score is overwritten with logzero anyway (:173).
-    auto tile_chunks = [&](int b) -> int {
+    // Chunks of a tile that are streamed: count -1 = the tile is skipped altogether (no epilogue either), else `count` chunks from
+    // `first`: from c0 (or the group's first chunk with a nonzero lin) up to the chunk that holds the utterance's last frame (or the
+    // group's last chunk with a nonzero lin).  Past the length x is logzero for every token but blank (:39-42), exp(x) is
+    // exactly 0 and lin * 0 + acc == acc bit for bit; the blank column's score is overwritten with logzero anyway (:173).
+    auto tile_chunks = [&](int b, int g, int &first) -> int {
+        first = c0;
         if (tile_skipped(b)) return -1;
-        if (a.xlens == nullptr) return nchunk;
-        const long long lraw = a.xlens[b];
-        long long l = lraw < 0 ? lraw + T : lraw;  // the length as K-a applied it
-        if (l < 0) l = 0;
-        if (lraw >= T) l = T;
-        const int last = l > 0 ? (int)((l - 1) / TT) : -1;
-        const int n = (last < cN ? last : cN) - c0 + 1;
+        int last = cN;
+        if (a.xlens != nullptr) {
+            const long long lraw = a.xlens[b];
+            long long l = lraw < 0 ? lraw + T : lraw;  // the length as K-a applied it
+            if (l < 0) l = 0;
+            if (lraw >= T) l = T;
+            const int ll = l > 0 ? (int)((l - 1) / TT) : -1;
+            last = ll < last ? ll : last;
+        }
+        if (a.frange != nullptr) {
+            const int2 r = a.frange[b * a.G + g];
+            last = r.y < last ? r.y : last;
+            if (a.ol != 0) first = r.x > first ? r.x : first;  // the first step reads x[0] out of chunk 0 (:112-113)
+            else if (last < 0) last = 0;
+        }
+        const int n = last - first + 1;
         return n > 0 ? n : 0;
     };
     int nitems = my_tiles * nchunk;
-    if ((TOPK && a.tk.done != nullptr) || a.xlens != nullptr) {
+    if ((TOPK && a.tk.done != nullptr) || a.xlens != nullptr || a.frange != nullptr) {
         nitems = 0;
         for (int ti = 0; ti < my_tiles; ++ti) {
-            int b, vt, g;
+            int b, vt, g, first;
             decode_tile((int)blockIdx.x + ti * (int)gridDim.x, b, vt, g);
-            const int n = tile_chunks(b);
+            const int n = tile_chunks(b, g, first);
             nitems += n > 0 ? n : 0;
         }
     }
+    if (a.counter != nullptr && tid == 0) atomicAdd(a.counter, (unsigned long long)nitems);
     // Thread 0 walks the CTA's flat chunk sequence twice ahead of the consumers, with two cursors that advance
     // incrementally (a tile is decoded once, when a cursor enters it -- no division per chunk):
     //   `is`  the next item to load into the shared-memory ring (NSTAGE items ahead of the one being consumed);
@@ -408,20 +455,20 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
     //         be in flight towards shared memory (4 CTAs x 3 stages x 16 KB per SM, a third of it being read at any time);
     //         the L2 prefetches carry the rest of the HBM queue depth, and the ring's own loads then mostly hit L2.
     struct Cursor {
-        int k, ti, ci, b, vt, g, nch;
+        int k, ti, ci, b, vt, g, nch, cs;
     };
     auto cursor_load = [&](int which) {
         const int *p = sm.cursor[which];
-        return Cursor{p[0], p[1], p[2], p[3], p[4], p[5], p[6]};
+        return Cursor{p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7]};
     };
     auto cursor_store = [&](int which, const Cursor &c) {
         int *p = sm.cursor[which];
-        p[0] = c.k, p[1] = c.ti, p[2] = c.ci, p[3] = c.b, p[4] = c.vt, p[5] = c.g, p[6] = c.nch;
+        p[0] = c.k, p[1] = c.ti, p[2] = c.ci, p[3] = c.b, p[4] = c.vt, p[5] = c.g, p[6] = c.nch, p[7] = c.cs;
     };
     auto cursor_enter = [&](Cursor &c) {  // decode the cursor's tile, stepping over tiles that stream nothing
         while (c.ti < my_tiles) {
             decode_tile((int)blockIdx.x + c.ti * (int)gridDim.x, c.b, c.vt, c.g);
-            c.nch = tile_chunks(c.b);
+            c.nch = tile_chunks(c.b, c.g, c.cs);
             if (c.nch > 0) break;
             ++c.ti;
         }
@@ -436,7 +483,7 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
     };
     auto issue = [&](const Cursor &c) {  // chunk c0 + c.ci of tile (c.b, c.vt, c.g) into stage c.k % NSTAGE
         const int s = c.k % NSTAGE;
-        const int ch = c0 + c.ci;
+        const int ch = c.cs + c.ci;
         mbar_expect_tx(&sm.full[s], STAGE_BYTES);
 #pragma unroll
         for (int bx = 0; bx < NBOX; ++bx)
@@ -444,7 +491,7 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
         bulk_load_1d(&sm.lin[s][0][0], a.lin + ((size_t)(c.b * a.G + c.g) * a.Tpad + (size_t)ch * TT) * HWP, TT * HWP * 4, &sm.full[s]);
     };
     auto prefetch = [&](const Cursor &c) {
-        const int ch = c0 + c.ci;
+        const int ch = c.cs + c.ci;
 #pragma unroll
         for (int bx = 0; bx < NBOX; ++bx) tma_prefetch_2d(&tmx, c.vt * VTILE + bx * BOXC, c.b * T + ch * TT);
     };
@@ -453,7 +500,7 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&sm.full[s], 1), mbar_init(&sm.empty[s], NWARP);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        Cursor is = {0, 0, 0, 0, 0, 0, 0}, pf = {0, 0, 0, 0, 0, 0, 0};
+        Cursor is = {0, 0, 0, 0, 0, 0, 0, 0}, pf = {0, 0, 0, 0, 0, 0, 0, 0};
         if (nitems > 0) {
             cursor_enter(is);
             while (is.k < nitems && is.k < NSTAGE) {  // prologue: fill the ring
@@ -476,7 +523,8 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
     for (int ti = 0; ti < my_tiles; ++ti) {
         int b, vt, g;
         decode_tile((int)blockIdx.x + ti * (int)gridDim.x, b, vt, g);
-        const int nch = tile_chunks(b);
+        int cfirst;
+        const int nch = tile_chunks(b, g, cfirst);
         if (nch < 0) continue;  // its candidate list keeps the last step's contents: the beam step ignores a finished utterance
         unsigned long long acc2[HP][4];  // (hyp 2p, hyp 2p+1) of token j, packed for FFMA2
         float x0[4];

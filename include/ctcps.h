@@ -67,6 +67,15 @@ int ctcps_set_psi_prefetch(int chunks);
  * result); the hypotheses returned are bit-identical.  0 = score every row every step.  Returns the previous setting; any
  * other argument only queries. */
 int ctcps_set_skip_done(int on);
+/* Lazy scoring kernel: 1 (default; env CTCPS_FRAME_WINDOW) = stream only the 8-frame chunks in which the previous state puts a
+ * nonzero weight on some hypothesis of the group -- exp(r_sum[t-1] - offset) underflows to exactly 0 far behind and far ahead
+ * of where a prefix ends in the audio, and such chunks add exactly 0 to every prefix score; results are bit-identical.
+ * 0 = stream every frame from the prefix length to T.  Returns the previous setting; any other argument only queries. */
+int ctcps_set_frame_window(int on);
+/* Instrumentation (bench.py's roofline): a device uint64 every lazy scoring launch adds the number of chunks it streams to
+ * (NULL = off); ctcps_stream_chunk_bytes(W) = bytes of one chunk (8 frames x 512 tokens of posteriors + the group's weights). */
+int ctcps_set_stream_counter(void *device_u64);
+int ctcps_stream_chunk_bytes(int W);
 
 /* Widest hypothesis group one thread of the lazy scoring kernel accumulates (2..20, default 20, env CTCPS_PSI_MAX_GROUP):
  * beams wider than the group are split into several groups that each stream the x tile.  Changes the layout of the scoring

@@ -314,3 +314,62 @@ def test_leaving_out_padded_frames_is_bit_identical(B, W, T, V, kind, n_steps):
     for a, b in zip(*outs):
         assert not torch.isnan(a).any()
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B,W,T,V,kind", [(6, 10, 200, 1000, "peaky"), (4, 20, 300, 516, "peaky"), (5, 4, 120, 2048, "flat"), (3, 3, 40, 64, "peaky")])
+def test_streaming_only_the_frames_with_nonzero_weight_is_bit_identical(B, W, T, V, kind):
+    """ctcps_set_frame_window (default on): the lazy scoring kernel streams only the chunks in which exp(r_sum - offset) is nonzero
+    for some hypothesis of the group.  Whole decodes (native loop: n-best, scores) and the processor's dense outputs at every
+    step must be bit-identical with the switch off -- and the switch must actually save chunks on a long utterance."""
+    from huggingface_asr_b200 import _lib
+    from huggingface_asr_b200.beam_search import joint_beam_search_native
+    from huggingface_asr_b200.decoding.ctc_scorer import CTCRescorerLogitsProcessor
+    from huggingface_asr_b200.synthetic import SyntheticDecoder, make_attention_scores, make_encoder_logits
+
+    logits, lens, tr = make_encoder_logits(B, T, V, kind, True, seed=47)
+    L = _lib.lib()
+    prev = L.ctcps_set_frame_window(-1)
+    counter = torch.zeros(1, dtype=torch.int64, device="cuda")
+    outs, dense, chunks = [], [], []
+    try:
+        for on in (0, 1):
+            L.ctcps_set_frame_window(on)
+            L.ctcps_set_stream_counter(counter.data_ptr())
+            counter.zero_()
+            if kind == "peaky":
+                dec = SyntheticDecoder(tr, W, V, 64, seed=2, device="cuda")
+            else:
+                dec = lambda ids, n: make_attention_scores(B * W, V, n, seed=3, scale=0.5).cuda()  # noqa: E731
+            proc = CTCRescorerLogitsProcessor(logits.cuda(), lens.cuda(), BLANK, EOS, 0, 0.3, W, -1, False, 1.0, materialize_state=False)
+            outs.append(joint_beam_search_native(proc, dec, B, W, V, BOS, EOS, BLANK, max_length=min(64, T // 2), device=torch.device("cuda"),
+                                                 done_check_lag=0, fuse_topk=True, num_return_sequences=min(W, 3)))
+            torch.cuda.synchronize()
+            chunks.append(int(counter.item()))
+            # the processor's own __call__ (dense joint scores), a few steps of a plain beam update
+            proc = CTCRescorerLogitsProcessor(logits.cuda(), lens.cuda(), BLANK, EOS, 0, 0.3, W, -1, False, 1.0, materialize_state=False)
+            ids = torch.zeros((B * W, 1), dtype=torch.long, device="cuda")
+            beam_scores = torch.zeros(B, W, device="cuda")
+            beam_scores[:, 1:] = -1e9
+            steps = []
+            for n in range(6):
+                att = make_attention_scores(B * W, V, n, seed=5, scale=0.5).cuda()
+                out = proc(ids, att)
+                steps.append(out.clone())
+                top, idx = (out + beam_scores.view(-1, 1)).view(B, W * V).topk(W, dim=1)
+                base = (torch.arange(B, device="cuda") * W).view(B, 1)
+                ids = torch.cat([ids[(idx // V + base).view(-1)], (idx % V).view(-1, 1)], dim=1)
+                beam_scores = top
+            dense.append(steps)
+    finally:
+        L.ctcps_set_stream_counter(None)
+        L.ctcps_set_frame_window(prev)
+    a, b = outs
+    assert a.steps == b.steps
+    assert torch.equal(a.sequences, b.sequences) and torch.equal(a.lengths, b.lengths) and torch.equal(a.scores, b.scores)
+    assert torch.equal(a.nbest_sequences, b.nbest_sequences) and torch.equal(a.nbest_scores, b.nbest_scores)
+    for n, (x, y) in enumerate(zip(*dense)):
+        assert torch.equal(x, y), f"processor output of step {n} differs by {(x - y).abs().max().item()}"
+    print(f"chunks streamed by the native decode: all frames {chunks[0]}, windowed {chunks[1]}")
+    assert chunks[1] <= chunks[0]
+    if T >= 200:
+        assert chunks[1] < 0.8 * chunks[0], "the window should leave out a fair share of a long utterance"
