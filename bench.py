@@ -488,6 +488,7 @@ class Runner:
             d["avg_launch_ms"] = r["score_ms_total"] / r["n_score_all"]
             d["launches_timed"] = r["n_score_all"]
             d["launches_on_finished_batches_not_counted"] = 0
+            d["traffic"] = None  # per-launch DRAM bytes vary with the window; one captured launch: profiles/r3h_psi_ncu.md (596 MB)
             d["streamed_bytes_per_launch"] = moved / r["n_score_all"]
             d["streamed_fraction_of_all_frames"] = moved / (r["n_score_all"] * true_bytes)
             d["algorithmic_bytes_per_launch_note"] = ("all frames from the prefix length to T; the kernel leaves out the chunks whose weights "
