@@ -126,6 +126,20 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
         : "memory");
 }
+// the same with an L2 eviction-priority hint (createpolicy): a stream far larger than L2 that is read once per launch should
+// not push out what the launch re-reads (decoder scores, the lin stream) or what the next kernel reads (log_psi)
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
 // TMA prefetch of a box into L2 (no shared-memory destination, no barrier): SASS UTMAPF.L2
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
@@ -2293,6 +2307,14 @@ static int score_lazy_impl(const float *x_logp, int ldx, const float *r_prev, co
     a.prefetch = psi_prefetch_chunks();
     a.xlens = xlens;
     a.frange = frame_window() ? frange : nullptr;
+    {   // posteriors that cannot stay in L2 anyway (> 96 MB) are streamed with evict-first priority (CTCPS_PSI_EVICT_FIRST=0: off)
+        static int ef = -1;
+        if (ef < 0) {
+            const char *ev = getenv("CTCPS_PSI_EVICT_FIRST");
+            ef = (ev != nullptr && atoi(ev) == 0) ? 0 : 1;
+        }
+        a.evict_first = (ef && (size_t)B * T * V * sizeof(float) > ((size_t)96 << 20)) ? 1 : 0;
+    }
     a.counter = g_stream_counter;
     a.tk.beam_scores = nullptr, a.tk.lists = nullptr, a.tk.K = 0, a.tk.done = nullptr;
     if (tk != nullptr) {

@@ -50,6 +50,7 @@ struct PsiArgs {
     const int64_t *xlens; // (B) utterance lengths or null: frames past the length hold exp(x) == 0 and are not streamed
     const int2 *frange;   // (B*G) or null: first / last 8-frame chunk in which any hypothesis of the group has lin != 0 (k_lin_range)
     unsigned long long *counter;  // or null: every launch adds the number of chunks it streams (instrumentation of bench.py)
+    int evict_first;      // 1: the x stream is loaded with L2 evict-first priority
     PsiTopk tk;
 };
 
@@ -481,13 +482,20 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
             cursor_enter(c);
         }
     };
-    auto issue = [&](const Cursor &c) {  // chunk c0 + c.ci of tile (c.b, c.vt, c.g) into stage c.k % NSTAGE
+    const uint64_t l2_stream_policy = l2_policy_evict_first();
+    auto issue = [&](const Cursor &c) {  // chunk c.cs + c.ci of tile (c.b, c.vt, c.g) into stage c.k % NSTAGE
         const int s = c.k % NSTAGE;
         const int ch = c.cs + c.ci;
         mbar_expect_tx(&sm.full[s], STAGE_BYTES);
+        if (a.evict_first) {
 #pragma unroll
-        for (int bx = 0; bx < NBOX; ++bx)
-            tma_load_2d(&sm.xs[s][bx][0][0], &tmx, c.vt * VTILE + bx * BOXC, c.b * T + ch * TT, &sm.full[s]);
+            for (int bx = 0; bx < NBOX; ++bx)
+                tma_load_2d_hint(&sm.xs[s][bx][0][0], &tmx, c.vt * VTILE + bx * BOXC, c.b * T + ch * TT, &sm.full[s], l2_stream_policy);
+        } else {
+#pragma unroll
+            for (int bx = 0; bx < NBOX; ++bx)
+                tma_load_2d(&sm.xs[s][bx][0][0], &tmx, c.vt * VTILE + bx * BOXC, c.b * T + ch * TT, &sm.full[s]);
+        }
         bulk_load_1d(&sm.lin[s][0][0], a.lin + ((size_t)(c.b * a.G + c.g) * a.Tpad + (size_t)ch * TT) * HWP, TT * HWP * 4, &sm.full[s]);
     };
     auto prefetch = [&](const Cursor &c) {

@@ -8,6 +8,6 @@ python - <<'P'
 import json
 d = json.loads(open("gpurun_out/r2x_bench_n2.json").read().strip().splitlines()[-1])
 print("N=2 C2", round(d["value"]), "e2e", round(d["e2e"]["value"]), "n_gpus", d["n_gpus"], "scaling", d["scaling"])
-print("hidden", {k: (round(v["value"]), round(v["ctc_head_ms"], 3)) for k, v in d["e2e_from_hidden"].items() if isinstance(v, dict)})
+print("hidden", {k: (round(v["value"]), round(v["ctc_head_ms"], 3)) for k, v in d["e2e_from_hidden"].items() if isinstance(v, dict) and "value" in v})
 print("c5", {k: d["c5_job"].get(k) for k in ("value", "ms", "ranks", "utterances_differing_from_aligned_transcript", "copies_of_an_utterance_agree", "hypotheses_checksum")})
 P
