@@ -55,6 +55,7 @@ struct PsiArgs {
 };
 
 constexpr int PSI_NT = 128;      // threads of the lazy scoring kernel (512-token tiles)
+constexpr int PSI_MAXT = 256;      // tiles of a CTA whose chunk range is looked up once at kernel start (the rest: on the fly)
 constexpr int PSI_TOPK_CAP = 256;  // elements of a tile at or above the threshold that the exact ranking takes
 
 template <int HWP, int NT, int NSTAGE>
@@ -66,6 +67,7 @@ struct PsiSmem {
     alignas(8) uint64_t full[NSTAGE];
     alignas(8) uint64_t empty[NSTAGE];
     int cursor[2][8];  // thread 0's two look-ahead cursors (kept here, not in registers: every thread would pay for them)
+    short tfirst[PSI_MAXT], tcnt[PSI_MAXT];  // first chunk / number of chunks of this CTA's first PSI_MAXT tiles (tile_chunks, once per launch)
 };
 
 // one warp per (padded) hypothesis: lin stream, Gmax and the last-label column sum
@@ -438,13 +440,40 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
         const int n = last - first + 1;
         return n > 0 ? n : 0;
     };
-    int nitems = my_tiles * nchunk;
-    if ((TOPK && a.tk.done != nullptr) || a.xlens != nullptr || a.frange != nullptr) {
-        nitems = 0;
-        for (int ti = 0; ti < my_tiles; ++ti) {
+    // The chunk range of a tile hangs on three words of global memory (done flag, length, lin range): looked up for all tiles
+    // of the CTA at once, by a thread each, and kept in shared memory -- one round trip per launch.  (Looked up where they were
+    // needed they were a chain of dependent loads in front of every tile, for the producer and again for the consumers: 8 % of
+    // the warp samples before the first TMA issue plus ~1.5 us per tile, ncu r3m.)
+    const bool clipped = (TOPK && a.tk.done != nullptr) || a.xlens != nullptr || a.frange != nullptr;
+    const bool table = clipped && cN < 32767;  // chunk indices fit the 16-bit table
+    if (table) {
+        for (int ti = tid; ti < my_tiles && ti < PSI_MAXT; ti += NT) {
             int b, vt, g, first;
             decode_tile((int)blockIdx.x + ti * (int)gridDim.x, b, vt, g);
             const int n = tile_chunks(b, g, first);
+            sm.tfirst[ti] = (short)first, sm.tcnt[ti] = (short)n;
+        }
+        __syncthreads();
+    }
+    auto tile_info = [&](int ti, int b, int g, int &first) -> int {
+        if (!clipped) {
+            first = c0;
+            return nchunk;
+        }
+        if (table && ti < PSI_MAXT) {
+            first = sm.tfirst[ti];
+            return sm.tcnt[ti];
+        }
+        return tile_chunks(b, g, first);
+    };
+    int nitems = my_tiles * nchunk;  // used by thread 0 only
+    if (clipped && tid == 0) {
+        nitems = 0;
+        for (int ti = 0; ti < my_tiles; ++ti) {
+            int b, vt, g, first;
+            if (!table || ti >= PSI_MAXT) decode_tile((int)blockIdx.x + ti * (int)gridDim.x, b, vt, g);
+            else b = vt = g = 0;
+            const int n = tile_info(ti, b, g, first);
             nitems += n > 0 ? n : 0;
         }
     }
@@ -469,7 +498,7 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
     auto cursor_enter = [&](Cursor &c) {  // decode the cursor's tile, stepping over tiles that stream nothing
         while (c.ti < my_tiles) {
             decode_tile((int)blockIdx.x + c.ti * (int)gridDim.x, c.b, c.vt, c.g);
-            c.nch = tile_chunks(c.b, c.g, c.cs);
+            c.nch = tile_info(c.ti, c.b, c.g, c.cs);
             if (c.nch > 0) break;
             ++c.ti;
         }
@@ -532,7 +561,7 @@ __global__ void __launch_bounds__(NT, MINB) k_psi_full(const __grid_constant__ C
         int b, vt, g;
         decode_tile((int)blockIdx.x + ti * (int)gridDim.x, b, vt, g);
         int cfirst;
-        const int nch = tile_chunks(b, g, cfirst);
+        const int nch = tile_info(ti, b, g, cfirst);
         if (nch < 0) continue;  // its candidate list keeps the last step's contents: the beam step ignores a finished utterance
         unsigned long long acc2[HP][4];  // (hyp 2p, hyp 2p+1) of token j, packed for FFMA2
         float x0[4];
