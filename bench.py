@@ -289,16 +289,19 @@ class Runner:
         # whose weights underflowed to zero are left out): the roofline divides THOSE bytes by the time of the calls
         stream_counter = torch.zeros(1, dtype=torch.int64, device=self.dev)
         L_.ctcps_set_stream_counter(stream_counter.data_ptr())
-        self.sync_all()
-        e0.record()
-        steps_total = 0
-        out = None
-        for _ in range(steps):
-            out = run(wl.logits_d, wl.lens_d, score_events)
-            steps_total += out.steps
-        e1.record()
-        self.sync_all()
-        L_.ctcps_set_stream_counter(None)
+        try:
+            self.sync_all()
+            e0.record()
+            steps_total = 0
+            out = None
+            for _ in range(steps):
+                out = run(wl.logits_d, wl.lens_d, score_events)
+                steps_total += out.steps
+            e1.record()
+            self.sync_all()
+        finally:  # never leave the library pointing at a tensor that is about to be freed
+            torch.cuda.synchronize(self.dev)
+            L_.ctcps_set_stream_counter(None)
         streamed_chunks = int(stream_counter.item())
         clk = sampler.stop() if (self.rank == 0 and clocks) else None
         ms = e0.elapsed_time(e1)
