@@ -2047,7 +2047,7 @@ int beam_step_impl(const float *joint, const int64_t *cand_ids, int S, float *be
 
 extern "C" {
 
-int ctcps_version(void) { return 110; }
+int ctcps_version(void) { return 120; }  // 120: score_window, score_lazy_lens, score_lazy_topk_active, frame window, 3xFP16 head
 
 const char *ctcps_error_string(int code) {
     if (code == 0) return "ok";
